@@ -1,0 +1,154 @@
+/*
+ * pertshade.h — C ABI of the B200-native perturbed shading hot path.
+ *
+ * One shared library (libpertshade.so, built for sm_100a from pertrenderer_b200/csrc) exports the
+ * functions below.  Plain pointers and sizes only: no torch / C++ types cross this boundary, the
+ * library never allocates, frees or retains device memory, holds no global or thread-local state,
+ * never synchronises the device and launches on the stream it is given.  Every function returns
+ * PERT_OK (0) or a negative PERT_E_* code; nothing throws across the ABI.
+ *
+ * What each entry point replaces in the reference (paths relative to quentinll/pertrenderer):
+ *
+ *   pert_shade_fwd   randomras/random_rasterizer.py:34-56  smooth_rgb_blend          (forward), with
+ *                    randomras/smoothrast.py:15-37         randomHeaviside.forward
+ *                    randomras/smoothagg.py:196-205        GaussianAgg.aggregate
+ *                    randomras/smoothagg.py:13-42          randomArgmax.forward
+ *   pert_shade_bwd   the autograd backward of the same chain:
+ *                    randomras/smoothagg.py:45-73          randomArgmax.backward
+ *                    randomras/smoothagg.py:303-311,325-337 log_corrected / prod_corrected backward
+ *                    randomras/smoothrast.py:40-59         randomHeaviside.backward
+ *   pert_rast_fwd / pert_rast_bwd     randomras/smoothrast.py:12-59   (stand-alone randomHeaviside)
+ *   pert_argmax_fwd / pert_argmax_bwd randomras/smoothagg.py:10-73    (stand-alone randomArgmax)
+ *   pert_noise_fill  the two torch.normal draws, smoothrast.py:21 and smoothagg.py:21 (test aid:
+ *                    materialises the counter-based noise the fused kernels generate in registers)
+ *
+ * Layouts (all contiguous, innermost last), P = N*H*W pixels, K faces per pixel, K1 = K+1:
+ *   pix_to_face int64 (P,K)   zbuf, dists float (P,K)   colors float (P,K,3)
+ *   znear, zfar float (N) or (1)   image / grad_image float (P,4)
+ *   explicit noise: noise_rast float (S_rast,P,K), noise_agg float (S_agg,P,K1)   [optional]
+ * Saved state written by forward and read by backward (caller-allocated):
+ *   counts  uint16 (P,K)   number of coverage samples with h=1 among the local sample shard
+ *   rsum    float  (P,K)   sum_s (h_s - h0) * U_s over the local sample shard
+ *   winners uint8  (P,S_agg_local) if K1 <= 256 else uint16: argmax index of every sample
+ */
+#ifndef PERTSHADE_H_
+#define PERTSHADE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PERT_ABI_VERSION 1
+
+/* error codes */
+#define PERT_OK 0
+#define PERT_E_NULL (-1)        /* a required pointer is NULL */
+#define PERT_E_SHAPE (-2)       /* non-positive / inconsistent sizes */
+#define PERT_E_UNSUPPORTED (-3) /* K or S outside what the kernels support */
+#define PERT_E_ALIGN (-4)       /* pointer not aligned to its element type */
+#define PERT_E_SAMPLES (-5)     /* bad sample shard: begin must be a multiple of 4, begin < end <= S */
+#define PERT_E_CUDA (-6)        /* CUDA launch / runtime error (see pert_last_cuda_error) */
+#define PERT_E_SCALAR (-7)      /* sigma, gamma or alpha not finite and > 0 */
+
+/* flags */
+#define PERT_F_NO_SKIP 1u        /* brute force: draw every sample of every entry (test / audit) */
+#define PERT_F_SKIP_DEAD_NOISE 2u /* backward: do not draw noise for -inf logits; their zero-mean
+                                     contribution is dropped and the ||V||^2 term uses its expectation
+                                     (same expectation, lower variance, not sample-path identical) */
+/* phases of the fused kernels; 0 means "all".  Used for noise-sample sharding where collectives sit
+ * between the phases. */
+#define PERT_PH_RAST 0x10u  /* fwd: draw coverage samples -> counts, rsum */
+#define PERT_PH_AGG 0x20u   /* fwd: logits + perturbed argmax -> hist, winners   (reads counts if !RAST) */
+#define PERT_PH_BLEND 0x40u /* fwd: hist -> image                                (reads hist if !AGG) */
+#define PERT_PH_BWD_SAMPLE 0x100u /* bwd: per-logit score sums -> acc, pixstat */
+#define PERT_PH_BWD_FINISH 0x200u /* bwd: chain rule -> grad_dists, grad_zbuf, scalars (reads acc if !SAMPLE) */
+
+typedef struct pert_problem {
+    /* geometry */
+    int64_t N, H, W;
+    int32_t K;
+    /* hyper-parameters (GaussianRast.sigma, GaussianAgg.gamma/.alpha/.eps, BlendParams.background_color) */
+    float sigma, gamma, alpha, eps;
+    float background[3];
+    /* sample counts: totals are the estimator's denominators; [begin,end) is this call's shard */
+    int32_t S_rast, S_agg;
+    int32_t s_rast_begin, s_rast_end;
+    int32_t s_agg_begin, s_agg_end;
+    /* counter-based noise: seeds of the two stages, global index of this call's first pixel */
+    uint64_t seed_rast, seed_agg;
+    int64_t pixel_offset;
+    uint32_t flags;
+    int32_t depth_len; /* length of znear/zfar: 1 (broadcast) or N */
+    /* inputs (device pointers) */
+    const int64_t* pix_to_face;
+    const float* zbuf;
+    const float* dists;
+    const float* colors;
+    const float* znear;
+    const float* zfar;
+    /* optional explicit noise (device); NULL -> in-register Philox4x32-10 + Box-Muller */
+    const float* noise_rast;
+    const float* noise_agg;
+} pert_problem;
+
+int pert_version(void);
+const char* pert_strerror(int code);
+/* last cudaError_t name seen by this thread's most recent failing call (diagnostic only) */
+const char* pert_last_cuda_error(void);
+
+/* number of tiles the fused kernels split the P pixels into; scalar_partials needs 4*tiles floats */
+int64_t pert_num_tiles(const pert_problem* pb);
+/* element size in bytes of the winners buffer for this K (1 or 2) */
+int pert_winner_bytes(int32_t K);
+
+/*
+ * Forward.  Outputs: image (P,4).  Saved state: counts, rsum, winners (see top).  `hist` int32
+ * (P,K1) is optional unless the AGG and BLEND phases run in separate calls.  With phase flags,
+ * buffers produced by an earlier phase are inputs.
+ */
+int pert_shade_fwd(const pert_problem* pb, float* image, uint16_t* counts, float* rsum, void* winners,
+                   int32_t* hist, void* stream);
+
+/*
+ * Backward.  grad_image (P,4).  Outputs grad_dists, grad_zbuf (P,K), grad_colors (P,K,3; may be
+ * NULL), grad_scalars float[3] = d/d(sigma, gamma, alpha).  scalar_partials: workspace of
+ * 4*pert_num_tiles floats.  acc float (P,K1) and pixstat float (P,2) are optional unless the two
+ * backward phases run in separate calls (sample sharding); hist int32 (P,K1) is the all-shard
+ * winner histogram of forward, needed only then (NULL: rebuilt from `winners`).
+ */
+int pert_shade_bwd(const pert_problem* pb, const float* grad_image, const uint16_t* counts,
+                   const float* rsum, const void* winners, float* grad_dists, float* grad_zbuf,
+                   float* grad_colors, float* scalar_partials, float* grad_scalars, float* acc,
+                   float* pixstat, const int32_t* hist, void* stream);
+
+/*
+ * Stand-alone perturbed Heaviside on x (P,K) (x = -dists in the shader).  prob = counts/S.
+ * Explicit noise (S,P,K) optional.
+ */
+int pert_rast_fwd(const float* x, int64_t P, int32_t K, int32_t S, int32_t s_begin, int32_t s_end,
+                  float sigma, uint64_t seed, int64_t pixel_offset, const float* noise, uint32_t flags,
+                  float* prob, float* rsum, void* stream);
+int pert_rast_bwd(const float* grad_l, const float* rsum, int64_t n, int32_t S, float sigma,
+                  float* grad_x, float* scalar_partials, float* grad_sigma, void* stream);
+
+/* Stand-alone perturbed argmax on logits z (P,K1). */
+int pert_argmax_fwd(const float* z, int64_t P, int32_t K1, int32_t S, int32_t s_begin, int32_t s_end,
+                    float gamma, uint64_t seed, int64_t pixel_offset, const float* noise, uint32_t flags,
+                    float* weights, void* winners, void* stream);
+int pert_argmax_bwd(const float* grad_l, const float* z, const void* winners, int64_t P, int32_t K1,
+                    int32_t S, int32_t s_begin, int32_t s_end, float gamma, uint64_t seed,
+                    int64_t pixel_offset, const float* noise, uint32_t flags, float* grad_z,
+                    float* scalar_partials, float* grad_gamma, void* stream);
+
+/* Materialise the counter-based noise: out float (s_end-s_begin, P, slots), stage 0 = coverage
+ * (slots = K), 1 = aggregation (slots = K1). */
+int pert_noise_fill(uint64_t seed, int32_t stage, int64_t P, int32_t slots, int32_t s_begin, int32_t s_end,
+                    int64_t pixel_offset, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PERTSHADE_H_ */

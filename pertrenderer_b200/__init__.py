@@ -1,0 +1,19 @@
+"""pertrenderer_b200 — B200-native perturbed shading (GaussianRast -> GaussianAgg -> blend).
+
+Drop-in for the hot path of quentinll/pertrenderer (``randomras``): the same public names
+(``randomras/__init__.py:1-3``), backed by hand-written sm_100a kernels behind a C ABI
+(``include/pertshade.h``).  CUDA only: there is no CPU or PyTorch fallback on this path.
+"""
+
+from .random_rasterizer import RandomSimpleShader, smooth_rgb_blend
+from .smoothagg import GaussianAgg, SoftAgg, randomArgmax
+from .smoothrast import GaussianRast, SoftRast, randomHeaviside
+from .structures import BlendParams, DepthCameras, Fragments, TexelMeshes, synthetic_fragments
+from .ops import explicit_noise, kernel_flags
+
+__all__ = [
+    "RandomSimpleShader", "smooth_rgb_blend", "GaussianAgg", "SoftAgg", "randomArgmax", "GaussianRast",
+    "SoftRast", "randomHeaviside", "BlendParams", "DepthCameras", "Fragments", "TexelMeshes",
+    "synthetic_fragments", "explicit_noise", "kernel_flags",
+]
+__version__ = "0.1.0"

@@ -1,0 +1,58 @@
+"""Build the sm_100a shared library of the perturbed shading kernels, in-tree.
+
+    python -m pertrenderer_b200.build [--force]
+
+Produces ``pertrenderer_b200/libpertshade.so`` (git-ignored, travels to the GPU box with the
+repository snapshot).  nvcc cross-compiles without a GPU.
+"""
+
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC_DIR = os.path.join(HERE, "csrc")
+SOURCES = [os.path.join(SRC_DIR, "pertshade.cu")]
+HEADERS = [os.path.join(SRC_DIR, "philox.cuh"), os.path.join(os.path.dirname(HERE), "include", "pertshade.h")]
+LIB_PATH = os.path.join(HERE, "libpertshade.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-shared",
+    # no --use_fast_math: the explicit-noise parity mode needs IEEE division / logf and
+    # uncontracted multiply-add where the kernels ask for it (__fmul_rn / __fadd_rn)
+]
+
+
+def find_nvcc() -> str:
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build libpertshade.so")
+    return nvcc
+
+
+def is_stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(p) > t for p in SOURCES + HEADERS)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    if not force and not is_stale():
+        return LIB_PATH
+    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + SOURCES
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    if verbose:
+        print(proc.stderr)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,94 @@
+// Counter-based noise for the perturbed shader: Philox4x32-10 (Salmon et al., SC'11) + Box-Muller.
+//
+// One Philox call yields the four standard normals of samples 4q..4q+3 for ONE noise coordinate:
+//     counter = (q, slot, pixel_lo, pixel_hi | stage << 31),  key = seed
+// where `pixel` is the GLOBAL pixel index (batch shards of one job draw the same noise as the
+// unsharded job), `slot` is the face index k (coverage stage) or logit index j (aggregation stage,
+// j = K is the background), and `q = s >> 2`.  Nothing sample-sized is ever stored: forward and
+// backward regenerate the same values from the same counters.
+//
+// Replaces the two materialised draws of the reference, torch.normal(zeros(S,N,H,W,K)) at
+// randomras/smoothrast.py:21 and torch.normal(zeros(S,N,H,W,K+1)) at randomras/smoothagg.py:21.
+#pragma once
+#include <cstdint>
+
+namespace pert {
+
+// |n| <= sqrt(-2 ln 2^-33) = 6.764 for every value normal4() can return; the kernels use this
+// bound to skip draws that cannot change any output bit.
+constexpr float kNoiseAbsMax = 6.8f;
+
+template <int ROUNDS>
+__device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                           uint32_t k1, uint32_t (&out)[4]) {
+#pragma unroll
+    for (int r = 0; r < ROUNDS; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0;
+    out[1] = c1;
+    out[2] = c2;
+    out[3] = c3;
+}
+
+// u in (0, 1]: (x + 0.5) * 2^-32
+__device__ __forceinline__ float u01(uint32_t x) { return fmaf((float)x, 2.3283064365386963e-10f, 1.1641532182693481e-10f); }
+
+__device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
+    const float u = u01(a);
+    // radius = sqrt(-2 ln u): MUFU.LG2 + MUFU.SQRT;  angle = 2 pi v: MUFU.SIN / MUFU.COS
+    float rad;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * __log2f(u)));
+    const float ang = fmaf((float)b, 1.4629180792671596e-9f, 7.314590396335798e-10f);  // 2 pi (b + .5) 2^-32
+    float s, c;
+    __sincosf(ang, &s, &c);
+    n0 = rad * c;
+    n1 = rad * s;
+}
+
+struct PhiloxNoise {
+    uint32_t k0, k1;
+    uint32_t stage_bit;  // 0 or 0x80000000
+    int64_t pixel_offset;
+
+    __host__ __device__ __forceinline__ PhiloxNoise(uint64_t seed, int stage, int64_t pixel_off)
+        : k0((uint32_t)seed), k1((uint32_t)(seed >> 32)), stage_bit(stage ? 0x80000000u : 0u), pixel_offset(pixel_off) {}
+
+    // normals of samples 4q..4q+3 for (pixel_local, slot)
+    __device__ __forceinline__ void get4(uint32_t q, uint32_t slot, int64_t pixel_local, float (&n)[4]) const {
+        const uint64_t gp = (uint64_t)(pixel_local + pixel_offset);
+        uint32_t r[4];
+        philox4x32<10>(q, slot, (uint32_t)gp, ((uint32_t)(gp >> 32) & 0x7fffffffu) | stage_bit, k0, k1, r);
+        box_muller(r[0], r[1], n[0], n[1]);
+        box_muller(r[2], r[3], n[2], n[3]);
+    }
+    static constexpr bool kBounded = true;
+};
+
+// Explicit noise tensor (S, P, slots), e.g. the reference's own draws: used for exact-noise parity.
+struct ExplicitNoise {
+    const float* base;
+    int64_t P;
+    int32_t slots;
+    int32_t S;
+
+    __device__ __forceinline__ void get4(uint32_t q, uint32_t slot, int64_t pixel_local, float (&n)[4]) const {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const int64_t s = (int64_t)q * 4 + t;
+            n[t] = (s < S) ? __ldg(base + (s * P + pixel_local) * slots + slot) : 0.0f;
+        }
+    }
+    static constexpr bool kBounded = false;
+};
+
+}  // namespace pert

@@ -1,0 +1,174 @@
+"""Shader layer — the reference-facing mirror of ``randomras/random_rasterizer.py``.
+
+``smooth_rgb_blend`` (random_rasterizer.py:34-56) and ``RandomSimpleShader`` (:132-191) keep the
+reference's signatures, so ``MeshRenderer(rasterizer=..., shader=RandomSimpleShader(...))`` works
+unchanged.  With the (GaussianRast, GaussianAgg) pair the whole chain — coverage sampling, mask,
+alpha, logits, perturbed argmax, blend, and the score-function backward — is ONE forward and ONE
+backward sm_100a kernel (``pert_shade_fwd`` / ``pert_shade_bwd``).  Any other operator pair falls
+through to the operator-by-operator composition of the reference, where the Gaussian operators
+still run on their own CUDA kernels.
+"""
+
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from . import ops
+from .smoothagg import GaussianAgg, SoftAgg
+from .smoothrast import GaussianRast, SoftRast
+from .structures import BlendParams
+
+
+def _background_tuple(blend_params):
+    bg = blend_params.background_color
+    if torch.is_tensor(bg):
+        bg = bg.detach().reshape(-1).tolist()
+    bg = tuple(float(v) for v in bg)
+    if len(bg) != 3:
+        raise ValueError("background_color must have 3 components")
+    return bg
+
+
+class _PerturbedShade(Function):
+    """Fused GaussianRast -> mask/alpha -> GaussianAgg -> blend.
+
+    Differentiable inputs: colors, dists, zbuf and the three 0-dim scalars sigma, gamma, alpha
+    (CPU leaves in the reference: smoothrast.py:116, smoothagg.py:153-154).  Saved for backward:
+    uint16 hit counts and float score sums per pixel·face, one winner index per pixel·sample —
+    nothing of size (S,N,H,W,K)."""
+
+    @staticmethod
+    def forward(ctx, colors, dists, zbuf, sigma, gamma, alpha, pix_to_face, znear, zfar, cfg):
+        noise_r, noise_a = ops.current_explicit_noise()
+        # noise order of the reference: coverage draw first (smoothrast.py:21), then the optional
+        # global reseed (smoothagg.py:18-19), then the aggregation draw (smoothagg.py:21)
+        seed_r = 0 if noise_r is not None else ops.draw_seed()
+        if cfg["fixed_noise"]:
+            torch.manual_seed(1)
+        seed_a = 0 if noise_a is not None else ops.draw_seed()
+        pr = ops.ShadeProblem(
+            pix_to_face=pix_to_face, zbuf=zbuf, dists=dists, colors=colors, znear=znear, zfar=zfar,
+            background=cfg["background"], sigma=float(sigma), gamma=float(gamma), alpha=float(alpha),
+            eps=float(cfg["eps"]), S_rast=int(cfg["S_rast"]), S_agg=int(cfg["S_agg"]),
+            seed_rast=seed_r, seed_agg=seed_a, pixel_offset=int(cfg.get("pixel_offset", 0)),
+            flags=ops.current_flags() | int(cfg.get("flags", 0)), noise_rast=noise_r, noise_agg=noise_a)
+        image, saved = ops.shade_forward(pr)
+        ctx.pr, ctx.saved = pr, saved
+        ctx.scalars = (sigma, gamma, alpha)
+        return image
+
+    @staticmethod
+    def backward(ctx, grad_image):
+        need = ctx.needs_input_grad
+        gd, gz, gc, scal = ops.shade_backward(ctx.pr, ctx.saved, grad_image, need_colors=need[0])
+        out_scal = [None, None, None]
+        if any(need[3:6]):
+            host = scal.cpu()  # one 12-byte read; the reference moves each scalar grad to the CPU leaf
+            for i, t in enumerate(ctx.scalars):
+                if need[3 + i] and torch.is_tensor(t):
+                    out_scal[i] = host[i].to(dtype=t.dtype).reshape(t.shape).to(t.device)
+        return (gc if need[0] else None, gd if need[1] else None, gz if need[2] else None,
+                out_scal[0], out_scal[1], out_scal[2], None, None, None, None)
+
+
+def smooth_rgb_blend(colors, fragments, smoothrast, smoothagg, blend_params, znear: float = 1.0,
+                     zfar: float = 100) -> torch.Tensor:
+    """random_rasterizer.py:34-56.  Returns the (N,H,W,4) RGBA image.
+
+    ``colors`` (N,H,W,K,3); ``fragments`` with ``pix_to_face`` / ``zbuf`` / ``dists`` (N,H,W,K);
+    ``znear`` / ``zfar`` python floats or tensors broadcastable to (N,1,1,1)."""
+    ops.require_cuda(colors, fragments.pix_to_face, fragments.zbuf, fragments.dists)
+    if isinstance(smoothrast, GaussianRast) and isinstance(smoothagg, GaussianAgg):
+        cfg = dict(background=_background_tuple(blend_params), eps=smoothagg.eps,
+                   S_rast=smoothrast.nb_samples, S_agg=smoothagg.nb_samples,
+                   fixed_noise=bool(smoothagg.fixed_noise))
+        return _PerturbedShade.apply(colors, fragments.dists, fragments.zbuf, smoothrast.sigma,
+                                     smoothagg.gamma, smoothagg.alpha, fragments.pix_to_face, znear, zfar, cfg)
+
+    # operator-by-operator composition for every other pair (e.g. GaussianRast + SoftAgg)
+    device = fragments.pix_to_face.device
+    background = blend_params.background_color
+    if not torch.is_tensor(background):
+        background = torch.tensor(background, dtype=torch.float32, device=device)
+    else:
+        background = background.to(device)
+    mask = fragments.pix_to_face >= 0
+    prob_map = smoothrast.rasterize(fragments.dists) * mask
+    transmittance = torch.prod(1.0 - prob_map, dim=-1)
+    weights = smoothagg.aggregate(fragments.zbuf, zfar, znear, prob_map, mask)
+    rgb = (weights[..., :-1, None] * colors).sum(dim=-2) + weights[..., -1:] * background
+    return torch.cat((rgb, (1.0 - transmittance)[..., None]), dim=-1).to(colors.dtype)
+
+
+def _default_lights_materials(device):
+    """The reference builds pytorch3d PointLights / Materials defaults (random_rasterizer.py:145-148);
+    they are stored but never read on the Simple path.  pytorch3d is optional here."""
+    try:
+        from pytorch3d.renderer import Materials, PointLights  # type: ignore
+        return PointLights(device=device), Materials(device=device)
+    except Exception:
+        return None, None
+
+
+class RandomSimpleShader(nn.Module):
+    """random_rasterizer.py:132-191: texels -> smooth_rgb_blend.  Same constructor, ``forward``,
+    ``to``, ``get_smoothing``, ``get_nb_samples``, ``update_smoothing``, ``update_nb_samples``."""
+
+    def __init__(self, device="cpu", cameras=None, lights=None, materials=None, smoothrast=SoftRast(),
+                 smoothagg=SoftAgg(), blend_params=None):
+        super().__init__()
+        d_lights, d_materials = (None, None) if (lights is not None and materials is not None) \
+            else _default_lights_materials(device)
+        self.lights = lights if lights is not None else d_lights
+        self.materials = materials if materials is not None else d_materials
+        if cameras is None:
+            try:  # reference default: a camera 2.7 units away (random_rasterizer.py:152-153)
+                from pytorch3d.renderer import OpenGLPerspectiveCameras, look_at_view_transform  # type: ignore
+                R, T = look_at_view_transform(dist=2.7, elev=torch.zeros((1)), azim=torch.zeros((1)))
+                cameras = OpenGLPerspectiveCameras(device=device, R=R, T=T)
+            except Exception:
+                from .structures import DepthCameras
+                cameras = DepthCameras(znear=1.0, zfar=100.0, n=1, device=device)
+        self.cameras = cameras
+        self.blend_params = blend_params if blend_params is not None else BlendParams()
+        self.smoothrast = smoothrast
+        self.smoothagg = smoothagg
+
+    def to(self, device):
+        # like the reference (random_rasterizer.py:158-162) this moves the non-Module members and
+        # returns None
+        self.cameras = None if self.cameras is None else self.cameras.to(device)
+        self.materials = None if self.materials is None else self.materials.to(device)
+        self.lights = None if self.lights is None else self.lights.to(device)
+
+    def forward(self, fragments, meshes, **kwargs) -> torch.Tensor:
+        cameras = kwargs.get("cameras", self.cameras)
+        if cameras is None:
+            raise ValueError("Cameras must be specified either at initialization "
+                             "or in the forward pass of RandomSimpleShader")
+        texels = meshes.sample_textures(fragments)
+        blend_params = kwargs.get("blend_params", self.blend_params)
+        znear = kwargs.get("znear", getattr(cameras, "znear", 1.0))
+        zfar = kwargs.get("zfar", getattr(cameras, "zfar", 100.0))
+        if torch.is_tensor(znear):
+            znear = znear[:, None, None, None]
+        if torch.is_tensor(zfar):
+            zfar = zfar[:, None, None, None]
+        return smooth_rgb_blend(texels, fragments, self.smoothrast, self.smoothagg, blend_params,
+                                znear=znear, zfar=zfar)
+
+    def get_smoothing(self):
+        return self.smoothrast.sigma, self.smoothagg.gamma, self.smoothagg.alpha
+
+    def get_nb_samples(self):
+        return self.smoothagg.nb_samples
+
+    def update_smoothing(self, sigma=4e-4, gamma=4e-2, alpha=1.):
+        self.smoothrast.update_smoothing(sigma)
+        self.smoothagg.update_smoothing(gamma, alpha)
+
+    def update_nb_samples(self, nb_samples=16):
+        self.smoothrast.update_nb_samples(nb_samples)
+        self.smoothagg.update_nb_samples(nb_samples)

@@ -1,0 +1,159 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/pertshade.h
+declares; the reference-facing host classes keep the reference's surface and error behaviour."""
+
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+
+import pertrenderer_b200 as pb
+from pertrenderer_b200 import _cabi, ops
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "pertshade.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(pert_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _cabi.load()
+    declared = _declared_functions()
+    assert len(declared) >= 12
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in pertshade.h but not exported"
+    assert sorted(_cabi.EXPORTS) == declared
+    assert lib.pert_version() == _cabi.ABI_VERSION
+    assert lib.pert_strerror(0) == b"ok"
+    assert b"NULL" in lib.pert_strerror(-1)
+
+
+def test_struct_layout_matches_header():
+    """ctypes mirror of pert_problem: field order / sizes as in the header (LP64)."""
+    assert ctypes.sizeof(_cabi.PertProblem) == 176
+    assert _cabi.PertProblem.pix_to_face.offset == 112
+    assert _cabi.PertProblem.seed_rast.offset == 80
+
+
+def test_argument_validation_without_gpu():
+    """Validation happens before any launch, so it is testable on a CPU-only box."""
+    lib = _cabi.load()
+    p = _cabi.PertProblem()
+    assert lib.pert_shade_fwd(None, None, None, None, None, None, None) == -1
+    p.N, p.H, p.W, p.K = 1, 2, 2, 0
+    assert lib.pert_shade_fwd(p, None, None, None, None, None, None) == -2  # bad shape
+    p.K = 5000
+    assert lib.pert_shade_fwd(p, None, None, None, None, None, None) == -3  # unsupported K
+    p.K = 4
+    p.S_rast = p.S_agg = 8
+    p.depth_len = 1
+    p.sigma, p.gamma, p.alpha = 1e-3, 0.0, 1.0
+    assert lib.pert_shade_fwd(p, None, None, None, None, None, None) == -7  # gamma must be > 0
+    p.gamma = 1e-2
+    p.s_rast_begin, p.s_rast_end, p.s_agg_begin, p.s_agg_end = 2, 8, 0, 8
+    assert lib.pert_shade_fwd(p, None, None, None, None, None, None) == -5  # shard begin % 4
+    p.s_rast_begin = 0
+    assert lib.pert_shade_fwd(p, None, None, None, None, None, None) == -1  # null inputs
+    assert lib.pert_winner_bytes(50) == 1 and lib.pert_winner_bytes(255) == 1 and lib.pert_winner_bytes(256) == 2
+    p.N, p.H, p.W, p.K = 8, 256, 256, 50
+    assert lib.pert_num_tiles(p) == (8 * 256 * 256 + 19) // 20
+    assert lib.pert_rast_fwd(None, 1, 1, 1, 0, 1, 1.0, 0, 0, None, 0, None, None, None) == -1
+    assert lib.pert_noise_fill(0, 0, 4, 4, 0, 4, 0, None, None) == -1
+
+
+def test_cpu_tensors_fail_loudly():
+    """No CPU fallback: the product path refuses CPU tensors instead of computing something."""
+    frag = pb.Fragments(torch.zeros(1, 2, 2, 3, dtype=torch.int64), torch.ones(1, 2, 2, 3), None,
+                        torch.zeros(1, 2, 2, 3))
+    colors = torch.rand(1, 2, 2, 3, 3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pb.smooth_rgb_blend(colors, frag, pb.GaussianRast(), pb.GaussianAgg(), pb.BlendParams())
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pb.GaussianRast().rasterize(torch.zeros(1, 2, 2, 3))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pb.randomArgmax.apply(torch.zeros(1, 2, 2, 4), 4, torch.tensor(1e-2))
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    monkeypatch.setattr(_cabi, "_lib", None)
+    monkeypatch.setattr(_cabi, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_cabi.PertLibraryError, match="no CPU or PyTorch fallback"):
+        _cabi.load()
+
+
+def test_operator_surface_matches_reference():
+    """constructor defaults, attributes and setters."""
+    r = pb.GaussianRast()
+    assert r.nb_samples == 16 and abs(r.sigma.item() - 2e-4) < 1e-9
+    assert r.sigma.requires_grad and r.sigma.dim() == 0 and r.sigma.device.type == "cpu"
+    assert not isinstance(r.sigma, torch.nn.Parameter)
+    old = r.sigma
+    r.update_smoothing(5e-4)
+    assert r.sigma is not old and abs(r.sigma.item() - 5e-4) < 1e-9
+    r.update_nb_samples(64)
+    assert r.nb_samples == 64
+    a = pb.GaussianAgg()
+    assert (a.nb_samples, a.eps, a.fixed_noise) == (16, 1e-10, False)
+    assert abs(a.gamma.item() - 4e-2) < 1e-9 and a.alpha.item() == 1.0
+    a.update_smoothing(gamma=1e-3, alpha=2.0)
+    assert abs(a.gamma.item() - 1e-3) < 1e-9 and a.alpha.item() == 2.0
+    a.update_nb_samples(8)
+    assert a.nb_samples == 8
+    sh = pb.RandomSimpleShader(smoothrast=r, smoothagg=a, cameras=pb.DepthCameras())
+    assert sh.get_nb_samples() == 8
+    s, g, al = sh.get_smoothing()
+    assert s is r.sigma and g is a.gamma and al is a.alpha
+    sh.update_smoothing(sigma=1e-3, gamma=1e-2, alpha=1.0)
+    sh.update_nb_samples(32)
+    assert r.nb_samples == 32 and a.nb_samples == 32 and abs(r.sigma.item() - 1e-3) < 1e-9
+    assert sh.to("cpu") is None  # reference quirk B7
+    sh.cameras = None
+    with pytest.raises(ValueError):
+        sh.forward(None, None)
+
+
+def test_unsupported_noise_type_raises():
+    with pytest.raises(ValueError, match="not implemented"):
+        pb.randomHeaviside.apply(torch.zeros(1, 1, 1, 2), 4, torch.tensor(1e-3), "cauchy")
+    with pytest.raises(ValueError, match="not implemented"):
+        pb.randomArgmax.apply(torch.zeros(1, 1, 1, 2), 4, torch.tensor(1e-3), "gumbel")
+
+
+def test_soft_operators_cpu():
+    """SoftRast / SoftAgg (the shaders' default arguments) are plain torch and run anywhere."""
+    d = torch.tensor([[[[-1e-4, 0.0, 2e-4]]]])
+    p = pb.SoftRast(sigma=1e-4).rasterize(d)
+    assert torch.allclose(p, torch.sigmoid(-d / 1e-4))
+    agg = pb.SoftAgg(gamma=1e-2)
+    z = torch.tensor([[[[5.0, 6.0, -1.0]]]])
+    mask = torch.tensor([[[[True, True, False]]]])
+    prob = torch.tensor([[[[1.0, 0.5, 0.0]]]], requires_grad=True)
+    w = agg.aggregate(z, 100.0, 1.0, prob, mask)
+    assert w.shape == (1, 1, 1, 4) and abs(w.sum().item() - 1) < 1e-6 and w[0, 0, 0, 2] == 0
+    w[..., 0].sum().backward()
+    assert torch.isfinite(prob.grad).all() and prob.grad[0, 0, 0, 2] == 0
+
+
+def test_seed_follows_torch_generator():
+    torch.manual_seed(123)
+    a = ops.draw_seed()
+    b = ops.draw_seed()
+    torch.manual_seed(123)
+    assert ops.draw_seed() == a and ops.draw_seed() == b and a != b
+
+
+def test_synthetic_fragments_contract():
+    for kind in ("dense", "realistic"):
+        fr, col = pb.synthetic_fragments(2, 16, 16, 10, kind=kind, device="cpu", seed=3)
+        valid = fr.pix_to_face >= 0
+        assert fr.pix_to_face.dtype == torch.int64 and fr.zbuf.dtype == torch.float32
+        assert (fr.zbuf[~valid] == -1).all() and (fr.dists[~valid] == -1).all() and (col[~valid] == 0).all()
+        # padding last, depth ascending among valid entries
+        assert (valid[..., 1:] <= valid[..., :-1]).all()
+        dz = fr.zbuf[..., 1:] - fr.zbuf[..., :-1]
+        assert (dz[valid[..., 1:]] >= 0).all()
+    assert valid.float().mean() < 0.5

@@ -1,0 +1,392 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the reference's golden
+vectors.  Tolerances (north_star): images and gradients within 1e-5 relative in fp32 when fed the
+reference's exact noise; indices (hit counts, argmax winners) bit-exact."""
+
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+from oracle import pert_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def _scalars_close(got, ref, what):
+    assert abs(got - ref) <= 2e-5 * max(abs(ref), 1e-12) + 1e-8, (what, got, ref)
+
+
+def test_explicit_noise_matches_reference_golden(shade_case):
+    """Tier 2: the reference's own noise tensors -> reference's outputs."""
+    from gpu_util import problem_from_case, run_cuda
+    g = shade_case
+    out = run_cuda(problem_from_case(g), g["grad_image"])
+    mask = g["pix_to_face"] >= 0
+    S_a = int(g["S_a"])
+    # indices: bit-exact
+    assert torch.equal(out["counts"][mask], g["counts"][mask])
+    assert torch.equal(out["winners"].permute(3, 0, 1, 2).long(), g["a_s"])
+    assert torch.equal(out["hist"].float() / S_a, g["weights"])
+    # image and gradients
+    assert rel_err(out["image"], g["image"]) <= RTOL
+    assert (out["image"] - g["image"]).abs().max() <= 1e-6
+    assert rel_err(out["grad_colors"], g["grad_colors"]) <= RTOL
+    assert rel_err(out["grad_dists"], g["grad_dists"]) <= RTOL
+    assert rel_err(out["grad_zbuf"], g["grad_zbuf"]) <= RTOL
+    _scalars_close(out["scalars"][0].item(), g["grad_sigma"], "sigma")
+    _scalars_close(out["scalars"][1].item(), g["grad_gamma"], "gamma")
+    _scalars_close(out["scalars"][2].item(), g["grad_alpha"], "alpha")
+    # padded entries: exactly zero gradients (Appendix A.4)
+    assert (out["grad_dists"][~mask] == 0).all() and (out["grad_zbuf"][~mask] == 0).all()
+
+
+def test_public_api_autograd_matches_golden(shade_case):
+    """Same comparison through smooth_rgb_blend + autograd (what MeshRenderer calls)."""
+    import pertrenderer_b200 as pb
+    g = shade_case
+    dev = "cuda"
+    rast = pb.GaussianRast(nb_samples=int(g["S_r"]), sigma=float(g["sigma"]))
+    agg = pb.GaussianAgg(nb_samples=int(g["S_a"]), gamma=float(g["gamma"]), alpha=float(g["alpha"]))
+    d = g["dists"].to(dev).requires_grad_(True)
+    z = g["zbuf"].to(dev).requires_grad_(True)
+    c = g["colors"].to(dev).requires_grad_(True)
+    frag = pb.Fragments(g["pix_to_face"].to(dev), z, None, d)
+    blend = pb.BlendParams(background_color=tuple(g["background"].tolist()))
+    with pb.explicit_noise(g["U"].to(dev), g["V"].to(dev)):
+        img = pb.smooth_rgb_blend(c, frag, rast, agg, blend, znear=g["znear_t"].to(dev), zfar=g["zfar_t"].to(dev))
+        (img * g["grad_image"].to(dev)).sum().backward()
+    assert rel_err(img.detach().cpu(), g["image"]) <= RTOL
+    assert rel_err(d.grad.cpu(), g["grad_dists"]) <= RTOL
+    assert rel_err(z.grad.cpu(), g["grad_zbuf"]) <= RTOL
+    assert rel_err(c.grad.cpu(), g["grad_colors"]) <= RTOL
+    assert rast.sigma.grad.device.type == "cpu" and agg.gamma.grad.dim() == 0
+    _scalars_close(rast.sigma.grad.item(), g["grad_sigma"], "sigma")
+    _scalars_close(agg.gamma.grad.item(), g["grad_gamma"], "gamma")
+    _scalars_close(agg.alpha.grad.item(), g["grad_alpha"], "alpha")
+
+
+def test_unfused_operator_composition_matches_golden(shade_case):
+    """GaussianRast.rasterize and GaussianAgg.aggregate used one by one (mixed-pair path): the
+    stand-alone kernels + torch glue reproduce the same golden outputs."""
+    import pertrenderer_b200 as pb
+    g = shade_case
+    dev = "cuda"
+    rast = pb.GaussianRast(nb_samples=int(g["S_r"]), sigma=float(g["sigma"]))
+    agg = pb.GaussianAgg(nb_samples=int(g["S_a"]), gamma=float(g["gamma"]), alpha=float(g["alpha"]))
+    d = g["dists"].to(dev).requires_grad_(True)
+    z = g["zbuf"].to(dev).requires_grad_(True)
+    mask = (g["pix_to_face"] >= 0).to(dev)
+    with pb.explicit_noise(g["U"].to(dev), g["V"].to(dev)):
+        prob = rast.rasterize(d) * mask
+        w = agg.aggregate(z, g["zfar_t"].to(dev), g["znear_t"].to(dev), prob, mask)
+    assert torch.equal(prob.detach().cpu(), g["prob"])
+    assert torch.equal(w.detach().cpu(), g["weights"])
+    colors = g["colors"].to(dev)
+    bg = g["background"].to(dev)
+    rgb = (w[..., :-1, None] * colors).sum(-2) + w[..., -1:] * bg
+    img = torch.cat((rgb, (1 - torch.prod(1 - prob, -1))[..., None]), -1)
+    (img * g["grad_image"].to(dev)).sum().backward()
+    assert rel_err(d.grad.cpu(), g["grad_dists"]) <= RTOL
+    assert rel_err(z.grad.cpu(), g["grad_zbuf"]) <= RTOL
+    _scalars_close(rast.sigma.grad.item(), g["grad_sigma"], "sigma")
+    _scalars_close(agg.gamma.grad.item(), g["grad_gamma"], "gamma")
+    _scalars_close(agg.alpha.grad.item(), g["grad_alpha"], "alpha")
+
+
+def test_standalone_functions_match_golden():
+    """randomHeaviside / randomArgmax autograd Functions with arbitrary upstream gradients."""
+    import pertrenderer_b200 as pb
+    g = load_golden("ops_small")
+    dev = "cuda"
+    x = g["x"].to(dev).requires_grad_(True)
+    sig = torch.tensor(float(g["sigma"]), requires_grad=True)
+    with pb.explicit_noise(g["U"].to(dev), None):
+        y = pb.randomHeaviside.apply(x, int(g["S"]), sig)
+    (y * g["grad_l"].to(dev)).sum().backward()
+    assert torch.equal(y.detach().cpu(), g["prob"])
+    assert rel_err(x.grad.cpu(), g["grad_x"]) <= RTOL
+    _scalars_close(sig.grad.item(), g["grad_sigma"], "sigma")
+    z = g["z"].to(dev).requires_grad_(True)
+    gam = torch.tensor(float(g["gamma"]), requires_grad=True)
+    with pb.explicit_noise(None, g["V"].to(dev)):
+        w = pb.randomArgmax.apply(z, int(g["S"]), gam, "gaussian", False)
+    (w * g["grad_w"].to(dev)).sum().backward()
+    assert torch.equal(w.detach().cpu(), g["weights"])
+    assert rel_err(z.grad.cpu(), g["grad_z"]) <= RTOL
+    _scalars_close(gam.grad.item(), g["grad_gamma"], "gamma")
+
+
+@pytest.mark.parametrize("shape", [(1, 16, 16, 50, 16, 16, "realistic"), (2, 8, 12, 50, 64, 64, "dense"),
+                                   (1, 9, 7, 100, 12, 20, "realistic"), (1, 4, 4, 300, 8, 8, "dense")])
+def test_explicit_noise_matches_oracle_seeded(shape):
+    """Fresh seeded inputs at sizes the oracle finishes in seconds, incl. K=100, K>255 (16-bit
+    winners), S not a multiple of 4 and S_rast != S_agg."""
+    from gpu_util import problem_from_case, run_cuda, run_oracle, synthetic_case
+    N, H, W, K, S_r, S_a, kind = shape
+    g = synthetic_case(N, H, W, K, S_r, S_a, kind=kind, seed=K + S_r, znear=[1.0 + 0.1 * n for n in range(N)],
+                       background=(0.3, 0.6, 0.9), alpha=1.2)
+    U, V = O.draw_noise((N, H, W, K), S_r, S_a, generator=torch.Generator().manual_seed(5))
+    g["U"], g["V"] = U, V
+    st, gr = run_oracle(g, U, V)
+    out = run_cuda(problem_from_case(g), g["grad_image"])
+    mask = g["pix_to_face"] >= 0
+    assert torch.equal(out["counts"][mask], st.counts[mask])
+    assert torch.equal(out["winners"].permute(3, 0, 1, 2).long(), st.a_s)
+    assert (out["image"] - st.image).abs().max() <= 2e-6
+    assert rel_err(out["grad_colors"], gr["colors"]) <= RTOL
+    assert rel_err(out["grad_dists"], gr["dists"]) <= RTOL
+    assert rel_err(out["grad_zbuf"], gr["zbuf"]) <= RTOL
+    for i, k in enumerate(("sigma", "gamma", "alpha")):
+        _scalars_close(out["scalars"][i].item(), gr[k].item(), k)
+
+
+@pytest.mark.parametrize("kind", ["realistic", "dense"])
+def test_philox_equals_explicit_with_materialised_noise(kind):
+    """The in-register Philox path is the explicit path fed with pert_noise_fill's tensor: bit-exact
+    indices, and the CPU oracle on that same noise agrees (so Philox mode is oracle-checked too)."""
+    from gpu_util import problem_from_case, run_cuda, run_oracle, synthetic_case
+    from pertrenderer_b200 import ops
+    N, H, W, K, S_r, S_a = 2, 10, 10, 50, 16, 32
+    g = synthetic_case(N, H, W, K, S_r, S_a, kind=kind, seed=7)
+    seed_r, seed_a = 0x1234567890ABCDEF, 0x0FEDCBA987654321
+    U = ops.noise_fill(seed_r, 0, (N, H, W, K), S_r, "cuda")
+    V = ops.noise_fill(seed_a, 1, (N, H, W, K), S_a, "cuda")
+    g["U"], g["V"] = U.cpu(), V.cpu()
+    a = run_cuda(problem_from_case(g, explicit=False, seed_rast=seed_r, seed_agg=seed_a), g["grad_image"])
+    b = run_cuda(problem_from_case(g, explicit=True), g["grad_image"])
+    mask = g["pix_to_face"] >= 0
+    assert torch.equal(a["counts"][mask], b["counts"][mask])
+    assert torch.equal(a["winners"], b["winners"])
+    assert torch.equal(a["hist"], b["hist"])
+    assert torch.equal(a["image"], b["image"])
+    assert rel_err(a["grad_dists"], b["grad_dists"]) <= 1e-6
+    assert rel_err(a["grad_zbuf"], b["grad_zbuf"]) <= RTOL
+    assert torch.equal(a["grad_colors"], b["grad_colors"])
+    st, gr = run_oracle(g, g["U"], g["V"])
+    assert torch.equal(a["counts"][mask], st.counts[mask])
+    assert torch.equal(a["winners"].permute(3, 0, 1, 2).long(), st.a_s)
+    assert (a["image"] - st.image).abs().max() <= 2e-6
+    assert rel_err(a["grad_dists"], gr["dists"]) <= RTOL
+    assert rel_err(a["grad_zbuf"], gr["zbuf"]) <= RTOL
+
+
+@pytest.mark.parametrize("kind", ["realistic", "dense"])
+def test_skipping_is_exact(kind):
+    """The work-skipping rules (masked entries, |x| beyond the noise bound, logits that cannot win,
+    samples with c_s = 0) change no output bit: default == PERT_F_NO_SKIP brute force."""
+    from gpu_util import problem_from_case, run_cuda, synthetic_case
+    from pertrenderer_b200 import _cabi
+    g = synthetic_case(2, 12, 12, 50, 16, 16, kind=kind, seed=11, gamma=1e-3)
+    a = run_cuda(problem_from_case(g, explicit=False, seed_rast=3, seed_agg=4), g["grad_image"])
+    b = run_cuda(problem_from_case(g, explicit=False, seed_rast=3, seed_agg=4, flags=_cabi.F_NO_SKIP), g["grad_image"])
+    mask = g["pix_to_face"] >= 0
+    assert torch.equal(a["counts"][mask], b["counts"][mask])
+    assert torch.equal(a["rsum"][mask], b["rsum"][mask])
+    for k in ("winners", "hist", "image", "grad_dists", "grad_zbuf", "grad_colors", "scalars"):
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_noise_stream_is_standard_normal():
+    from pertrenderer_b200 import ops
+    n = ops.noise_fill(42, 1, (4, 32, 32, 50), 32, "cuda").double().flatten()
+    m = n.numel()
+    assert abs(n.mean().item()) < 5 / m ** 0.5
+    assert abs(n.var().item() - 1) < 5 * (2 / m) ** 0.5
+    assert abs((n ** 3).mean().item()) < 5 * (15 / m) ** 0.5
+    assert abs((n ** 4).mean().item() - 3) < 5 * (96 / m) ** 0.5
+    assert n.abs().max().item() <= 6.8
+    # Kolmogorov-Smirnov on a subsample
+    s = n[:: max(1, m // 200000)].sort().values
+    cdf = O.normal_cdf(s)
+    emp = torch.arange(1, s.numel() + 1, dtype=torch.float64, device=s.device) / s.numel()
+    assert (cdf.to(s.device) - emp).abs().max().item() < 1.95 / s.numel() ** 0.5
+    # different stages / seeds / samples decorrelate
+    a = ops.noise_fill(42, 0, (1, 16, 16, 51), 8, "cuda").flatten()
+    b = ops.noise_fill(42, 1, (1, 16, 16, 50), 8, "cuda").flatten()
+    c = ops.noise_fill(43, 1, (1, 16, 16, 50), 8, "cuda").flatten()
+    assert abs(torch.corrcoef(torch.stack((a, b)))[0, 1].item()) < 0.02
+    assert abs(torch.corrcoef(torch.stack((b, c)))[0, 1].item()) < 0.02
+
+
+def test_philox_closed_forms():
+    """Tier 3 (Appendix A.4): with in-kernel noise, E[P_k] = Phi(-d/sigma), the coverage score is
+    phi(x/sigma)/sigma, the two-way weight is Phi(dzeta/(gamma sqrt2)), within Monte-Carlo CIs."""
+    import pertrenderer_b200 as pb
+    dev = "cuda"
+    sigma, gamma, S = 1e-3, 1e-2, 4096
+    n = 21
+    d = torch.linspace(-3e-3, 3e-3, n, device=dev).reshape(1, 1, n, 1).contiguous().requires_grad_(True)
+    torch.manual_seed(0)
+    p = pb.GaussianRast(nb_samples=S, sigma=sigma).rasterize(d)
+    p.sum().backward()
+    e = O.expected_coverage(d.detach().cpu(), sigma)
+    se = (e * (1 - e) / S).sqrt() + 1e-4
+    assert ((p.detach().cpu().double() - e).abs() <= 5 * se).all()
+    eg = -O.expected_coverage_score(d.detach().cpu(), sigma)
+    assert ((d.grad.cpu().double() - eg).abs() <= 6 * (1 / sigma) / S ** 0.5).all()
+    zeta = torch.tensor([0.0, -0.7e-2, float("-inf")], device=dev).reshape(1, 1, 1, 3).repeat(1, 8, 8, 1)
+    w = pb.randomArgmax.apply(zeta, S, torch.tensor(gamma))
+    ew = O.expected_two_way_weight(0.0, -0.7e-2, gamma).item()
+    assert (w[..., 2] == 0).all() and torch.allclose(w.sum(-1), torch.ones_like(w[..., 0]))
+    assert ((w[..., 0].cpu().double() - ew).abs() <= 5 * (ew * (1 - ew) / S) ** 0.5).all()
+
+
+def test_philox_statistics_match_reference_estimator():
+    """Tier 3: the mean image / mean gradients over many Philox seeds agree with the mean of the
+    reference estimator (oracle with torch.normal noise) within Monte-Carlo confidence intervals."""
+    from gpu_util import problem_from_case, run_cuda, run_oracle, synthetic_case
+    N, H, W, K, S = 1, 6, 6, 8, 16
+    g = synthetic_case(N, H, W, K, S, S, kind="dense", seed=21)
+    reps = 300
+    acc = {k: [] for k in ("image", "grad_dists", "grad_zbuf")}
+    ref = {k: [] for k in acc}
+    gen = torch.Generator().manual_seed(1)
+    for r in range(reps):
+        out = run_cuda(problem_from_case(g, explicit=False, seed_rast=1000 + r, seed_agg=5000 + r), g["grad_image"])
+        for k in acc:
+            acc[k].append(out[k])
+        U, V = O.draw_noise((N, H, W, K), S, S, generator=gen)
+        st, gr = run_oracle(g, U, V)
+        ref["image"].append(st.image)
+        ref["grad_dists"].append(gr["dists"])
+        ref["grad_zbuf"].append(gr["zbuf"])
+    for k in acc:
+        a, b = torch.stack(acc[k]).double(), torch.stack(ref[k]).double()
+        diff = a.mean(0) - b.mean(0)
+        se = (a.var(0) / reps + b.var(0) / reps).sqrt()
+        scale = se.max()
+        z = diff.abs() / (se + 1e-3 * scale)
+        # ~600 comparisons: a 5.5 sigma bound keeps the family-wise false-alarm rate < 1e-4
+        assert z.max().item() < 5.5, (k, z.max().item())
+
+
+def test_batch_shards_reproduce_the_whole_job():
+    """Row (e): pixels are independent and the Philox counter uses the global pixel index, so a job
+    split by batch element over ranks gives bit-identical images / gradients; only the three scalar
+    gradients need a sum."""
+    from gpu_util import problem_from_case, run_cuda, synthetic_case
+    g = synthetic_case(4, 8, 8, 50, 16, 16, kind="realistic", seed=31, znear=[1.0, 1.1, 1.2, 1.3])
+    whole = run_cuda(problem_from_case(g, explicit=False, seed_rast=9, seed_agg=10), g["grad_image"])
+    parts = []
+    for r in range(2):
+        sl = slice(2 * r, 2 * r + 2)
+        gs = dict(g)
+        for k in ("pix_to_face", "zbuf", "dists", "colors", "znear", "zfar", "grad_image"):
+            gs[k] = g[k][sl].contiguous()
+        pr = problem_from_case(gs, explicit=False, seed_rast=9, seed_agg=10, pixel_offset=2 * r * 64)
+        parts.append(run_cuda(pr, gs["grad_image"]))
+    for k in ("image", "grad_dists", "grad_zbuf", "grad_colors"):
+        assert torch.equal(torch.cat([p[k] for p in parts]), whole[k]), k
+    tot = parts[0]["scalars"] + parts[1]["scalars"]
+    assert torch.allclose(tot, whole["scalars"], rtol=1e-5, atol=1e-7)
+
+
+def test_sample_shards_reproduce_the_whole_job():
+    """Row (e), noise-sample sharding: phases with sums in between (counts, rsum | hist | acc,
+    pixstat) reproduce the single-call result: integer state exactly, gradients to rounding."""
+    from gpu_util import counts_u16, problem_from_case, run_cuda, synthetic_case
+    from pertrenderer_b200 import _cabi, ops
+    g = synthetic_case(1, 8, 8, 50, 32, 32, kind="dense", seed=41)
+    whole = run_cuda(problem_from_case(g, explicit=False, seed_rast=9, seed_agg=10), g["grad_image"])
+    R = 2
+    prs = [problem_from_case(g, explicit=False, seed_rast=9, seed_agg=10, s_rast=(16 * r, 16 * r + 16),
+                             s_agg=(16 * r, 16 * r + 16)) for r in range(R)]
+    # fwd phase 1 on every shard, then "all-reduce" counts and rsum
+    saved = [ops.shade_forward(pr, want_hist=True, phases=_cabi.PH_RAST)[1] for pr in prs]
+    counts = sum(counts_u16(s) for s in saved)
+    rsum = sum(s.rsum for s in saved)
+    for s in saved:
+        s.counts.copy_(counts.to(torch.int16))
+        s.rsum.copy_(rsum)
+    for pr, s in zip(prs, saved):
+        ops.shade_forward(pr, phases=_cabi.PH_AGG, saved=s)
+    hist = sum(s.hist for s in saved)
+    for s in saved:
+        s.hist.copy_(hist)
+    images = [ops.shade_forward(pr, phases=_cabi.PH_BLEND, saved=s)[0] for pr, s in zip(prs, saved)]
+    assert torch.equal(counts.cpu(), whole["counts"])
+    assert torch.equal(hist.cpu(), whole["hist"])
+    assert torch.equal(torch.cat([s.winners for s in saved], -1).cpu().to(torch.int32), whole["winners"])
+    for im in images:
+        assert torch.equal(im.cpu(), whole["image"])
+    assert torch.allclose(rsum.cpu(), whole["rsum"], rtol=1e-6, atol=1e-6)
+    # bwd: sample phase per shard, sum, finish everywhere
+    P, K1 = 64, 51
+    gi = g["grad_image"].cuda()
+    accs = [torch.empty((P, K1), device="cuda") for _ in range(R)]
+    stats = [torch.empty((P, 2), device="cuda") for _ in range(R)]
+    for pr, s, a, t in zip(prs, saved, accs, stats):
+        ops.shade_backward(pr, s, gi, phases=_cabi.PH_BWD_SAMPLE, acc=a, pixstat=t, use_hist=True)
+    acc, stat = sum(accs), sum(stats)
+    for pr, s in zip(prs, saved):
+        gd, gz, gc, scal = ops.shade_backward(pr, s, gi, phases=_cabi.PH_BWD_FINISH, acc=acc, pixstat=stat,
+                                              use_hist=True)
+        assert rel_err(gd.cpu(), whole["grad_dists"]) <= RTOL
+        assert rel_err(gz.cpu(), whole["grad_zbuf"]) <= RTOL
+        assert torch.equal(gc.cpu(), whole["grad_colors"])
+        assert torch.allclose(scal.cpu(), whole["scalars"], rtol=1e-4, atol=1e-6)
+
+
+def test_skip_dead_noise_flag_keeps_expectation():
+    """PERT_F_SKIP_DEAD_NOISE: forward unchanged; gradients of live entries unchanged; padded
+    entries still exactly zero; the flag only removes the pure-noise terms (Appendix B2/B3)."""
+    from gpu_util import problem_from_case, run_cuda, synthetic_case
+    from pertrenderer_b200 import _cabi
+    g = synthetic_case(1, 12, 12, 20, 32, 32, kind="realistic", seed=51)
+    a = run_cuda(problem_from_case(g, explicit=False, seed_rast=1, seed_agg=2), g["grad_image"])
+    b = run_cuda(problem_from_case(g, explicit=False, seed_rast=1, seed_agg=2, flags=_cabi.F_SKIP_DEAD_NOISE),
+                 g["grad_image"])
+    assert torch.equal(a["image"], b["image"]) and torch.equal(a["winners"], b["winners"])
+    assert torch.equal(a["grad_colors"], b["grad_colors"])
+    assert torch.equal(a["grad_dists"], b["grad_dists"])  # dead logits have P = 0: no path to dists
+    mask = g["pix_to_face"] >= 0
+    assert (b["grad_zbuf"][~mask] == 0).all()
+    assert torch.isfinite(b["scalars"]).all()
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 (N=8, 256x256, K=50, S=64) through the public API: size-independent
+    properties — determinism under a fixed torch seed, alpha in [0,1] and quantised, empty pixels
+    render the background with zero gradients, weights sum to one (rgb of an all-ones colour
+    tensor is exactly 1 where covered by a white background), finite gradients."""
+    import pertrenderer_b200 as pb
+    dev = "cuda"
+    N, H, W, K, S = 8, 256, 256, 50, 64
+    fr, col = pb.synthetic_fragments(N, H, W, K, kind="realistic", sigma=1e-3, seed=0, device=dev)
+    col = torch.ones_like(col)
+    shader = pb.RandomSimpleShader(device=dev, cameras=pb.DepthCameras(n=N, device=dev),
+                                   smoothrast=pb.GaussianRast(nb_samples=S, sigma=1e-3),
+                                   smoothagg=pb.GaussianAgg(nb_samples=S, gamma=1e-2),
+                                   blend_params=pb.BlendParams(background_color=(1.0, 1.0, 1.0)))
+
+    def render():
+        d = fr.dists.clone().requires_grad_(True)
+        z = fr.zbuf.clone().requires_grad_(True)
+        c = col.clone().requires_grad_(True)
+        torch.manual_seed(7)
+        img = shader(pb.Fragments(fr.pix_to_face, z, None, d), pb.TexelMeshes(c))
+        img.square().sum().backward()
+        return img.detach(), d.grad, z.grad, c.grad
+
+    img, gd, gz, gc = render()
+    img2, gd2, gz2, gc2 = render()
+    assert torch.equal(img, img2) and torch.equal(gd, gd2) and torch.equal(gz, gz2) and torch.equal(gc, gc2)
+    assert img.shape == (N, H, W, 4)
+    assert (img[..., 3] >= 0).all() and (img[..., 3] <= 1).all()
+    assert (img[..., :3] - 1).abs().max() <= 1e-5  # weights sum to one
+    empty = (fr.pix_to_face < 0).all(-1)
+    assert (img[empty][:, 3] == 0).all()
+    pad = fr.pix_to_face < 0
+    assert (gd[pad] == 0).all() and (gz[pad] == 0).all()
+    assert torch.isfinite(gd).all() and torch.isfinite(gz).all() and torch.isfinite(gc).all()
+    # grad_colors = w_k * dL/drgb: per pixel the colour gradients sum to dL/drgb * (1 - w_bg)
+    assert (gc.sum(-2) <= 2 * img[..., :3].abs() + 1e-5).all()
+    s, gm, al = shader.get_smoothing()
+    assert all(torch.isfinite(t.grad) for t in (s, gm, al))
