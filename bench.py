@@ -1,0 +1,392 @@
+#!/usr/bin/env python
+"""Benchmark of the perturbed shading hot path (BASELINE.json metric:
+"perturbed shader fwd+bwd pixel·face·samples/sec; % HBM roofline; 1/2/4/8 GPU").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--fragments realistic|dense] [--impl reference]
+
+A step is one fused forward + one fused backward of the shader over one batch of synthetic
+fragments (BASELINE config 2 per GPU: 8 views, 256x256, K=50, nb_samples=64; weak scaling: every
+rank shades its own 8 views, the only collective on the path is the all-reduce of the three scalar
+gradients).  Prints ONE JSON line (rank 0).  See DESIGN.md §Measurement for every field.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "perturbed shader fwd+bwd pixel·face·samples/sec"
+UNIT = "pixel·face·samples/s"
+SIGMA, GAMMA, ALPHA, EPS = 1e-3, 1e-2, 1.0, 1e-10  # experiments/eval.py:69 defaults
+BACKGROUND = (1.0, 1.0, 1.0)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--fragments", default="realistic", choices=["realistic", "dense"])
+    ap.add_argument("--views", type=int, default=8)
+    ap.add_argument("--image-size", type=int, default=256)
+    ap.add_argument("--faces-per-pixel", type=int, default=50)
+    ap.add_argument("--nb-samples", type=int, default=64)
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary fragment set")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def alg_bytes(P, K):
+    """fwd reads pix_to_face 8 + zbuf 4 + dists 4 + colors 12 per pixel·face and
+    writes RGBA 16 per pixel; bwd re-reads the same 28, writes grad_dists 4 + grad_zbuf 4 +
+    grad_colors 12 and reads grad_image 16 per pixel."""
+    PF = P * K
+    return 28 * PF + 16 * P, 48 * PF + 16 * P
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons (NVML) while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop = index, [], set(), None, threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def finish(self):
+        self._stop.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's CPU implementation
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_run(args, steps, warmup, budget_s=25.0):
+    """Times the CPU restatement of the reference operators (oracle/pert_oracle.py; the Python
+    reference itself cannot travel to the GPU box) on a bounded pixel sample of the same workload,
+    with every host thread torch can use.  Pixels are independent, so units/s extrapolates."""
+    from oracle import pert_oracle as O
+    from pertrenderer_b200 import synthetic_fragments
+    K, S = args.faces_per_pixel, args.nb_samples
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    side = 96  # 9216 pixels: ~0.4 GB of (S,N,H,W,K) temporaries per tensor at K=50, S=64
+    fr, col = synthetic_fragments(1, side, side, K, kind=args.fragments, sigma=SIGMA, seed=0, device="cpu")
+    G = torch.randn((1, side, side, 4), generator=torch.Generator().manual_seed(1))
+    units = side * side * K * S
+
+    def one():
+        U, V = O.draw_noise((1, side, side, K), S, S)  # the reference draws its noise inside forward
+        O.shade_fwd_bwd(fr.pix_to_face, fr.zbuf, fr.dists, col, BACKGROUND, 1.0, 100.0, SIGMA, GAMMA, ALPHA, EPS, U, V, G)
+
+    t_start = time.perf_counter()
+    for _ in range(warmup):
+        one()
+        if time.perf_counter() - t_start > budget_s / 2:
+            break
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        one()
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s and len(times) >= 2:
+            break
+    t = sum(times) / len(times)
+    return {"value": units / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"1x{side}x{side} pixels, K={K}, S={S}, {args.fragments} fragments, fwd+bwd incl. noise draw, "
+                      f"mean of {len(times)} runs, torch CPU {torch.get_num_threads()} threads",
+            "ms_per_step": t * 1e3, "steps_run": len(times)}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cb = cpu_reference_run(args, max(args.steps, 2), max(args.warmup, 1), budget_s=120.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": cb["steps_run"], "warmup": args.warmup, "ms_per_step": cb["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, world):
+    return {
+        "workload": f"BASELINE config 2 per GPU: {args.views} views x {args.image_size}x{args.image_size}, "
+                    f"K={args.faces_per_pixel}, nb_samples={args.nb_samples}, RandomSimpleShader "
+                    "(GaussianRast+GaussianAgg) fwd+bwd",
+        "fragments": args.fragments, "views_per_gpu": args.views, "global_views": args.views * world,
+        "image_size": args.image_size, "faces_per_pixel": args.faces_per_pixel, "nb_samples": args.nb_samples,
+        "sigma": SIGMA, "gamma": GAMMA, "alpha": ALPHA, "parallelism": f"batch-shard x{world}",
+        "l2": "inputs (0.73 GB per step) exceed the 126 MB L2; no explicit flush",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------
+def device_timed(args, kind, dev, steps, warmup, world, rank, sampler=None):
+    """Inputs resident in HBM; K steps of pert_shade_fwd + pert_shade_bwd through the C ABI."""
+    import torch.distributed as dist
+    from pertrenderer_b200 import ops, synthetic_fragments
+    N, HW, K, S = args.views, args.image_size, args.faces_per_pixel, args.nb_samples
+    fr, col = synthetic_fragments(N, HW, HW, K, kind=kind, sigma=SIGMA, seed=rank, device=dev)
+    G = torch.randn((N, HW, HW, 4), device=dev, generator=torch.Generator(device=dev).manual_seed(1 + rank))
+    P = N * HW * HW
+    torch.manual_seed(1234 + rank)
+
+    def problem():
+        return ops.ShadeProblem(pix_to_face=fr.pix_to_face, zbuf=fr.zbuf, dists=fr.dists, colors=col, znear=1.0,
+                                zfar=100.0, background=BACKGROUND, sigma=SIGMA, gamma=GAMMA, alpha=ALPHA, eps=EPS,
+                                S_rast=S, S_agg=S, seed_rast=ops.draw_seed(), seed_agg=ops.draw_seed(),
+                                pixel_offset=rank * P)
+
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+
+    def step(i=None):
+        pr = problem()
+        if i is not None:
+            ev[i][0].record()
+        image, saved = ops.shade_forward(pr)
+        if i is not None:
+            ev[i][1].record()
+        gd, gz, gc, scal = ops.shade_backward(pr, saved, G)
+        if i is not None:
+            ev[i][2].record()
+        if world > 1:
+            dist.all_reduce(scal)  # the only collective of batch sharding: d/d(sigma, gamma, alpha)
+        return image, scal
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    if sampler is not None:
+        sampler.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(steps):
+        step(i)
+    t1.record()
+    torch.cuda.synchronize(dev)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    total_ms = t0.elapsed_time(t1)
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = t.item()
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / steps
+    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / steps
+    units = P * K * S
+    fb, bb = alg_bytes(P, K)
+    peak, peak_src = peaks()
+    dom = "pert_shade_bwd" if bwd_ms >= fwd_ms else "pert_shade_fwd"
+    dom_ms, dom_bytes = (bwd_ms, bb) if bwd_ms >= fwd_ms else (fwd_ms, fb)
+    roof = {"bound": "hbm", "kernel": dom, "achieved": dom_bytes / dom_ms / 1e6, "peak": peak, "unit": "GB/s",
+            "frac": dom_bytes / dom_ms / 1e6 / peak, "traffic": None, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
+            "fwd": {"ms": fwd_ms, "alg_bytes": fb, "gbs": fb / fwd_ms / 1e6, "frac": fb / fwd_ms / 1e6 / peak},
+            "bwd": {"ms": bwd_ms, "alg_bytes": bb, "gbs": bb / bwd_ms / 1e6, "frac": bb / bwd_ms / 1e6 / peak},
+            "fwd_bwd_frac": (fb + bb) / (fwd_ms + bwd_ms) / 1e6 / peak}
+    return {"value": units * world * steps / (total_ms * 1e-3), "ms_per_step": total_ms / steps, "roofline": roof,
+            "launches": 3 * steps}
+
+
+def e2e_timed(args, kind, dev, steps, warmup, world, rank):
+    """End to end through the public API (RandomSimpleShader + autograd) with HOST buffers: every
+    step copies that step's Fragments and texels from pinned host memory (double-buffered on a copy
+    stream, so the copy of step i+1 overlaps the kernels of step i) and reads the image, the loss
+    and the scalar gradients back to the host."""
+    import pertrenderer_b200 as pb
+    N, HW, K, S = args.views, args.image_size, args.faces_per_pixel, args.nb_samples
+    fr, col = pb.synthetic_fragments(N, HW, HW, K, kind=kind, sigma=SIGMA, seed=rank, device=dev)
+    host = [t.cpu().pin_memory() for t in (fr.pix_to_face, fr.zbuf, fr.dists, col)]
+    G = torch.randn((N, HW, HW, 4), device=dev, generator=torch.Generator(device=dev).manual_seed(1 + rank))
+    del fr, col
+    bufs = [[torch.empty_like(h, device=dev) for h in host] for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    img_host = torch.empty((N, HW, HW, 4), dtype=torch.float32).pin_memory()
+    shader = pb.RandomSimpleShader(device=dev, cameras=pb.DepthCameras(n=N, device=dev),
+                                   smoothrast=pb.GaussianRast(nb_samples=S, sigma=SIGMA),
+                                   smoothagg=pb.GaussianAgg(nb_samples=S, gamma=GAMMA, alpha=ALPHA),
+                                   blend_params=pb.BlendParams(background_color=BACKGROUND))
+    h2d = sum(h.numel() * h.element_size() for h in host)
+    d2h = img_host.numel() * 4 + 4 + 12
+    main = torch.cuda.current_stream(dev)
+
+    def upload(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])
+            for b, h in zip(bufs[slot], host):
+                b.copy_(h, non_blocking=True)
+            ready[slot].record(copy_stream)
+
+    def step(i, last):
+        slot = i & 1
+        if not last:
+            upload((i + 1) & 1)
+        main.wait_event(ready[slot])
+        p2f, z, d, c = bufs[slot]
+        z, d, c = (t.detach().requires_grad_(True) for t in (z, d, c))  # fresh leaves sharing the buffers
+        img = shader(pb.Fragments(p2f, z, None, d), pb.TexelMeshes(c))
+        loss = (img * G).sum()
+        loss.backward()
+        consumed[slot].record(main)
+        img_host.copy_(img.detach(), non_blocking=True)
+        s, g, a = shader.get_smoothing()
+        out = (loss.item(), s.grad.item(), g.grad.item(), a.grad.item())  # device -> host reads (sync)
+        for t in (s, g, a):
+            t.grad = None
+        return out
+
+    for e in consumed:
+        e.record(main)
+    total = warmup + steps
+    upload(0)
+    for i in range(warmup):
+        step(i, False)
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(warmup, total):
+        step(i, i == total - 1)
+    e1.record()
+    torch.cuda.synchronize(dev)
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ms = max(e0.elapsed_time(e1), wall_ms)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    units = N * HW * HW * K * S
+    return {"value": units * world * steps / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "d2h_bytes_per_step": d2h, "ms_per_step": ms / steps,
+            "note": "public API (RandomSimpleShader+autograd), pinned host inputs, double-buffered H2D on a copy stream"}
+
+
+def run_b200_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the perturbed shading path has no CPU fallback")
+    from pertrenderer_b200 import _cabi
+    _cabi.load()  # fail loudly if the sm_100a library is missing
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    sampler = ClockSampler(local) if rank == 0 else None
+    main = device_timed(args, args.fragments, dev, args.steps, args.warmup, world, rank, sampler)
+    clocks = sampler.finish() if sampler is not None else None
+    other_kind = "dense" if args.fragments == "realistic" else "realistic"
+    also = None
+    if not args.no_also:
+        o = device_timed(args, other_kind, dev, max(3, args.steps // 4), 3, world, rank)
+        also = {"fragments": other_kind, "value": o["value"], "unit": UNIT, "ms_per_step": o["ms_per_step"],
+                "roofline": o["roofline"]}
+    e2e = None
+    if not args.no_e2e:
+        e2e = e2e_timed(args, args.fragments, dev, args.steps, args.warmup, world, rank)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cb = cpu_reference_run(args, 3, 1, budget_s=25.0)
+        cpu = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args, world),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": main["launches"], "roofline": main["roofline"],
+        "cpu_baseline": cpu, "also": also,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()
