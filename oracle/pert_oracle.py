@@ -208,29 +208,16 @@ def _prod_excluding_self(t):
     return left * right
 
 
-def shade_backward(st: ShadeState, grad_image, zbuf, colors, sigma, gamma, alpha, eps, U, V):
-    """Gradients of <grad_image, image> w.r.t. dists, zbuf, colors, sigma, gamma, alpha.
-
-    Follows, in reverse, random_rasterizer.py:50-54 (blend), smoothagg.py:45-73
-    (randomArgmax.backward), :303-311 / :325-337 (log_corrected / prod_corrected backward),
-    the autograd rules of cat / max / clamp / div used at :198-202, torch.prod (:48 of
-    random_rasterizer.py) and smoothrast.py:40-59."""
-    sig = torch.as_tensor(sigma, dtype=F32)
+def _finish_backward(prob, weights, aux, grad_image, zbuf, colors, gamma, alpha, eps, grad_zeta, grad_gamma_score,
+                     coverage_score):
+    """Chain rule from (grad_zeta, coverage score) to the inputs — everything in backward that is not
+    a sum over noise samples.  ``coverage_score`` = mean_s (h-h0) U / sigma (smoothrast.py:46,53)."""
     g = torch.as_tensor(gamma, dtype=F32)
     a = torch.as_tensor(alpha, dtype=F32)
-    aux = st.aux
     maskf = aux["mask"].to(F32)
     K = zbuf.shape[-1]
     G_rgb, G_a = grad_image[..., :3], grad_image[..., 3]
-
-    # blend backward: rgb = sum_k w_k c_k + w_K bg
-    grad_colors = st.weights[..., :-1, None] * G_rgb[..., None, :]
-    g_face = (colors * G_rgb[..., None, :]).sum(dim=-1)
-    g_bg = (G_rgb * aux["bg"]).sum(dim=-1, keepdim=True)
-    grad_w = torch.cat((g_face, g_bg), dim=-1)  # (N,H,W,K1)
-
-    # perturbed argmax backward
-    grad_zeta, grad_gamma = random_argmax_bwd(grad_w, st.a_s, st.a_0, V, g)
+    grad_colors = weights[..., :-1, None] * G_rgb[..., None, :]
 
     # zeta = cat(gal*logP + zi - zmax, eps - zmax)
     gz_faces = grad_zeta[..., :K]
@@ -246,23 +233,105 @@ def shade_backward(st: ShadeState, grad_image, zbuf, colors, sigma, gamma, alpha
     logp = aux["logp"]
     logp_fin = torch.where(torch.isinf(logp), torch.zeros_like(logp), logp)
     q = (logp_fin * gz_faces).nansum()
-    grad_gamma = grad_gamma + q / a
+    grad_gamma = grad_gamma_score + q / a
     grad_alpha = -q * g / (a * a)
     g_logp = (g / a) * gz_faces
     g_logp = torch.where(torch.isnan(g_logp), torch.zeros_like(g_logp), g_logp)
     # log_corrected: 1/x with inf -> 0
-    inv = 1.0 / st.prob
+    inv = 1.0 / prob
     inv = torch.where(torch.isinf(inv), torch.zeros_like(inv), inv)
     g_prob = inv * g_logp
     # alpha channel: image[...,3] = 1 - prod_k (1 - P_k)
-    g_prob = g_prob + G_a[..., None] * _prod_excluding_self(1.0 - st.prob)
+    g_prob = g_prob + G_a[..., None] * _prod_excluding_self(1.0 - prob)
     # P = p_hat * mask
     g_phat = g_prob * maskf
-    grad_x, grad_sigma = random_heaviside_bwd(g_phat, st.h, st.h0, U, sig)
-    grad_dists = -grad_x
-    return dict(dists=grad_dists, zbuf=grad_zbuf, colors=grad_colors,
-                sigma=grad_sigma, gamma=grad_gamma, alpha=grad_alpha,
-                zeta=grad_zeta, prob=g_prob)
+    grad_x = coverage_score * g_phat  # smoothrast.py:56
+    grad_sigma = grad_x.sum()  # smoothrast.py:57-58
+    return dict(dists=-grad_x, zbuf=grad_zbuf, colors=grad_colors, sigma=grad_sigma, gamma=grad_gamma,
+                alpha=grad_alpha, zeta=grad_zeta, prob=g_prob)
+
+
+def _grad_weights(colors, grad_image, bg):
+    """d loss / d w_j = <G_rgb, colour_j> (blend backward, random_rasterizer.py:50-53)."""
+    G_rgb = grad_image[..., :3]
+    g_face = (colors * G_rgb[..., None, :]).sum(dim=-1)
+    g_bg = (G_rgb * bg).sum(dim=-1, keepdim=True)
+    return torch.cat((g_face, g_bg), dim=-1)  # (N,H,W,K1)
+
+
+def shade_backward(st: ShadeState, grad_image, zbuf, colors, sigma, gamma, alpha, eps, U, V):
+    """Gradients of <grad_image, image> w.r.t. dists, zbuf, colors, sigma, gamma, alpha.
+
+    Follows, in reverse, random_rasterizer.py:50-54 (blend), smoothagg.py:45-73
+    (randomArgmax.backward), :303-311 / :325-337 (log_corrected / prod_corrected backward),
+    the autograd rules of cat / max / clamp / div used at :198-202, torch.prod (:48 of
+    random_rasterizer.py) and smoothrast.py:40-59."""
+    sig = torch.as_tensor(sigma, dtype=F32)
+    g = torch.as_tensor(gamma, dtype=F32)
+    grad_w = _grad_weights(colors, grad_image, st.aux["bg"])
+    grad_zeta, grad_gamma = random_argmax_bwd(grad_w, st.a_s, st.a_0, V, g)
+    S = U.shape[0]
+    score = ((st.h - st.h0.unsqueeze(0)) * U / sig).sum(dim=0) / S
+    return _finish_backward(st.prob, st.weights, st.aux, grad_image, zbuf, colors, gamma, alpha, eps, grad_zeta,
+                            grad_gamma, score)
+
+
+# ----------------------------------------------------------------------------
+# noise-sample shards (SURVEY.md §8e): per-shard sums, and the finish from reduced sums
+# ----------------------------------------------------------------------------
+def rast_shard_sums(dists, U_shard, sigma):
+    """Coverage phase on a shard of samples: (hit counts, sum_s (h-h0) U), both (N,H,W,K) float."""
+    _, h, h0 = random_heaviside_fwd(-dists, U_shard, sigma)
+    return h.sum(dim=0), ((h - h0.unsqueeze(0)) * U_shard).sum(dim=0)
+
+
+def logits_from_counts(pix_to_face, zbuf, counts, S_rast, znear, zfar, gamma, alpha, eps):
+    """Logits from ALL-shard hit counts (the non-linear log needs the full-S mean)."""
+    N = pix_to_face.shape[0]
+    mask = pix_to_face >= 0
+    prob = (counts / S_rast) * mask
+    zn, zf = _as_depth_plane(znear, N), _as_depth_plane(zfar, N)
+    zeta, aux = build_logits(zbuf, zf, zn, prob, mask, gamma, alpha, eps)
+    return zeta, prob, dict(aux, mask=mask, zn=zn, zf=zf)
+
+
+def argmax_shard(zeta, V_shard, gamma):
+    """Argmax phase on a shard: (winner histogram (N,H,W,K1) int32, a_s, a_0)."""
+    w, a_s, a_0 = random_argmax_fwd(zeta, V_shard, gamma)
+    return (w * V_shard.shape[0]).round().to(torch.int32), a_s, a_0
+
+
+def blend_from_hist(hist, S_agg, prob, colors, background):
+    weights = hist.to(F32) / S_agg
+    bg = _as_background(background)
+    rgb = (weights[..., :-1, None] * colors).sum(dim=-2) + weights[..., -1:] * bg
+    alpha_chan = torch.prod(1.0 - prob, dim=-1)
+    return torch.cat((rgb, (1.0 - alpha_chan)[..., None]), dim=-1), weights
+
+
+def argmax_score_sums(grad_w, a_s, a_0, V_shard):
+    """Backward sample phase on a shard, packed (N,H,W,K1+2):
+    [..., :K1] = sum_s c_s V_sj, [..., K1] = sum_s c_s ||V_s||^2, [..., K1+1] = sum_s c_s."""
+    S = V_shard.shape[0]
+    gl_s = grad_w.unsqueeze(0).expand(S, *grad_w.shape)
+    c = torch.gather(gl_s, -1, a_s.unsqueeze(-1)).squeeze(-1) - torch.gather(grad_w, -1, a_0.unsqueeze(-1)).squeeze(-1)
+    acc = (c.unsqueeze(-1) * V_shard).sum(dim=0)
+    t2 = (c * (V_shard * V_shard).sum(dim=-1)).sum(dim=0)
+    return torch.cat((acc, t2[..., None], c.sum(dim=0)[..., None]), dim=-1)
+
+
+def shade_backward_from_sums(prob, weights, aux, grad_image, zbuf, colors, sigma, gamma, alpha, eps, S_rast, S_agg,
+                             rsum, packed):
+    """Finish phase from all-shard sums: grad_zeta = acc/(S gamma), score term of gamma =
+    sum_pixels (t2 - csum)/(S gamma) (smoothagg.py:52-56,71-72), coverage score = rsum/(S sigma)."""
+    K1 = zbuf.shape[-1] + 1
+    g = float(gamma)
+    grad_zeta = packed[..., :K1] / (S_agg * g)
+    grad_gamma = ((packed[..., K1] - packed[..., K1 + 1]) / (S_agg * g)).sum()
+    score = rsum / (S_rast * float(sigma))
+    aux = dict(aux, bg=_as_background(aux["bg"]) if "bg" in aux else None)
+    return _finish_backward(prob, weights, aux, grad_image, zbuf, colors, gamma, alpha, eps, grad_zeta, grad_gamma,
+                            score)
 
 
 def shade_fwd_bwd(pix_to_face, zbuf, dists, colors, background, znear, zfar,

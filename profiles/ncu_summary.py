@@ -1,0 +1,18 @@
+import csv,subprocess,sys,io
+rep=sys.argv[1]
+out=subprocess.run(["ncu","-i",rep,"--page","raw","--csv"],capture_output=True,text=True).stdout
+rows=list(csv.reader(io.StringIO(out)))
+hdr=rows[0]; units=rows[1]; data=rows[2:]
+want=["Kernel Name","gpu__time_duration.sum","dram__bytes_read.sum","dram__bytes_write.sum","gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed","sm__throughput.avg.pct_of_peak_sustained_elapsed","sm__warps_active.avg.pct_of_peak_sustained_active","launch__registers_per_thread","launch__occupancy_limit_registers","launch__occupancy_limit_shared_mem","launch__occupancy_limit_warps","launch__occupancy_limit_blocks","sm__inst_executed.sum","smsp__inst_executed.avg.per_cycle_active","sm__inst_executed_pipe_xu.sum","smsp__issue_active.avg.pct_of_peak_sustained_active","smsp__thread_inst_executed_per_inst_executed.ratio","launch__grid_size","launch__shared_mem_per_block_dynamic","smsp__warps_eligible.avg.per_cycle_active","l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum","lts__t_sectors_op_read.sum","smsp__cycles_active.avg","sm__cycles_elapsed.max","smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio","smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio"]
+for d in data:
+    print("="*100)
+    for w in want:
+        if w in hdr:
+            i=hdr.index(w); print(f"{w:80s} {d[i]:>20s} {units[i]}")
+    # stall reasons
+    st=[(hdr[i],d[i]) for i in range(len(hdr)) if "smsp__average_warps_issue_stalled" in hdr[i] and "per_issue_active" in hdr[i]]
+    st=sorted(st,key=lambda x:-float(x[1].replace(',','') or 0))[:8]
+    for k,v in st: print("   stall",k.replace("smsp__average_warps_issue_stalled_","").replace("_per_issue_active.ratio",""),v)
+    pipes=[(hdr[i],d[i]) for i in range(len(hdr)) if hdr[i].startswith("sm__inst_executed_pipe_") and hdr[i].endswith(".sum")]
+    pipes=sorted(pipes,key=lambda x:-float(x[1].replace(',','') or 0))[:10]
+    for k,v in pipes: print("   pipe",k,v)
