@@ -43,16 +43,36 @@ __device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2
 // u in (0, 1]: (x + 0.5) * 2^-32
 __device__ __forceinline__ float u01(uint32_t x) { return fmaf((float)x, 2.3283064365386963e-10f, 1.1641532182693481e-10f); }
 
+__device__ __forceinline__ float mufu_lg2(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float mufu_sqrt(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float mufu_sin(float x) {
+    float r;
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float mufu_cos(float x) {
+    float r;
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// Two standard normals from two 32-bit words: radius = sqrt(-2 ln u) (MUFU.LG2 + MUFU.SQRT),
+// angle = 2 pi v (MUFU.SIN / MUFU.COS).  u >= 2^-33 is never denormal, so the .ftz forms are exact
+// substitutes and save the denormal fix-up code.
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
     const float u = u01(a);
-    // radius = sqrt(-2 ln u): MUFU.LG2 + MUFU.SQRT;  angle = 2 pi v: MUFU.SIN / MUFU.COS
-    float rad;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * __log2f(u)));
+    const float rad = mufu_sqrt(-1.3862943611198906f * mufu_lg2(u));
     const float ang = fmaf((float)b, 1.4629180792671596e-9f, 7.314590396335798e-10f);  // 2 pi (b + .5) 2^-32
-    float s, c;
-    __sincosf(ang, &s, &c);
-    n0 = rad * c;
-    n1 = rad * s;
+    n0 = rad * mufu_cos(ang);
+    n1 = rad * mufu_sin(ang);
 }
 
 struct PhiloxNoise {
@@ -71,6 +91,16 @@ struct PhiloxNoise {
         box_muller(r[0], r[1], n[0], n[1]);
         box_muller(r[2], r[3], n[2], n[3]);
     }
+    // same values; a pair whose `need` flag is false is returned as zeros (its MUFU work is skipped)
+    __device__ __forceinline__ void get4_pairs(uint32_t q, uint32_t slot, int64_t pixel_local, bool need01, bool need23,
+                                               float (&n)[4]) const {
+        const uint64_t gp = (uint64_t)(pixel_local + pixel_offset);
+        uint32_t r[4];
+        philox4x32<10>(q, slot, (uint32_t)gp, ((uint32_t)(gp >> 32) & 0x7fffffffu) | stage_bit, k0, k1, r);
+        n[0] = n[1] = n[2] = n[3] = 0.0f;
+        if (need01) box_muller(r[0], r[1], n[0], n[1]);
+        if (need23) box_muller(r[2], r[3], n[2], n[3]);
+    }
     static constexpr bool kBounded = true;
 };
 
@@ -87,6 +117,10 @@ struct ExplicitNoise {
             const int64_t s = (int64_t)q * 4 + t;
             n[t] = (s < S) ? __ldg(base + (s * P + pixel_local) * slots + slot) : 0.0f;
         }
+    }
+    __device__ __forceinline__ void get4_pairs(uint32_t q, uint32_t slot, int64_t pixel_local, bool, bool,
+                                               float (&n)[4]) const {
+        get4(q, slot, pixel_local, n);
     }
     static constexpr bool kBounded = false;
 };
