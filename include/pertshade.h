@@ -29,7 +29,12 @@
  * Saved state written by forward and read by backward (caller-allocated):
  *   counts  uint16 (P,K)   number of coverage samples with h=1 among the local sample shard
  *   rsum    float  (P,K)   sum_s (h_s - h0) * U_s over the local sample shard
- *   winners uint8  (P,S_agg_local) if K1 <= 256 else uint16: argmax index of every sample
+ *   winners uint8  (P,S_agg_local) if K1 <= 256 else uint16: argmax index of every sample; rows are
+ *                  written only for pixels whose pixstate has the ACTIVE bit
+ *   pixstate uint16 (P)    a0 | 0x8000 * active: a0 = unperturbed argmax (K = background), active =
+ *                  some local sample picked another logit (inactive pixels: every sample picked a0)
+ * Only entries with pix_to_face >= 0 are ever read or written in counts / rsum: real fragments are
+ * sparse in K and the kernels touch zbuf / dists / saved state for valid entries only.
  */
 #ifndef PERTSHADE_H_
 #define PERTSHADE_H_
@@ -41,7 +46,7 @@
 extern "C" {
 #endif
 
-#define PERT_ABI_VERSION 1
+#define PERT_ABI_VERSION 2
 
 /* error codes */
 #define PERT_OK 0
@@ -54,10 +59,20 @@ extern "C" {
 #define PERT_E_SCALAR (-7)      /* sigma, gamma or alpha not finite and > 0 */
 
 /* flags */
-#define PERT_F_NO_SKIP 1u        /* brute force: draw every sample of every entry (test / audit) */
-#define PERT_F_SKIP_DEAD_NOISE 2u /* backward: do not draw noise for -inf logits; their zero-mean
-                                     contribution is dropped and the ||V||^2 term uses its expectation
-                                     (same expectation, lower variance, not sample-path identical) */
+#define PERT_F_NO_SKIP 1u /* audit: no noise-bound based skipping (|x| > sigma*Umax entries, logits that
+                             cannot win, radius gate, c_s = 0 quads); implies PERT_F_PER_SAMPLE_NOISE */
+/* Backward, in-kernel (Philox) noise only.  A logit that can never win a sample (-inf, masked, or
+ * further than 2*gamma*Umax below the largest) has noise V_sj independent of every winner a_s, so
+ * given the c_s its score sum  sum_s c_s V_sj  is EXACTLY N(0, sum_s c_s^2).  Default: draw that
+ * normal once per logit instead of S_agg times (same joint law of all gradients of dists / zbuf /
+ * colors; the gamma-gradient's  sum_s c_s V_sj^2  keeps its mean and variance).
+ *   PERT_F_PER_SAMPLE_NOISE: regenerate every V_sj of every logit instead, as the reference does
+ *     (always the case with explicit noise): backward is then the explicit-noise kernel fed with
+ *     pert_noise_fill's tensor, bit for bit.
+ *   PERT_F_SKIP_DEAD_NOISE: replace those zero-mean terms by their expectation (0, and n*sum_s c_s
+ *     for the squared term): same expectation, lower variance. */
+#define PERT_F_SKIP_DEAD_NOISE 2u
+#define PERT_F_PER_SAMPLE_NOISE 4u
 /* phases of the fused kernels; 0 means "all".  Used for noise-sample sharding where collectives sit
  * between the phases. */
 #define PERT_PH_RAST 0x10u  /* fwd: draw coverage samples -> counts, rsum */
@@ -99,30 +114,31 @@ const char* pert_strerror(int code);
 /* last cudaError_t name seen by this thread's most recent failing call (diagnostic only) */
 const char* pert_last_cuda_error(void);
 
-/* number of tiles the fused kernels split the P pixels into; scalar_partials needs 4*tiles floats */
+/* number of CTAs the fused kernels launch for this problem; scalar_partials needs 4 floats per CTA,
+ * 16-byte aligned */
 int64_t pert_num_tiles(const pert_problem* pb);
 /* element size in bytes of the winners buffer for this K (1 or 2) */
 int pert_winner_bytes(int32_t K);
 
 /*
- * Forward.  Outputs: image (P,4).  Saved state: counts, rsum, winners (see top).  `hist` int32
+ * Forward.  Outputs: image (P,4).  Saved state: counts, rsum, winners, pixstate (see top).  `hist` int32
  * (P,K1) is optional unless the AGG and BLEND phases run in separate calls.  With phase flags,
  * buffers produced by an earlier phase are inputs.
  */
 int pert_shade_fwd(const pert_problem* pb, float* image, uint16_t* counts, float* rsum, void* winners,
-                   int32_t* hist, void* stream);
+                   uint16_t* pixstate, int32_t* hist, void* stream);
 
 /*
  * Backward.  grad_image (P,4).  Outputs grad_dists, grad_zbuf (P,K), grad_colors (P,K,3; may be
  * NULL), grad_scalars float[3] = d/d(sigma, gamma, alpha).  scalar_partials: workspace of
  * 4*pert_num_tiles floats.  acc float (P,K1) and pixstat float (P,2) are optional unless the two
  * backward phases run in separate calls (sample sharding); hist int32 (P,K1) is the all-shard
- * winner histogram of forward, needed only then (NULL: rebuilt from `winners`).
+ * winner histogram of forward, needed only then (NULL: rebuilt from `winners` / `pixstate`).
  */
 int pert_shade_bwd(const pert_problem* pb, const float* grad_image, const uint16_t* counts,
-                   const float* rsum, const void* winners, float* grad_dists, float* grad_zbuf,
-                   float* grad_colors, float* scalar_partials, float* grad_scalars, float* acc,
-                   float* pixstat, const int32_t* hist, void* stream);
+                   const float* rsum, const void* winners, const uint16_t* pixstate, float* grad_dists,
+                   float* grad_zbuf, float* grad_colors, float* scalar_partials, float* grad_scalars,
+                   float* acc, float* pixstat, const int32_t* hist, void* stream);
 
 /*
  * Stand-alone perturbed Heaviside on x (P,K) (x = -dists in the shader).  prob = counts/S.

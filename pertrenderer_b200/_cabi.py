@@ -15,11 +15,12 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpertshade.so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 # flags (include/pertshade.h)
 F_NO_SKIP = 1
 F_SKIP_DEAD_NOISE = 2
+F_PER_SAMPLE_NOISE = 4
 PH_RAST, PH_AGG, PH_BLEND = 0x10, 0x20, 0x40
 PH_BWD_SAMPLE, PH_BWD_FINISH = 0x100, 0x200
 
@@ -84,9 +85,9 @@ def load():
         lib.pert_winner_bytes.restype = C.c_int
         lib.pert_winner_bytes.argtypes = [i32]
         lib.pert_shade_fwd.restype = C.c_int
-        lib.pert_shade_fwd.argtypes = [pp, vp, vp, vp, vp, vp, vp]
+        lib.pert_shade_fwd.argtypes = [pp] + [vp] * 7
         lib.pert_shade_bwd.restype = C.c_int
-        lib.pert_shade_bwd.argtypes = [pp] + [vp] * 13
+        lib.pert_shade_bwd.argtypes = [pp] + [vp] * 14
         lib.pert_rast_fwd.restype = C.c_int
         lib.pert_rast_fwd.argtypes = [vp, i64, i32, i32, i32, i32, f32, u64, i64, vp, u32, vp, vp, vp]
         lib.pert_rast_bwd.restype = C.c_int

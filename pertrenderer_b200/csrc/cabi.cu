@@ -1,0 +1,220 @@
+// C ABI of libpertshade.so (include/pertshade.h): argument validation and launch geometry.  Nothing
+// here allocates, frees, retains or synchronises; every launch goes to the caller's stream.
+#include "kernels.h"
+
+using namespace pert;
+
+static thread_local const char* g_last_cuda = "none";
+
+static int cuda_fail(int e) {
+    g_last_cuda = cudaGetErrorName((cudaError_t)e);
+    return PERT_E_CUDA;
+}
+static int cuda_rc(int e) { return e == 0 ? PERT_OK : cuda_fail(e); }
+
+extern "C" int pert_version(void) { return PERT_ABI_VERSION; }
+
+extern "C" const char* pert_last_cuda_error(void) { return g_last_cuda; }
+
+extern "C" const char* pert_strerror(int code) {
+    switch (code) {
+        case PERT_OK: return "ok";
+        case PERT_E_NULL: return "required pointer is NULL";
+        case PERT_E_SHAPE: return "bad shape";
+        case PERT_E_UNSUPPORTED: return "K or S not supported by the kernels";
+        case PERT_E_ALIGN: return "pointer not aligned";
+        case PERT_E_SAMPLES: return "bad sample shard (begin must be a multiple of 4, begin < end <= S)";
+        case PERT_E_CUDA: return "CUDA error";
+        case PERT_E_SCALAR: return "sigma, gamma and alpha must be finite and > 0";
+        default: return "unknown error";
+    }
+}
+
+// pixels per warp tile: a power of two in [4, 32] with about 512 fragment entries per tile
+static int pick_tp(int K) {
+    if (K <= 16) return 32;
+    if (K <= 32) return 16;
+    if (K <= 64) return 8;
+    return 4;
+}
+
+static int check_problem(const pert_problem* pb) {
+    if (!pb) return PERT_E_NULL;
+    if (pb->N <= 0 || pb->H <= 0 || pb->W <= 0 || pb->K <= 0) return PERT_E_SHAPE;
+    if (pb->K > 1023) return PERT_E_UNSUPPORTED;
+    if (pb->S_rast <= 0 || pb->S_agg <= 0 || pb->S_rast > 65535 || pb->S_agg > (1 << 24)) return PERT_E_UNSUPPORTED;
+    if (pb->depth_len != 1 && pb->depth_len != pb->N) return PERT_E_SHAPE;
+    if (!(pb->sigma > 0.f) || !(pb->gamma > 0.f) || !(pb->alpha > 0.f) || isinf(pb->sigma) || isinf(pb->gamma) ||
+        isinf(pb->alpha))
+        return PERT_E_SCALAR;
+    if ((pb->s_rast_begin & 3) || pb->s_rast_begin < 0 || pb->s_rast_begin >= pb->s_rast_end || pb->s_rast_end > pb->S_rast)
+        return PERT_E_SAMPLES;
+    if ((pb->s_agg_begin & 3) || pb->s_agg_begin < 0 || pb->s_agg_begin >= pb->s_agg_end || pb->s_agg_end > pb->S_agg)
+        return PERT_E_SAMPLES;
+    if (!pb->pix_to_face || !pb->zbuf || !pb->dists || !pb->znear || !pb->zfar) return PERT_E_NULL;
+    if (((uintptr_t)pb->pix_to_face & 7) || ((uintptr_t)pb->zbuf & 3) || ((uintptr_t)pb->dists & 3)) return PERT_E_ALIGN;
+    return PERT_OK;
+}
+
+static Launch make_launch(const pert_problem* pb) {
+    Launch L;
+    L.tp = pick_tp(pb->K);
+    L.G = 32 / L.tp;
+    L.gshift = 0;
+    while ((1 << L.gshift) < L.G) L.gshift++;
+    L.P = pb->N * pb->H * pb->W;
+    L.HW = pb->H * pb->W;
+    L.ntiles = (L.P + L.tp - 1) / L.tp;
+    L.win_bytes = pert_winner_bytes(pb->K);
+    L.sa_loc = pb->s_agg_end - pb->s_agg_begin;
+    int sc = 1024 / L.tp;  // c_s staging: about 4 KB per warp
+    const int s32 = (L.sa_loc + 31) & ~31;
+    if (sc > s32) sc = s32;
+    L.sc = sc;
+    L.warp_smem = 0;
+    L.vec_ok = 0;
+    L.invK = 1.0f / (float)pb->K;
+    return L;
+}
+
+extern "C" int64_t pert_num_tiles(const pert_problem* pb) {
+    if (!pb || pb->K <= 0) return 0;
+    const int tp = pick_tp(pb->K);
+    const int64_t P = pb->N * pb->H * pb->W;
+    const int64_t tiles = (P + tp - 1) / tp;
+    return (tiles + NW - 1) / NW;  // one row of scalar partials per CTA
+}
+
+extern "C" int pert_winner_bytes(int32_t K) { return (K + 1 <= 256) ? 1 : 2; }
+
+static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+
+extern "C" int pert_shade_fwd(const pert_problem* pb_in, float* image, uint16_t* counts, float* rsum, void* winners,
+                              uint16_t* pixstate, int32_t* hist, void* stream) {
+    int rc = check_problem(pb_in);
+    if (rc) return rc;
+    FwdArgs a;
+    a.pb = *pb_in;
+    if (!(a.pb.flags & (PERT_PH_RAST | PERT_PH_AGG | PERT_PH_BLEND))) a.pb.flags |= PERT_PH_RAST | PERT_PH_AGG | PERT_PH_BLEND;
+    const uint32_t f = a.pb.flags;
+    if (!counts) return PERT_E_NULL;
+    if ((f & PERT_PH_RAST) && !rsum) return PERT_E_NULL;
+    if ((f & PERT_PH_AGG) && (!winners || !pixstate)) return PERT_E_NULL;
+    if ((f & PERT_PH_BLEND) && (!image || !a.pb.colors)) return PERT_E_NULL;
+    if (((f & PERT_PH_AGG) != 0) != ((f & PERT_PH_BLEND) != 0) && !hist) return PERT_E_NULL;
+    if (((uintptr_t)image & 15) || ((uintptr_t)counts & 1) || ((uintptr_t)rsum & 3) || ((uintptr_t)hist & 3) ||
+        ((uintptr_t)a.pb.colors & 3) || ((uintptr_t)pixstate & 1) || ((uintptr_t)winners & 3))
+        return PERT_E_ALIGN;
+    a.L = make_launch(&a.pb);
+    a.L.vec_ok = aligned16(a.pb.pix_to_face);
+    a.L.warp_smem = (int)fwd_warp_smem(a.L.tp, a.pb.K);
+    if ((size_t)a.L.warp_smem * NW > 200 * 1024) return PERT_E_UNSUPPORTED;
+    if ((a.L.ntiles + NW - 1) / NW > 0x7fffffff) return PERT_E_UNSUPPORTED;
+    a.image = image;
+    a.counts = counts;
+    a.rsum = rsum;
+    a.winners = winners;
+    a.pixstate = pixstate;
+    a.hist = hist;
+    return cuda_rc(launch_shade_fwd(a, (cudaStream_t)stream));
+}
+
+extern "C" int pert_shade_bwd(const pert_problem* pb_in, const float* grad_image, const uint16_t* counts,
+                              const float* rsum, const void* winners, const uint16_t* pixstate, float* grad_dists,
+                              float* grad_zbuf, float* grad_colors, float* scalar_partials, float* grad_scalars,
+                              float* acc, float* pixstat, const int32_t* hist, void* stream) {
+    int rc = check_problem(pb_in);
+    if (rc) return rc;
+    BwdArgs a;
+    a.pb = *pb_in;
+    if (!(a.pb.flags & (PERT_PH_BWD_SAMPLE | PERT_PH_BWD_FINISH))) a.pb.flags |= PERT_PH_BWD_SAMPLE | PERT_PH_BWD_FINISH;
+    const uint32_t f = a.pb.flags;
+    const bool smp = f & PERT_PH_BWD_SAMPLE, fin = f & PERT_PH_BWD_FINISH;
+    if (!grad_image || !counts || !rsum || !pixstate || !a.pb.colors) return PERT_E_NULL;
+    if (smp && !winners) return PERT_E_NULL;
+    if (fin && (!grad_dists || !grad_zbuf || !scalar_partials || !grad_scalars)) return PERT_E_NULL;
+    if (smp != fin && (!acc || !pixstat)) return PERT_E_NULL;
+    if (fin && !smp && grad_colors && !hist) return PERT_E_NULL;
+    if (((uintptr_t)grad_image & 15) || ((uintptr_t)grad_colors & 3) || ((uintptr_t)grad_dists & 3) ||
+        ((uintptr_t)grad_zbuf & 3) || ((uintptr_t)counts & 1) || ((uintptr_t)rsum & 3) || ((uintptr_t)pixstate & 1) ||
+        ((uintptr_t)scalar_partials & 15) || ((uintptr_t)acc & 3) || ((uintptr_t)pixstat & 3) || ((uintptr_t)hist & 3))
+        return PERT_E_ALIGN;
+    a.L = make_launch(&a.pb);
+    a.L.vec_ok = aligned16(a.pb.pix_to_face) && aligned16(grad_dists) && aligned16(grad_zbuf) && aligned16(grad_colors);
+    if (a.L.win_bytes == 2 && ((uintptr_t)winners & 1)) return PERT_E_ALIGN;
+    a.L.warp_smem = (int)bwd_warp_smem(a.L.tp, a.pb.K, a.L.sc);
+    if ((size_t)a.L.warp_smem * NW > 200 * 1024) return PERT_E_UNSUPPORTED;
+    if ((a.L.ntiles + NW - 1) / NW > 0x7fffffff) return PERT_E_UNSUPPORTED;
+    a.grad_image = grad_image;
+    a.counts = counts;
+    a.rsum = rsum;
+    a.winners = winners;
+    a.pixstate = pixstate;
+    a.grad_dists = grad_dists;
+    a.grad_zbuf = grad_zbuf;
+    a.grad_colors = grad_colors;
+    a.partials = scalar_partials;
+    a.acc = acc;
+    a.pixstat = pixstat;
+    a.hist = hist;
+    return cuda_rc(launch_shade_bwd(a, grad_scalars, (cudaStream_t)stream));
+}
+
+extern "C" int pert_rast_fwd(const float* x, int64_t P, int32_t K, int32_t S, int32_t s_begin, int32_t s_end,
+                             float sigma, uint64_t seed, int64_t pixel_offset, const float* noise, uint32_t flags,
+                             float* prob, float* rsum, void* stream) {
+    if (!x || !prob || !rsum) return PERT_E_NULL;
+    if (P <= 0 || K <= 0) return PERT_E_SHAPE;
+    if (S <= 0 || S > 65535) return PERT_E_UNSUPPORTED;
+    if ((s_begin & 3) || s_begin < 0 || s_begin >= s_end || s_end > S) return PERT_E_SAMPLES;
+    if (!(sigma > 0.f) || isinf(sigma)) return PERT_E_SCALAR;
+    if ((P * K + 1023) / 1024 > 0x7fffffff) return PERT_E_UNSUPPORTED;
+    return cuda_rc(launch_rast_fwd(x, P, K, S, s_begin, s_end, sigma, seed, pixel_offset, noise, flags, prob, rsum,
+                                   (cudaStream_t)stream));
+}
+
+extern "C" int pert_rast_bwd(const float* grad_l, const float* rsum, int64_t n, int32_t S, float sigma, float* grad_x,
+                             float* scalar_partials, float* grad_sigma, void* stream) {
+    if (!grad_l || !rsum || !grad_x || !scalar_partials || !grad_sigma) return PERT_E_NULL;
+    if (n <= 0 || S <= 0) return PERT_E_SHAPE;
+    if (!(sigma > 0.f)) return PERT_E_SCALAR;
+    if ((n + 255) / 256 > 0x7fffffff) return PERT_E_UNSUPPORTED;
+    return cuda_rc(launch_rast_bwd(grad_l, rsum, n, S, sigma, grad_x, scalar_partials, grad_sigma, (cudaStream_t)stream));
+}
+
+extern "C" int pert_argmax_fwd(const float* z, int64_t P, int32_t K1, int32_t S, int32_t s_begin, int32_t s_end,
+                               float gamma, uint64_t seed, int64_t pixel_offset, const float* noise, uint32_t flags,
+                               float* weights, void* winners, void* stream) {
+    if (!z || !weights || !winners) return PERT_E_NULL;
+    if (P <= 0 || K1 <= 0) return PERT_E_SHAPE;
+    if (K1 > 1024 || S <= 0 || S > (1 << 24)) return PERT_E_UNSUPPORTED;
+    if ((s_begin & 3) || s_begin < 0 || s_begin >= s_end || s_end > S) return PERT_E_SAMPLES;
+    if (!(gamma > 0.f) || isinf(gamma)) return PERT_E_SCALAR;
+    if ((P + NW - 1) / NW > 0x7fffffff) return PERT_E_UNSUPPORTED;
+    return cuda_rc(launch_argmax_fwd(z, P, K1, S, s_begin, s_end, gamma, seed, pixel_offset, noise, flags, weights,
+                                     winners, (cudaStream_t)stream));
+}
+
+extern "C" int pert_argmax_bwd(const float* grad_l, const float* z, const void* winners, int64_t P, int32_t K1,
+                               int32_t S, int32_t s_begin, int32_t s_end, float gamma, uint64_t seed,
+                               int64_t pixel_offset, const float* noise, uint32_t flags, float* grad_z,
+                               float* scalar_partials, float* grad_gamma, void* stream) {
+    if (!grad_l || !z || !winners || !grad_z || !scalar_partials || !grad_gamma) return PERT_E_NULL;
+    if (P <= 0 || K1 <= 0) return PERT_E_SHAPE;
+    if (K1 > 1024 || S <= 0) return PERT_E_UNSUPPORTED;
+    if ((s_begin & 3) || s_begin < 0 || s_begin >= s_end || s_end > S) return PERT_E_SAMPLES;
+    if (!(gamma > 0.f) || isinf(gamma)) return PERT_E_SCALAR;
+    if ((P + NW - 1) / NW > 0x7fffffff) return PERT_E_UNSUPPORTED;
+    return cuda_rc(launch_argmax_bwd(grad_l, z, winners, P, K1, S, s_begin, s_end, gamma, seed, pixel_offset, noise,
+                                     flags, grad_z, scalar_partials, grad_gamma, (cudaStream_t)stream));
+}
+
+extern "C" int pert_noise_fill(uint64_t seed, int32_t stage, int64_t P, int32_t slots, int32_t s_begin, int32_t s_end,
+                               int64_t pixel_offset, float* out, void* stream) {
+    if (!out) return PERT_E_NULL;
+    if (P <= 0 || slots <= 0) return PERT_E_SHAPE;
+    if ((s_begin & 3) || s_begin < 0 || s_begin >= s_end) return PERT_E_SAMPLES;
+    const int qn = ((s_end + 3) >> 2) - (s_begin >> 2);
+    if (((int64_t)qn * P * slots + 255) / 256 > 0x7fffffff) return PERT_E_UNSUPPORTED;
+    return cuda_rc(launch_noise_fill(seed, stage, P, slots, s_begin, s_end, pixel_offset, out, (cudaStream_t)stream));
+}

@@ -1,0 +1,55 @@
+// Host-side launch interface between the C ABI (cabi.cu) and the kernel translation units.
+#pragma once
+#include "common.cuh"
+
+namespace pert {
+
+struct FwdArgs {
+    pert_problem pb;
+    Launch L;
+    float* image;
+    uint16_t* counts;
+    float* rsum;
+    void* winners;
+    uint16_t* pixstate;
+    int32_t* hist;
+};
+
+struct BwdArgs {
+    pert_problem pb;
+    Launch L;
+    const float* grad_image;
+    const uint16_t* counts;
+    const float* rsum;
+    const void* winners;
+    const uint16_t* pixstate;
+    float* grad_dists;
+    float* grad_zbuf;
+    float* grad_colors;
+    float* partials;
+    float* acc;
+    float* pixstat;
+    const int32_t* hist;
+};
+
+size_t fwd_warp_smem(int tp, int K);
+size_t bwd_warp_smem(int tp, int K, int sc);
+
+// return a cudaError_t as int (0 = success)
+int launch_shade_fwd(const FwdArgs& a, cudaStream_t st);
+int launch_shade_bwd(const BwdArgs& a, float* grad_scalars, cudaStream_t st);
+
+int launch_rast_fwd(const float* x, int64_t P, int K, int S, int s_begin, int s_end, float sigma, uint64_t seed,
+                    int64_t pixel_offset, const float* noise, uint32_t flags, float* prob, float* rsum, cudaStream_t st);
+int launch_rast_bwd(const float* grad_l, const float* rsum, int64_t n, int S, float sigma, float* grad_x,
+                    float* partials, float* grad_sigma, cudaStream_t st);
+int launch_argmax_fwd(const float* z, int64_t P, int K1, int S, int s_begin, int s_end, float gamma, uint64_t seed,
+                      int64_t pixel_offset, const float* noise, uint32_t flags, float* weights, void* winners,
+                      cudaStream_t st);
+int launch_argmax_bwd(const float* grad_l, const float* z, const void* winners, int64_t P, int K1, int S, int s_begin,
+                      int s_end, float gamma, uint64_t seed, int64_t pixel_offset, const float* noise, uint32_t flags,
+                      float* grad_z, float* partials, float* grad_gamma, cudaStream_t st);
+int launch_noise_fill(uint64_t seed, int stage, int64_t P, int slots, int s_begin, int s_end, int64_t pixel_offset,
+                      float* out, cudaStream_t st);
+
+}  // namespace pert

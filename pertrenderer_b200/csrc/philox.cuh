@@ -14,9 +14,11 @@
 
 namespace pert {
 
-// |n| <= sqrt(-2 ln 2^-33) = 6.764 for every value normal4() can return; the kernels use this
-// bound to skip draws that cannot change any output bit.
-constexpr float kNoiseAbsMax = 6.8f;
+// Every uniform is built from the top 23 bits of a Philox word (mantissa trick, no I2F on the
+// quarter-rate conversion pipe): u in [2^-23, 1], so |n| <= sqrt(-2 ln 2^-23) = 5.647 for every value
+// box_muller() can return; the kernels use this bound to skip draws that cannot change any output
+// bit.  (The truncated tail has probability 1.6e-8 per draw.)
+constexpr float kNoiseAbsMax = 5.66f;
 
 template <int ROUNDS>
 __device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
@@ -40,8 +42,8 @@ __device__ __forceinline__ void philox4x32(uint32_t c0, uint32_t c1, uint32_t c2
     out[3] = c3;
 }
 
-// u in (0, 1]: (x + 0.5) * 2^-32
-__device__ __forceinline__ float u01(uint32_t x) { return fmaf((float)x, 2.3283064365386963e-10f, 1.1641532182693481e-10f); }
+// top 23 bits of a word as a float in [1, 2)
+__device__ __forceinline__ float mant12(uint32_t x) { return __uint_as_float((x >> 9) | 0x3f800000u); }
 
 __device__ __forceinline__ float mufu_lg2(float x) {
     float r;
@@ -64,13 +66,13 @@ __device__ __forceinline__ float mufu_cos(float x) {
     return r;
 }
 
-// Two standard normals from two 32-bit words: radius = sqrt(-2 ln u) (MUFU.LG2 + MUFU.SQRT),
-// angle = 2 pi v (MUFU.SIN / MUFU.COS).  u >= 2^-33 is never denormal, so the .ftz forms are exact
-// substitutes and save the denormal fix-up code.
+// Two standard normals from two 32-bit words: u = 2 - mant12(a) in [2^-23, 1], radius =
+// sqrt(-2 ln u) (MUFU.LG2 + MUFU.SQRT), angle = 2 pi (mant12(b) - 1.5) in [-pi, pi) (MUFU.SIN /
+// MUFU.COS).  u is never denormal, so the .ftz forms are exact substitutes.
 __device__ __forceinline__ void box_muller(uint32_t a, uint32_t b, float& n0, float& n1) {
-    const float u = u01(a);
+    const float u = 2.0f - mant12(a);
     const float rad = mufu_sqrt(-1.3862943611198906f * mufu_lg2(u));
-    const float ang = fmaf((float)b, 1.4629180792671596e-9f, 7.314590396335798e-10f);  // 2 pi (b + .5) 2^-32
+    const float ang = fmaf(mant12(b), 6.283185307179586f, -9.42477796076938f);
     n0 = rad * mufu_cos(ang);
     n1 = rad * mufu_sin(ang);
 }
@@ -91,15 +93,10 @@ struct PhiloxNoise {
         box_muller(r[0], r[1], n[0], n[1]);
         box_muller(r[2], r[3], n[2], n[3]);
     }
-    // same values; a pair whose `need` flag is false is returned as zeros (its MUFU work is skipped)
-    __device__ __forceinline__ void get4_pairs(uint32_t q, uint32_t slot, int64_t pixel_local, bool need01, bool need23,
-                                               float (&n)[4]) const {
+    // the raw Philox words of (q, slot, pixel): r[0],r[1] make samples 4q, 4q+1 and r[2],r[3] make 4q+2, 4q+3
+    __device__ __forceinline__ void words(uint32_t q, uint32_t slot, int64_t pixel_local, uint32_t (&r)[4]) const {
         const uint64_t gp = (uint64_t)(pixel_local + pixel_offset);
-        uint32_t r[4];
         philox4x32<10>(q, slot, (uint32_t)gp, ((uint32_t)(gp >> 32) & 0x7fffffffu) | stage_bit, k0, k1, r);
-        n[0] = n[1] = n[2] = n[3] = 0.0f;
-        if (need01) box_muller(r[0], r[1], n[0], n[1]);
-        if (need23) box_muller(r[2], r[3], n[2], n[3]);
     }
     static constexpr bool kBounded = true;
 };
@@ -118,11 +115,17 @@ struct ExplicitNoise {
             n[t] = (s < S) ? __ldg(base + (s * P + pixel_local) * slots + slot) : 0.0f;
         }
     }
-    __device__ __forceinline__ void get4_pairs(uint32_t q, uint32_t slot, int64_t pixel_local, bool, bool,
-                                               float (&n)[4]) const {
-        get4(q, slot, pixel_local, n);
-    }
     static constexpr bool kBounded = false;
 };
+
+// Radius bound on the raw word: box_muller(a, .) returns |n| < t for every angle whenever
+// (a >> 9) < radius_gate(t).  u = 1 - (a >> 9) 2^-23 exactly, and rad < t  <=>  u > exp(-t^2/2); the
+// 1.001 factor on exp(.) and the -2 cover the MUFU approximation errors of rad, cos and sin by a wide
+// margin (a conservative gate only costs a wasted Box-Muller, never a wrong sample).
+__device__ __forceinline__ uint32_t radius_gate(float t) {
+    const float e = exp2f(-0.72134752f * t * t) * 1.001f;
+    const float g = (1.0f - e) * 8388608.0f - 2.0f;
+    return g > 0.0f ? (uint32_t)g : 0u;
+}
 
 }  // namespace pert

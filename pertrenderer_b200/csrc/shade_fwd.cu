@@ -1,0 +1,313 @@
+// Fused forward of the perturbed shader (pert_shade_fwd in include/pertshade.h).
+//
+// Reference path: smooth_rgb_blend (randomras/random_rasterizer.py:34-56) -> randomHeaviside.forward
+// (randomras/smoothrast.py:15-37) -> GaussianAgg.aggregate (randomras/smoothagg.py:196-205) ->
+// randomArgmax.forward (randomras/smoothagg.py:13-42) -> blend.
+//
+// One warp per tile of tp pixels, no block-level synchronisation.  Phases of a tile:
+//   0  scan pix_to_face (128-bit loads) -> compact list of valid entries; zbuf/dists only for those
+//   1  coverage samples of the entries whose sign can flip (Philox in registers) -> counts, rsum
+//   2  per-pixel logits (G lanes per pixel), list of logits that can win a sample
+//   3  perturbed argmax samples over (pixel, sample-quad) items -> winners, histogram
+//   4  blend -> image; per-pixel state (a0, active) for backward
+#include "kernels.h"
+#include "tile.cuh"
+
+namespace pert {
+
+size_t fwd_warp_smem(int tp, int K) {
+    const size_t E = (size_t)tp * K, E1 = (size_t)tp * (K + 1);
+    return carve(E, 2) /*vlist*/ + carve(E1, 4) /*xs|lz*/ + carve(E, 4) /*zs*/ + carve(E, 2) /*cnt*/ +
+           carve(E1, 4) /*rs|hl*/ + carve(E1, 2) /*rlist|lj*/ + carve(tp + 1, 4) /*vstart*/ + carve(tp, 4) /*pinfo*/ +
+           carve(tp, 2) /*plist*/ + 16;
+}
+
+template <class NoiseR, class NoiseA>
+__global__ void __launch_bounds__(NT) shade_fwd_kernel(const FwdArgs a, const NoiseR noise_r, const NoiseA noise_a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const pert_problem& pb = a.pb;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tile = (int64_t)blockIdx.x * NW + warp;
+    if (tile >= a.L.ntiles) return;
+    const int K = pb.K, K1 = K + 1, tp = a.L.tp, G = a.L.G;
+    const int64_t pix0 = tile * tp;
+    const int npx = (int)min((int64_t)tp, a.L.P - pix0);
+    const int E = npx * K;
+    const int64_t g0 = pix0 * K;
+    const uint32_t flags = pb.flags;
+    const bool do_rast = flags & PERT_PH_RAST, do_agg = flags & PERT_PH_AGG, do_blend = flags & PERT_PH_BLEND;
+    const bool no_skip = flags & PERT_F_NO_SKIP;
+    const int p = lane >> a.L.gshift, lig = lane & (G - 1);
+    const bool pvalid = p < npx;
+    const int64_t gp = pix0 + p;
+    const unsigned lt = (1u << lane) - 1u;
+
+    Carver cv(smem_raw + (size_t)warp * a.L.warp_smem);
+    uint16_t* vlist = cv.take<uint16_t>(tp * K);
+    float* xs = cv.take<float>(tp * K1);  // x = -dists (compact); later lz: logits of the live list
+    float* zs = cv.take<float>(tp * K);   // zbuf -> zi -> zeta (compact)
+    uint16_t* cnt = cv.take<uint16_t>(tp * K);
+    float* rs = cv.take<float>(tp * K1);  // sum_s (h-h0) U (compact); later hl: histogram of the live list
+    uint16_t* rlist = cv.take<uint16_t>(tp * K1);  // entries that need coverage samples; later lj: live logit ids
+    int* vstart = cv.take<int>(tp + 1);
+    int* pinfo = cv.take<int>(tp);  // nlive | a0l << 16 of every pixel
+    uint16_t* plist = cv.take<uint16_t>(tp);
+    float* lz = xs;
+    int* hl = reinterpret_cast<int*>(rs);
+    uint16_t* lj = rlist;
+
+    // ---- phase 0 -----------------------------------------------------------------------------------
+    const int nv = scan_valid(pb.pix_to_face + g0, E, a.L.vec_ok, vlist);
+    const int sa_loc = a.L.sa_loc;
+    if (nv == 0) {
+        // nothing but padding: background, alpha 0, every sample picks the background (index K)
+        if (do_agg && a.hist) {
+            for (int i = lane; i < npx * K1; i += 32) a.hist[pix0 * K1 + i] = ((i % K1) == K) ? sa_loc : 0;
+        }
+        if (do_agg && lane < npx) a.pixstate[pix0 + lane] = (uint16_t)K;
+        if (do_blend && lane < npx)
+            reinterpret_cast<float4*>(a.image)[pix0 + lane] =
+                make_float4(pb.background[0], pb.background[1], pb.background[2], 0.0f);
+        return;
+    }
+    __syncwarp();
+    pixel_ranges(vlist, nv, K, tp, vstart);
+
+    // ---- phase 1: stage valid entries, coverage samples ---------------------------------------------
+    const int sr_loc = pb.s_rast_end - pb.s_rast_begin;
+    const float thr = (NoiseR::kBounded && !no_skip) ? pb.sigma * kNoiseAbsMax * 1.0001f : CUDART_INF_F;
+    int nlist = 0;
+    for (int n0 = 0; n0 < nv; n0 += 32) {
+        const int n = n0 + lane;
+        bool need = false;
+        if (n < nv) {
+            const int e = vlist[n];
+            zs[n] = __ldg(pb.zbuf + g0 + e);
+            if (do_rast) {
+                const float x = -__ldg(pb.dists + g0 + e);
+                xs[n] = x;
+                // |x| beyond the largest possible sigma*|U| cannot flip: exact, not an approximation
+                need = fabsf(x) <= thr;
+                if (!need) {
+                    cnt[n] = (x >= 0.0f) ? (uint16_t)sr_loc : (uint16_t)0;
+                    rs[n] = 0.0f;
+                }
+            } else {
+                cnt[n] = a.counts[g0 + e];
+            }
+        }
+        if (do_rast) {
+            const unsigned b = __ballot_sync(FULL, need);
+            if (need) rlist[nlist + __popc(b & lt)] = (uint16_t)n;
+            nlist += __popc(b);
+        }
+    }
+    __syncwarp();
+    if (do_rast) {
+        rast_sample_list(noise_r, rlist, nlist, vlist, xs, cnt, rs, K, a.L.invK, pix0, pb.sigma, pb.s_rast_begin,
+                         pb.s_rast_end, !no_skip);
+        __syncwarp();
+        for (int n = lane; n < nv; n += 32) {
+            const int e = vlist[n];
+            a.counts[g0 + e] = cnt[n];
+            a.rsum[g0 + e] = rs[n];
+        }
+    }
+    if (!do_agg && !do_blend) return;
+    __syncwarp();
+
+    // ---- phase 2: logits, alpha, live lists ---------------------------------------------------------
+    const float gal = pb.gamma / pb.alpha;  // fp32 scalar division, smoothagg.py:201
+    float zn = 1.0f, zf = 100.0f;
+    if (pvalid) {
+        const int b = pb.depth_len > 1 ? (int)(gp / a.L.HW) : 0;
+        zn = __ldg(pb.znear + b);
+        zf = __ldg(pb.zfar + b);
+    }
+    const PixPrep pi = prep_pixels(p, lig, G, pvalid, K, vstart, vlist, cnt, zs, zn, zf, pb.S_rast, gal, pb.eps);
+    const float px_alpha = 1.0f - (pi.nzero ? 0.0f : pi.prod_nz);
+    const int vs = pvalid ? vstart[p] : 0, ve = pvalid ? vstart[p + 1] : 0;
+    const int nvp = ve - vs;
+    const int lb = vs + p;  // this pixel's slots in lz / lj / hl: nvp + 1 of them
+    int nlive = 0, a0l = 0;
+    bool active = false;
+    __syncwarp();
+    if (do_agg) {
+        // a logit can win some sample only if zeta_j + gamma*Umax >= zeta_max - gamma*Umax
+        const float floor_v = pi.zeta_max - live_cut(pb.gamma, pi.zeta_max, NoiseA::kBounded && !no_skip);
+        const int iters = warp_max_i((nvp + G) / G);  // ceil((nvp + 1) / G), uniform for the ballots
+        const unsigned gmask = (G == 32) ? FULL : ((1u << G) - 1u);
+        const int gsh = p * G;
+        for (int it = 0; it < iters; ++it) {
+            const int idx = it * G + lig;
+            float z = -CUDART_INF_F;
+            int j = K;
+            if (pvalid && idx < nvp) {
+                z = zs[vs + idx];
+                j = (int)vlist[vs + idx] - p * K;
+            } else if (pvalid && idx == nvp) {
+                z = pi.zbg;
+            }
+            const bool lv = z > -CUDART_INF_F && z >= floor_v;
+            const unsigned gb = (__ballot_sync(FULL, lv) >> gsh) & gmask;
+            if (lv) {
+                const int pos = lb + nlive + __popc(gb & ((1u << lig) - 1u));
+                lz[pos] = z;
+                lj[pos] = (uint16_t)j;
+                hl[pos] = 0;
+            }
+            const unsigned a0b = (__ballot_sync(FULL, lv && j == pi.a0) >> gsh) & gmask;
+            if (a0b) a0l = nlive + __popc(gb & ((1u << (__ffs(a0b) - 1)) - 1u));
+            nlive += __popc(gb);
+        }
+        __syncwarp();
+
+        // ---- phase 3: perturbed argmax samples (smoothagg.py:33-36) ---------------------------------
+        const bool multi = pvalid && lig == 0 && nlive > 1;
+        const unsigned mb = __ballot_sync(FULL, multi);
+        if (multi) plist[__popc(mb & lt)] = (uint16_t)p;
+        if (pvalid && lig == 0) pinfo[p] = nlive | (a0l << 16);
+        const int np = __popc(mb);
+        __syncwarp();
+        if (np > 0) {
+            const int qb = pb.s_agg_begin >> 2, qe = (pb.s_agg_end + 3) >> 2;
+            const int lpe = min(32, pow2_ceil(qe - qb));
+            const int gpw = 32 / lpe;
+            const int lq = lane & (lpe - 1);
+            const float gamma = pb.gamma;
+            const bool pack = a.L.win_bytes == 1 && (sa_loc & 3) == 0;
+            for (int base = 0; base < np; base += gpw) {
+                const int pe = base + lane / lpe;
+                if (pe >= np) continue;
+                const int pp = plist[pe];
+                const int plb = vstart[pp] + pp;
+                const int pn = pinfo[pp] & 0xffff, pa0 = pinfo[pp] >> 16;
+                const int64_t pgp = pix0 + pp;
+                for (int q = qb + lq; q < qe; q += lpe) {
+                    float best[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
+                    int bi[4] = {0, 0, 0, 0};
+                    for (int l = 0; l < pn; ++l) {
+                        const int j = lj[plb + l];
+                        const float z = lz[plb + l];
+                        float nz[4];
+                        noise_a.get4(q, j, pgp, nz);
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const float v = __fadd_rn(z, __fmul_rn(gamma, nz[t]));
+                            if (v > best[t]) {
+                                best[t] = v;
+                                bi[t] = l;
+                            }
+                        }
+                    }
+                    int wj[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        wj[t] = lj[plb + bi[t]];
+                        const int s = q * 4 + t;
+                        if (s >= pb.s_agg_begin && s < pb.s_agg_end && bi[t] != pa0) atomicAdd(&hl[plb + bi[t]], 1);
+                    }
+                    const int s0 = q * 4 - pb.s_agg_begin;
+                    if (pack && q * 4 + 3 < pb.s_agg_end) {
+                        reinterpret_cast<uint32_t*>(a.winners)[(pgp * sa_loc + s0) >> 2] =
+                            (uint32_t)wj[0] | ((uint32_t)wj[1] << 8) | ((uint32_t)wj[2] << 16) | ((uint32_t)wj[3] << 24);
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+                            if (q * 4 + t < pb.s_agg_end) store_winner(a.winners, a.L.win_bytes, pgp * sa_loc + s0 + t, wj[t]);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+        // histogram of the unperturbed winner = all the samples nobody else won
+        int others = 0;
+        for (int l = lig; l < nlive; l += G)
+            if (l != a0l) others += hl[lb + l];
+        others = group_sum_i(others, G);
+        active = others > 0;
+        if (pvalid && lig == 0) {
+            hl[lb + a0l] = sa_loc - others;
+            a.pixstate[gp] = (uint16_t)(pi.a0 | (active ? 0x8000 : 0));
+        }
+        __syncwarp();
+        if (a.hist) {
+            // dense (P,K1) histogram for the sample-sharded job: zeros, then the live entries
+            for (int i = lane; i < npx * K1; i += 32) a.hist[pix0 * K1 + i] = 0;
+            __syncwarp();
+            for (int l = lig; l < nlive; l += G) a.hist[gp * K1 + lj[lb + l]] = hl[lb + l];
+        }
+    }
+    if (!do_blend) return;
+
+    // ---- phase 4: blend (random_rasterizer.py:50-54) ------------------------------------------------
+    float r = 0.f, g = 0.f, bl = 0.f;
+    const float fS = (float)pb.S_agg;
+    if (do_agg) {
+        for (int l = lig; l < nlive; l += G) {
+            const int hcount = hl[lb + l];
+            if (hcount > 0) {
+                const float w = (float)hcount / fS;
+                const int j = lj[lb + l];
+                if (j < K) {
+                    const float* c = pb.colors + (gp * K + j) * 3;
+                    r += w * __ldg(c);
+                    g += w * __ldg(c + 1);
+                    bl += w * __ldg(c + 2);
+                } else {
+                    r += w * pb.background[0];
+                    g += w * pb.background[1];
+                    bl += w * pb.background[2];
+                }
+            }
+        }
+    } else {
+        // histogram summed over all sample shards (read from global memory)
+        const int32_t* hg = a.hist + gp * K1;
+        for (int idx = lig; idx <= nvp && pvalid; idx += G) {
+            const int j = idx < nvp ? (int)vlist[vs + idx] - p * K : K;
+            const int hcount = hg[j];
+            if (hcount > 0) {
+                const float w = (float)hcount / fS;
+                if (j < K) {
+                    const float* c = pb.colors + (gp * K + j) * 3;
+                    r += w * __ldg(c);
+                    g += w * __ldg(c + 1);
+                    bl += w * __ldg(c + 2);
+                } else {
+                    r += w * pb.background[0];
+                    g += w * pb.background[1];
+                    bl += w * pb.background[2];
+                }
+            }
+        }
+    }
+    r = group_sum(r, G);
+    g = group_sum(g, G);
+    bl = group_sum(bl, G);
+    if (pvalid && lig == 0) reinterpret_cast<float4*>(a.image)[gp] = make_float4(r, g, bl, px_alpha);
+}
+
+template <class NR, class NA>
+static int launch_fwd_t(const FwdArgs& a, const NR& nr, const NA& na, size_t smem, unsigned blocks, cudaStream_t st) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(shade_fwd_kernel<NR, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    shade_fwd_kernel<NR, NA><<<blocks, NT, smem, st>>>(a, nr, na);
+    return (int)cudaGetLastError();
+}
+
+int launch_shade_fwd(const FwdArgs& a, cudaStream_t st) {
+    const size_t smem = (size_t)a.L.warp_smem * NW;
+    const unsigned blocks = (unsigned)((a.L.ntiles + NW - 1) / NW);
+    const bool er = a.pb.noise_rast != nullptr, ea = a.pb.noise_agg != nullptr;
+    PhiloxNoise pr(a.pb.seed_rast, 0, a.pb.pixel_offset), pa(a.pb.seed_agg, 1, a.pb.pixel_offset);
+    ExplicitNoise xr{a.pb.noise_rast, a.L.P, a.pb.K, a.pb.S_rast}, xa{a.pb.noise_agg, a.L.P, a.pb.K + 1, a.pb.S_agg};
+    if (!er && !ea) return launch_fwd_t(a, pr, pa, smem, blocks, st);
+    if (er && ea) return launch_fwd_t(a, xr, xa, smem, blocks, st);
+    if (er) return launch_fwd_t(a, xr, pa, smem, blocks, st);
+    return launch_fwd_t(a, pr, xa, smem, blocks, st);
+}
+
+}  // namespace pert

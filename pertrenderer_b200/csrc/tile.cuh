@@ -1,0 +1,257 @@
+// Per-warp tile machinery shared by the fused forward and backward kernels.
+//
+// A warp owns `tp` consecutive pixels.  Real fragments are sparse in K (a handful of valid faces per
+// pixel, padding last), so the tile is first reduced to a COMPACT list of its valid entries
+// (pix_to_face >= 0); zbuf / dists / saved state are then touched only for those, and every later
+// phase runs over compact indices n in [0, nv).  Reference semantics being reproduced:
+//   random_rasterizer.py:46-48  mask, P = p_hat*mask, alpha = prod(1-P)
+//   smoothagg.py:198-202        zi, zmax, zeta_k = (gamma/alpha) log P_k + zi_k - zmax, zeta_K = eps - zmax
+#pragma once
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace pert {
+
+// ------------------------------------------------------------------------------------------------
+// phase 0: scan pix_to_face of the tile (128-bit loads), build the ascending list of valid entries
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int scan_valid(const int64_t* __restrict__ p2f /* tile base */, int E, bool vec_ok,
+                                          uint16_t* vlist) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    int total = 0;
+    constexpr int U = 4;  // loads in flight per lane
+    for (int base = 0; base < E; base += 64 * U) {
+        long long a[U], b[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int e0 = base + u * 64 + 2 * lane;
+            a[u] = -1;
+            b[u] = -1;
+            if (e0 + 1 < E) {
+                if (vec_ok) {
+                    const longlong2 v = __ldg(reinterpret_cast<const longlong2*>(p2f + e0));
+                    a[u] = v.x;
+                    b[u] = v.y;
+                } else {
+                    a[u] = __ldg(p2f + e0);
+                    b[u] = __ldg(p2f + e0 + 1);
+                }
+            } else if (e0 < E) {
+                a[u] = __ldg(p2f + e0);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (base + u * 64 >= E) break;  // warp-uniform
+            const int e0 = base + u * 64 + 2 * lane;
+            const bool v0 = a[u] >= 0, v1 = b[u] >= 0;
+            const unsigned be = __ballot_sync(FULL, v0), bo = __ballot_sync(FULL, v1);
+            const int pos = total + __popc(be & lt) + __popc(bo & lt);
+            if (v0) vlist[pos] = (uint16_t)e0;
+            if (v1) vlist[pos + (v0 ? 1 : 0)] = (uint16_t)(e0 + 1);
+            total += __popc(be) + __popc(bo);
+        }
+    }
+    return total;
+}
+
+// vstart[p] = first compact index of pixel p (p = 0..tp), by binary search on the ascending vlist
+__device__ __forceinline__ void pixel_ranges(const uint16_t* vlist, int nv, int K, int tp, int* vstart) {
+    const int lane = threadIdx.x & 31;
+    for (int p = lane; p <= tp; p += 32) {
+        const int target = p * K;
+        int lo = 0, hi = nv;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if ((int)vlist[mid] < target) lo = mid + 1;
+            else hi = mid;
+        }
+        vstart[p] = lo;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// stage 1: coverage samples of the listed entries
+//   randomras/smoothrast.py:32-36: h = 1[x + sigma*U >= 0] (rounded multiply, rounded add), mean over s
+//   saved for backward: cnt = sum_s h, rs = sum_s (h - h0) U   (smoothrast.py:46)
+// rlist holds compact indices n; xs/cnt/rs are compact arrays.
+// ------------------------------------------------------------------------------------------------
+template <class NoiseT>
+__device__ __forceinline__ void rast_sample_list(const NoiseT& noise, const uint16_t* rlist, int nlist,
+                                                 const uint16_t* vlist, const float* xs, uint16_t* cnt, float* rs,
+                                                 int K, float invK, int64_t pix0, float sigma, int s_begin, int s_end,
+                                                 bool gate_ok) {
+    const int lane = threadIdx.x & 31;
+    const int qb = s_begin >> 2, qe = (s_end + 3) >> 2;
+    const int lpe = min(32, pow2_ceil(qe - qb));  // lanes per entry
+    const int gpw = 32 / lpe;                     // entries per warp pass
+    const int lig = lane & (lpe - 1);
+    const float inv_sigma = 1.0f / sigma;
+    for (int base = 0; base < nlist; base += gpw) {
+        const int li = base + lane / lpe;
+        const bool active = li < nlist;
+        const int n = active ? rlist[li] : 0;
+        const int e = vlist[n];
+        const int pix = entry_pixel(e, invK), k = e - pix * K;
+        const float x = xs[n];
+        const bool h0 = x >= 0.0f;
+        int c = 0;
+        float r = 0.0f;
+        if (active) {
+            if constexpr (NoiseT::kBounded) {
+                // a pair of samples can only flip when its Box-Muller radius reaches |x|/sigma: decide that
+                // on the raw word and skip the transcendental work otherwise (exact, see radius_gate)
+                const uint32_t gate = gate_ok ? radius_gate(fabsf(x) * inv_sigma * 0.99999f) : 0u;
+                for (int q = qb + lig; q < qe; q += lpe) {
+                    uint32_t w[4];
+                    noise.words(q, k, pix0 + pix, w);
+#pragma unroll
+                    for (int hp = 0; hp < 2; ++hp) {
+                        const int s0 = q * 4 + hp * 2;
+                        const bool in0 = s0 >= s_begin && s0 < s_end, in1 = s0 + 1 >= s_begin && s0 + 1 < s_end;
+                        if ((w[hp * 2] >> 9) < gate) {
+                            if (h0) c += (in0 ? 1 : 0) + (in1 ? 1 : 0);
+                        } else {
+                            float n0, n1;
+                            box_muller(w[hp * 2], w[hp * 2 + 1], n0, n1);
+                            const bool ha = __fadd_rn(x, __fmul_rn(sigma, n0)) >= 0.0f;
+                            const bool hb = __fadd_rn(x, __fmul_rn(sigma, n1)) >= 0.0f;
+                            if (in0) {
+                                c += ha ? 1 : 0;
+                                if (ha != h0) r += ha ? n0 : -n0;
+                            }
+                            if (in1) {
+                                c += hb ? 1 : 0;
+                                if (hb != h0) r += hb ? n1 : -n1;
+                            }
+                        }
+                    }
+                }
+            } else {
+                for (int q = qb + lig; q < qe; q += lpe) {
+                    float nz[4];
+                    noise.get4(q, k, pix0 + pix, nz);
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const int s = q * 4 + t;
+                        const bool h = __fadd_rn(x, __fmul_rn(sigma, nz[t])) >= 0.0f;
+                        if (s >= s_begin && s < s_end) {
+                            c += h ? 1 : 0;
+                            if (h != h0) r += h ? nz[t] : -nz[t];
+                        }
+                    }
+                }
+            }
+        }
+        for (int o = lpe >> 1; o > 0; o >>= 1) {
+            c += __shfl_xor_sync(FULL, c, o);
+            r += __shfl_xor_sync(FULL, r, o);
+        }
+        if (active && lig == 0) {
+            cnt[n] = (uint16_t)c;
+            rs[n] = r;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-pixel preparation, G lanes per pixel, all pixels of the tile at once.
+// In:  zs[n] = raw zbuf, cnt[n] = hit count over ALL coverage samples.   Out: zs[n] = zeta_k.
+// Values returned are uniform over the lanes of a pixel's group.
+// ------------------------------------------------------------------------------------------------
+struct PixPrep {
+    float zmax;      // max(max_k zi_k, eps)
+    float zimax;     // max_k zi_k (padded entries contribute zi = 0)
+    float prod_nz;   // prod over entries with P != 1 of (1 - P)
+    float zeta_max;  // max_j zeta_j (incl. background)
+    float zbg;       // zeta_K = eps - zmax
+    int argzi;       // argmax_k zi_k (first index)
+    int nzero;       // number of entries with P == 1
+    int a0;          // argmax_j zeta_j (first index), K = background
+    int kpad;        // first padded k, K if none
+};
+
+__device__ __forceinline__ PixPrep prep_pixels(int p, int lig, int G, bool pvalid, int K, const int* vstart,
+                                               const uint16_t* vlist, const uint16_t* cnt, float* zs, float zn,
+                                               float zf, int S_rast, float gal, float eps) {
+    const int vs = pvalid ? vstart[p] : 0, ve = pvalid ? vstart[p + 1] : 0;
+    const int nv = ve - vs;
+    const int e_base = p * K;
+    float zimax = -CUDART_INF_F;
+    int argzi = 0x7fffffff;
+    float prod = 1.0f;
+    int nzero = 0;
+    int kpad = 0x7fffffff;
+    const float denom = zf - zn;
+    const float fS = (float)S_rast;
+    for (int n = vs + lig; n < ve; n += G) {
+        const int k = (int)vlist[n] - e_base;
+        const float pk = (float)cnt[n] / fS;
+        const float om = 1.0f - pk;
+        if (om == 0.0f) nzero++; else prod *= om;
+        const float zi = __fdiv_rn(zf - zs[n], denom);
+        zs[n] = zi;
+        if (zi > zimax) {
+            zimax = zi;
+            argzi = k;
+        }
+        if (k != n - vs) kpad = min(kpad, n - vs);
+    }
+    __syncwarp();
+    group_argmax(zimax, argzi, G);
+    prod = group_prod(prod, G);
+    nzero = group_sum_i(nzero, G);
+    kpad = group_min_i(kpad, G);
+    if (kpad == 0x7fffffff) kpad = nv;  // valid entries are a prefix: first padded index is nv (== K: none)
+    if (kpad < K) {
+        // masked entries have zi = (..)*0 = 0 and take part in the max (smoothagg.py:198-199)
+        if (0.0f > zimax || (0.0f == zimax && kpad < argzi)) {
+            zimax = 0.0f;
+            argzi = kpad;
+        }
+    }
+    const float zmax = fmaxf(zimax, eps);
+    const float zbg = __fadd_rn(eps, -zmax);
+    float best = -CUDART_INF_F;
+    int a0 = 0x7fffffff;
+    for (int n = vs + lig; n < ve; n += G) {
+        const int k = (int)vlist[n] - e_base;
+        const int c = cnt[n];
+        float z = -CUDART_INF_F;
+        if (c != 0) {
+            const float lg = (c == S_rast) ? 0.0f : logf((float)c / fS);
+            z = __fadd_rn(__fadd_rn(__fmul_rn(gal, lg), zs[n]), -zmax);
+        }
+        zs[n] = z;
+        if (z > best) {
+            best = z;
+            a0 = k;
+        }
+    }
+    __syncwarp();
+    group_argmax(best, a0, G);
+    if (!(best >= zbg)) {  // background wins ties only against nothing: it is the LAST index
+        best = zbg;
+        a0 = K;
+    }
+    PixPrep pi;
+    pi.zmax = zmax;
+    pi.zimax = zimax;
+    pi.prod_nz = prod;
+    pi.nzero = nzero;
+    pi.argzi = argzi;
+    pi.a0 = a0;
+    pi.zeta_max = best;
+    pi.zbg = zbg;
+    pi.kpad = kpad;
+    return pi;
+}
+
+// logits further than this below the largest one can never win a sample (bounded noise); the absolute
+// term covers the rounding of z + gamma*n
+__device__ __forceinline__ float live_cut(float gamma, float zeta_max, bool bounded) {
+    return bounded ? 2.0f * gamma * kNoiseAbsMax * 1.0001f + 4e-7f * fmaxf(1.0f, fabsf(zeta_max)) : CUDART_INF_F;
+}
+
+}  // namespace pert

@@ -15,7 +15,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _cabi
-from ._cabi import (F_NO_SKIP, F_SKIP_DEAD_NOISE, PH_AGG, PH_BLEND, PH_BWD_FINISH, PH_BWD_SAMPLE, PH_RAST,
+from ._cabi import (F_NO_SKIP, F_PER_SAMPLE_NOISE, F_SKIP_DEAD_NOISE, PH_AGG, PH_BLEND, PH_BWD_FINISH, PH_BWD_SAMPLE, PH_RAST,
                     PertProblem, check, ptr, require_cuda, stream_ptr)
 
 _tls = threading.local()
@@ -175,10 +175,23 @@ class ShadeProblem:
 
 @dataclass
 class ShadeSaved:
+    """State forward leaves for backward.  counts / rsum are defined only where pix_to_face >= 0;
+    winners rows only for pixels whose pixstate has the ACTIVE bit (0x8000)."""
     counts: torch.Tensor  # int16 storage of uint16 (N,H,W,K)
     rsum: torch.Tensor  # float (N,H,W,K)
     winners: torch.Tensor  # (N,H,W,S_agg_local) uint8 / int16
+    pixstate: torch.Tensor  # int16 storage of uint16 (N,H,W): a0 | 0x8000 * active
     hist: Optional[torch.Tensor] = None  # int32 (N,H,W,K1), only when requested
+
+    def winners_full(self) -> torch.Tensor:
+        """(N,H,W,S_agg_local) int32 winner of every sample: inactive pixels picked a0 every time."""
+        w = self.winners.to(torch.int32)
+        if self.winners.dtype == torch.int16:
+            w = w & 0xFFFF
+        st = self.pixstate.to(torch.int32) & 0xFFFF
+        active = (st & 0x8000) != 0
+        a0 = (st & 0x7FFF)[..., None].expand_as(w)
+        return torch.where(active[..., None], w, a0)
 
 
 def shade_forward(pr: ShadeProblem, want_hist: bool = False, phases: int = 0, saved: Optional[ShadeSaved] = None):
@@ -189,16 +202,19 @@ def shade_forward(pr: ShadeProblem, want_hist: bool = False, phases: int = 0, sa
     with torch.cuda.device(dev):
         sa_loc = pr.s_agg[1] - pr.s_agg[0]
         if saved is None:
+            # phase-split (sample-sharded) jobs all-reduce counts / rsum as whole tensors: define every entry
+            alloc = torch.zeros if phases else torch.empty
             saved = ShadeSaved(
-                counts=torch.empty((N, H, W, K), dtype=torch.int16, device=dev),
-                rsum=torch.empty((N, H, W, K), dtype=torch.float32, device=dev),
+                counts=alloc((N, H, W, K), dtype=torch.int16, device=dev),
+                rsum=alloc((N, H, W, K), dtype=torch.float32, device=dev),
                 winners=torch.empty((N, H, W, sa_loc), dtype=pr.winner_dtype(), device=dev),
+                pixstate=torch.empty((N, H, W), dtype=torch.int16, device=dev),
                 hist=torch.empty((N, H, W, K + 1), dtype=torch.int32, device=dev) if want_hist else None)
         do_blend = (phases == 0) or bool(phases & PH_BLEND)
         image = torch.empty((N, H, W, 4), dtype=torch.float32, device=dev) if do_blend else None
         pb = pr.c_struct(flags=pr.flags | phases)
         rc = lib.pert_shade_fwd(pb, ptr(image), ptr(saved.counts), ptr(saved.rsum), ptr(saved.winners),
-                                ptr(saved.hist), stream_ptr(dev))
+                                ptr(saved.pixstate), ptr(saved.hist), stream_ptr(dev))
     check(rc, "pert_shade_fwd")
     return image, saved
 
@@ -220,7 +236,7 @@ def shade_backward(pr: ShadeProblem, saved: ShadeSaved, grad_image: torch.Tensor
         scal = torch.empty((3,), dtype=torch.float32, device=dev) if finish else None
         pb = pr.c_struct(flags=pr.flags | phases)
         rc = lib.pert_shade_bwd(pb, ptr(grad_image), ptr(saved.counts), ptr(saved.rsum), ptr(saved.winners),
-                                ptr(gd), ptr(gz), ptr(gc), ptr(partials), ptr(scal), ptr(acc), ptr(pixstat),
+                                ptr(saved.pixstate), ptr(gd), ptr(gz), ptr(gc), ptr(partials), ptr(scal), ptr(acc), ptr(pixstat),
                                 ptr(saved.hist) if use_hist else None, stream_ptr(dev))
     check(rc, "pert_shade_bwd")
     return gd, gz, gc, scal

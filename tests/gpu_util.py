@@ -27,16 +27,17 @@ def counts_u16(saved):
 
 
 def winners_long(saved):
-    w = saved.winners
-    if w.dtype == torch.int16:
-        return w.to(torch.int32) & 0xFFFF
-    return w.to(torch.int32)
+    """Winner of every sample; rows of inactive pixels (never written by the kernel) are a0."""
+    return saved.winners_full()
 
 
 def run_cuda(pr, grad_image, need_colors=True):
     image, saved = ops.shade_forward(pr, want_hist=True)
     gd, gz, gc, scal = ops.shade_backward(pr, saved, grad_image.to(DEV), need_colors=need_colors)
     torch.cuda.synchronize()
+    mask = pr.pix_to_face >= 0
+    saved.counts.masked_fill_(~mask, 0)  # only valid entries are defined
+    saved.rsum.masked_fill_(~mask, 0)
     return dict(image=image.cpu(), counts=counts_u16(saved).cpu(), winners=winners_long(saved).cpu(),
                 hist=saved.hist.cpu(), rsum=saved.rsum.cpu(), grad_dists=gd.cpu(), grad_zbuf=gz.cpu(),
                 grad_colors=None if gc is None else gc.cpu(), scalars=scal.cpu(), saved=saved)
@@ -50,10 +51,10 @@ def run_oracle(g, U, V):
 
 
 def synthetic_case(N, H, W, K, S_r, S_a, kind="realistic", sigma=1e-3, gamma=1e-2, alpha=1.0, seed=0,
-                   background=(1.0, 1.0, 1.0), znear=None, zfar=None):
+                   background=(1.0, 1.0, 1.0), znear=None, zfar=None, **frag_kw):
     """A dict with the golden keys, built on the CPU from the package's synthetic generator."""
     from pertrenderer_b200 import synthetic_fragments
-    fr, col = synthetic_fragments(N, H, W, K, kind=kind, sigma=sigma, seed=seed, device="cpu")
+    fr, col = synthetic_fragments(N, H, W, K, kind=kind, sigma=sigma, seed=seed, device="cpu", **frag_kw)
     gen = torch.Generator().manual_seed(seed + 99)
     return dict(pix_to_face=fr.pix_to_face, zbuf=fr.zbuf, dists=fr.dists, colors=col,
                 znear=torch.tensor(znear if znear is not None else [1.0] * N),
