@@ -114,7 +114,7 @@ const char* pert_strerror(int code);
 /* last cudaError_t name seen by this thread's most recent failing call (diagnostic only) */
 const char* pert_last_cuda_error(void);
 
-/* number of CTAs the fused kernels launch for this problem; scalar_partials needs 4 floats per CTA,
+/* number of warp tiles (= CTAs) the fused kernels launch; scalar_partials needs 4 floats per tile,
  * 16-byte aligned */
 int64_t pert_num_tiles(const pert_problem* pb);
 /* element size in bytes of the winners buffer for this K (1 or 2) */

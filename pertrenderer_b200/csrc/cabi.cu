@@ -71,6 +71,15 @@ static Launch make_launch(const pert_problem* pb) {
     const int s32 = (L.sa_loc + 31) & ~31;
     if (sc > s32) sc = s32;
     L.sc = sc;
+    L.nchunks = (L.sa_loc + sc - 1) / sc;
+    const int nq_r = ((pb->s_rast_end + 3) >> 2) - (pb->s_rast_begin >> 2), nq_a = (L.sa_loc + 3) >> 2;
+    auto lg2 = [](int v) { int s = 0; while ((1 << s) < v) s++; return s; };
+    L.lpe_r = pow2_ceil(nq_r) < 32 ? pow2_ceil(nq_r) : 32;
+    L.lpe_r_shift = lg2(L.lpe_r);
+    L.lpe_a = pow2_ceil(nq_a) < 32 ? pow2_ceil(nq_a) : 32;
+    L.lpe_a_shift = lg2(L.lpe_a);
+    L.lpp = pow2_floor(nq_a) < 8 ? pow2_floor(nq_a) : 8;
+    L.lpp_shift = lg2(L.lpp);
     L.warp_smem = 0;
     L.vec_ok = 0;
     L.invK = 1.0f / (float)pb->K;
@@ -81,8 +90,7 @@ extern "C" int64_t pert_num_tiles(const pert_problem* pb) {
     if (!pb || pb->K <= 0) return 0;
     const int tp = pick_tp(pb->K);
     const int64_t P = pb->N * pb->H * pb->W;
-    const int64_t tiles = (P + tp - 1) / tp;
-    return (tiles + NW - 1) / NW;  // one row of scalar partials per CTA
+    return (P + tp - 1) / tp;  // one warp tile per CTA, one row of scalar partials each
 }
 
 extern "C" int pert_winner_bytes(int32_t K) { return (K + 1 <= 256) ? 1 : 2; }
@@ -108,8 +116,8 @@ extern "C" int pert_shade_fwd(const pert_problem* pb_in, float* image, uint16_t*
     a.L = make_launch(&a.pb);
     a.L.vec_ok = aligned16(a.pb.pix_to_face);
     a.L.warp_smem = (int)fwd_warp_smem(a.L.tp, a.pb.K);
-    if ((size_t)a.L.warp_smem * NW > 200 * 1024) return PERT_E_UNSUPPORTED;
-    if ((a.L.ntiles + NW - 1) / NW > 0x7fffffff) return PERT_E_UNSUPPORTED;
+    if ((size_t)a.L.warp_smem > 200 * 1024) return PERT_E_UNSUPPORTED;
+    if (a.L.ntiles > 0x7fffffff) return PERT_E_UNSUPPORTED;
     a.image = image;
     a.counts = counts;
     a.rsum = rsum;
@@ -142,9 +150,9 @@ extern "C" int pert_shade_bwd(const pert_problem* pb_in, const float* grad_image
     a.L = make_launch(&a.pb);
     a.L.vec_ok = aligned16(a.pb.pix_to_face) && aligned16(grad_dists) && aligned16(grad_zbuf) && aligned16(grad_colors);
     if (a.L.win_bytes == 2 && ((uintptr_t)winners & 1)) return PERT_E_ALIGN;
-    a.L.warp_smem = (int)bwd_warp_smem(a.L.tp, a.pb.K, a.L.sc);
-    if ((size_t)a.L.warp_smem * NW > 200 * 1024) return PERT_E_UNSUPPORTED;
-    if ((a.L.ntiles + NW - 1) / NW > 0x7fffffff) return PERT_E_UNSUPPORTED;
+    a.L.warp_smem = (int)bwd_warp_smem(a.L.tp, a.pb.K, a.L.sc, a.L.nchunks);
+    if ((size_t)a.L.warp_smem > 200 * 1024) return PERT_E_UNSUPPORTED;
+    if (a.L.ntiles > 0x7fffffff) return PERT_E_UNSUPPORTED;
     a.grad_image = grad_image;
     a.counts = counts;
     a.rsum = rsum;

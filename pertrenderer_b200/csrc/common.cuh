@@ -8,8 +8,12 @@
 
 namespace pert {
 
-constexpr int NT = 128;  // threads per CTA
+constexpr int NT = 128;  // threads per CTA of the stand-alone operator kernels
 constexpr int NW = NT / 32;
+// The fused shader kernels run ONE WARP per CTA: tiles differ a lot in cost (sparse fragments), and a
+// CTA only gives its shared memory back when its slowest warp is done; with one-warp CTAs the hardware
+// CTA scheduler balances the load per tile.
+constexpr int FNT = 32;
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -50,24 +54,30 @@ __device__ __forceinline__ void warp_argmax(float& v, int& i) {
     }
 }
 
-// ---- reductions over an aligned group of G lanes (G a power of two, warp-uniform) ---------------
+// ---- reductions over an aligned group of G lanes (G a power of two, warp-uniform; a compile-time
+// constant in the production instantiations, so these loops unroll) -------------------------------
 __device__ __forceinline__ float group_sum(float v, int G) {
+#pragma unroll
     for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
 }
 __device__ __forceinline__ int group_sum_i(int v, int G) {
+#pragma unroll
     for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
 }
 __device__ __forceinline__ int group_min_i(int v, int G) {
+#pragma unroll
     for (int o = G >> 1; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(FULL, v, o));
     return v;
 }
 __device__ __forceinline__ float group_prod(float v, int G) {
+#pragma unroll
     for (int o = G >> 1; o > 0; o >>= 1) v *= __shfl_xor_sync(FULL, v, o);
     return v;
 }
 __device__ __forceinline__ void group_argmax(float& v, int& i, int G) {
+#pragma unroll
     for (int o = G >> 1; o > 0; o >>= 1) {
         const float ov = __shfl_xor_sync(FULL, v, o);
         const int oi = __shfl_xor_sync(FULL, i, o);
@@ -101,12 +111,13 @@ __device__ __forceinline__ void list_append(bool flag, uint16_t item, uint16_t* 
 }
 
 struct Carver {
-    unsigned char* p;
-    __device__ explicit Carver(unsigned char* base) : p(base) {}
+    unsigned char* base;
+    unsigned off;
+    __device__ explicit Carver(unsigned char* b) : base(b), off(0) {}
     template <typename T>
     __device__ T* take(int n) {
-        T* r = reinterpret_cast<T*>(p);
-        p += (((size_t)n * sizeof(T)) + 15) & ~(size_t)15;
+        T* r = reinterpret_cast<T*>(base + off);
+        off += ((unsigned)n * (unsigned)sizeof(T) + 15u) & ~15u;
         return r;
     }
 };
@@ -134,6 +145,10 @@ struct Launch {
     int win_bytes;  // 1 or 2
     int sa_loc;     // local aggregation samples (s_agg_end - s_agg_begin)
     int sc;         // backward: samples per shared-memory chunk (multiple of 32)
+    int nchunks;    // backward: ceil(sa_loc / sc)
+    int lpe_r, lpe_r_shift;  // coverage sampling: lanes per entry = min(32, pow2_ceil(local quads))
+    int lpe_a, lpe_a_shift;  // argmax sampling: lanes per pixel = min(32, pow2_ceil(local quads))
+    int lpp, lpp_shift;      // backward: lanes per (pixel, logit) pair = min(8, pow2_floor(local quads))
     int warp_smem;  // bytes of shared memory per warp
     int vec_ok;     // tile rows are 16-byte aligned in every (P,K) tensor
     float invK;     // 1/K for the entry -> pixel division

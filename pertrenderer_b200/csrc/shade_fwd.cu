@@ -4,7 +4,7 @@
 // (randomras/smoothrast.py:15-37) -> GaussianAgg.aggregate (randomras/smoothagg.py:196-205) ->
 // randomArgmax.forward (randomras/smoothagg.py:13-42) -> blend.
 //
-// One warp per tile of tp pixels, no block-level synchronisation.  Phases of a tile:
+// One warp (= one CTA) per tile of tp pixels, no block-level synchronisation.  Phases of a tile:
 //   0  scan pix_to_face (128-bit loads) -> compact list of valid entries; zbuf/dists only for those
 //   1  coverage samples of the entries whose sign can flip (Philox in registers) -> counts, rsum
 //   2  per-pixel logits (G lanes per pixel), list of logits that can win a sample
@@ -22,14 +22,16 @@ size_t fwd_warp_smem(int tp, int K) {
            carve(tp, 2) /*plist*/ + 16;
 }
 
-template <class NoiseR, class NoiseA>
-__global__ void __launch_bounds__(NT) shade_fwd_kernel(const FwdArgs a, const NoiseR noise_r, const NoiseA noise_a) {
+// GT = lanes per pixel as a compile-time constant (1, 2, 4, 8), or 0 to read it from the launch record
+template <class NoiseR, class NoiseA, int GT>
+__global__ void __launch_bounds__(FNT) shade_fwd_kernel(const FwdArgs a, const NoiseR noise_r, const NoiseA noise_a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const pert_problem& pb = a.pb;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t tile = (int64_t)blockIdx.x * NW + warp;
-    if (tile >= a.L.ntiles) return;
-    const int K = pb.K, K1 = K + 1, tp = a.L.tp, G = a.L.G;
+    const int lane = threadIdx.x;
+    const int64_t tile = blockIdx.x;
+    const int G = GT ? GT : a.L.G;
+    const int gshift = GT ? (GT == 8 ? 3 : GT == 4 ? 2 : GT == 2 ? 1 : 0) : a.L.gshift;
+    const int K = pb.K, K1 = K + 1, tp = 32 >> gshift;
     const int64_t pix0 = tile * tp;
     const int npx = (int)min((int64_t)tp, a.L.P - pix0);
     const int E = npx * K;
@@ -37,12 +39,12 @@ __global__ void __launch_bounds__(NT) shade_fwd_kernel(const FwdArgs a, const No
     const uint32_t flags = pb.flags;
     const bool do_rast = flags & PERT_PH_RAST, do_agg = flags & PERT_PH_AGG, do_blend = flags & PERT_PH_BLEND;
     const bool no_skip = flags & PERT_F_NO_SKIP;
-    const int p = lane >> a.L.gshift, lig = lane & (G - 1);
+    const int p = lane >> gshift, lig = lane & (G - 1);
     const bool pvalid = p < npx;
     const int64_t gp = pix0 + p;
     const unsigned lt = (1u << lane) - 1u;
 
-    Carver cv(smem_raw + (size_t)warp * a.L.warp_smem);
+    Carver cv(smem_raw);
     uint16_t* vlist = cv.take<uint16_t>(tp * K);
     float* xs = cv.take<float>(tp * K1);  // x = -dists (compact); later lz: logits of the live list
     float* zs = cv.take<float>(tp * K);   // zbuf -> zi -> zeta (compact)
@@ -105,7 +107,7 @@ __global__ void __launch_bounds__(NT) shade_fwd_kernel(const FwdArgs a, const No
     __syncwarp();
     if (do_rast) {
         rast_sample_list(noise_r, rlist, nlist, vlist, xs, cnt, rs, K, a.L.invK, pix0, pb.sigma, pb.s_rast_begin,
-                         pb.s_rast_end, !no_skip);
+                         pb.s_rast_end, !no_skip, a.L.lpe_r, a.L.lpe_r_shift);
         __syncwarp();
         for (int n = lane; n < nv; n += 32) {
             const int e = vlist[n];
@@ -171,13 +173,13 @@ __global__ void __launch_bounds__(NT) shade_fwd_kernel(const FwdArgs a, const No
         __syncwarp();
         if (np > 0) {
             const int qb = pb.s_agg_begin >> 2, qe = (pb.s_agg_end + 3) >> 2;
-            const int lpe = min(32, pow2_ceil(qe - qb));
-            const int gpw = 32 / lpe;
+            const int lpe = a.L.lpe_a;
+            const int gpw = 32 >> a.L.lpe_a_shift;
             const int lq = lane & (lpe - 1);
             const float gamma = pb.gamma;
             const bool pack = a.L.win_bytes == 1 && (sa_loc & 3) == 0;
             for (int base = 0; base < np; base += gpw) {
-                const int pe = base + lane / lpe;
+                const int pe = base + (lane >> a.L.lpe_a_shift);
                 if (pe >= np) continue;
                 const int pp = plist[pe];
                 const int plb = vstart[pp] + pp;
@@ -288,26 +290,32 @@ __global__ void __launch_bounds__(NT) shade_fwd_kernel(const FwdArgs a, const No
     if (pvalid && lig == 0) reinterpret_cast<float4*>(a.image)[gp] = make_float4(r, g, bl, px_alpha);
 }
 
-template <class NR, class NA>
-static int launch_fwd_t(const FwdArgs& a, const NR& nr, const NA& na, size_t smem, unsigned blocks, cudaStream_t st) {
+template <class NR, class NA, int GT>
+static int launch_fwd_t(const FwdArgs& a, const NR& nr, const NA& na, cudaStream_t st) {
+    const size_t smem = (size_t)a.L.warp_smem;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(shade_fwd_kernel<NR, NA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(shade_fwd_kernel<NR, NA, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    shade_fwd_kernel<NR, NA><<<blocks, NT, smem, st>>>(a, nr, na);
+    shade_fwd_kernel<NR, NA, GT><<<(unsigned)a.L.ntiles, FNT, smem, st>>>(a, nr, na);
     return (int)cudaGetLastError();
 }
 
 int launch_shade_fwd(const FwdArgs& a, cudaStream_t st) {
-    const size_t smem = (size_t)a.L.warp_smem * NW;
-    const unsigned blocks = (unsigned)((a.L.ntiles + NW - 1) / NW);
     const bool er = a.pb.noise_rast != nullptr, ea = a.pb.noise_agg != nullptr;
     PhiloxNoise pr(a.pb.seed_rast, 0, a.pb.pixel_offset), pa(a.pb.seed_agg, 1, a.pb.pixel_offset);
     ExplicitNoise xr{a.pb.noise_rast, a.L.P, a.pb.K, a.pb.S_rast}, xa{a.pb.noise_agg, a.L.P, a.pb.K + 1, a.pb.S_agg};
-    if (!er && !ea) return launch_fwd_t(a, pr, pa, smem, blocks, st);
-    if (er && ea) return launch_fwd_t(a, xr, xa, smem, blocks, st);
-    if (er) return launch_fwd_t(a, xr, pa, smem, blocks, st);
-    return launch_fwd_t(a, pr, xa, smem, blocks, st);
+    if (!er && !ea) {  // production path: lanes per pixel known at compile time
+        switch (a.L.G) {
+            case 1: return launch_fwd_t<PhiloxNoise, PhiloxNoise, 1>(a, pr, pa, st);
+            case 2: return launch_fwd_t<PhiloxNoise, PhiloxNoise, 2>(a, pr, pa, st);
+            case 4: return launch_fwd_t<PhiloxNoise, PhiloxNoise, 4>(a, pr, pa, st);
+            default: return launch_fwd_t<PhiloxNoise, PhiloxNoise, 8>(a, pr, pa, st);
+        }
+    }
+    if (er && ea) return launch_fwd_t<ExplicitNoise, ExplicitNoise, 0>(a, xr, xa, st);
+    if (er) return launch_fwd_t<ExplicitNoise, PhiloxNoise, 0>(a, xr, pa, st);
+    return launch_fwd_t<PhiloxNoise, ExplicitNoise, 0>(a, pr, xa, st);
 }
 
 }  // namespace pert

@@ -81,15 +81,14 @@ template <class NoiseT>
 __device__ __forceinline__ void rast_sample_list(const NoiseT& noise, const uint16_t* rlist, int nlist,
                                                  const uint16_t* vlist, const float* xs, uint16_t* cnt, float* rs,
                                                  int K, float invK, int64_t pix0, float sigma, int s_begin, int s_end,
-                                                 bool gate_ok) {
+                                                 bool gate_ok, int lpe /* lanes per entry */, int lpe_shift) {
     const int lane = threadIdx.x & 31;
     const int qb = s_begin >> 2, qe = (s_end + 3) >> 2;
-    const int lpe = min(32, pow2_ceil(qe - qb));  // lanes per entry
-    const int gpw = 32 / lpe;                     // entries per warp pass
+    const int gpw = 32 >> lpe_shift;  // entries per warp pass
     const int lig = lane & (lpe - 1);
     const float inv_sigma = 1.0f / sigma;
     for (int base = 0; base < nlist; base += gpw) {
-        const int li = base + lane / lpe;
+        const int li = base + (lane >> lpe_shift);
         const bool active = li < nlist;
         const int n = active ? rlist[li] : 0;
         const int e = vlist[n];
