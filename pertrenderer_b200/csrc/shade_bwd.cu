@@ -32,14 +32,18 @@ __device__ __forceinline__ void zero_fill(float* dst, int n, bool vec_ok) {
     if (vec_ok && (n & 3) == 0) {
         float4* d4 = reinterpret_cast<float4*>(dst);
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
         for (int i = lane; i < (n >> 2); i += 32) d4[i] = z;
     } else {
+#pragma unroll 1
         for (int i = lane; i < n; i += 32) dst[i] = 0.f;
     }
 }
 
-// GT = lanes per pixel as a compile-time constant (1, 2, 4, 8), or 0 to read it from the launch record
-template <class NoiseA, int GT>
+// GT = lanes per pixel as a compile-time constant (1, 2, 4, 8), or 0 to read it from the launch record.
+// PHASED = false is the production instantiation: both phases in one launch, histogram rebuilt from the
+// saved winners (the phase-split code of the sample-sharded job is compiled out to keep the hot code small).
+template <class NoiseA, int GT, bool PHASED>
 __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const NoiseA noise_a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const pert_problem& pb = a.pb;
@@ -49,7 +53,8 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
     const int gshift = GT ? (GT == 8 ? 3 : GT == 4 ? 2 : GT == 2 ? 1 : 0) : a.L.gshift;
     const int K = pb.K, K1 = K + 1, tp = 32 >> gshift, sc = a.L.sc;
     const uint32_t flags = pb.flags;
-    const bool do_sample = flags & PERT_PH_BWD_SAMPLE, do_finish = flags & PERT_PH_BWD_FINISH;
+    const bool do_sample = !PHASED || (flags & PERT_PH_BWD_SAMPLE), do_finish = !PHASED || (flags & PERT_PH_BWD_FINISH);
+    const int32_t* const ghist = PHASED ? a.hist : nullptr;
     const bool no_skip = flags & PERT_F_NO_SKIP;
     // how the noise of logits that can never win (zero-mean, independent of everything) is handled
     const bool per_sample = !NoiseA::kBounded || no_skip || (flags & PERT_F_PER_SAMPLE_NOISE);
@@ -111,10 +116,15 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
     if (nv > 0) {
         __syncwarp();
         pixel_ranges(vlist, nv, K, tp, vstart);
-        for (int n = lane; n < nv; n += 32) {
-            const int e = vlist[n];
-            zs[n] = __ldg(pb.zbuf + g0 + e);
-            cnt[n] = a.counts[g0 + e];
+        {
+            const float* const zbuf_t = pb.zbuf + g0;
+            const uint16_t* const counts_t = a.counts + g0;
+#pragma unroll 1
+            for (int n = lane; n < nv; n += 32) {
+                const int e = vlist[n];
+                zs[n] = __ldg(zbuf_t + e);
+                cnt[n] = counts_t[e];
+            }
         }
         __syncwarp();
 
@@ -130,6 +140,7 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
         const float floor_v = pi.zeta_max - live_cut(pb.gamma, pi.zeta_max, NoiseA::kBounded && !no_skip);
         float t2sum = 0.f, csum = 0.f;
         const float* gacc = a.acc + gp * K1;  // FINISH-only: sums over all sample shards
+        const float* const colors_p = pb.colors + gp * K * 3;
         __syncwarp();
 
         // ---- phase 2 -------------------------------------------------------------------------------
@@ -146,6 +157,7 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                     pa0[p] = a0;
                 }
                 if (act) {
+#pragma unroll 1
                     for (int j = lig; j < K1; j += G) {
                         hj[p * K1 + j] = 0;
                         accs[p * K1 + j] = 0.f;
@@ -153,6 +165,7 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                 }
                 const int span = per_sample ? max(K1, nvp + 1) : nvp + 1;
                 const int iters = warp_max_i(act ? (span + G - 1) / G : 0);
+#pragma unroll 1
                 for (int it = 0; it < iters; ++it) {
                     const int idx = it * G + lig;
                     bool want = false;
@@ -164,7 +177,7 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                         if (live) {
                             float gj;
                             if (j < K) {
-                                const float* c = pb.colors + (gp * K + j) * 3;
+                                const float* c = colors_p + j * 3;
                                 gj = Gi.x * __ldg(c) + Gi.y * __ldg(c + 1) + Gi.z * __ldg(c + 2);
                             } else {
                                 gj = Gi.x * pb.background[0] + Gi.y * pb.background[1] + Gi.z * pb.background[2];
@@ -195,9 +208,11 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
             const int LPP = a.L.lpp;  // lanes per pair: fixed by S so that every sum has one order
             const int lq = lane & (LPP - 1);
             float C2 = 0.f;
+#pragma unroll 1
             for (int c0 = 0; c0 < sa_loc; c0 += sc) {  // c0 multiple of 32
                 const int cn = min(sc, sa_loc - c0);
                 const int cn4 = (cn + 3) & ~3;
+#pragma unroll 1
                 for (int ai = 0; ai < na; ++ai) {
                     const int pp = apx[ai];
                     const float* gs = gsel + pp * K1;
@@ -205,6 +220,7 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                     const float g0v = pg0[pp];
                     const int ppa0 = pa0[pp];
                     const int64_t wbase = (pix0 + pp) * sa_loc + c0;
+#pragma unroll 1
                     for (int s = lane; s < cn4; s += 32) {
                         float c = 0.f;
                         if (s < cn) {
@@ -226,6 +242,7 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                     float c1 = 0.f, c2 = 0.f;
                     if (act) {
                         const float g0v = pg0[p];
+#pragma unroll 1
                         for (int idx = lig; idx <= nvp; idx += G) {
                             const int j = idx < nvp ? (int)vlist[vs + idx] - p * K : K;
                             const int h = hj[p * K1 + j];
@@ -244,6 +261,7 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                     __syncwarp();
                 }
                 const int nqc = cn4 >> 2;
+#pragma unroll 1
                 for (int it0 = 0; it0 < (np2 << a.L.lpp_shift); it0 += 32) {
                     const int it = it0 + lane;
                     const int pr = it >> a.L.lpp_shift;
@@ -254,6 +272,7 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                     float acc = 0.f, t2 = 0.f;
                     if (on) {
                         const float4* c4p = reinterpret_cast<const float4*>(cs + ai * sc);
+#pragma unroll 1
                         for (int ql = lq; ql < nqc; ql += LPP) {
                             const float4 c4 = c4p[ql];
                             if (!no_skip && c4.x == 0.f && c4.y == 0.f && c4.z == 0.f && c4.w == 0.f) continue;
@@ -264,6 +283,7 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                             t2 += (cv0 * nz[0] + cv1 * nz[1]) + (cv2 * nz[2] + cv3 * nz[3]);
                         }
                     }
+#pragma unroll 1
                     for (int o = LPP >> 1; o > 0; o >>= 1) {
                         acc += __shfl_xor_sync(FULL, acc, o);
                         t2 += __shfl_xor_sync(FULL, t2, o);
@@ -286,14 +306,17 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
             {
                 float t = 0.f;
                 if (per_sample) {
-                    if (act)
+                    if (act) {
+#pragma unroll 1
                         for (int j = lig; j < K1; j += G) t += t2s[p * K1 + j];
+                    }
                     t2sum = group_sum(t, G);
                 } else {
                     int nlive = 0;
                     const float sC2 = sqrtf(C2);
                     const uint32_t qx = 0xC0000000u + (uint32_t)qb;  // counters no sample quad uses
                     if (act) {
+#pragma unroll 1
                         for (int idx = lig; idx <= nvp; idx += G) {
                             const int j = idx < nvp ? (int)vlist[vs + idx] - p * K : K;
                             const float z = idx < nvp ? zs[vs + idx] : pi.zbg;
@@ -330,6 +353,7 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
         if (!do_finish) {
             // sample-sharded job: publish the partial sums, the caller all-reduces them
             if (act) {
+#pragma unroll 1
                 for (int j = lig; j < K1; j += G) a.acc[gp * K1 + j] = accs[p * K1 + j];
                 if (lig == 0) {
                     a.pixstat[gp * 2 + 0] = t2sum;
@@ -341,7 +365,7 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
             const float invSg = 1.0f / ((float)pb.S_agg * pb.gamma);
             const float inv_sr = 1.0f / ((float)pb.S_rast * pb.sigma);
             const float invS = 1.0f / (float)pb.S_agg;
-            const bool from_global = !do_sample;
+            const bool from_global = PHASED && !do_sample;
             const bool has_acc = act || (from_global && pvalid);
             if (from_global && pvalid) {
                 t2sum = a.pixstat[gp * 2];
@@ -351,10 +375,13 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
             float sg = 0.f;
             if (has_acc) {
                 if (from_global) {
+#pragma unroll 1
                     for (int j = lig; j < K1; j += G) sg += gacc[j] * invSg;
                 } else if (per_sample) {
+#pragma unroll 1
                     for (int j = lig; j < K1; j += G) sg += accs[p * K1 + j] * invSg;
                 } else {
+#pragma unroll 1
                     for (int idx = lig; idx <= nvp; idx += G) {
                         const int j = idx < nvp ? (int)vlist[vs + idx] - p * K : K;
                         sg += accs[p * K1 + j] * invSg;
@@ -367,14 +394,19 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
             const float denom = zf - zn;
             const bool pass = pi.zimax >= pb.eps;
             const float fS = (float)pb.S_rast;
+            const float* const rsum_t = a.rsum + g0;
+            float* const gd_t = a.grad_dists + g0;
+            float* const gz_t = a.grad_zbuf + g0;
+            float* const gc_t = a.grad_colors ? a.grad_colors + g0 * 3 : nullptr;
+#pragma unroll 1
             for (int n = vs + lig; n < ve; n += G) {
                 const int e = vlist[n];
                 const int k = e - p * K;
-                const float rsn = a.rsum[g0 + e];
+                const float rsn = rsum_t[e];
                 float gz = 0.f;
                 if (has_acc) gz = (from_global ? gacc[k] : accs[p * K1 + k]) * invSg;
                 const float gzi = gz + ((k == pi.argzi && pass) ? gzmax : 0.f);
-                a.grad_zbuf[g0 + e] = -gzi / denom;
+                gz_t[e] = -gzi / denom;
                 const int c = cnt[n];
                 const float pk = (float)c / fS;
                 float gP = 0.f;
@@ -390,17 +422,17 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                 else excl = 0.f;
                 gP += Gi.w * excl;
                 const float gx = gP * (rsn * inv_sr);
-                a.grad_dists[g0 + e] = -gx;
+                gd_t[e] = -gx;
                 p_sigma += gx;
                 // grad_colors = w_k * G_rgb
-                if (a.grad_colors) {
+                if (gc_t) {
                     int h;
-                    if (a.hist) h = a.hist[gp * K1 + k];  // all-shard histogram when sample-sharded
+                    if (ghist) h = ghist[gp * K1 + k];  // all-shard histogram when sample-sharded
                     else if (act) h = hj[p * K1 + k];
                     else h = (k == a0) ? sa_loc : 0;
                     if (h > 0) {
                         const float w = (float)h * invS;
-                        float* gc = a.grad_colors + (g0 + e) * 3;
+                        float* gc = gc_t + e * 3;
                         gc[0] = w * Gi.x;
                         gc[1] = w * Gi.y;
                         gc[2] = w * Gi.z;
@@ -458,29 +490,36 @@ __global__ void __launch_bounds__(1024) finalize_scalars_kernel(const float* par
     }
 }
 
-template <class NA, int GT>
+template <class NA, int GT, bool PHASED>
 static int launch_bwd_t(const BwdArgs& a, const NA& na, cudaStream_t st) {
     const size_t smem = (size_t)a.L.warp_smem;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(shade_bwd_kernel<NA, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(shade_bwd_kernel<NA, GT, PHASED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    shade_bwd_kernel<NA, GT><<<(unsigned)a.L.ntiles, FNT, smem, st>>>(a, na);
+    shade_bwd_kernel<NA, GT, PHASED><<<(unsigned)a.L.ntiles, FNT, smem, st>>>(a, na);
     return (int)cudaGetLastError();
 }
 
 int launch_shade_bwd(const BwdArgs& a, float* grad_scalars, cudaStream_t st) {
     int rc;
+    const uint32_t both = PERT_PH_BWD_SAMPLE | PERT_PH_BWD_FINISH;
+    const bool phased = (a.pb.flags & both) != both || a.hist != nullptr;
     if (a.pb.noise_agg) {
         ExplicitNoise xa{a.pb.noise_agg, a.L.P, a.pb.K + 1, a.pb.S_agg};
-        rc = launch_bwd_t<ExplicitNoise, 0>(a, xa, st);
+        rc = launch_bwd_t<ExplicitNoise, 0, true>(a, xa, st);
     } else {
         PhiloxNoise pa(a.pb.seed_agg, 1, a.pb.pixel_offset);
-        switch (a.L.G) {  // production path: lanes per pixel known at compile time
-            case 1: rc = launch_bwd_t<PhiloxNoise, 1>(a, pa, st); break;
-            case 2: rc = launch_bwd_t<PhiloxNoise, 2>(a, pa, st); break;
-            case 4: rc = launch_bwd_t<PhiloxNoise, 4>(a, pa, st); break;
-            default: rc = launch_bwd_t<PhiloxNoise, 8>(a, pa, st); break;
+        if (phased) {
+            rc = launch_bwd_t<PhiloxNoise, 0, true>(a, pa, st);
+        } else {
+            switch (a.L.G) {  // production path: lanes per pixel known at compile time
+                case 1: rc = launch_bwd_t<PhiloxNoise, 1, false>(a, pa, st); break;
+                case 2: rc = launch_bwd_t<PhiloxNoise, 2, false>(a, pa, st); break;
+                case 4: rc = launch_bwd_t<PhiloxNoise, 4, false>(a, pa, st); break;
+                default: rc = launch_bwd_t<PhiloxNoise, 8, false>(a, pa, st); break;
+            }
         }
     }
     if (rc) return rc;

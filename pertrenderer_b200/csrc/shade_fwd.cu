@@ -22,8 +22,11 @@ size_t fwd_warp_smem(int tp, int K) {
            carve(tp, 2) /*plist*/ + 16;
 }
 
-// GT = lanes per pixel as a compile-time constant (1, 2, 4, 8), or 0 to read it from the launch record
-template <class NoiseR, class NoiseA, int GT>
+// GT = lanes per pixel as a compile-time constant (1, 2, 4, 8), or 0 to read it from the launch record.
+// PHASED = false is the production instantiation: all three phases in one launch, no global histogram
+// (the phase-split code of the sample-sharded job is compiled out, which keeps the hot code small: the
+// kernel is instruction-fetch sensitive, every warp walks the whole body once per tile).
+template <class NoiseR, class NoiseA, int GT, bool PHASED>
 __global__ void __launch_bounds__(FNT) shade_fwd_kernel(const FwdArgs a, const NoiseR noise_r, const NoiseA noise_a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const pert_problem& pb = a.pb;
@@ -37,7 +40,13 @@ __global__ void __launch_bounds__(FNT) shade_fwd_kernel(const FwdArgs a, const N
     const int E = npx * K;
     const int64_t g0 = pix0 * K;
     const uint32_t flags = pb.flags;
-    const bool do_rast = flags & PERT_PH_RAST, do_agg = flags & PERT_PH_AGG, do_blend = flags & PERT_PH_BLEND;
+    const bool do_rast = !PHASED || (flags & PERT_PH_RAST), do_agg = !PHASED || (flags & PERT_PH_AGG),
+               do_blend = !PHASED || (flags & PERT_PH_BLEND);
+    int32_t* const ghist = PHASED ? a.hist : nullptr;
+    const float* const zbuf_t = pb.zbuf + g0;
+    const float* const dists_t = pb.dists + g0;
+    uint16_t* const counts_t = a.counts + g0;
+    float* const rsum_t = a.rsum + g0;
     const bool no_skip = flags & PERT_F_NO_SKIP;
     const int p = lane >> gshift, lig = lane & (G - 1);
     const bool pvalid = p < npx;
@@ -63,8 +72,9 @@ __global__ void __launch_bounds__(FNT) shade_fwd_kernel(const FwdArgs a, const N
     const int sa_loc = a.L.sa_loc;
     if (nv == 0) {
         // nothing but padding: background, alpha 0, every sample picks the background (index K)
-        if (do_agg && a.hist) {
-            for (int i = lane; i < npx * K1; i += 32) a.hist[pix0 * K1 + i] = ((i % K1) == K) ? sa_loc : 0;
+        if (do_agg && ghist) {
+#pragma unroll 1
+            for (int i = lane; i < npx * K1; i += 32) ghist[pix0 * K1 + i] = ((i % K1) == K) ? sa_loc : 0;
         }
         if (do_agg && lane < npx) a.pixstate[pix0 + lane] = (uint16_t)K;
         if (do_blend && lane < npx)
@@ -79,14 +89,15 @@ __global__ void __launch_bounds__(FNT) shade_fwd_kernel(const FwdArgs a, const N
     const int sr_loc = pb.s_rast_end - pb.s_rast_begin;
     const float thr = (NoiseR::kBounded && !no_skip) ? pb.sigma * kNoiseAbsMax * 1.0001f : CUDART_INF_F;
     int nlist = 0;
+#pragma unroll 1
     for (int n0 = 0; n0 < nv; n0 += 32) {
         const int n = n0 + lane;
         bool need = false;
         if (n < nv) {
             const int e = vlist[n];
-            zs[n] = __ldg(pb.zbuf + g0 + e);
+            zs[n] = __ldg(zbuf_t + e);
             if (do_rast) {
-                const float x = -__ldg(pb.dists + g0 + e);
+                const float x = -__ldg(dists_t + e);
                 xs[n] = x;
                 // |x| beyond the largest possible sigma*|U| cannot flip: exact, not an approximation
                 need = fabsf(x) <= thr;
@@ -95,7 +106,7 @@ __global__ void __launch_bounds__(FNT) shade_fwd_kernel(const FwdArgs a, const N
                     rs[n] = 0.0f;
                 }
             } else {
-                cnt[n] = a.counts[g0 + e];
+                cnt[n] = counts_t[e];
             }
         }
         if (do_rast) {
@@ -109,10 +120,11 @@ __global__ void __launch_bounds__(FNT) shade_fwd_kernel(const FwdArgs a, const N
         rast_sample_list(noise_r, rlist, nlist, vlist, xs, cnt, rs, K, a.L.invK, pix0, pb.sigma, pb.s_rast_begin,
                          pb.s_rast_end, !no_skip, a.L.lpe_r, a.L.lpe_r_shift);
         __syncwarp();
+#pragma unroll 1
         for (int n = lane; n < nv; n += 32) {
             const int e = vlist[n];
-            a.counts[g0 + e] = cnt[n];
-            a.rsum[g0 + e] = rs[n];
+            counts_t[e] = cnt[n];
+            rsum_t[e] = rs[n];
         }
     }
     if (!do_agg && !do_blend) return;
@@ -140,6 +152,7 @@ __global__ void __launch_bounds__(FNT) shade_fwd_kernel(const FwdArgs a, const N
         const int iters = warp_max_i((nvp + G) / G);  // ceil((nvp + 1) / G), uniform for the ballots
         const unsigned gmask = (G == 32) ? FULL : ((1u << G) - 1u);
         const int gsh = p * G;
+#pragma unroll 1
         for (int it = 0; it < iters; ++it) {
             const int idx = it * G + lig;
             float z = -CUDART_INF_F;
@@ -178,6 +191,7 @@ __global__ void __launch_bounds__(FNT) shade_fwd_kernel(const FwdArgs a, const N
             const int lq = lane & (lpe - 1);
             const float gamma = pb.gamma;
             const bool pack = a.L.win_bytes == 1 && (sa_loc & 3) == 0;
+#pragma unroll 1
             for (int base = 0; base < np; base += gpw) {
                 const int pe = base + (lane >> a.L.lpe_a_shift);
                 if (pe >= np) continue;
@@ -185,9 +199,11 @@ __global__ void __launch_bounds__(FNT) shade_fwd_kernel(const FwdArgs a, const N
                 const int plb = vstart[pp] + pp;
                 const int pn = pinfo[pp] & 0xffff, pa0 = pinfo[pp] >> 16;
                 const int64_t pgp = pix0 + pp;
+#pragma unroll 1
                 for (int q = qb + lq; q < qe; q += lpe) {
                     float best[4] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
                     int bi[4] = {0, 0, 0, 0};
+#pragma unroll 1
                     for (int l = 0; l < pn; ++l) {
                         const int j = lj[plb + l];
                         const float z = lz[plb + l];
@@ -224,6 +240,7 @@ __global__ void __launch_bounds__(FNT) shade_fwd_kernel(const FwdArgs a, const N
         __syncwarp();
         // histogram of the unperturbed winner = all the samples nobody else won
         int others = 0;
+#pragma unroll 1
         for (int l = lig; l < nlive; l += G)
             if (l != a0l) others += hl[lb + l];
         others = group_sum_i(others, G);
@@ -233,11 +250,13 @@ __global__ void __launch_bounds__(FNT) shade_fwd_kernel(const FwdArgs a, const N
             a.pixstate[gp] = (uint16_t)(pi.a0 | (active ? 0x8000 : 0));
         }
         __syncwarp();
-        if (a.hist) {
+        if (ghist) {
             // dense (P,K1) histogram for the sample-sharded job: zeros, then the live entries
-            for (int i = lane; i < npx * K1; i += 32) a.hist[pix0 * K1 + i] = 0;
+#pragma unroll 1
+            for (int i = lane; i < npx * K1; i += 32) ghist[pix0 * K1 + i] = 0;
             __syncwarp();
-            for (int l = lig; l < nlive; l += G) a.hist[gp * K1 + lj[lb + l]] = hl[lb + l];
+#pragma unroll 1
+            for (int l = lig; l < nlive; l += G) ghist[gp * K1 + lj[lb + l]] = hl[lb + l];
         }
     }
     if (!do_blend) return;
@@ -245,14 +264,16 @@ __global__ void __launch_bounds__(FNT) shade_fwd_kernel(const FwdArgs a, const N
     // ---- phase 4: blend (random_rasterizer.py:50-54) ------------------------------------------------
     float r = 0.f, g = 0.f, bl = 0.f;
     const float fS = (float)pb.S_agg;
+    const float* const colors_p = pb.colors + gp * K * 3;
     if (do_agg) {
+#pragma unroll 1
         for (int l = lig; l < nlive; l += G) {
             const int hcount = hl[lb + l];
             if (hcount > 0) {
                 const float w = (float)hcount / fS;
                 const int j = lj[lb + l];
                 if (j < K) {
-                    const float* c = pb.colors + (gp * K + j) * 3;
+                    const float* c = colors_p + j * 3;
                     r += w * __ldg(c);
                     g += w * __ldg(c + 1);
                     bl += w * __ldg(c + 2);
@@ -263,16 +284,17 @@ __global__ void __launch_bounds__(FNT) shade_fwd_kernel(const FwdArgs a, const N
                 }
             }
         }
-    } else {
+    } else if (PHASED) {
         // histogram summed over all sample shards (read from global memory)
-        const int32_t* hg = a.hist + gp * K1;
+        const int32_t* hg = ghist + gp * K1;
+#pragma unroll 1
         for (int idx = lig; idx <= nvp && pvalid; idx += G) {
             const int j = idx < nvp ? (int)vlist[vs + idx] - p * K : K;
             const int hcount = hg[j];
             if (hcount > 0) {
                 const float w = (float)hcount / fS;
                 if (j < K) {
-                    const float* c = pb.colors + (gp * K + j) * 3;
+                    const float* c = colors_p + j * 3;
                     r += w * __ldg(c);
                     g += w * __ldg(c + 1);
                     bl += w * __ldg(c + 2);
@@ -290,32 +312,36 @@ __global__ void __launch_bounds__(FNT) shade_fwd_kernel(const FwdArgs a, const N
     if (pvalid && lig == 0) reinterpret_cast<float4*>(a.image)[gp] = make_float4(r, g, bl, px_alpha);
 }
 
-template <class NR, class NA, int GT>
+template <class NR, class NA, int GT, bool PHASED>
 static int launch_fwd_t(const FwdArgs& a, const NR& nr, const NA& na, cudaStream_t st) {
     const size_t smem = (size_t)a.L.warp_smem;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(shade_fwd_kernel<NR, NA, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(shade_fwd_kernel<NR, NA, GT, PHASED>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    shade_fwd_kernel<NR, NA, GT><<<(unsigned)a.L.ntiles, FNT, smem, st>>>(a, nr, na);
+    shade_fwd_kernel<NR, NA, GT, PHASED><<<(unsigned)a.L.ntiles, FNT, smem, st>>>(a, nr, na);
     return (int)cudaGetLastError();
 }
 
 int launch_shade_fwd(const FwdArgs& a, cudaStream_t st) {
     const bool er = a.pb.noise_rast != nullptr, ea = a.pb.noise_agg != nullptr;
+    const uint32_t all = PERT_PH_RAST | PERT_PH_AGG | PERT_PH_BLEND;
+    const bool phased = (a.pb.flags & all) != all || a.hist != nullptr;
     PhiloxNoise pr(a.pb.seed_rast, 0, a.pb.pixel_offset), pa(a.pb.seed_agg, 1, a.pb.pixel_offset);
     ExplicitNoise xr{a.pb.noise_rast, a.L.P, a.pb.K, a.pb.S_rast}, xa{a.pb.noise_agg, a.L.P, a.pb.K + 1, a.pb.S_agg};
-    if (!er && !ea) {  // production path: lanes per pixel known at compile time
-        switch (a.L.G) {
-            case 1: return launch_fwd_t<PhiloxNoise, PhiloxNoise, 1>(a, pr, pa, st);
-            case 2: return launch_fwd_t<PhiloxNoise, PhiloxNoise, 2>(a, pr, pa, st);
-            case 4: return launch_fwd_t<PhiloxNoise, PhiloxNoise, 4>(a, pr, pa, st);
-            default: return launch_fwd_t<PhiloxNoise, PhiloxNoise, 8>(a, pr, pa, st);
+    if (!er && !ea) {
+        if (phased) return launch_fwd_t<PhiloxNoise, PhiloxNoise, 0, true>(a, pr, pa, st);
+        switch (a.L.G) {  // production path: lanes per pixel known at compile time
+            case 1: return launch_fwd_t<PhiloxNoise, PhiloxNoise, 1, false>(a, pr, pa, st);
+            case 2: return launch_fwd_t<PhiloxNoise, PhiloxNoise, 2, false>(a, pr, pa, st);
+            case 4: return launch_fwd_t<PhiloxNoise, PhiloxNoise, 4, false>(a, pr, pa, st);
+            default: return launch_fwd_t<PhiloxNoise, PhiloxNoise, 8, false>(a, pr, pa, st);
         }
     }
-    if (er && ea) return launch_fwd_t<ExplicitNoise, ExplicitNoise, 0>(a, xr, xa, st);
-    if (er) return launch_fwd_t<ExplicitNoise, PhiloxNoise, 0>(a, xr, pa, st);
-    return launch_fwd_t<PhiloxNoise, ExplicitNoise, 0>(a, pr, xa, st);
+    if (er && ea) return launch_fwd_t<ExplicitNoise, ExplicitNoise, 0, true>(a, xr, xa, st);
+    if (er) return launch_fwd_t<ExplicitNoise, PhiloxNoise, 0, true>(a, xr, pa, st);
+    return launch_fwd_t<PhiloxNoise, ExplicitNoise, 0, true>(a, pr, xa, st);
 }
 
 }  // namespace pert

@@ -59,6 +59,7 @@ __device__ __forceinline__ int scan_valid(const int64_t* __restrict__ p2f /* til
 // vstart[p] = first compact index of pixel p (p = 0..tp), by binary search on the ascending vlist
 __device__ __forceinline__ void pixel_ranges(const uint16_t* vlist, int nv, int K, int tp, int* vstart) {
     const int lane = threadIdx.x & 31;
+#pragma unroll 1
     for (int p = lane; p <= tp; p += 32) {
         const int target = p * K;
         int lo = 0, hi = nv;
@@ -87,6 +88,7 @@ __device__ __forceinline__ void rast_sample_list(const NoiseT& noise, const uint
     const int gpw = 32 >> lpe_shift;  // entries per warp pass
     const int lig = lane & (lpe - 1);
     const float inv_sigma = 1.0f / sigma;
+#pragma unroll 1
     for (int base = 0; base < nlist; base += gpw) {
         const int li = base + (lane >> lpe_shift);
         const bool active = li < nlist;
@@ -102,6 +104,7 @@ __device__ __forceinline__ void rast_sample_list(const NoiseT& noise, const uint
                 // a pair of samples can only flip when its Box-Muller radius reaches |x|/sigma: decide that
                 // on the raw word and skip the transcendental work otherwise (exact, see radius_gate)
                 const uint32_t gate = gate_ok ? radius_gate(fabsf(x) * inv_sigma * 0.99999f) : 0u;
+#pragma unroll 1
                 for (int q = qb + lig; q < qe; q += lpe) {
                     uint32_t w[4];
                     noise.words(q, k, pix0 + pix, w);
@@ -128,6 +131,7 @@ __device__ __forceinline__ void rast_sample_list(const NoiseT& noise, const uint
                     }
                 }
             } else {
+#pragma unroll 1
                 for (int q = qb + lig; q < qe; q += lpe) {
                     float nz[4];
                     noise.get4(q, k, pix0 + pix, nz);
@@ -143,6 +147,7 @@ __device__ __forceinline__ void rast_sample_list(const NoiseT& noise, const uint
                 }
             }
         }
+#pragma unroll 1
         for (int o = lpe >> 1; o > 0; o >>= 1) {
             c += __shfl_xor_sync(FULL, c, o);
             r += __shfl_xor_sync(FULL, r, o);
@@ -184,6 +189,7 @@ __device__ __forceinline__ PixPrep prep_pixels(int p, int lig, int G, bool pvali
     int kpad = 0x7fffffff;
     const float denom = zf - zn;
     const float fS = (float)S_rast;
+#pragma unroll 1
     for (int n = vs + lig; n < ve; n += G) {
         const int k = (int)vlist[n] - e_base;
         const float pk = (float)cnt[n] / fS;
@@ -214,6 +220,7 @@ __device__ __forceinline__ PixPrep prep_pixels(int p, int lig, int G, bool pvali
     const float zbg = __fadd_rn(eps, -zmax);
     float best = -CUDART_INF_F;
     int a0 = 0x7fffffff;
+#pragma unroll 1
     for (int n = vs + lig; n < ve; n += G) {
         const int k = (int)vlist[n] - e_base;
         const int c = cnt[n];

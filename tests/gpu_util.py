@@ -32,9 +32,15 @@ def winners_long(saved):
 
 
 def run_cuda(pr, grad_image, need_colors=True):
-    image, saved = ops.shade_forward(pr, want_hist=True)
+    """One fused forward + backward exactly as the product launches them (no phase flags, no global
+    histogram: the production kernel instantiation); the winner histogram is rebuilt from the winners."""
+    image, saved = ops.shade_forward(pr)
     gd, gz, gc, scal = ops.shade_backward(pr, saved, grad_image.to(DEV), need_colors=need_colors)
     torch.cuda.synchronize()
+    K1 = pr.shape[3] + 1
+    w = saved.winners_full().long()
+    saved.hist = torch.zeros(w.shape[:-1] + (K1,), dtype=torch.int32, device=w.device).scatter_add_(
+        -1, w, torch.ones_like(w, dtype=torch.int32))
     mask = pr.pix_to_face >= 0
     saved.counts.masked_fill_(~mask, 0)  # only valid entries are defined
     saved.rsum.masked_fill_(~mask, 0)
