@@ -24,7 +24,8 @@ size_t bwd_warp_smem(int tp, int K, int sc, int nchunks) {
     const size_t E = (size_t)tp * K, E1 = (size_t)tp * (K + 1);
     return carve(E, 2) /*vlist*/ + carve(E, 4) /*zs*/ + carve(E, 2) /*cnt*/ + carve(E1, 4) * (nchunks > 1 ? 4 : 3)
            /*hj gsel accs [t2s]*/ + carve(E1, 2) /*pair_j*/ + carve(E1, 1) /*pair_p*/ + carve((size_t)tp * sc, 4) /*cs*/ +
-           carve(tp + 1, 4) /*vstart*/ + carve(tp, 4) * 2 /*pa0, pg0*/ + carve(tp, 1) /*apx*/ + 16;
+           carve(tp + 1, 4) /*vstart*/ + carve(tp, 4) * 2 /*pa0, pg0*/ + carve(tp, 1) /*apx*/ +
+           (nchunks == 1 ? carve((size_t)tp * sc, 2) : 0) /*wst*/ + 16;
 }
 
 __device__ __forceinline__ void zero_fill(float* dst, int n, bool vec_ok) {
@@ -88,6 +89,16 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
     int* pa0 = cv.take<int>(tp);
     float* pg0 = cv.take<float>(tp);
     uint8_t* apx = cv.take<uint8_t>(tp);
+    // single-chunk jobs: the tile's saved winners (tp rows of sa_loc entries, contiguous) are copied to
+    // shared memory asynchronously at the very start, off the critical path
+    const bool early_w = a.L.nchunks == 1 && ((sa_loc * wb) & 15) == 0 && do_sample;
+    unsigned char* wst = a.L.nchunks == 1 ? cv.take<unsigned char>(tp * sc * 2) : nullptr;
+    if (early_w) {
+        const unsigned char* src = reinterpret_cast<const unsigned char*>(a.winners) + pix0 * sa_loc * wb;
+        const int nbytes = npx * sa_loc * wb;
+#pragma unroll 1
+        for (int o = lane * 16; o < nbytes; o += 32 * 16) cp_async16(wst + o, src + o);
+    }
 
     // ---- phase 0 -----------------------------------------------------------------------------------
     // per-pixel inputs do not depend on the scan: issue their loads first
@@ -119,11 +130,16 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
         {
             const float* const zbuf_t = pb.zbuf + g0;
             const uint16_t* const counts_t = a.counts + g0;
+            const float* const colors_t = pb.colors + g0 * 3;
+            const float* const rsum_t = a.rsum + g0;
 #pragma unroll 1
             for (int n = lane; n < nv; n += 32) {
                 const int e = vlist[n];
                 zs[n] = __ldg(zbuf_t + e);
                 cnt[n] = counts_t[e];
+                // needed a few round trips later (g_j of the logits that can win; chain rule): start them now
+                prefetch_l1(colors_t + e * 3);
+                prefetch_l1(rsum_t + e);
             }
         }
         __syncwarp();
@@ -205,6 +221,10 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
             // ---- phase 3: one pass over the saved winners per sample chunk: histogram + c_s, then the
             //      score sums of the pairs ------------------------------------------------------------------
             const int qb = pb.s_agg_begin >> 2;
+            if (early_w) {
+                cp_async_wait_all();
+                __syncwarp();
+            }
             const int LPP = a.L.lpp;  // lanes per pair: fixed by S so that every sum has one order
             const int lq = lane & (LPP - 1);
             float C2 = 0.f;
@@ -224,7 +244,7 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                     for (int s = lane; s < cn4; s += 32) {
                         float c = 0.f;
                         if (s < cn) {
-                            const int w = load_winner(a.winners, wb, wbase + s);
+                            const int w = early_w ? load_winner(wst, wb, pp * sa_loc + s) : load_winner(a.winners, wb, wbase + s);
                             if (w != ppa0) {  // a0 (the most frequent by far) is counted as the remainder
                                 atomicAdd(&hp[w], 1);
                                 c = gs[w] - g0v;

@@ -27,7 +27,7 @@ size_t fwd_warp_smem(int tp, int K) {
 // (the phase-split code of the sample-sharded job is compiled out, which keeps the hot code small: the
 // kernel is instruction-fetch sensitive, every warp walks the whole body once per tile).
 template <class NoiseR, class NoiseA, int GT, bool PHASED>
-__global__ void __launch_bounds__(FNT) shade_fwd_kernel(const FwdArgs a, const NoiseR noise_r, const NoiseA noise_a) {
+__global__ void __launch_bounds__(FNT, 32) shade_fwd_kernel(const FwdArgs a, const NoiseR noise_r, const NoiseA noise_a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const pert_problem& pb = a.pb;
     const int lane = threadIdx.x;
@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(FNT) shade_fwd_kernel(const FwdArgs a, const N
         if (n < nv) {
             const int e = vlist[n];
             zs[n] = __ldg(zbuf_t + e);
+            prefetch_l1(pb.colors + (g0 + e) * 3);  // blended at the very end of the tile: start the round trip now
             if (do_rast) {
                 const float x = -__ldg(dists_t + e);
                 xs[n] = x;
