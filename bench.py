@@ -58,6 +58,19 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def measured_traffic(kernel, kind, args):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu --set full
+    capture of this workload (profiles/traffic.json, written from the .ncu-rep by profiles/ncu_summary.py);
+    None when the workload is not the profiled one."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(p))
+        key = f"{kind}:{args.views}x{args.image_size}x{args.faces_per_pixel}x{args.nb_samples}"
+        return t[key][kernel]
+    except Exception:
+        return None
+
+
 def alg_bytes(P, K):
     """fwd reads pix_to_face 8 + zbuf 4 + dists 4 + colors 12 per pixel·face and
     writes RGBA 16 per pixel; bwd re-reads the same 28, writes grad_dists 4 + grad_zbuf 4 +
@@ -105,7 +118,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._halt.wait(0.05)
+            self._halt.wait(0.002)
 
     def finish(self):
         self._halt.set()
@@ -188,7 +201,7 @@ def workload_config(args, world):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
-def device_timed(args, kind, dev, steps, warmup, world, rank, sampler=None):
+def device_timed(args, kind, dev, steps, warmup, world, rank, sampler=None, flags=0):
     """Inputs resident in HBM; K steps of pert_shade_fwd + pert_shade_bwd through the C ABI."""
     import torch.distributed as dist
     from pertrenderer_b200 import ops, synthetic_fragments
@@ -202,7 +215,7 @@ def device_timed(args, kind, dev, steps, warmup, world, rank, sampler=None):
         return ops.ShadeProblem(pix_to_face=fr.pix_to_face, zbuf=fr.zbuf, dists=fr.dists, colors=col, znear=1.0,
                                 zfar=100.0, background=BACKGROUND, sigma=SIGMA, gamma=GAMMA, alpha=ALPHA, eps=EPS,
                                 S_rast=S, S_agg=S, seed_rast=ops.draw_seed(), seed_agg=ops.draw_seed(),
-                                pixel_offset=rank * P)
+                                pixel_offset=rank * P, flags=flags)
 
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
 
@@ -250,7 +263,7 @@ def device_timed(args, kind, dev, steps, warmup, world, rank, sampler=None):
     dom = "pert_shade_bwd" if bwd_ms >= fwd_ms else "pert_shade_fwd"
     dom_ms, dom_bytes = (bwd_ms, bb) if bwd_ms >= fwd_ms else (fwd_ms, fb)
     roof = {"bound": "hbm", "kernel": dom, "achieved": dom_bytes / dom_ms / 1e6, "peak": peak, "unit": "GB/s",
-            "frac": dom_bytes / dom_ms / 1e6 / peak, "traffic": None, "peak_source": peak_src,
+            "frac": dom_bytes / dom_ms / 1e6 / peak, "traffic": measured_traffic(dom, kind, args), "peak_source": peak_src,
             "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
             "fwd": {"ms": fwd_ms, "alg_bytes": fb, "gbs": fb / fwd_ms / 1e6, "frac": fb / fwd_ms / 1e6 / peak},
             "bwd": {"ms": bwd_ms, "alg_bytes": bb, "gbs": bb / bwd_ms / 1e6, "frac": bb / bwd_ms / 1e6 / peak},
@@ -354,9 +367,16 @@ def run_b200_arm(args):
     other_kind = "dense" if args.fragments == "realistic" else "realistic"
     also = None
     if not args.no_also:
+        from pertrenderer_b200 import _cabi
         o = device_timed(args, other_kind, dev, max(3, args.steps // 4), 3, world, rank)
-        also = {"fragments": other_kind, "value": o["value"], "unit": UNIT, "ms_per_step": o["ms_per_step"],
-                "roofline": o["roofline"]}
+        ps = device_timed(args, args.fragments, dev, max(3, args.steps // 2), 3, world, rank, flags=_cabi.F_PER_SAMPLE_NOISE)
+        also = {"fragments_" + other_kind: {"fragments": other_kind, "value": o["value"], "unit": UNIT,
+                                             "ms_per_step": o["ms_per_step"], "roofline": o["roofline"]},
+                "per_sample_noise": {"fragments": args.fragments, "flags": "PERT_F_PER_SAMPLE_NOISE",
+                                     "note": "backward regenerates every V_sj of every logit (reference-like sample "
+                                             "path); default draws never-winning logits' score noise once per logit",
+                                     "value": ps["value"], "unit": UNIT, "ms_per_step": ps["ms_per_step"],
+                                     "roofline": ps["roofline"]}}
     e2e = None
     if not args.no_e2e:
         e2e = e2e_timed(args, args.fragments, dev, args.steps, args.warmup, world, rank)

@@ -1,4 +1,6 @@
-import csv,subprocess,sys,io
+"""Summary of an ncu --set full report: python profiles/ncu_summary.py report.ncu-rep [traffic-key]
+With a traffic key (e.g. realistic:8x256x50x64) the per-launch DRAM bytes are merged into profiles/traffic.json."""
+import csv,subprocess,sys,io,json,os
 rep=sys.argv[1]
 out=subprocess.run(["ncu","-i",rep,"--page","raw","--csv"],capture_output=True,text=True).stdout
 rows=list(csv.reader(io.StringIO(out)))
@@ -16,3 +18,17 @@ for d in data:
     pipes=[(hdr[i],d[i]) for i in range(len(hdr)) if hdr[i].startswith("sm__inst_executed_pipe_") and hdr[i].endswith(".sum")]
     pipes=sorted(pipes,key=lambda x:-float(x[1].replace(',','') or 0))[:10]
     for k,v in pipes: print("   pipe",k,v)
+
+if len(sys.argv)>2:
+    key=sys.argv[2]; path=os.path.join(os.path.dirname(os.path.abspath(__file__)),"traffic.json")
+    t=json.load(open(path)) if os.path.exists(path) else {}
+    ent=t.setdefault(key,{})
+    def num(d,name):
+        i=hdr.index(name); v=float(d[i].replace(",","")); u=units[i].lower()
+        return v*{"byte":1,"kbyte":1e3,"mbyte":1e6,"gbyte":1e9}[u]
+    for d in data:
+        kn=d[hdr.index("Kernel Name")]
+        name="pert_shade_fwd" if "shade_fwd" in kn else ("pert_shade_bwd" if "shade_bwd" in kn else None)
+        if name: ent[name]=num(d,"dram__bytes_read.sum")+num(d,"dram__bytes_write.sum")
+    ent["source"]=os.path.basename(rep)
+    json.dump(t,open(path,"w"),indent=1)

@@ -4,8 +4,10 @@ python bench.py --steps 10 --warmup 3 --no-cpu-baseline --no-e2e > gpurun_out/be
 python - <<PY
 import json
 d=json.load(open("gpurun_out/bench_$1.json"))
-r=d["roofline"]; o=d["also"]["roofline"]
+r=d["roofline"]; o=d["also"]["fragments_dense"]["roofline"]; ps=d["also"]["per_sample_noise"]
 print("realistic ms/step %.4f fwd %.4f (%.3f) bwd %.4f (%.3f)" % (d["ms_per_step"], r["fwd"]["ms"], r["fwd"]["frac"], r["bwd"]["ms"], r["bwd"]["frac"]))
-print("dense     ms/step %.4f fwd %.4f (%.3f) bwd %.4f (%.3f)" % (d["also"]["ms_per_step"], o["fwd"]["ms"], o["fwd"]["frac"], o["bwd"]["ms"], o["bwd"]["frac"]))
+print("dense     ms/step %.4f fwd %.4f (%.3f) bwd %.4f (%.3f)" % (d["also"]["fragments_dense"]["ms_per_step"], o["fwd"]["ms"], o["fwd"]["frac"], o["bwd"]["ms"], o["bwd"]["frac"]))
+print("persample ms/step %.4f bwd %.4f (%.3f)" % (ps["ms_per_step"], ps["roofline"]["bwd"]["ms"], ps["roofline"]["bwd"]["frac"]))
+print("clocks", d["clocks"])
 PY
 tail -3 gpurun_out/bench_$1.err
