@@ -1,5 +1,7 @@
 // C ABI of libpertshade.so (include/pertshade.h): argument validation and launch geometry.  Nothing
 // here allocates, frees, retains or synchronises; every launch goes to the caller's stream.
+#include <stdlib.h>
+
 #include "kernels.h"
 
 using namespace pert;
@@ -32,6 +34,10 @@ extern "C" const char* pert_strerror(int code) {
 
 // pixels per warp tile: a power of two in [4, 32] with about 512 fragment entries per tile
 static int pick_tp(int K) {
+    if (const char* e = getenv("PERT_TP")) {  // experiments only
+        const int v = atoi(e);
+        if (v == 4 || v == 8 || v == 16 || v == 32) return v;
+    }
     if (K <= 16) return 32;
     if (K <= 32) return 16;
     if (K <= 64) return 8;

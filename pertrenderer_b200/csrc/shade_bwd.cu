@@ -25,7 +25,7 @@ size_t bwd_warp_smem(int tp, int K, int sc, int nchunks) {
     return carve(E, 2) /*vlist*/ + carve(E, 4) /*zs*/ + carve(E, 2) /*cnt*/ + carve(E1, 4) * (nchunks > 1 ? 4 : 3)
            /*hj gsel accs [t2s]*/ + carve(E1, 2) /*pair_j*/ + carve(E1, 1) /*pair_p*/ + carve((size_t)tp * sc, 4) /*cs*/ +
            carve(tp + 1, 4) /*vstart*/ + carve(tp, 4) * 2 /*pa0, pg0*/ + carve(tp, 1) /*apx*/ +
-           (nchunks == 1 ? carve((size_t)tp * sc, 2) : 0) /*wst*/ + 16;
+           (nchunks == 1 ? carve((size_t)tp * sc, 2) : 0) /*wst (u16 winners at most)*/ + 16;
 }
 
 __device__ __forceinline__ void zero_fill(float* dst, int n, bool vec_ok) {
@@ -225,7 +225,9 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                 cp_async_wait_all();
                 __syncwarp();
             }
-            const int LPP = a.L.lpp;  // lanes per pair: fixed by S so that every sum has one order
+            // lanes per pair: as many as keep the warp full, at most a.L.lpp
+            const int lpp_shift = np2 == 0 ? 0 : min(a.L.lpp_shift, np2 >= 32 ? 0 : 31 - __clz(32 / np2));
+            const int LPP = 1 << lpp_shift;
             const int lq = lane & (LPP - 1);
             float C2 = 0.f;
 #pragma unroll 1
@@ -282,9 +284,9 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                 }
                 const int nqc = cn4 >> 2;
 #pragma unroll 1
-                for (int it0 = 0; it0 < (np2 << a.L.lpp_shift); it0 += 32) {
+                for (int it0 = 0; it0 < (np2 << lpp_shift); it0 += 32) {
                     const int it = it0 + lane;
-                    const int pr = it >> a.L.lpp_shift;
+                    const int pr = it >> lpp_shift;
                     const bool on = pr < np2;
                     const int j = on ? pair_j[pr] : 0;
                     const int ai = on ? pair_p[pr] : 0;

@@ -119,7 +119,7 @@ __global__ void __launch_bounds__(FNT, 32) shade_fwd_kernel(const FwdArgs a, con
     __syncwarp();
     if (do_rast) {
         rast_sample_list(noise_r, rlist, nlist, vlist, xs, cnt, rs, K, a.L.invK, pix0, pb.sigma, pb.s_rast_begin,
-                         pb.s_rast_end, !no_skip, a.L.lpe_r, a.L.lpe_r_shift);
+                         pb.s_rast_end, !no_skip, a.L.lpe_r);
         __syncwarp();
 #pragma unroll 1
         for (int n = lane; n < nv; n += 32) {

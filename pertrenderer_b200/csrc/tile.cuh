@@ -82,9 +82,14 @@ template <class NoiseT>
 __device__ __forceinline__ void rast_sample_list(const NoiseT& noise, const uint16_t* rlist, int nlist,
                                                  const uint16_t* vlist, const float* xs, uint16_t* cnt, float* rs,
                                                  int K, float invK, int64_t pix0, float sigma, int s_begin, int s_end,
-                                                 bool gate_ok, int lpe /* lanes per entry */, int lpe_shift) {
+                                                 bool gate_ok, int lpe_max /* lanes per entry at most */) {
     const int lane = threadIdx.x & 31;
     const int qb = s_begin >> 2, qe = (s_end + 3) >> 2;
+    if (nlist == 0) return;
+    // lanes per entry: as many as keep the warp full (few listed entries -> split an entry's samples over
+    // more lanes; many -> one lane walks all the quads of its entry and no cross-lane reduction is needed)
+    const int lpe_shift = min(31 - __clz(lpe_max), nlist >= 32 ? 0 : 31 - __clz(32 / nlist));
+    const int lpe = 1 << lpe_shift;
     const int gpw = 32 >> lpe_shift;  // entries per warp pass
     const int lig = lane & (lpe - 1);
     const float inv_sigma = 1.0f / sigma;

@@ -191,9 +191,13 @@ def test_skipping_is_exact(kind):
     b = run_cuda(problem_from_case(g, explicit=False, seed_rast=3, seed_agg=4, flags=_cabi.F_NO_SKIP), g["grad_image"])
     mask = g["pix_to_face"] >= 0
     assert torch.equal(a["counts"][mask], b["counts"][mask])
-    assert torch.equal(a["rsum"][mask], b["rsum"][mask])
-    for k in ("winners", "hist", "image", "grad_dists", "grad_zbuf", "grad_colors", "scalars"):
+    for k in ("winners", "hist", "image", "grad_colors"):
         assert torch.equal(a[k], b[k]), k
+    # float sums: same terms (skipped ones are exact zeros), but the number of lanes that share one
+    # sum adapts to how much work a tile has, so the association order may differ
+    assert rel_err(a["rsum"], b["rsum"]) <= 1e-6
+    for k in ("grad_dists", "grad_zbuf", "scalars"):
+        assert rel_err(a[k], b[k]) <= 2e-6, k
 
 
 def test_noise_stream_is_standard_normal():
