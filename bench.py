@@ -360,6 +360,7 @@ def run_b200_arm(args):
     torch.cuda.set_device(dev)
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     sampler = ClockSampler(local) if rank == 0 else None
     main = device_timed(args, args.fragments, dev, args.steps, args.warmup, world, rank, sampler)
