@@ -201,7 +201,7 @@ def workload_config(args, world):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
-def device_timed(args, kind, dev, steps, warmup, world, rank, sampler=None, flags=0):
+def device_timed(args, kind, dev, steps, warmup, world, rank, sampler=None, flags=0, face=False):
     """Inputs resident in HBM; K steps of pert_shade_fwd + pert_shade_bwd through the C ABI."""
     import torch.distributed as dist
     from pertrenderer_b200 import ops, synthetic_fragments
@@ -210,9 +210,14 @@ def device_timed(args, kind, dev, steps, warmup, world, rank, sampler=None, flag
     G = torch.randn((N, HW, HW, 4), device=dev, generator=torch.Generator(device=dev).manual_seed(1 + rank))
     P = N * HW * HW
     torch.manual_seed(1234 + rank)
+    F = 1280  # faces of data/objs/sphere/sphere_642.obj
+    table = None
+    if face:  # texels gathered through pix_to_face inside the kernels: no (N,H,W,K,3) tensor at all
+        table = torch.rand((F, 3), device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+        col = None
 
     def problem():
-        return ops.ShadeProblem(pix_to_face=fr.pix_to_face, zbuf=fr.zbuf, dists=fr.dists, colors=col, znear=1.0,
+        return ops.ShadeProblem(pix_to_face=fr.pix_to_face, zbuf=fr.zbuf, dists=fr.dists, colors=col, face_colors=table, znear=1.0,
                                 zfar=100.0, background=BACKGROUND, sigma=SIGMA, gamma=GAMMA, alpha=ALPHA, eps=EPS,
                                 S_rast=S, S_agg=S, seed_rast=ops.draw_seed(), seed_agg=ops.draw_seed(),
                                 pixel_offset=rank * P, flags=flags)
@@ -259,6 +264,8 @@ def device_timed(args, kind, dev, steps, warmup, world, rank, sampler=None, flag
     bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / steps
     units = P * K * S
     fb, bb = alg_bytes(P, K)
+    if face:  # SURVEY.md §8d, inlined gather variant: 40 PF + 32 P + 24 F over forward + backward
+        fb, bb = 16 * P * K + 16 * P + 12 * F, 24 * P * K + 16 * P + 12 * F
     peak, peak_src = peaks()
     dom = "pert_shade_bwd" if bwd_ms >= fwd_ms else "pert_shade_fwd"
     dom_ms, dom_bytes = (bwd_ms, bb) if bwd_ms >= fwd_ms else (fwd_ms, fb)
@@ -371,7 +378,14 @@ def run_b200_arm(args):
         from pertrenderer_b200 import _cabi
         o = device_timed(args, other_kind, dev, max(3, args.steps // 4), 3, world, rank)
         ps = device_timed(args, args.fragments, dev, max(3, args.steps // 2), 3, world, rank, flags=_cabi.F_PER_SAMPLE_NOISE)
-        also = {"fragments_" + other_kind: {"fragments": other_kind, "value": o["value"], "unit": UNIT,
+        fc = device_timed(args, args.fragments, dev, max(3, args.steps // 2), 3, world, rank, face=True)
+        also = {"face_colour_gather": {"fragments": args.fragments,
+                                       "note": "texel colours gathered through pix_to_face inside the kernels (per-face "
+                                               "colour table of 1280 faces), gradient scattered by atomics; algorithmic "
+                                               "bytes 40 PF + 32 P + 24 F",
+                                       "value": fc["value"], "unit": UNIT, "ms_per_step": fc["ms_per_step"],
+                                       "roofline": fc["roofline"]},
+                "fragments_" + other_kind: {"fragments": other_kind, "value": o["value"], "unit": UNIT,
                                              "ms_per_step": o["ms_per_step"], "roofline": o["roofline"]},
                 "per_sample_noise": {"fragments": args.fragments, "flags": "PERT_F_PER_SAMPLE_NOISE",
                                      "note": "backward regenerates every V_sj of every logit (reference-like sample "

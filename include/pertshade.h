@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define PERT_ABI_VERSION 2
+#define PERT_ABI_VERSION 3
 
 /* error codes */
 #define PERT_OK 0
@@ -107,6 +107,11 @@ typedef struct pert_problem {
     /* optional explicit noise (device); NULL -> in-register Philox4x32-10 + Box-Muller */
     const float* noise_rast;
     const float* noise_agg;
+    /* optional per-face colours float (num_faces,3): when set, `colors` is ignored (may be NULL) and the
+     * colour of entry (p,k) is face_colors[pix_to_face[p,k]] gathered inside the kernels — the (P,K,3)
+     * texel tensor of Meshes.sample_textures (random_rasterizer.py:170) is never materialised */
+    const float* face_colors;
+    int64_t num_faces;
 } pert_problem;
 
 int pert_version(void);
@@ -130,7 +135,9 @@ int pert_shade_fwd(const pert_problem* pb, float* image, uint16_t* counts, float
 
 /*
  * Backward.  grad_image (P,4).  Outputs grad_dists, grad_zbuf (P,K), grad_colors (P,K,3; may be
- * NULL), grad_scalars float[3] = d/d(sigma, gamma, alpha).  scalar_partials: workspace of
+ * NULL), grad_scalars float[3] = d/d(sigma, gamma, alpha).  With pb->face_colors set, grad_colors is
+ * instead float (num_faces,3), ZEROED BY THE CALLER, and receives w_k * dL/drgb by atomic adds (the
+ * scatter of Meshes.sample_textures' backward; summation order is not fixed).  scalar_partials: workspace of
  * 4*pert_num_tiles floats.  acc float (P,K1) and pixstat float (P,2) are optional unless the two
  * backward phases run in separate calls (sample sharding); hist int32 (P,K1) is the all-shard
  * winner histogram of forward, needed only then (NULL: rebuilt from `winners` / `pixstate`).

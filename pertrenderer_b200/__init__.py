@@ -8,12 +8,13 @@ Drop-in for the hot path of quentinll/pertrenderer (``randomras``): the same pub
 from .random_rasterizer import RandomSimpleShader, smooth_rgb_blend
 from .smoothagg import GaussianAgg, SoftAgg, randomArgmax
 from .smoothrast import GaussianRast, SoftRast, randomHeaviside
-from .structures import BlendParams, DepthCameras, Fragments, TexelMeshes, synthetic_fragments
+from .structures import (BlendParams, DepthCameras, FaceColorMeshes, FaceTexels, Fragments, TexelMeshes,
+                         synthetic_fragments)
 from .ops import explicit_noise, kernel_flags
 
 __all__ = [
     "RandomSimpleShader", "smooth_rgb_blend", "GaussianAgg", "SoftAgg", "randomArgmax", "GaussianRast",
     "SoftRast", "randomHeaviside", "BlendParams", "DepthCameras", "Fragments", "TexelMeshes",
-    "synthetic_fragments", "explicit_noise", "kernel_flags",
+    "synthetic_fragments", "explicit_noise", "kernel_flags", "FaceColorMeshes", "FaceTexels",
 ]
 __version__ = "0.1.0"

@@ -15,7 +15,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpertshade.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 # flags (include/pertshade.h)
 F_NO_SKIP = 1
@@ -48,6 +48,7 @@ class PertProblem(C.Structure):
         ("pix_to_face", C.c_void_p), ("zbuf", C.c_void_p), ("dists", C.c_void_p), ("colors", C.c_void_p),
         ("znear", C.c_void_p), ("zfar", C.c_void_p),
         ("noise_rast", C.c_void_p), ("noise_agg", C.c_void_p),
+        ("face_colors", C.c_void_p), ("num_faces", C.c_int64),
     ]
 
 

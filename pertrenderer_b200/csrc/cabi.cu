@@ -58,6 +58,8 @@ static int check_problem(const pert_problem* pb) {
     if ((pb->s_agg_begin & 3) || pb->s_agg_begin < 0 || pb->s_agg_begin >= pb->s_agg_end || pb->s_agg_end > pb->S_agg)
         return PERT_E_SAMPLES;
     if (!pb->pix_to_face || !pb->zbuf || !pb->dists || !pb->znear || !pb->zfar) return PERT_E_NULL;
+    if (pb->face_colors && (pb->num_faces <= 0 || pb->num_faces > 0x7fffffff / 3)) return PERT_E_SHAPE;
+    if ((uintptr_t)pb->face_colors & 3) return PERT_E_ALIGN;
     if (((uintptr_t)pb->pix_to_face & 7) || ((uintptr_t)pb->zbuf & 3) || ((uintptr_t)pb->dists & 3)) return PERT_E_ALIGN;
     return PERT_OK;
 }
@@ -114,7 +116,7 @@ extern "C" int pert_shade_fwd(const pert_problem* pb_in, float* image, uint16_t*
     if (!counts) return PERT_E_NULL;
     if ((f & PERT_PH_RAST) && !rsum) return PERT_E_NULL;
     if ((f & PERT_PH_AGG) && (!winners || !pixstate)) return PERT_E_NULL;
-    if ((f & PERT_PH_BLEND) && (!image || !a.pb.colors)) return PERT_E_NULL;
+    if ((f & PERT_PH_BLEND) && (!image || (!a.pb.colors && !a.pb.face_colors))) return PERT_E_NULL;
     if (((f & PERT_PH_AGG) != 0) != ((f & PERT_PH_BLEND) != 0) && !hist) return PERT_E_NULL;
     if (((uintptr_t)image & 15) || ((uintptr_t)counts & 1) || ((uintptr_t)rsum & 3) || ((uintptr_t)hist & 3) ||
         ((uintptr_t)a.pb.colors & 3) || ((uintptr_t)pixstate & 1) || ((uintptr_t)winners & 3))
@@ -144,7 +146,7 @@ extern "C" int pert_shade_bwd(const pert_problem* pb_in, const float* grad_image
     if (!(a.pb.flags & (PERT_PH_BWD_SAMPLE | PERT_PH_BWD_FINISH))) a.pb.flags |= PERT_PH_BWD_SAMPLE | PERT_PH_BWD_FINISH;
     const uint32_t f = a.pb.flags;
     const bool smp = f & PERT_PH_BWD_SAMPLE, fin = f & PERT_PH_BWD_FINISH;
-    if (!grad_image || !counts || !rsum || !pixstate || !a.pb.colors) return PERT_E_NULL;
+    if (!grad_image || !counts || !rsum || !pixstate || (!a.pb.colors && !a.pb.face_colors)) return PERT_E_NULL;
     if (smp && !winners) return PERT_E_NULL;
     if (fin && (!grad_dists || !grad_zbuf || !scalar_partials || !grad_scalars)) return PERT_E_NULL;
     if (smp != fin && (!acc || !pixstat)) return PERT_E_NULL;
@@ -154,7 +156,8 @@ extern "C" int pert_shade_bwd(const pert_problem* pb_in, const float* grad_image
         ((uintptr_t)scalar_partials & 15) || ((uintptr_t)acc & 3) || ((uintptr_t)pixstat & 3) || ((uintptr_t)hist & 3))
         return PERT_E_ALIGN;
     a.L = make_launch(&a.pb);
-    a.L.vec_ok = aligned16(a.pb.pix_to_face) && aligned16(grad_dists) && aligned16(grad_zbuf) && aligned16(grad_colors);
+    a.L.vec_ok = aligned16(a.pb.pix_to_face) && aligned16(grad_dists) && aligned16(grad_zbuf) &&
+                 (a.pb.face_colors || aligned16(grad_colors));
     if (a.L.win_bytes == 2 && ((uintptr_t)winners & 1)) return PERT_E_ALIGN;
     a.L.warp_smem = (int)bwd_warp_smem(a.L.tp, a.pb.K, a.L.sc, a.L.nchunks);
     if ((size_t)a.L.warp_smem > 200 * 1024) return PERT_E_UNSUPPORTED;

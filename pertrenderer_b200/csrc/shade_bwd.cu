@@ -44,7 +44,8 @@ __device__ __forceinline__ void zero_fill(float* dst, int n, bool vec_ok) {
 // GT = lanes per pixel as a compile-time constant (1, 2, 4, 8), or 0 to read it from the launch record.
 // PHASED = false is the production instantiation: both phases in one launch, histogram rebuilt from the
 // saved winners (the phase-split code of the sample-sharded job is compiled out to keep the hot code small).
-template <class NoiseA, int GT, bool PHASED>
+// FACE = true: colours gathered through pix_to_face from pb.face_colors, grad scattered by atomics
+template <class NoiseA, int GT, bool PHASED, bool FACE>
 __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const NoiseA noise_a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const pert_problem& pb = a.pb;
@@ -115,7 +116,7 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
     if (do_finish) {
         zero_fill(a.grad_dists + g0, E, a.L.vec_ok);
         zero_fill(a.grad_zbuf + g0, E, a.L.vec_ok);
-        if (a.grad_colors) zero_fill(a.grad_colors + g0 * 3, E * 3, a.L.vec_ok);
+        if (a.grad_colors && !FACE) zero_fill(a.grad_colors + g0 * 3, E * 3, a.L.vec_ok);
     } else {
         zero_fill(a.acc + pix0 * K1, npx * K1, false);
         if (lane < npx) {
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                 zs[n] = __ldg(zbuf_t + e);
                 cnt[n] = counts_t[e];
                 // needed a few round trips later (g_j of the logits that can win; chain rule): start them now
-                prefetch_l1(colors_t + e * 3);
+                if (!FACE) prefetch_l1(colors_t + e * 3);
                 prefetch_l1(rsum_t + e);
             }
         }
@@ -157,6 +158,8 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
         float t2sum = 0.f, csum = 0.f;
         const float* gacc = a.acc + gp * K1;  // FINISH-only: sums over all sample shards
         const float* const colors_p = pb.colors + gp * K * 3;
+        const float* const fcol = FACE ? pb.face_colors : nullptr;  // per-face colours gathered through pix_to_face
+        const int64_t* const p2f_p = pb.pix_to_face + gp * K;
         __syncwarp();
 
         // ---- phase 2 -------------------------------------------------------------------------------
@@ -193,7 +196,7 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                         if (live) {
                             float gj;
                             if (j < K) {
-                                const float* c = colors_p + j * 3;
+                                const float* c = fcol ? fcol + 3 * (int)__ldg(p2f_p + j) : colors_p + j * 3;
                                 gj = Gi.x * __ldg(c) + Gi.y * __ldg(c + 1) + Gi.z * __ldg(c + 2);
                             } else {
                                 gj = Gi.x * pb.background[0] + Gi.y * pb.background[1] + Gi.z * pb.background[2];
@@ -419,7 +422,8 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
             const float* const rsum_t = a.rsum + g0;
             float* const gd_t = a.grad_dists + g0;
             float* const gz_t = a.grad_zbuf + g0;
-            float* const gc_t = a.grad_colors ? a.grad_colors + g0 * 3 : nullptr;
+            float* const gc_t = (a.grad_colors && !fcol) ? a.grad_colors + g0 * 3 : nullptr;
+            float* const gfc = fcol ? a.grad_colors : nullptr;  // (num_faces,3), atomic scatter
 #pragma unroll 1
             for (int n = vs + lig; n < ve; n += G) {
                 const int e = vlist[n];
@@ -447,17 +451,24 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                 gd_t[e] = -gx;
                 p_sigma += gx;
                 // grad_colors = w_k * G_rgb
-                if (gc_t) {
+                if (gc_t || gfc) {
                     int h;
                     if (ghist) h = ghist[gp * K1 + k];  // all-shard histogram when sample-sharded
                     else if (act) h = hj[p * K1 + k];
                     else h = (k == a0) ? sa_loc : 0;
                     if (h > 0) {
                         const float w = (float)h * invS;
-                        float* gc = gc_t + e * 3;
-                        gc[0] = w * Gi.x;
-                        gc[1] = w * Gi.y;
-                        gc[2] = w * Gi.z;
+                        if (gfc) {
+                            float* gc = gfc + 3 * (int)__ldg(p2f_p + k);
+                            atomicAdd(gc, w * Gi.x);
+                            atomicAdd(gc + 1, w * Gi.y);
+                            atomicAdd(gc + 2, w * Gi.z);
+                        } else {
+                            float* gc = gc_t + e * 3;
+                            gc[0] = w * Gi.x;
+                            gc[1] = w * Gi.y;
+                            gc[2] = w * Gi.z;
+                        }
                     }
                 }
             }
@@ -512,16 +523,20 @@ __global__ void __launch_bounds__(1024) finalize_scalars_kernel(const float* par
     }
 }
 
-template <class NA, int GT, bool PHASED>
-static int launch_bwd_t(const BwdArgs& a, const NA& na, cudaStream_t st) {
+template <class NA, int GT, bool PHASED, bool FACE>
+static int launch_bwd_f(const BwdArgs& a, const NA& na, cudaStream_t st) {
     const size_t smem = (size_t)a.L.warp_smem;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(shade_bwd_kernel<NA, GT, PHASED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(shade_bwd_kernel<NA, GT, PHASED, FACE>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    shade_bwd_kernel<NA, GT, PHASED><<<(unsigned)a.L.ntiles, FNT, smem, st>>>(a, na);
+    shade_bwd_kernel<NA, GT, PHASED, FACE><<<(unsigned)a.L.ntiles, FNT, smem, st>>>(a, na);
     return (int)cudaGetLastError();
+}
+template <class NA, int GT, bool PHASED>
+static int launch_bwd_t(const BwdArgs& a, const NA& na, cudaStream_t st) {
+    return a.pb.face_colors ? launch_bwd_f<NA, GT, PHASED, true>(a, na, st) : launch_bwd_f<NA, GT, PHASED, false>(a, na, st);
 }
 
 int launch_shade_bwd(const BwdArgs& a, float* grad_scalars, cudaStream_t st) {

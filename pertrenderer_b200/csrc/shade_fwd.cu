@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(FNT, 32) shade_fwd_kernel(const FwdArgs a, con
         if (n < nv) {
             const int e = vlist[n];
             zs[n] = __ldg(zbuf_t + e);
-            prefetch_l1(pb.colors + (g0 + e) * 3);  // blended at the very end of the tile: start the round trip now
+            if (!pb.face_colors) prefetch_l1(pb.colors + (g0 + e) * 3);  // blended at the very end of the tile
             if (do_rast) {
                 const float x = -__ldg(dists_t + e);
                 xs[n] = x;
@@ -266,6 +266,8 @@ __global__ void __launch_bounds__(FNT, 32) shade_fwd_kernel(const FwdArgs a, con
     float r = 0.f, g = 0.f, bl = 0.f;
     const float fS = (float)pb.S_agg;
     const float* const colors_p = pb.colors + gp * K * 3;
+    const float* const fcol = pb.face_colors;  // per-face colours gathered through pix_to_face, or NULL
+    const int64_t* const p2f_p = pb.pix_to_face + gp * K;
     if (do_agg) {
 #pragma unroll 1
         for (int l = lig; l < nlive; l += G) {
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(FNT, 32) shade_fwd_kernel(const FwdArgs a, con
                 const float w = (float)hcount / fS;
                 const int j = lj[lb + l];
                 if (j < K) {
-                    const float* c = colors_p + j * 3;
+                    const float* c = fcol ? fcol + 3 * (int)__ldg(p2f_p + j) : colors_p + j * 3;
                     r += w * __ldg(c);
                     g += w * __ldg(c + 1);
                     bl += w * __ldg(c + 2);
@@ -295,7 +297,7 @@ __global__ void __launch_bounds__(FNT, 32) shade_fwd_kernel(const FwdArgs a, con
             if (hcount > 0) {
                 const float w = (float)hcount / fS;
                 if (j < K) {
-                    const float* c = colors_p + j * 3;
+                    const float* c = fcol ? fcol + 3 * (int)__ldg(p2f_p + j) : colors_p + j * 3;
                     r += w * __ldg(c);
                     g += w * __ldg(c + 1);
                     bl += w * __ldg(c + 2);

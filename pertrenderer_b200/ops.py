@@ -102,10 +102,12 @@ class ShadeProblem:
     s_agg: Optional[Tuple[int, int]] = None
     noise_rast: Optional[torch.Tensor] = None
     noise_agg: Optional[torch.Tensor] = None
+    face_colors: Optional[torch.Tensor] = None  # (F,3): colours gathered through pix_to_face inside the kernels
     _keep: list = field(default_factory=list)
 
     def __post_init__(self):
-        require_cuda(self.pix_to_face, self.zbuf, self.dists, self.colors, self.noise_rast, self.noise_agg)
+        require_cuda(self.pix_to_face, self.zbuf, self.dists, self.colors, self.noise_rast, self.noise_agg,
+                     self.face_colors)
         if self.pix_to_face.dim() != 4:
             raise ValueError("pix_to_face must be (N,H,W,K)")
         if self.pix_to_face.dtype != torch.int64:
@@ -118,6 +120,12 @@ class ShadeProblem:
             raise ValueError("zbuf and dists must have the shape of pix_to_face")
         if self.colors is not None and tuple(self.colors.shape) != (N, H, W, K, 3):
             raise ValueError("colors must be (N,H,W,K,3)")
+        if self.face_colors is not None:
+            self.face_colors = _f32c(self.face_colors.detach())
+            if self.face_colors.dim() != 2 or self.face_colors.shape[1] != 3:
+                raise ValueError("face_colors must be (F,3)")
+        elif self.colors is None:
+            raise ValueError("either colors (N,H,W,K,3) or face_colors (F,3) is required")
         dev = self.pix_to_face.device
         self.znear = depth_plane(self.znear, N, dev)
         self.zfar = depth_plane(self.zfar, N, dev)
@@ -163,6 +171,8 @@ class ShadeProblem:
         pb.znear, pb.zfar = self.znear.data_ptr(), self.zfar.data_ptr()
         pb.noise_rast = self.noise_rast.data_ptr() if self.noise_rast is not None else None
         pb.noise_agg = self.noise_agg.data_ptr() if self.noise_agg is not None else None
+        if self.face_colors is not None:
+            pb.face_colors, pb.num_faces = self.face_colors.data_ptr(), self.face_colors.shape[0]
         return pb
 
     def winner_dtype(self):
@@ -231,7 +241,10 @@ def shade_backward(pr: ShadeProblem, saved: ShadeSaved, grad_image: torch.Tensor
         finish = (phases == 0) or bool(phases & PH_BWD_FINISH)
         gd = torch.empty((N, H, W, K), dtype=torch.float32, device=dev) if finish else None
         gz = torch.empty((N, H, W, K), dtype=torch.float32, device=dev) if finish else None
-        gc = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev) if (finish and need_colors) else None
+        if pr.face_colors is not None:  # scatter target of the in-kernel gather: atomics into zeros
+            gc = torch.zeros_like(pr.face_colors) if (finish and need_colors) else None
+        else:
+            gc = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev) if (finish and need_colors) else None
         partials = torch.empty((pr.num_tiles(), 4), dtype=torch.float32, device=dev) if finish else None
         scal = torch.empty((3,), dtype=torch.float32, device=dev) if finish else None
         pb = pr.c_struct(flags=pr.flags | phases)

@@ -18,7 +18,7 @@ from torch.autograd import Function
 from . import ops
 from .smoothagg import GaussianAgg, SoftAgg
 from .smoothrast import GaussianRast, SoftRast
-from .structures import BlendParams
+from .structures import BlendParams, FaceTexels
 
 
 def _background_tuple(blend_params):
@@ -48,8 +48,10 @@ class _PerturbedShade(Function):
         if cfg["fixed_noise"]:
             torch.manual_seed(1)
         seed_a = 0 if noise_a is not None else ops.draw_seed()
+        face = bool(cfg.get("face_colors", False))  # `colors` is then the (F,3) per-face table
         pr = ops.ShadeProblem(
-            pix_to_face=pix_to_face, zbuf=zbuf, dists=dists, colors=colors, znear=znear, zfar=zfar,
+            pix_to_face=pix_to_face, zbuf=zbuf, dists=dists, colors=None if face else colors,
+            face_colors=colors if face else None, znear=znear, zfar=zfar,
             background=cfg["background"], sigma=float(sigma), gamma=float(gamma), alpha=float(alpha),
             eps=float(cfg["eps"]), S_rast=int(cfg["S_rast"]), S_agg=int(cfg["S_agg"]),
             seed_rast=seed_r, seed_agg=seed_a, pixel_offset=int(cfg.get("pixel_offset", 0)),
@@ -79,15 +81,18 @@ def smooth_rgb_blend(colors, fragments, smoothrast, smoothagg, blend_params, zne
 
     ``colors`` (N,H,W,K,3); ``fragments`` with ``pix_to_face`` / ``zbuf`` / ``dists`` (N,H,W,K);
     ``znear`` / ``zfar`` python floats or tensors broadcastable to (N,1,1,1)."""
-    ops.require_cuda(colors, fragments.pix_to_face, fragments.zbuf, fragments.dists)
+    face = isinstance(colors, FaceTexels)
+    ops.require_cuda(colors.face_colors if face else colors, fragments.pix_to_face, fragments.zbuf, fragments.dists)
     if isinstance(smoothrast, GaussianRast) and isinstance(smoothagg, GaussianAgg):
         cfg = dict(background=_background_tuple(blend_params), eps=smoothagg.eps,
                    S_rast=smoothrast.nb_samples, S_agg=smoothagg.nb_samples,
-                   fixed_noise=bool(smoothagg.fixed_noise))
-        return _PerturbedShade.apply(colors, fragments.dists, fragments.zbuf, smoothrast.sigma,
+                   fixed_noise=bool(smoothagg.fixed_noise), face_colors=face)
+        return _PerturbedShade.apply(colors.face_colors if face else colors, fragments.dists, fragments.zbuf, smoothrast.sigma,
                                      smoothagg.gamma, smoothagg.alpha, fragments.pix_to_face, znear, zfar, cfg)
 
     # operator-by-operator composition for every other pair (e.g. GaussianRast + SoftAgg)
+    if face:
+        colors = colors.materialize(fragments.pix_to_face)
     device = fragments.pix_to_face.device
     background = blend_params.background_color
     if not torch.is_tensor(background):

@@ -60,6 +60,33 @@ class TexelMeshes:
         return self.texels
 
 
+class FaceTexels:
+    """Lazy texels: the colour of fragment (n,h,w,k) is ``face_colors[pix_to_face[n,h,w,k]]``.
+    ``smooth_rgb_blend`` gathers it inside the fused kernels (and scatters the gradient back to
+    ``face_colors``), so the (N,H,W,K,3) tensor of ``Meshes.sample_textures``
+    (random_rasterizer.py:170) is never materialised."""
+
+    def __init__(self, face_colors: torch.Tensor):
+        if face_colors.dim() != 2 or face_colors.shape[1] != 3:
+            raise ValueError("face_colors must be (F,3)")
+        self.face_colors = face_colors
+
+    def materialize(self, pix_to_face: torch.Tensor) -> torch.Tensor:
+        mask = pix_to_face >= 0
+        return self.face_colors[pix_to_face.clamp(min=0)] * mask[..., None]
+
+
+class FaceColorMeshes:
+    """Stand-in for ``Meshes`` with one colour per (packed) face: ``sample_textures`` returns lazy
+    :class:`FaceTexels` instead of a texel tensor."""
+
+    def __init__(self, face_colors: torch.Tensor):
+        self.face_colors = face_colors
+
+    def sample_textures(self, fragments):
+        return FaceTexels(self.face_colors)
+
+
 def blur_radius(sigma: float) -> float:
     """experiments/eval.py:137: log(1/1e-4 - 1) * sigma."""
     return math.log(1.0 / 1e-4 - 1.0) * sigma

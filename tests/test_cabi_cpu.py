@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     """ctypes mirror of pert_problem: field order / sizes as in the header (LP64)."""
-    assert ctypes.sizeof(_cabi.PertProblem) == 176
+    assert ctypes.sizeof(_cabi.PertProblem) == 192
     assert _cabi.PertProblem.pix_to_face.offset == 112
     assert _cabi.PertProblem.seed_rast.offset == 80
 

@@ -401,6 +401,40 @@ def test_once_per_logit_noise_has_the_reference_distribution():
         assert (ratio - 1).abs().max().item() < tol, (k, "var", ratio.min().item(), ratio.max().item())
 
 
+def test_face_colour_gather_matches_texel_tensor():
+    """north_star: the texel gather through pix_to_face inlined into the fused kernels.  Rendering with
+    lazy FaceTexels equals rendering with the materialised (N,H,W,K,3) tensor (same forward bits), and the
+    gradient scattered onto the (F,3) table equals the index_add of the dense texel gradient."""
+    import pertrenderer_b200 as pb
+    dev = "cuda"
+    N, H, W, K, S, F = 2, 24, 24, 50, 16, 37
+    fr, _ = pb.synthetic_fragments(N, H, W, K, kind="realistic", sigma=1e-3, n_faces=F, seed=9, device=dev)
+    G = torch.randn((N, H, W, 4), device=dev, generator=torch.Generator(device=dev).manual_seed(2))
+    table = torch.rand((F, 3), device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+
+    def run(use_face):
+        fc = table.clone().requires_grad_(True)
+        d = fr.dists.clone().requires_grad_(True)
+        z = fr.zbuf.clone().requires_grad_(True)
+        frag = pb.Fragments(fr.pix_to_face, z, None, d)
+        shader = pb.RandomSimpleShader(device=dev, cameras=pb.DepthCameras(n=N, device=dev),
+                                       smoothrast=pb.GaussianRast(nb_samples=S, sigma=1e-3),
+                                       smoothagg=pb.GaussianAgg(nb_samples=S, gamma=1e-2),
+                                       blend_params=pb.BlendParams(background_color=(0.1, 0.2, 0.3)))
+        meshes = pb.FaceColorMeshes(fc) if use_face else pb.TexelMeshes(pb.FaceTexels(fc).materialize(fr.pix_to_face))
+        torch.manual_seed(11)
+        img = shader(frag, meshes)
+        (img * G).sum().backward()
+        return img.detach(), fc.grad, d.grad, z.grad
+
+    img_f, gfc_f, gd_f, gz_f = run(True)
+    img_t, gfc_t, gd_t, gz_t = run(False)
+    assert torch.equal(img_f, img_t)
+    assert torch.equal(gd_f, gd_t) and torch.equal(gz_f, gz_t)
+    assert rel_err(gfc_f.cpu(), gfc_t.cpu()) <= 1e-5
+    assert gfc_f.abs().sum() > 0
+
+
 def test_full_size_properties_config2():
     """BASELINE config 2 (N=8, 256x256, K=50, S=64) through the public API: size-independent
     properties — determinism under a fixed torch seed, alpha in [0,1] and quantised, empty pixels

@@ -8,6 +8,8 @@ r=d["roofline"]; o=d["also"]["fragments_dense"]["roofline"]; ps=d["also"]["per_s
 print("realistic ms/step %.4f fwd %.4f (%.3f) bwd %.4f (%.3f)" % (d["ms_per_step"], r["fwd"]["ms"], r["fwd"]["frac"], r["bwd"]["ms"], r["bwd"]["frac"]))
 print("dense     ms/step %.4f fwd %.4f (%.3f) bwd %.4f (%.3f)" % (d["also"]["fragments_dense"]["ms_per_step"], o["fwd"]["ms"], o["fwd"]["frac"], o["bwd"]["ms"], o["bwd"]["frac"]))
 print("persample ms/step %.4f bwd %.4f (%.3f)" % (ps["ms_per_step"], ps["roofline"]["bwd"]["ms"], ps["roofline"]["bwd"]["frac"]))
+fc=d["also"]["face_colour_gather"]
+print("facecol   ms/step %.4f fwd %.4f (%.3f) bwd %.4f (%.3f)" % (fc["ms_per_step"], fc["roofline"]["fwd"]["ms"], fc["roofline"]["fwd"]["frac"], fc["roofline"]["bwd"]["ms"], fc["roofline"]["bwd"]["frac"]))
 print("clocks", d["clocks"])
 PY
 tail -3 gpurun_out/bench_$1.err
