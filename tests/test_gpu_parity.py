@@ -147,6 +147,85 @@ def test_explicit_noise_matches_oracle_seeded(shape):
         _scalars_close(out["scalars"][i].item(), gr[k].item(), k)
 
 
+def _holey_case(N, H, W, K, S_r, S_a, seed):
+    """Fragments whose valid entries are NOT a prefix of K (holes anywhere, some pixels empty, some
+    full), unsorted depths, depths beyond zfar and coverage counts of 0 and S: the reference takes the
+    mask from pix_to_face >= 0 wherever it is (random_rasterizer.py:46)."""
+    from gpu_util import synthetic_case
+    g = synthetic_case(N, H, W, K, S_r, S_a, kind="dense", seed=seed, background=(0.7, 0.1, 0.4),
+                       znear=[0.5 + 0.25 * n for n in range(N)], zfar=[7.0 + n for n in range(N)], alpha=0.9)
+    gen = torch.Generator().manual_seed(seed)
+    keep = torch.rand((N, H, W, K), generator=gen) < 0.3
+    keep[0, 0, 0] = False  # an empty pixel
+    keep[0, 0, 1 % W] = True  # a full one
+    g["pix_to_face"] = torch.where(keep, g["pix_to_face"], torch.full_like(g["pix_to_face"], -1))
+    g["zbuf"] = torch.where(keep, 5.5 + 2.5 * torch.rand((N, H, W, K), generator=gen), torch.full_like(g["zbuf"], -1.0))
+    g["dists"] = torch.where(keep, g["dists"] * 0.6, torch.full_like(g["dists"], -1.0))
+    g["colors"] = g["colors"] * keep[..., None]
+    return g
+
+
+@pytest.mark.parametrize("shape", [
+    (1, 5, 7, 1, 8, 8), (2, 3, 3, 2, 5, 3), (1, 6, 5, 16, 4, 4), (1, 5, 5, 17, 7, 9), (1, 3, 7, 33, 16, 16),
+    (1, 3, 5, 64, 8, 8), (1, 3, 3, 65, 8, 8), (1, 2, 3, 255, 4, 4), (1, 2, 2, 256, 4, 4), (1, 1, 3, 1023, 4, 4),
+    (1, 3, 3, 50, 1, 2), (1, 2, 2, 50, 600, 520)])
+def test_edge_shapes_holes_and_sample_counts(shape):
+    """Every tile geometry (K = 1 .. 1023: 32, 16, 8, 4 pixels per warp tile; 8- and 16-bit winners),
+    pixel counts that are not a multiple of the tile, masks with holes, S not a multiple of 4, S = 1,
+    S_rast != S_agg and S large enough for several backward sample chunks."""
+    from gpu_util import problem_from_case, run_cuda, run_oracle
+    N, H, W, K, S_r, S_a = shape
+    g = _holey_case(N, H, W, K, S_r, S_a, seed=1000 + K + S_r)
+    U, V = O.draw_noise((N, H, W, K), S_r, S_a, generator=torch.Generator().manual_seed(K))
+    g["U"], g["V"] = U, V
+    st, gr = run_oracle(g, U, V)
+    out = run_cuda(problem_from_case(g), g["grad_image"])
+    mask = g["pix_to_face"] >= 0
+    assert torch.equal(out["counts"][mask], st.counts[mask])
+    assert torch.equal(out["winners"].permute(3, 0, 1, 2).long(), st.a_s)
+    assert (out["image"] - st.image).abs().max() <= 2e-6
+    assert rel_err(out["grad_colors"], gr["colors"]) <= RTOL
+    assert rel_err(out["grad_dists"], gr["dists"]) <= RTOL
+    assert rel_err(out["grad_zbuf"], gr["zbuf"]) <= RTOL
+    assert (out["grad_dists"][~mask] == 0).all() and (out["grad_zbuf"][~mask] == 0).all()
+    assert (out["grad_colors"][~mask] == 0).all()
+    for i, k in enumerate(("sigma", "gamma", "alpha")):
+        _scalars_close(out["scalars"][i].item(), gr[k].item(), k)
+    # the in-kernel noise path on the same inputs: Philox == explicit(noise_fill) on indices
+    from pertrenderer_b200 import _cabi, ops
+    Up = ops.noise_fill(5, 0, (N, H, W, K), S_r, "cuda")
+    Vp = ops.noise_fill(6, 1, (N, H, W, K), S_a, "cuda")
+    a = run_cuda(problem_from_case(g, explicit=False, seed_rast=5, seed_agg=6, flags=_cabi.F_PER_SAMPLE_NOISE), g["grad_image"])
+    g2 = dict(g, U=Up.cpu(), V=Vp.cpu())
+    b = run_cuda(problem_from_case(g2, explicit=True), g["grad_image"])
+    assert torch.equal(a["counts"][mask], b["counts"][mask]) and torch.equal(a["winners"], b["winners"])
+    # same weights; bounded noise prunes logits that cannot win, so the blend may sum in another lane order
+    assert (a["image"] - b["image"]).abs().max() <= 1e-6
+    assert rel_err(a["grad_zbuf"], b["grad_zbuf"]) <= RTOL and rel_err(a["grad_dists"], b["grad_dists"]) <= RTOL
+
+
+def test_unaligned_views_take_the_scalar_path():
+    """Tensors whose storage offset breaks the 16-byte alignment of the tile rows (a view into a larger
+    buffer) give the same results as aligned copies."""
+    from gpu_util import problem_from_case, run_cuda, synthetic_case
+    g = synthetic_case(1, 5, 5, 7, 8, 8, kind="realistic", seed=71)
+    a = run_cuda(problem_from_case(g, explicit=False, seed_rast=1, seed_agg=2), g["grad_image"])
+
+    def shifted(t, elems):
+        buf = torch.zeros(t.numel() + elems, dtype=t.dtype, device="cuda")
+        v = buf[elems:].view(t.shape)
+        v.copy_(t)
+        return v
+
+    pr = problem_from_case(g, explicit=False, seed_rast=1, seed_agg=2)
+    pr.pix_to_face = shifted(pr.pix_to_face, 1)  # 8-byte offset
+    pr.zbuf, pr.dists = shifted(pr.zbuf, 1), shifted(pr.dists, 3)
+    assert pr.pix_to_face.data_ptr() % 16 == 8
+    b = run_cuda(pr, g["grad_image"])
+    for k in ("image", "winners", "grad_dists", "grad_zbuf", "grad_colors", "scalars"):
+        assert torch.equal(a[k], b[k]), k
+
+
 @pytest.mark.parametrize("kind", ["realistic", "dense"])
 def test_philox_equals_explicit_with_materialised_noise(kind):
     """The in-register Philox path is the explicit path fed with pert_noise_fill's tensor: bit-exact
