@@ -159,7 +159,7 @@ extern "C" int pert_shade_bwd(const pert_problem* pb_in, const float* grad_image
     a.L.vec_ok = aligned16(a.pb.pix_to_face) && aligned16(grad_dists) && aligned16(grad_zbuf) &&
                  (a.pb.face_colors || aligned16(grad_colors));
     if (a.L.win_bytes == 2 && ((uintptr_t)winners & 1)) return PERT_E_ALIGN;
-    a.L.warp_smem = (int)bwd_warp_smem(a.L.tp, a.pb.K, a.L.sc, a.L.nchunks);
+    a.L.warp_smem = (int)bwd_warp_smem(a.L.tp, a.pb.K, a.L.sc, a.L.nchunks, a.L.win_bytes);
     if ((size_t)a.L.warp_smem > 200 * 1024) return PERT_E_UNSUPPORTED;
     if (a.L.ntiles > 0x7fffffff) return PERT_E_UNSUPPORTED;
     a.grad_image = grad_image;

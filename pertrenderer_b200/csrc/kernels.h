@@ -33,7 +33,7 @@ struct BwdArgs {
 };
 
 size_t fwd_warp_smem(int tp, int K);
-size_t bwd_warp_smem(int tp, int K, int sc, int nchunks);
+size_t bwd_warp_smem(int tp, int K, int sc, int nchunks, int win_bytes);
 
 // return a cudaError_t as int (0 = success)
 int launch_shade_fwd(const FwdArgs& a, cudaStream_t st);

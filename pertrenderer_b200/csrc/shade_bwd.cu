@@ -20,12 +20,12 @@
 
 namespace pert {
 
-size_t bwd_warp_smem(int tp, int K, int sc, int nchunks) {
+size_t bwd_warp_smem(int tp, int K, int sc, int nchunks, int win_bytes) {
     const size_t E = (size_t)tp * K, E1 = (size_t)tp * (K + 1);
     return carve(E, 2) /*vlist*/ + carve(E, 4) /*zs*/ + carve(E, 2) /*cnt*/ + carve(E1, 4) * (nchunks > 1 ? 4 : 3)
            /*hj gsel accs [t2s]*/ + carve(E1, 2) /*pair_j*/ + carve(E1, 1) /*pair_p*/ + carve((size_t)tp * sc, 4) /*cs*/ +
            carve(tp + 1, 4) /*vstart*/ + carve(tp, 4) * 2 /*pa0, pg0*/ + carve(tp, 1) /*apx*/ +
-           (nchunks == 1 ? carve((size_t)tp * sc, 2) : 0) /*wst (u16 winners at most)*/ + 16;
+           (nchunks == 1 ? carve((size_t)tp * sc, win_bytes) : 0) /*wst*/ + 16;
 }
 
 __device__ __forceinline__ void zero_fill(float* dst, int n, bool vec_ok) {
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
     // single-chunk jobs: the tile's saved winners (tp rows of sa_loc entries, contiguous) are copied to
     // shared memory asynchronously at the very start, off the critical path
     const bool early_w = a.L.nchunks == 1 && ((sa_loc * wb) & 15) == 0 && do_sample;
-    unsigned char* wst = a.L.nchunks == 1 ? cv.take<unsigned char>(tp * sc * 2) : nullptr;
+    unsigned char* wst = a.L.nchunks == 1 ? cv.take<unsigned char>(tp * sc * wb) : nullptr;
     if (early_w) {
         const unsigned char* src = reinterpret_cast<const unsigned char*>(a.winners) + pix0 * sa_loc * wb;
         const int nbytes = npx * sa_loc * wb;

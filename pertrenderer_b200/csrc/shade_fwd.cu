@@ -185,6 +185,21 @@ __global__ void __launch_bounds__(FNT, 32) shade_fwd_kernel(const FwdArgs a, con
         if (pvalid && lig == 0) pinfo[p] = nlive | (a0l << 16);
         const int np = __popc(mb);
         __syncwarp();
+        if (np > 2) {
+            // order the listed pixels by their number of live logits: the pixels that share a warp pass then
+            // loop about equally long (less divergence)
+            const int myp = lane < np ? plist[lane] : 0;
+            const int myn = lane < np ? (pinfo[myp] & 0xffff) : -1;
+            int rank = 0;
+#pragma unroll 1
+            for (int i = 0; i < np; ++i) {
+                const int on = __shfl_sync(FULL, myn, i);
+                rank += (on > myn || (on == myn && i < lane)) ? 1 : 0;
+            }
+            __syncwarp();
+            if (lane < np) plist[rank] = (uint16_t)myp;
+            __syncwarp();
+        }
         if (np > 0) {
             const int qb = pb.s_agg_begin >> 2, qe = (pb.s_agg_end + 3) >> 2;
             const int lpe = a.L.lpe_a;
