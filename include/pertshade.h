@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define PERT_ABI_VERSION 3
+#define PERT_ABI_VERSION 4
 
 /* error codes */
 #define PERT_OK 0
@@ -119,8 +119,13 @@ const char* pert_strerror(int code);
 /* last cudaError_t name seen by this thread's most recent failing call (diagnostic only) */
 const char* pert_last_cuda_error(void);
 
-/* number of warp tiles (= CTAs) the fused kernels launch; scalar_partials needs 4 floats per tile,
- * 16-byte aligned */
+/* number of warp tiles (= CTAs) T the fused kernels launch.  Workspaces (caller-allocated, 16-byte aligned):
+ *   scalar_partials  float  4 * 3T   (one row per tile; rows T..3T belong to the fallback pass)
+ *   worklist         int32  4 + T    optional (NULL: off).  Sparse-first mode: the main pass holds half a
+ *                    tile's entries in shared memory (real fragments fill a few percent); tiles with more
+ *                    valid entries are listed here and redone by a fallback pass as half-size tiles.  The
+ *                    library zeroes the counter itself (cudaMemsetAsync on the caller's stream).  Results do
+ *                    not depend on which pass handled a tile, up to the association order of float sums. */
 int64_t pert_num_tiles(const pert_problem* pb);
 /* element size in bytes of the winners buffer for this K (1 or 2) */
 int pert_winner_bytes(int32_t K);
@@ -131,7 +136,7 @@ int pert_winner_bytes(int32_t K);
  * buffers produced by an earlier phase are inputs.
  */
 int pert_shade_fwd(const pert_problem* pb, float* image, uint16_t* counts, float* rsum, void* winners,
-                   uint16_t* pixstate, int32_t* hist, void* stream);
+                   uint16_t* pixstate, int32_t* hist, int32_t* worklist, void* stream);
 
 /*
  * Backward.  grad_image (P,4).  Outputs grad_dists, grad_zbuf (P,K), grad_colors (P,K,3; may be
@@ -145,7 +150,7 @@ int pert_shade_fwd(const pert_problem* pb, float* image, uint16_t* counts, float
 int pert_shade_bwd(const pert_problem* pb, const float* grad_image, const uint16_t* counts,
                    const float* rsum, const void* winners, const uint16_t* pixstate, float* grad_dists,
                    float* grad_zbuf, float* grad_colors, float* scalar_partials, float* grad_scalars,
-                   float* acc, float* pixstat, const int32_t* hist, void* stream);
+                   float* acc, float* pixstat, const int32_t* hist, int32_t* worklist, void* stream);
 
 /*
  * Stand-alone perturbed Heaviside on x (P,K) (x = -dists in the shader).  prob = counts/S.

@@ -15,7 +15,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpertshade.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 # flags (include/pertshade.h)
 F_NO_SKIP = 1
@@ -86,9 +86,9 @@ def load():
         lib.pert_winner_bytes.restype = C.c_int
         lib.pert_winner_bytes.argtypes = [i32]
         lib.pert_shade_fwd.restype = C.c_int
-        lib.pert_shade_fwd.argtypes = [pp] + [vp] * 7
+        lib.pert_shade_fwd.argtypes = [pp] + [vp] * 8
         lib.pert_shade_bwd.restype = C.c_int
-        lib.pert_shade_bwd.argtypes = [pp] + [vp] * 14
+        lib.pert_shade_bwd.argtypes = [pp] + [vp] * 15
         lib.pert_rast_fwd.restype = C.c_int
         lib.pert_rast_fwd.argtypes = [vp, i64, i32, i32, i32, i32, f32, u64, i64, vp, u32, vp, vp, vp]
         lib.pert_rast_bwd.restype = C.c_int

@@ -48,6 +48,7 @@ static int check_problem(const pert_problem* pb) {
     if (!pb) return PERT_E_NULL;
     if (pb->N <= 0 || pb->H <= 0 || pb->W <= 0 || pb->K <= 0) return PERT_E_SHAPE;
     if (pb->K > 1023) return PERT_E_UNSUPPORTED;
+    if (pb->N * pb->H * pb->W >= ((int64_t)1 << 31) / (pb->K + 1)) return PERT_E_UNSUPPORTED;  // 32-bit pixel·logit indices per call
     if (pb->S_rast <= 0 || pb->S_agg <= 0 || pb->S_rast > 65535 || pb->S_agg > (1 << 24)) return PERT_E_UNSUPPORTED;
     if (pb->depth_len != 1 && pb->depth_len != pb->N) return PERT_E_SHAPE;
     if (!(pb->sigma > 0.f) || !(pb->gamma > 0.f) || !(pb->alpha > 0.f) || isinf(pb->sigma) || isinf(pb->gamma) ||
@@ -64,9 +65,9 @@ static int check_problem(const pert_problem* pb) {
     return PERT_OK;
 }
 
-static Launch make_launch(const pert_problem* pb) {
+static Launch make_launch(const pert_problem* pb, int tp) {
     Launch L;
-    L.tp = pick_tp(pb->K);
+    L.tp = tp;
     L.G = 32 / L.tp;
     L.gshift = 0;
     while ((1 << L.gshift) < L.G) L.gshift++;
@@ -88,17 +89,35 @@ static Launch make_launch(const pert_problem* pb) {
     L.lpe_a_shift = lg2(L.lpe_a);
     L.lpp = pow2_floor(nq_a) < 8 ? pow2_floor(nq_a) : 8;
     L.lpp_shift = lg2(L.lpp);
+    L.cap = L.tp * pb->K;
     L.warp_smem = 0;
-    L.vec_ok = 0;
+    // 128-bit accesses on the tile rows need every tile to start on a 16-byte boundary in the fp32 tensors
+    L.vec_ok = ((L.tp * pb->K) & 3) == 0;
     L.invK = 1.0f / (float)pb->K;
+    L.gal = pb->gamma / pb->alpha;
+    L.inv_sigma = 1.0f / pb->sigma;
+    L.invSg = 1.0f / ((float)pb->S_agg * pb->gamma);
+    L.inv_sr = 1.0f / ((float)pb->S_rast * pb->sigma);
+    L.invS = 1.0f / (float)pb->S_agg;
     return L;
+}
+
+// Sparse-first mode (production default when the caller passes a work list): the main pass sizes its
+// compact arrays for HALF the entries of a tile -- real fragments fill a few percent -- which halves the
+// shared memory per warp; a tile with more valid entries is put on the work list and redone by the
+// fallback pass as two half-size tiles.
+static bool sparse_first_ok(const pert_problem* pb, const void* worklist, bool all_phases) {
+    if (!worklist || !all_phases || pb->noise_rast || pb->noise_agg) return false;
+    if (pb->flags & (PERT_F_NO_SKIP | PERT_F_PER_SAMPLE_NOISE)) return false;  // need logits dense in j
+    const int tp = pick_tp(pb->K);
+    return tp >= 4 && (tp / 2) * pb->K >= 8;
 }
 
 extern "C" int64_t pert_num_tiles(const pert_problem* pb) {
     if (!pb || pb->K <= 0) return 0;
     const int tp = pick_tp(pb->K);
     const int64_t P = pb->N * pb->H * pb->W;
-    return (P + tp - 1) / tp;  // one warp tile per CTA, one row of scalar partials each
+    return (P + tp - 1) / tp;  // one warp tile per CTA
 }
 
 extern "C" int pert_winner_bytes(int32_t K) { return (K + 1 <= 256) ? 1 : 2; }
@@ -106,7 +125,7 @@ extern "C" int pert_winner_bytes(int32_t K) { return (K + 1 <= 256) ? 1 : 2; }
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 extern "C" int pert_shade_fwd(const pert_problem* pb_in, float* image, uint16_t* counts, float* rsum, void* winners,
-                              uint16_t* pixstate, int32_t* hist, void* stream) {
+                              uint16_t* pixstate, int32_t* hist, int32_t* worklist, void* stream) {
     int rc = check_problem(pb_in);
     if (rc) return rc;
     FwdArgs a;
@@ -121,9 +140,14 @@ extern "C" int pert_shade_fwd(const pert_problem* pb_in, float* image, uint16_t*
     if (((uintptr_t)image & 15) || ((uintptr_t)counts & 1) || ((uintptr_t)rsum & 3) || ((uintptr_t)hist & 3) ||
         ((uintptr_t)a.pb.colors & 3) || ((uintptr_t)pixstate & 1) || ((uintptr_t)winners & 3))
         return PERT_E_ALIGN;
-    a.L = make_launch(&a.pb);
-    a.L.vec_ok = aligned16(a.pb.pix_to_face);
-    a.L.warp_smem = (int)fwd_warp_smem(a.L.tp, a.pb.K);
+    if ((uintptr_t)worklist & 15) return PERT_E_ALIGN;
+    const uint32_t all = PERT_PH_RAST | PERT_PH_AGG | PERT_PH_BLEND;
+    const bool sparse = sparse_first_ok(&a.pb, worklist, (f & all) == all && !hist);
+    a.L = make_launch(&a.pb, pick_tp(a.pb.K));
+    a.L.vec_ok = a.L.vec_ok && aligned16(a.pb.pix_to_face);
+    if (sparse) a.L.cap = a.L.cap / 2;
+    fwd_smem_layout(a.L.tp, a.L.cap, a.L.sm);
+    a.L.warp_smem = a.L.sm.bytes;
     if ((size_t)a.L.warp_smem > 200 * 1024) return PERT_E_UNSUPPORTED;
     if (a.L.ntiles > 0x7fffffff) return PERT_E_UNSUPPORTED;
     a.image = image;
@@ -132,13 +156,23 @@ extern "C" int pert_shade_fwd(const pert_problem* pb_in, float* image, uint16_t*
     a.winners = winners;
     a.pixstate = pixstate;
     a.hist = hist;
-    return cuda_rc(launch_shade_fwd(a, (cudaStream_t)stream));
+    a.worklist = worklist;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!sparse) return cuda_rc(launch_shade_fwd(a, nullptr, st));
+    FwdArgs fb = a;  // fallback pass: half-size tiles, full capacity
+    fb.L = make_launch(&a.pb, a.L.tp / 2);
+    fb.L.vec_ok = fb.L.vec_ok && aligned16(a.pb.pix_to_face);
+    fwd_smem_layout(fb.L.tp, fb.L.cap, fb.L.sm);
+    fb.L.warp_smem = fb.L.sm.bytes;
+    cudaError_t e = cudaMemsetAsync(worklist, 0, 16, st);
+    if (e != cudaSuccess) return cuda_fail((int)e);
+    return cuda_rc(launch_shade_fwd(a, &fb, st));
 }
 
 extern "C" int pert_shade_bwd(const pert_problem* pb_in, const float* grad_image, const uint16_t* counts,
                               const float* rsum, const void* winners, const uint16_t* pixstate, float* grad_dists,
                               float* grad_zbuf, float* grad_colors, float* scalar_partials, float* grad_scalars,
-                              float* acc, float* pixstat, const int32_t* hist, void* stream) {
+                              float* acc, float* pixstat, const int32_t* hist, int32_t* worklist, void* stream) {
     int rc = check_problem(pb_in);
     if (rc) return rc;
     BwdArgs a;
@@ -155,11 +189,16 @@ extern "C" int pert_shade_bwd(const pert_problem* pb_in, const float* grad_image
         ((uintptr_t)grad_zbuf & 3) || ((uintptr_t)counts & 1) || ((uintptr_t)rsum & 3) || ((uintptr_t)pixstate & 1) ||
         ((uintptr_t)scalar_partials & 15) || ((uintptr_t)acc & 3) || ((uintptr_t)pixstat & 3) || ((uintptr_t)hist & 3))
         return PERT_E_ALIGN;
-    a.L = make_launch(&a.pb);
-    a.L.vec_ok = aligned16(a.pb.pix_to_face) && aligned16(grad_dists) && aligned16(grad_zbuf) &&
-                 (a.pb.face_colors || aligned16(grad_colors));
+    if ((uintptr_t)worklist & 15) return PERT_E_ALIGN;
+    const bool sparse = sparse_first_ok(&a.pb, worklist, smp && fin && !hist);
+    const bool ptr_ok = aligned16(a.pb.pix_to_face) && aligned16(grad_dists) && aligned16(grad_zbuf) &&
+                        (a.pb.face_colors || aligned16(grad_colors));
+    a.L = make_launch(&a.pb, pick_tp(a.pb.K));
+    a.L.vec_ok = a.L.vec_ok && ptr_ok;
+    if (sparse) a.L.cap = a.L.cap / 2;
     if (a.L.win_bytes == 2 && ((uintptr_t)winners & 1)) return PERT_E_ALIGN;
-    a.L.warp_smem = (int)bwd_warp_smem(a.L.tp, a.pb.K, a.L.sc, a.L.nchunks, a.L.win_bytes);
+    bwd_smem_layout(a.L.tp, a.pb.K, a.L.cap, a.L.sc, a.L.nchunks, a.L.win_bytes, sparse, a.L.sm);
+    a.L.warp_smem = a.L.sm.bytes;
     if ((size_t)a.L.warp_smem > 200 * 1024) return PERT_E_UNSUPPORTED;
     if (a.L.ntiles > 0x7fffffff) return PERT_E_UNSUPPORTED;
     a.grad_image = grad_image;
@@ -174,7 +213,17 @@ extern "C" int pert_shade_bwd(const pert_problem* pb_in, const float* grad_image
     a.acc = acc;
     a.pixstat = pixstat;
     a.hist = hist;
-    return cuda_rc(launch_shade_bwd(a, grad_scalars, (cudaStream_t)stream));
+    a.worklist = worklist;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!sparse) return cuda_rc(launch_shade_bwd(a, nullptr, grad_scalars, st));
+    BwdArgs fb = a;  // fallback pass: half-size tiles, full capacity, dense per-logit arrays
+    fb.L = make_launch(&a.pb, a.L.tp / 2);
+    fb.L.vec_ok = fb.L.vec_ok && ptr_ok;
+    bwd_smem_layout(fb.L.tp, a.pb.K, fb.L.cap, fb.L.sc, fb.L.nchunks, fb.L.win_bytes, false, fb.L.sm);
+    fb.L.warp_smem = fb.L.sm.bytes;
+    cudaError_t e = cudaMemsetAsync(worklist, 0, 16, st);
+    if (e != cudaSuccess) return cuda_fail((int)e);
+    return cuda_rc(launch_shade_bwd(a, &fb, grad_scalars, st));
 }
 
 extern "C" int pert_rast_fwd(const float* x, int64_t P, int32_t K, int32_t S, int32_t s_begin, int32_t s_end,

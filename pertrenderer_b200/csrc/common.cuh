@@ -110,18 +110,34 @@ __device__ __forceinline__ void list_append(bool flag, uint16_t item, uint16_t* 
     if (flag) list[base + __popc(b & ((1u << lane) - 1u))] = item;
 }
 
-struct Carver {
-    unsigned char* base;
-    unsigned off;
-    __device__ explicit Carver(unsigned char* b) : base(b), off(0) {}
-    template <typename T>
-    __device__ T* take(int n) {
-        T* r = reinterpret_cast<T*>(base + off);
-        off += ((unsigned)n * (unsigned)sizeof(T) + 15u) & ~15u;
-        return r;
+// Shared-memory layout of a kernel: computed ONCE on the host (byte offsets in the launch record), so the
+// kernels spend one add per array instead of re-deriving the layout (the fused kernels are instruction-fetch
+// sensitive: every instruction of glue counts).
+static inline size_t carve(size_t n, size_t sz) { return ((n * sz) + 15) & ~(size_t)15; }
+constexpr int MAX_SMEM_ARRAYS = 20;
+struct SmemLayout {
+    int off[MAX_SMEM_ARRAYS];
+    int n;
+    int bytes;
+};
+struct Carver {  // host side
+    SmemLayout& L;
+    explicit Carver(SmemLayout& l) : L(l) { L.n = 0; L.bytes = 0; }
+    void take(size_t count, size_t elem) {
+        L.off[L.n++] = L.bytes;
+        L.bytes += (int)((count * elem + 15) & ~(size_t)15);
     }
 };
-static inline size_t carve(size_t n, size_t sz) { return ((n * sz) + 15) & ~(size_t)15; }
+struct Taker {  // device side
+    unsigned char* base;
+    const SmemLayout& L;
+    int i;
+    __device__ Taker(unsigned char* b, const SmemLayout& l) : base(b), L(l), i(0) {}
+    template <typename T>
+    __device__ __forceinline__ T* take() {
+        return reinterpret_cast<T*>(base + L.off[i++]);
+    }
+};
 
 __device__ __forceinline__ void store_winner(void* winners, int win_bytes, int64_t idx, int v) {
     if (win_bytes == 1) reinterpret_cast<uint8_t*>(winners)[idx] = (uint8_t)v;
@@ -149,9 +165,14 @@ struct Launch {
     int lpe_r, lpe_r_shift;  // coverage sampling: lanes per entry = min(32, pow2_ceil(local quads))
     int lpe_a, lpe_a_shift;  // argmax sampling: lanes per pixel = min(32, pow2_ceil(local quads))
     int lpp, lpp_shift;      // backward: lanes per (pixel, logit) pair = min(8, pow2_floor(local quads))
+    int cap;        // capacity (valid entries) of the tile's compact arrays: tp*K, or tp*K/2 in sparse-first mode
     int warp_smem;  // bytes of shared memory per warp
+    SmemLayout sm;  // where each array lives
     int vec_ok;     // tile rows are 16-byte aligned in every (P,K) tensor
     float invK;     // 1/K for the entry -> pixel division
+    // launch constants computed once on the host (IEEE fp32, the same values the kernels used to derive)
+    float gal;      // gamma / alpha (smoothagg.py:201)
+    float inv_sigma, invSg, inv_sr, invS;  // 1/sigma, 1/(S_agg gamma), 1/(S_rast sigma), 1/S_agg
 };
 
 // 16-byte asynchronous global -> shared copy (LDGSTS) and its completion wait
@@ -161,6 +182,46 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
+// Out-of-line helpers for rarely taken or bulky paths (code size, see SmemLayout)
+static __device__ __noinline__ float logf_exact(float x) { return logf(x); }
+static __device__ __noinline__ int lower_bound_u16(const uint16_t* v, int lo, int hi, int target) {
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if ((int)v[mid] < target) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+// zero n floats (one warp); 128-bit stores when the run is 16-byte aligned and a multiple of 4 floats
+static __device__ __noinline__ void zero_fill(float* dst, int n, bool vec_ok) {
+    const int lane = threadIdx.x & 31;
+    if (vec_ok && (n & 3) == 0) {
+        float4* d4 = reinterpret_cast<float4*>(dst);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int i = lane; i < (n >> 2); i += 32) d4[i] = z;
+    } else {
+#pragma unroll 1
+        for (int i = lane; i < n; i += 32) dst[i] = 0.f;
+    }
+}
+
+// floor(log2(32 / n)) for 1 <= n: lanes per item that keep a warp full (no integer division)
+__device__ __forceinline__ int fill_shift(int n) { return n >= 32 ? 0 : (n <= 1 ? 5 : 5 - (32 - __clz(n - 1))); }
+
+// batch element of pixel gp: pixels of a tile span at most two images, so one 32-bit division per tile
+__device__ __forceinline__ int batch_of(int64_t pix0, int p, int64_t HW) {
+    const unsigned hw = (unsigned)HW;
+    const unsigned b0 = (unsigned)pix0 / hw;  // P < 2^31 (checked by the C ABI)
+    unsigned r = (unsigned)pix0 - b0 * hw + (unsigned)p;
+    unsigned b = b0;
+    while (r >= hw) {  // tiny images: a tile may cover several
+        r -= hw;
+        b++;
+    }
+    return (int)b;
+}
 
 // entry index within a tile -> pixel of the tile.  Exact for e < 2^16, K < 2^10: (e + .5)/K is at
 // least .5/K away from an integer, far more than the fp32 rounding of the product.

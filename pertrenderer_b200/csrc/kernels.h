@@ -13,6 +13,7 @@ struct FwdArgs {
     void* winners;
     uint16_t* pixstate;
     int32_t* hist;
+    int32_t* worklist;  // [0] = number of tiles handed to the fallback pass, [4..] = their indices
 };
 
 struct BwdArgs {
@@ -30,14 +31,16 @@ struct BwdArgs {
     float* acc;
     float* pixstat;
     const int32_t* hist;
+    int32_t* worklist;
 };
 
-size_t fwd_warp_smem(int tp, int K);
-size_t bwd_warp_smem(int tp, int K, int sc, int nchunks, int win_bytes);
+void fwd_smem_layout(int tp, int cap, SmemLayout& L);
+void bwd_smem_layout(int tp, int K, int cap, int sc, int nchunks, int win_bytes, bool compact, SmemLayout& L);
 
 // return a cudaError_t as int (0 = success)
-int launch_shade_fwd(const FwdArgs& a, cudaStream_t st);
-int launch_shade_bwd(const BwdArgs& a, float* grad_scalars, cudaStream_t st);
+// `fb` (optional): launch record of the fallback pass of the sparse-first mode (half-size tiles)
+int launch_shade_fwd(const FwdArgs& a, const FwdArgs* fb, cudaStream_t st);
+int launch_shade_bwd(const BwdArgs& a, const BwdArgs* fb, float* grad_scalars, cudaStream_t st);
 
 int launch_rast_fwd(const float* x, int64_t P, int K, int S, int s_begin, int s_end, float sigma, uint64_t seed,
                     int64_t pixel_offset, const float* noise, uint32_t flags, float* prob, float* rsum, cudaStream_t st);

@@ -7,6 +7,19 @@
 
 namespace pert {
 
+namespace {
+struct DevCarver {  // carve dynamic shared memory into 16-byte aligned arrays
+    unsigned char* p;
+    __device__ explicit DevCarver(unsigned char* base) : p(base) {}
+    template <typename T>
+    __device__ T* take(int n) {
+        T* r = reinterpret_cast<T*>(p);
+        p += (((size_t)n * sizeof(T)) + 15) & ~(size_t)15;
+        return r;
+    }
+};
+}  // namespace
+
 // mode 1: out[0] = sum of column 0 only (stand-alone ops)
 __global__ void __launch_bounds__(256) finalize_single_kernel(const float* partials, int64_t n, float* out) {
     __shared__ double red[256];
@@ -139,7 +152,7 @@ __global__ void __launch_bounds__(NT) argmax_fwd_kernel(const float* z, int64_t 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t pixel = (int64_t)blockIdx.x * NW + warp;
     if (pixel >= P) return;
-    Carver cv(smem_raw);
+    DevCarver cv(smem_raw);
     float* zt = cv.take<float>(NW * K1) + warp * K1;
     int* hist = cv.take<int>(NW * K1) + warp * K1;
     uint16_t* live = cv.take<uint16_t>(NW * K1) + warp * K1;
@@ -207,7 +220,7 @@ __global__ void __launch_bounds__(NT) argmax_bwd_kernel(const float* grad_l, con
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t pixel = (int64_t)blockIdx.x * NW + warp;
     __shared__ float red[NW];
-    Carver cv(smem_raw);
+    DevCarver cv(smem_raw);
     float* gl = cv.take<float>(NW * K1) + warp * K1;
     float* cs = cv.take<float>(NW * 128) + warp * 128;  // chunk of 128 samples
     float p_gamma = 0.f;

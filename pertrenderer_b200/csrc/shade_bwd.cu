@@ -20,39 +20,44 @@
 
 namespace pert {
 
-size_t bwd_warp_smem(int tp, int K, int sc, int nchunks, int win_bytes) {
-    const size_t E = (size_t)tp * K, E1 = (size_t)tp * (K + 1);
-    return carve(E, 2) /*vlist*/ + carve(E, 4) /*zs*/ + carve(E, 2) /*cnt*/ + carve(E1, 4) * (nchunks > 1 ? 4 : 3)
-           /*hj gsel accs [t2s]*/ + carve(E1, 2) /*pair_j*/ + carve(E1, 1) /*pair_p*/ + carve((size_t)tp * sc, 4) /*cs*/ +
-           carve(tp + 1, 4) /*vstart*/ + carve(tp, 4) * 2 /*pa0, pg0*/ + carve(tp, 1) /*apx*/ +
-           (nchunks == 1 ? carve((size_t)tp * sc, win_bytes) : 0) /*wst*/ + 16;
-}
-
-__device__ __forceinline__ void zero_fill(float* dst, int n, bool vec_ok) {
-    const int lane = threadIdx.x & 31;
-    if (vec_ok && (n & 3) == 0) {
-        float4* d4 = reinterpret_cast<float4*>(dst);
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-        for (int i = lane; i < (n >> 2); i += 32) d4[i] = z;
-    } else {
-#pragma unroll 1
-        for (int i = lane; i < n; i += 32) dst[i] = 0.f;
-    }
+void bwd_smem_layout(int tp, int K, int cap, int sc, int nchunks, int win_bytes, bool compact, SmemLayout& L) {
+    const size_t ns = compact ? (size_t)cap + 2 * tp : (size_t)tp * (K + 1);
+    Carver cv(L);
+    cv.take(cap, 2);  // vlist
+    cv.take(cap, 4);  // zs
+    cv.take(cap, 2);  // cnt
+    cv.take(ns, 4);   // hj
+    cv.take(ns, 4);   // gsel (| t2s when there is one sample chunk)
+    cv.take(ns, 4);   // accs
+    cv.take(nchunks > 1 ? ns : 0, 4);  // t2s
+    cv.take(ns, 2);   // pair_j
+    cv.take(ns, 2);   // pair_s
+    cv.take(ns, 1);   // pair_p
+    cv.take((size_t)tp * sc, 4);  // cs
+    cv.take(tp + 1, 4);           // vstart
+    cv.take(tp, 4);               // pa0
+    cv.take(tp, 4);               // pg0
+    cv.take(tp, 4);               // psb
+    cv.take(tp, 4);               // pnv
+    cv.take(tp, 1);               // apx
+    cv.take(nchunks == 1 ? (size_t)tp * sc * win_bytes : 0, 1);  // wst
 }
 
 // GT = lanes per pixel as a compile-time constant (1, 2, 4, 8), or 0 to read it from the launch record.
 // PHASED = false is the production instantiation: both phases in one launch, histogram rebuilt from the
 // saved winners (the phase-split code of the sample-sharded job is compiled out to keep the hot code small).
 // FACE = true: colours gathered through pix_to_face from pb.face_colors, grad scattered by atomics
-template <class NoiseA, int GT, bool PHASED, bool FACE>
-__global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const NoiseA noise_a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+// COMPACT = true (sparse-first mode): the per-logit arrays are indexed by the position of the logit
+// among the pixel's valid entries (plus a background and a masked-logits slot) instead of densely by j,
+// and every array holds a.L.cap valid entries; tiles with more go to the fallback pass.
+template <class NoiseA, int GT, bool PHASED, bool FACE, bool COMPACT>
+__device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& noise_a, const int64_t tile,
+                                               const int64_t prow /* row of the scalar partials */,
+                                               unsigned char* smem_raw) {
     const pert_problem& pb = a.pb;
     const int lane = threadIdx.x;
-    const int64_t tile = blockIdx.x;
     const int G = GT ? GT : a.L.G;
-    const int gshift = GT ? (GT == 8 ? 3 : GT == 4 ? 2 : GT == 2 ? 1 : 0) : a.L.gshift;
+    const int gshift = GT ? (GT == 16 ? 4 : GT == 8 ? 3 : GT == 4 ? 2 : GT == 2 ? 1 : 0) : a.L.gshift;
     const int K = pb.K, K1 = K + 1, tp = 32 >> gshift, sc = a.L.sc;
     const uint32_t flags = pb.flags;
     const bool do_sample = !PHASED || (flags & PERT_PH_BWD_SAMPLE), do_finish = !PHASED || (flags & PERT_PH_BWD_FINISH);
@@ -74,26 +79,33 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
     const int sa_loc = a.L.sa_loc;
     const int wb = a.L.win_bytes;
 
-    Carver cv(smem_raw);
-    uint16_t* vlist = cv.take<uint16_t>(tp * K);
-    float* zs = cv.take<float>(tp * K);
-    uint16_t* cnt = cv.take<uint16_t>(tp * K);
-    int* hj = cv.take<int>(tp * K1);        // winner histogram, dense in j (active pixels)
-    float* gsel = cv.take<float>(tp * K1);  // g_j = <G_rgb, colour_j> of the logits that can win
-    float* accs = cv.take<float>(tp * K1);  // sum_s c_s V_sj
+    Taker cv(smem_raw, a.L.sm);  // layout: bwd_smem_layout
+    const int cap = a.L.cap;
+    uint16_t* vlist = cv.take<uint16_t>();
+    float* zs = cv.take<float>();
+    uint16_t* cnt = cv.take<uint16_t>();
+    // per-logit arrays.  Slot of logit j of pixel p: dense p*K1 + j, or (COMPACT) vstart[p] + 2p + idx with
+    // idx = position among the pixel's valid entries, nvp = background, nvp + 1 = all masked logits together
+    int* hj = cv.take<int>();        // winner histogram (active pixels)
+    float* gsel = cv.take<float>();  // g_j = <G_rgb, colour_j> of the logits that can win
+    float* accs = cv.take<float>();  // sum_s c_s V_sj
     // sum_s c_s V_sj^2: g_j is dead once the c_s of the (only) chunk are staged, so it reuses that array
-    float* t2s = a.L.nchunks > 1 ? cv.take<float>(tp * K1) : gsel;
-    uint16_t* pair_j = cv.take<uint16_t>(tp * K1);
-    uint8_t* pair_p = cv.take<uint8_t>(tp * K1);
-    float* cs = cv.take<float>(tp * sc);  // c_s of the current sample chunk, per active pixel
-    int* vstart = cv.take<int>(tp + 1);
-    int* pa0 = cv.take<int>(tp);
-    float* pg0 = cv.take<float>(tp);
-    uint8_t* apx = cv.take<uint8_t>(tp);
+    float* t2s_own = cv.take<float>();
+    float* t2s = a.L.nchunks > 1 ? t2s_own : gsel;
+    uint16_t* pair_j = cv.take<uint16_t>();
+    uint16_t* pair_s = cv.take<uint16_t>();
+    uint8_t* pair_p = cv.take<uint8_t>();
+    float* cs = cv.take<float>();  // c_s of the current sample chunk, per active pixel
+    int* vstart = cv.take<int>();
+    int* pa0 = cv.take<int>();
+    float* pg0 = cv.take<float>();
+    int* psb = cv.take<int>();  // slot base of every pixel
+    int* pnv = cv.take<int>();  // number of valid entries | 0x10000 if they are NOT a prefix 0..nvp-1 of K
+    uint8_t* apx = cv.take<uint8_t>();
     // single-chunk jobs: the tile's saved winners (tp rows of sa_loc entries, contiguous) are copied to
     // shared memory asynchronously at the very start, off the critical path
     const bool early_w = a.L.nchunks == 1 && ((sa_loc * wb) & 15) == 0 && do_sample;
-    unsigned char* wst = a.L.nchunks == 1 ? cv.take<unsigned char>(tp * sc * wb) : nullptr;
+    unsigned char* wst = cv.take<unsigned char>();
     if (early_w) {
         const unsigned char* src = reinterpret_cast<const unsigned char*>(a.winners) + pix0 * sa_loc * wb;
         const int nbytes = npx * sa_loc * wb;
@@ -108,7 +120,7 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
     int pstate = K;
     if (pvalid) {
         Gi = __ldg(reinterpret_cast<const float4*>(a.grad_image) + gp);
-        const int b = pb.depth_len > 1 ? (int)(gp / a.L.HW) : 0;
+        const int b = pb.depth_len > 1 ? batch_of(pix0, p, a.L.HW) : 0;
         zn = __ldg(pb.znear + b);
         zf = __ldg(pb.zfar + b);
         pstate = a.pixstate[gp];
@@ -124,8 +136,11 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
             a.pixstat[(pix0 + lane) * 2 + 1] = 0.f;
         }
     }
-    const int nv = scan_valid(pb.pix_to_face + g0, E, a.L.vec_ok, vlist);
-    if (nv > 0) {
+    const int nv = scan_valid(pb.pix_to_face + g0, E, a.L.vec_ok, vlist, cap);
+    if (COMPACT && nv > cap) {
+        // more valid entries than the compact arrays hold: the fallback pass redoes this tile
+        if (lane == 0) a.worklist[4 + atomicAdd(a.worklist, 1)] = (int32_t)tile;
+    } else if (nv > 0) {
         __syncwarp();
         pixel_ranges(vlist, nv, K, tp, vstart);
         {
@@ -146,7 +161,7 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
         __syncwarp();
 
         // ---- phase 1 -------------------------------------------------------------------------------
-        const float gal = pb.gamma / pb.alpha;
+        const float gal = a.L.gal;
         const PixPrep pi = prep_pixels(p, lig, G, pvalid, K, vstart, vlist, cnt, zs, zn, zf, pb.S_rast, gal, pb.eps);
         const int vs = pvalid ? vstart[p] : 0, ve = pvalid ? vstart[p + 1] : 0;
         const int nvp = ve - vs;
@@ -154,6 +169,18 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
         // a pixel whose samples all picked a0 has c_s = 0 for every s: every score sum is exactly 0
         // (and forward wrote no winners row for it)
         const bool act = pvalid && do_sample && (pstate & 0x8000);
+        const int sb = COMPACT ? vs + 2 * p : p * K1;                  // this pixel's slots
+        const int slot_pad = COMPACT ? sb + nvp + 1 : sb + pi.kpad;     // where the masked logits' joint draw goes
+        const bool prefix = pi.kpad == nvp;                             // valid entries are k = 0..nvp-1
+        // slot of logit j of pixel pp (j = a saved winner or a0: a valid entry or the background)
+        auto slot_of = [&](int pp, int j) -> int {
+            if (!COMPACT) return pp * K1 + j;
+            const int base = psb[pp], info = pnv[pp], n = info & 0xffff;
+            if (j == K) return base + n;
+            if (!(info & 0x10000)) return base + j;
+            const int lo = vstart[pp];  // holes in the mask: find the entry
+            return base + lower_bound_u16(vlist, lo, lo + n, pp * K + j) - lo;
+        };
         const float floor_v = pi.zeta_max - live_cut(pb.gamma, pi.zeta_max, NoiseA::kBounded && !no_skip);
         float t2sum = 0.f, csum = 0.f;
         const float* gacc = a.acc + gp * K1;  // FINISH-only: sums over all sample shards
@@ -174,15 +201,18 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                 if (act && lig == 0) {
                     apx[my_ai] = (uint8_t)p;
                     pa0[p] = a0;
+                    psb[p] = sb;
+                    pnv[p] = nvp | (prefix ? 0 : 0x10000);
                 }
                 if (act) {
+                    const int ns = COMPACT ? nvp + 2 : K1;
 #pragma unroll 1
-                    for (int j = lig; j < K1; j += G) {
-                        hj[p * K1 + j] = 0;
-                        accs[p * K1 + j] = 0.f;
+                    for (int j = lig; j < ns; j += G) {
+                        hj[sb + j] = 0;
+                        accs[sb + j] = 0.f;
                     }
                 }
-                const int span = per_sample ? max(K1, nvp + 1) : nvp + 1;
+                const int span = (!COMPACT && per_sample) ? max(K1, nvp + 1) : nvp + 1;
                 const int iters = warp_max_i(act ? (span + G - 1) / G : 0);
 #pragma unroll 1
                 for (int it = 0; it < iters; ++it) {
@@ -201,12 +231,12 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                             } else {
                                 gj = Gi.x * pb.background[0] + Gi.y * pb.background[1] + Gi.z * pb.background[2];
                             }
-                            gsel[p * K1 + j] = gj;
+                            gsel[COMPACT ? sb + idx : sb + j] = gj;
                             if (j == a0) pg0[p] = gj;
                         }
                         want = live && !per_sample;
                     }
-                    if (per_sample && act && idx < K1) {  // every logit, dense in j
+                    if (!COMPACT && per_sample && act && idx < K1) {  // every logit, dense in j
                         j = idx;
                         want = true;
                     }
@@ -214,6 +244,7 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                     if (want) {
                         const int pos = np2 + __popc(wbal & lt);
                         pair_j[pos] = (uint16_t)j;
+                        pair_s[pos] = (uint16_t)(COMPACT ? sb + idx : sb + j);
                         pair_p[pos] = (uint8_t)my_ai;
                     }
                     np2 += __popc(wbal);
@@ -229,7 +260,7 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                 __syncwarp();
             }
             // lanes per pair: as many as keep the warp full, at most a.L.lpp
-            const int lpp_shift = np2 == 0 ? 0 : min(a.L.lpp_shift, np2 >= 32 ? 0 : 31 - __clz(32 / np2));
+            const int lpp_shift = np2 == 0 ? 0 : min(a.L.lpp_shift, fill_shift(np2));
             const int LPP = 1 << lpp_shift;
             const int lq = lane & (LPP - 1);
             float C2 = 0.f;
@@ -240,8 +271,6 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
 #pragma unroll 1
                 for (int ai = 0; ai < na; ++ai) {
                     const int pp = apx[ai];
-                    const float* gs = gsel + pp * K1;
-                    int* hp = hj + pp * K1;
                     const float g0v = pg0[pp];
                     const int ppa0 = pa0[pp];
                     const int64_t wbase = (pix0 + pp) * sa_loc + c0;
@@ -251,8 +280,9 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                         if (s < cn) {
                             const int w = early_w ? load_winner(wst, wb, pp * sa_loc + s) : load_winner(a.winners, wb, wbase + s);
                             if (w != ppa0) {  // a0 (the most frequent by far) is counted as the remainder
-                                atomicAdd(&hp[w], 1);
-                                c = gs[w] - g0v;
+                                const int ws = slot_of(pp, w);
+                                atomicAdd(&hj[ws], 1);
+                                c = gsel[ws] - g0v;
                             }
                         }
                         cs[ai * sc + s] = c;
@@ -270,10 +300,11 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
 #pragma unroll 1
                         for (int idx = lig; idx <= nvp; idx += G) {
                             const int j = idx < nvp ? (int)vlist[vs + idx] - p * K : K;
-                            const int h = hj[p * K1 + j];
+                            const int sl = COMPACT ? sb + idx : sb + j;
+                            const int h = hj[sl];
                             if (h > 0 && j != a0) {
                                 others += h;
-                                const float d = gsel[p * K1 + j] - g0v;
+                                const float d = gsel[sl] - g0v;
                                 c1 += (float)h * d;
                                 c2 += (float)h * d * d;
                             }
@@ -282,7 +313,7 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                     others = group_sum_i(others, G);
                     csum = group_sum(c1, G);
                     C2 = group_sum(c2, G);
-                    if (act && lig == 0) hj[p * K1 + a0] = sa_loc - others;
+                    if (act && lig == 0) hj[slot_of(p, a0)] = sa_loc - others;
                     __syncwarp();
                 }
                 const int nqc = cn4 >> 2;
@@ -292,6 +323,7 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                     const int pr = it >> lpp_shift;
                     const bool on = pr < np2;
                     const int j = on ? pair_j[pr] : 0;
+                    const int ps = on ? pair_s[pr] : 0;
                     const int ai = on ? pair_p[pr] : 0;
                     const int pp = apx[ai];
                     float acc = 0.f, t2 = 0.f;
@@ -315,11 +347,11 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                     }
                     if (on && lq == 0) {
                         if (c0 == 0) {
-                            accs[pp * K1 + j] = acc;
-                            t2s[pp * K1 + j] = t2;
+                            accs[ps] = acc;
+                            t2s[ps] = t2;
                         } else {
-                            accs[pp * K1 + j] += acc;
-                            t2s[pp * K1 + j] += t2;
+                            accs[ps] += acc;
+                            t2s[ps] += t2;
                         }
                     }
                 }
@@ -330,7 +362,7 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
             //      sum_s c_s V_sj is N(0, sum_s c_s^2) exactly: ONE draw per logit instead of S_agg -------------
             {
                 float t = 0.f;
-                if (per_sample) {
+                if (!COMPACT && per_sample) {
                     if (act) {
 #pragma unroll 1
                         for (int j = lig; j < K1; j += G) t += t2s[p * K1 + j];
@@ -338,21 +370,22 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                     t2sum = group_sum(t, G);
                 } else {
                     int nlive = 0;
-                    const float sC2 = sqrtf(C2);
+                    const float sC2 = mufu_sqrt(C2);
                     const uint32_t qx = 0xC0000000u + (uint32_t)qb;  // counters no sample quad uses
                     if (act) {
 #pragma unroll 1
                         for (int idx = lig; idx <= nvp; idx += G) {
                             const int j = idx < nvp ? (int)vlist[vs + idx] - p * K : K;
                             const float z = idx < nvp ? zs[vs + idx] : pi.zbg;
+                            const int sl = COMPACT ? sb + idx : sb + j;
                             if (z > -CUDART_INF_F && z >= floor_v) {
                                 nlive++;
-                                t += t2s[p * K1 + j];
+                                t += t2s[sl];
                             } else if (!drop_dead) {
                                 if constexpr (NoiseA::kBounded) {
                                     float nz[4];
                                     noise_a.get4(qx, j, gp, nz);
-                                    accs[p * K1 + j] = sC2 * nz[0];
+                                    accs[sl] = sC2 * nz[0];
                                 }
                             }
                         }
@@ -366,9 +399,9 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                         if constexpr (NoiseA::kBounded) {
                             if (!drop_dead) noise_a.get4(qx, K1, gp, nz);
                         }
-                        if (lig == 0 && pi.kpad < K) accs[p * K1 + pi.kpad] = sqrtf((float)npad * C2) * nz[0];
+                        if (lig == 0 && pi.kpad < K) accs[slot_pad] = mufu_sqrt((float)npad * C2) * nz[0];
                         // sum_j sum_s c_s V_sj^2 over those logits: mean n*csum, variance 2 n sum_s c_s^2
-                        t2sum += (float)n_nl * csum + sqrtf(2.0f * (float)n_nl * C2) * nz[1];
+                        t2sum += (float)n_nl * csum + mufu_sqrt(2.0f * (float)n_nl * C2) * nz[1];
                     }
                 }
             }
@@ -387,9 +420,7 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
             }
         } else {
             // ---- phase 4: chain rule per pixel ----------------------------------
-            const float invSg = 1.0f / ((float)pb.S_agg * pb.gamma);
-            const float inv_sr = 1.0f / ((float)pb.S_rast * pb.sigma);
-            const float invS = 1.0f / (float)pb.S_agg;
+            const float invSg = a.L.invSg, inv_sr = a.L.inv_sr, invS = a.L.invS;
             const bool from_global = PHASED && !do_sample;
             const bool has_acc = act || (from_global && pvalid);
             if (from_global && pvalid) {
@@ -402,23 +433,23 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                 if (from_global) {
 #pragma unroll 1
                     for (int j = lig; j < K1; j += G) sg += gacc[j] * invSg;
-                } else if (per_sample) {
+                } else if (!COMPACT && per_sample) {
 #pragma unroll 1
                     for (int j = lig; j < K1; j += G) sg += accs[p * K1 + j] * invSg;
                 } else {
 #pragma unroll 1
                     for (int idx = lig; idx <= nvp; idx += G) {
                         const int j = idx < nvp ? (int)vlist[vs + idx] - p * K : K;
-                        sg += accs[p * K1 + j] * invSg;
+                        sg += accs[COMPACT ? sb + idx : sb + j] * invSg;
                     }
-                    if (lig == 0 && pi.kpad < K) sg += accs[p * K1 + pi.kpad] * invSg;
+                    if (lig == 0 && pi.kpad < K) sg += accs[slot_pad] * invSg;
                 }
             }
             const float gzmax = -group_sum(sg, G);
             if (has_acc && lig == 0) p_gamma += (t2sum - csum) * invSg;
-            const float denom = zf - zn;
+            const float rdenom = __fdividef(1.0f, zf - zn);
             const bool pass = pi.zimax >= pb.eps;
-            const float fS = (float)pb.S_rast;
+            const float rS = __fdividef(1.0f, (float)pb.S_rast);
             const float* const rsum_t = a.rsum + g0;
             float* const gd_t = a.grad_dists + g0;
             float* const gz_t = a.grad_zbuf + g0;
@@ -430,20 +461,21 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                 const int k = e - p * K;
                 const float rsn = rsum_t[e];
                 float gz = 0.f;
-                if (has_acc) gz = (from_global ? gacc[k] : accs[p * K1 + k]) * invSg;
+                const int sl = COMPACT ? sb + (n - vs) : sb + k;
+                if (has_acc) gz = (from_global ? gacc[k] : accs[sl]) * invSg;
                 const float gzi = gz + ((k == pi.argzi && pass) ? gzmax : 0.f);
-                gz_t[e] = -gzi / denom;
+                gz_t[e] = -gzi * rdenom;
                 const int c = cnt[n];
-                const float pk = (float)c / fS;
+                const float pk = (float)c * rS;
                 float gP = 0.f;
                 if (c != 0) {
-                    const float lp = (c == pb.S_rast) ? 0.0f : logf(pk);
+                    const float lp = (c == pb.S_rast) ? 0.0f : logf_exact(pk);
                     p_q += lp * gz;        // prod_corrected: inf -> 0 on the scalar side
-                    gP = (gal * gz) / pk;  // log_corrected: 1/0 -> 0
+                    gP = __fdividef(gal * gz, pk);  // log_corrected: 1/0 -> 0
                 }
                 const float om = 1.0f - pk;
                 float excl;
-                if (pi.nzero == 0) excl = pi.prod_nz / om;
+                if (pi.nzero == 0) excl = __fdividef(pi.prod_nz, om);
                 else if (pi.nzero == 1) excl = (om == 0.f) ? pi.prod_nz : 0.f;
                 else excl = 0.f;
                 gP += Gi.w * excl;
@@ -454,7 +486,7 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
                 if (gc_t || gfc) {
                     int h;
                     if (ghist) h = ghist[gp * K1 + k];  // all-shard histogram when sample-sharded
-                    else if (act) h = hj[p * K1 + k];
+                    else if (act) h = hj[sl];
                     else h = (k == a0) ? sa_loc : 0;
                     if (h > 0) {
                         const float w = (float)h * invS;
@@ -480,7 +512,35 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
         p_sigma = warp_sum(p_sigma);
         p_gamma = warp_sum(p_gamma);
         p_q = warp_sum(p_q);
-        if (lane == 0) reinterpret_cast<float4*>(a.partials)[tile] = make_float4(p_sigma, p_gamma, p_q, 0.f);
+        if (lane == 0) reinterpret_cast<float4*>(a.partials)[prow] = make_float4(p_sigma, p_gamma, p_q, 0.f);
+    }
+}
+
+template <class NoiseA, int GT, bool PHASED, bool FACE, bool COMPACT>
+__global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const NoiseA noise_a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    shade_bwd_tile<NoiseA, GT, PHASED, FACE, COMPACT>(a, noise_a, blockIdx.x, blockIdx.x, smem_raw);
+}
+
+// Fallback pass of the sparse-first mode (see shade_fwd.cu): work-list tiles as half-size tiles with dense
+// per-logit arrays; their scalar partials go to the rows after the main pass's.
+template <class NoiseA, int GT, bool FACE>
+__global__ void __launch_bounds__(FNT) shade_bwd_fallback_kernel(const BwdArgs a, const NoiseA noise_a, int64_t prow0) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = 2 * a.worklist[0];
+#pragma unroll 1
+    for (;;) {  // persistent warps fetch half-tiles dynamically
+        int i = 0;
+        if (threadIdx.x == 0) i = n > 0 ? atomicAdd(a.worklist + 1, 1) : 0;
+        i = __shfl_sync(FULL, i, 0);
+        if (i >= n) break;
+        const int64_t tile = (int64_t)a.worklist[4 + (i >> 1)] * 2 + (i & 1);
+        if (tile < a.L.ntiles) {
+            shade_bwd_tile<NoiseA, GT, false, FACE, false>(a, noise_a, tile, prow0 + i, smem_raw);
+        } else if (threadIdx.x == 0) {
+            reinterpret_cast<float4*>(a.partials)[prow0 + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncwarp();
     }
 }
 
@@ -488,9 +548,10 @@ __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const N
 //   out[0] = d/dsigma = sum gx                         (smoothrast.py:57-58)
 //   out[1] = d/dgamma = score term + q/alpha           (smoothagg.py:72 and :329-332 through gamma/alpha)
 //   out[2] = d/dalpha = -q gamma / alpha^2
-__global__ void __launch_bounds__(1024) finalize_scalars_kernel(const float* partials, int64_t n, float gamma,
-                                                                float alpha, float* out) {
+__global__ void __launch_bounds__(1024) finalize_scalars_kernel(const float* partials, int64_t n, const int32_t* worklist,
+                                                                float gamma, float alpha, float* out) {
     __shared__ double red[3][32];
+    if (worklist) n += 2 * (int64_t)worklist[0];  // rows of the fallback pass
     double s0 = 0, s1 = 0, s2 = 0;
     for (int64_t t = threadIdx.x; t < n; t += 1024) {
         const float4 v = reinterpret_cast<const float4*>(partials)[t];
@@ -523,23 +584,39 @@ __global__ void __launch_bounds__(1024) finalize_scalars_kernel(const float* par
     }
 }
 
-template <class NA, int GT, bool PHASED, bool FACE>
+template <class K>
+static int set_smem(K kern, size_t smem) {
+    if (smem > 48 * 1024) return (int)cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return 0;
+}
+
+template <class NA, int GT, bool PHASED, bool FACE, bool COMPACT>
 static int launch_bwd_f(const BwdArgs& a, const NA& na, cudaStream_t st) {
     const size_t smem = (size_t)a.L.warp_smem;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(shade_bwd_kernel<NA, GT, PHASED, FACE>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-    }
-    shade_bwd_kernel<NA, GT, PHASED, FACE><<<(unsigned)a.L.ntiles, FNT, smem, st>>>(a, na);
+    if (int rc = set_smem(shade_bwd_kernel<NA, GT, PHASED, FACE, COMPACT>, smem)) return rc;
+    shade_bwd_kernel<NA, GT, PHASED, FACE, COMPACT><<<(unsigned)a.L.ntiles, FNT, smem, st>>>(a, na);
     return (int)cudaGetLastError();
 }
 template <class NA, int GT, bool PHASED>
 static int launch_bwd_t(const BwdArgs& a, const NA& na, cudaStream_t st) {
-    return a.pb.face_colors ? launch_bwd_f<NA, GT, PHASED, true>(a, na, st) : launch_bwd_f<NA, GT, PHASED, false>(a, na, st);
+    return a.pb.face_colors ? launch_bwd_f<NA, GT, PHASED, true, false>(a, na, st)
+                            : launch_bwd_f<NA, GT, PHASED, false, false>(a, na, st);
+}
+// sparse-first main pass (compact per-logit arrays)
+template <int GT>
+static int launch_bwd_c(const BwdArgs& a, const PhiloxNoise& na, cudaStream_t st) {
+    return a.pb.face_colors ? launch_bwd_f<PhiloxNoise, GT, false, true, true>(a, na, st)
+                            : launch_bwd_f<PhiloxNoise, GT, false, false, true>(a, na, st);
+}
+template <int GT, bool FACE>
+static int launch_bwd_fb(const BwdArgs& a, const PhiloxNoise& na, int64_t prow0, cudaStream_t st) {
+    const size_t smem = (size_t)a.L.warp_smem;
+    if (int rc = set_smem(shade_bwd_fallback_kernel<PhiloxNoise, GT, FACE>, smem)) return rc;
+    shade_bwd_fallback_kernel<PhiloxNoise, GT, FACE><<<148 * 24, FNT, smem, st>>>(a, na, prow0);
+    return (int)cudaGetLastError();
 }
 
-int launch_shade_bwd(const BwdArgs& a, float* grad_scalars, cudaStream_t st) {
+int launch_shade_bwd(const BwdArgs& a, const BwdArgs* fb, float* grad_scalars, cudaStream_t st) {
     int rc;
     const uint32_t both = PERT_PH_BWD_SAMPLE | PERT_PH_BWD_FINISH;
     const bool phased = (a.pb.flags & both) != both || a.hist != nullptr;
@@ -550,8 +627,23 @@ int launch_shade_bwd(const BwdArgs& a, float* grad_scalars, cudaStream_t st) {
         PhiloxNoise pa(a.pb.seed_agg, 1, a.pb.pixel_offset);
         if (phased) {
             rc = launch_bwd_t<PhiloxNoise, 0, true>(a, pa, st);
+        } else if (fb) {  // sparse-first: compact main pass, then half-size tiles for whatever did not fit
+            switch (a.L.G) {
+                case 1: rc = launch_bwd_c<1>(a, pa, st); break;
+                case 2: rc = launch_bwd_c<2>(a, pa, st); break;
+                case 4: rc = launch_bwd_c<4>(a, pa, st); break;
+                default: rc = launch_bwd_c<8>(a, pa, st); break;
+            }
+            if (rc) return rc;
+            const bool face = a.pb.face_colors != nullptr;
+            switch (fb->L.G) {
+                case 2: rc = face ? launch_bwd_fb<2, true>(*fb, pa, a.L.ntiles, st) : launch_bwd_fb<2, false>(*fb, pa, a.L.ntiles, st); break;
+                case 4: rc = face ? launch_bwd_fb<4, true>(*fb, pa, a.L.ntiles, st) : launch_bwd_fb<4, false>(*fb, pa, a.L.ntiles, st); break;
+                case 8: rc = face ? launch_bwd_fb<8, true>(*fb, pa, a.L.ntiles, st) : launch_bwd_fb<8, false>(*fb, pa, a.L.ntiles, st); break;
+                default: rc = face ? launch_bwd_fb<16, true>(*fb, pa, a.L.ntiles, st) : launch_bwd_fb<16, false>(*fb, pa, a.L.ntiles, st); break;
+            }
         } else {
-            switch (a.L.G) {  // production path: lanes per pixel known at compile time
+            switch (a.L.G) {  // lanes per pixel known at compile time
                 case 1: rc = launch_bwd_t<PhiloxNoise, 1, false>(a, pa, st); break;
                 case 2: rc = launch_bwd_t<PhiloxNoise, 2, false>(a, pa, st); break;
                 case 4: rc = launch_bwd_t<PhiloxNoise, 4, false>(a, pa, st); break;
@@ -561,7 +653,8 @@ int launch_shade_bwd(const BwdArgs& a, float* grad_scalars, cudaStream_t st) {
     }
     if (rc) return rc;
     if (a.pb.flags & PERT_PH_BWD_FINISH) {
-        finalize_scalars_kernel<<<1, 1024, 0, st>>>(a.partials, a.L.ntiles, a.pb.gamma, a.pb.alpha, grad_scalars);
+        finalize_scalars_kernel<<<1, 1024, 0, st>>>(a.partials, a.L.ntiles, fb ? a.worklist : nullptr, a.pb.gamma,
+                                                    a.pb.alpha, grad_scalars);
         return (int)cudaGetLastError();
     }
     return 0;

@@ -15,11 +15,17 @@
 
 namespace pert {
 
-size_t fwd_warp_smem(int tp, int K) {
-    const size_t E = (size_t)tp * K, E1 = (size_t)tp * (K + 1);
-    return carve(E, 2) /*vlist*/ + carve(E1, 4) /*xs|lz*/ + carve(E, 4) /*zs*/ + carve(E, 2) /*cnt*/ +
-           carve(E1, 4) /*rs|hl*/ + carve(E1, 2) /*rlist|lj*/ + carve(tp + 1, 4) /*vstart*/ + carve(tp, 4) /*pinfo*/ +
-           carve(tp, 2) /*plist*/ + 16;
+void fwd_smem_layout(int tp, int cap, SmemLayout& L) {
+    Carver cv(L);
+    cv.take(cap, 2);       // vlist
+    cv.take(cap + tp, 4);  // xs | lz
+    cv.take(cap, 4);       // zs
+    cv.take(cap, 2);       // cnt
+    cv.take(cap + tp, 4);  // rs | hl
+    cv.take(cap + tp, 2);  // rlist | lj
+    cv.take(tp + 1, 4);    // vstart
+    cv.take(tp, 4);        // pinfo
+    cv.take(tp, 2);        // plist
 }
 
 // GT = lanes per pixel as a compile-time constant (1, 2, 4, 8), or 0 to read it from the launch record.
@@ -27,13 +33,12 @@ size_t fwd_warp_smem(int tp, int K) {
 // (the phase-split code of the sample-sharded job is compiled out, which keeps the hot code small: the
 // kernel is instruction-fetch sensitive, every warp walks the whole body once per tile).
 template <class NoiseR, class NoiseA, int GT, bool PHASED>
-__global__ void __launch_bounds__(FNT, 32) shade_fwd_kernel(const FwdArgs a, const NoiseR noise_r, const NoiseA noise_a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__device__ __forceinline__ void shade_fwd_tile(const FwdArgs& a, const NoiseR& noise_r, const NoiseA& noise_a,
+                                               const int64_t tile, unsigned char* smem_raw) {
     const pert_problem& pb = a.pb;
     const int lane = threadIdx.x;
-    const int64_t tile = blockIdx.x;
     const int G = GT ? GT : a.L.G;
-    const int gshift = GT ? (GT == 8 ? 3 : GT == 4 ? 2 : GT == 2 ? 1 : 0) : a.L.gshift;
+    const int gshift = GT ? (GT == 16 ? 4 : GT == 8 ? 3 : GT == 4 ? 2 : GT == 2 ? 1 : 0) : a.L.gshift;
     const int K = pb.K, K1 = K + 1, tp = 32 >> gshift;
     const int64_t pix0 = tile * tp;
     const int npx = (int)min((int64_t)tp, a.L.P - pix0);
@@ -53,23 +58,30 @@ __global__ void __launch_bounds__(FNT, 32) shade_fwd_kernel(const FwdArgs a, con
     const int64_t gp = pix0 + p;
     const unsigned lt = (1u << lane) - 1u;
 
-    Carver cv(smem_raw);
-    uint16_t* vlist = cv.take<uint16_t>(tp * K);
-    float* xs = cv.take<float>(tp * K1);  // x = -dists (compact); later lz: logits of the live list
-    float* zs = cv.take<float>(tp * K);   // zbuf -> zi -> zeta (compact)
-    uint16_t* cnt = cv.take<uint16_t>(tp * K);
-    float* rs = cv.take<float>(tp * K1);  // sum_s (h-h0) U (compact); later hl: histogram of the live list
-    uint16_t* rlist = cv.take<uint16_t>(tp * K1);  // entries that need coverage samples; later lj: live logit ids
-    int* vstart = cv.take<int>(tp + 1);
-    int* pinfo = cv.take<int>(tp);  // nlive | a0l << 16 of every pixel
-    uint16_t* plist = cv.take<uint16_t>(tp);
+    Taker cv(smem_raw, a.L.sm);  // layout: fwd_smem_layout (every array is compact: `cap` valid entries)
+    uint16_t* vlist = cv.take<uint16_t>();
+    float* xs = cv.take<float>();          // x = -dists (compact); later lz: logits of the live list
+    float* zs = cv.take<float>();          // zbuf -> zi -> zeta (compact)
+    uint16_t* cnt = cv.take<uint16_t>();
+    float* rs = cv.take<float>();          // sum_s (h-h0) U (compact); later hl: histogram of the live list
+    uint16_t* rlist = cv.take<uint16_t>();  // entries that need coverage samples; later lj: live logit ids
+    int* vstart = cv.take<int>();
+    int* pinfo = cv.take<int>();  // nlive | a0l << 16 of every pixel
+    uint16_t* plist = cv.take<uint16_t>();
+    const int cap = a.L.cap;
     float* lz = xs;
     int* hl = reinterpret_cast<int*>(rs);
     uint16_t* lj = rlist;
 
     // ---- phase 0 -----------------------------------------------------------------------------------
-    const int nv = scan_valid(pb.pix_to_face + g0, E, a.L.vec_ok, vlist);
+    const int nv = scan_valid(pb.pix_to_face + g0, E, a.L.vec_ok, vlist, cap);
     const int sa_loc = a.L.sa_loc;
+    if (nv > cap) {
+        // sparse-first mode: this tile has more valid entries than the compact arrays hold: hand it to the
+        // fallback pass (half-size tiles, full capacity)
+        if (lane == 0) a.worklist[4 + atomicAdd(a.worklist, 1)] = (int32_t)tile;
+        return;
+    }
     if (nv == 0) {
         // nothing but padding: background, alpha 0, every sample picks the background (index K)
         if (do_agg && ghist) {
@@ -118,7 +130,7 @@ __global__ void __launch_bounds__(FNT, 32) shade_fwd_kernel(const FwdArgs a, con
     }
     __syncwarp();
     if (do_rast) {
-        rast_sample_list(noise_r, rlist, nlist, vlist, xs, cnt, rs, K, a.L.invK, pix0, pb.sigma, pb.s_rast_begin,
+        rast_sample_list(noise_r, rlist, nlist, vlist, xs, cnt, rs, K, a.L.invK, pix0, pb.sigma, a.L.inv_sigma, pb.s_rast_begin,
                          pb.s_rast_end, !no_skip, a.L.lpe_r);
         __syncwarp();
 #pragma unroll 1
@@ -132,10 +144,10 @@ __global__ void __launch_bounds__(FNT, 32) shade_fwd_kernel(const FwdArgs a, con
     __syncwarp();
 
     // ---- phase 2: logits, alpha, live lists ---------------------------------------------------------
-    const float gal = pb.gamma / pb.alpha;  // fp32 scalar division, smoothagg.py:201
+    const float gal = a.L.gal;  // gamma / alpha as an fp32 scalar division (smoothagg.py:201), done on the host
     float zn = 1.0f, zf = 100.0f;
     if (pvalid) {
-        const int b = pb.depth_len > 1 ? (int)(gp / a.L.HW) : 0;
+        const int b = pb.depth_len > 1 ? batch_of(pix0, p, a.L.HW) : 0;
         zn = __ldg(pb.znear + b);
         zf = __ldg(pb.zfar + b);
     }
@@ -330,6 +342,31 @@ __global__ void __launch_bounds__(FNT, 32) shade_fwd_kernel(const FwdArgs a, con
     if (pvalid && lig == 0) reinterpret_cast<float4*>(a.image)[gp] = make_float4(r, g, bl, px_alpha);
 }
 
+template <class NoiseR, class NoiseA, int GT, bool PHASED>
+__global__ void __launch_bounds__(FNT, 32) shade_fwd_kernel(const FwdArgs a, const NoiseR noise_r, const NoiseA noise_a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    shade_fwd_tile<NoiseR, NoiseA, GT, PHASED>(a, noise_r, noise_a, blockIdx.x, smem_raw);
+}
+
+// Fallback pass of the sparse-first mode: the tiles whose valid entries did not fit the compact arrays,
+// as half-size tiles (GT lanes per pixel = twice the main pass's) with full capacity.  Few persistent CTAs
+// walk the work list; it is empty for sparse (real) fragments.
+template <class NoiseR, class NoiseA, int GT>
+__global__ void __launch_bounds__(FNT, 32) shade_fwd_fallback_kernel(const FwdArgs a, const NoiseR noise_r, const NoiseA noise_a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = 2 * a.worklist[0];
+#pragma unroll 1
+    for (;;) {  // persistent warps fetch half-tiles dynamically
+        int i = 0;
+        if (threadIdx.x == 0) i = n > 0 ? atomicAdd(a.worklist + 1, 1) : 0;
+        i = __shfl_sync(FULL, i, 0);
+        if (i >= n) break;
+        const int64_t tile = (int64_t)a.worklist[4 + (i >> 1)] * 2 + (i & 1);
+        if (tile < a.L.ntiles) shade_fwd_tile<NoiseR, NoiseA, GT, false>(a, noise_r, noise_a, tile, smem_raw);
+        __syncwarp();
+    }
+}
+
 template <class NR, class NA, int GT, bool PHASED>
 static int launch_fwd_t(const FwdArgs& a, const NR& nr, const NA& na, cudaStream_t st) {
     const size_t smem = (size_t)a.L.warp_smem;
@@ -342,7 +379,19 @@ static int launch_fwd_t(const FwdArgs& a, const NR& nr, const NA& na, cudaStream
     return (int)cudaGetLastError();
 }
 
-int launch_shade_fwd(const FwdArgs& a, cudaStream_t st) {
+template <int GT>
+static int launch_fwd_fallback(const FwdArgs& a, const PhiloxNoise& nr, const PhiloxNoise& na, cudaStream_t st) {
+    const size_t smem = (size_t)a.L.warp_smem;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(shade_fwd_fallback_kernel<PhiloxNoise, PhiloxNoise, GT>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    shade_fwd_fallback_kernel<PhiloxNoise, PhiloxNoise, GT><<<148 * 32, FNT, smem, st>>>(a, nr, na);
+    return (int)cudaGetLastError();
+}
+
+int launch_shade_fwd(const FwdArgs& a, const FwdArgs* fb, cudaStream_t st) {
     const bool er = a.pb.noise_rast != nullptr, ea = a.pb.noise_agg != nullptr;
     const uint32_t all = PERT_PH_RAST | PERT_PH_AGG | PERT_PH_BLEND;
     const bool phased = (a.pb.flags & all) != all || a.hist != nullptr;
@@ -350,11 +399,19 @@ int launch_shade_fwd(const FwdArgs& a, cudaStream_t st) {
     ExplicitNoise xr{a.pb.noise_rast, a.L.P, a.pb.K, a.pb.S_rast}, xa{a.pb.noise_agg, a.L.P, a.pb.K + 1, a.pb.S_agg};
     if (!er && !ea) {
         if (phased) return launch_fwd_t<PhiloxNoise, PhiloxNoise, 0, true>(a, pr, pa, st);
+        int rc;
         switch (a.L.G) {  // production path: lanes per pixel known at compile time
-            case 1: return launch_fwd_t<PhiloxNoise, PhiloxNoise, 1, false>(a, pr, pa, st);
-            case 2: return launch_fwd_t<PhiloxNoise, PhiloxNoise, 2, false>(a, pr, pa, st);
-            case 4: return launch_fwd_t<PhiloxNoise, PhiloxNoise, 4, false>(a, pr, pa, st);
-            default: return launch_fwd_t<PhiloxNoise, PhiloxNoise, 8, false>(a, pr, pa, st);
+            case 1: rc = launch_fwd_t<PhiloxNoise, PhiloxNoise, 1, false>(a, pr, pa, st); break;
+            case 2: rc = launch_fwd_t<PhiloxNoise, PhiloxNoise, 2, false>(a, pr, pa, st); break;
+            case 4: rc = launch_fwd_t<PhiloxNoise, PhiloxNoise, 4, false>(a, pr, pa, st); break;
+            default: rc = launch_fwd_t<PhiloxNoise, PhiloxNoise, 8, false>(a, pr, pa, st); break;
+        }
+        if (rc || !fb) return rc;
+        switch (fb->L.G) {  // sparse-first mode: half-size tiles for whatever did not fit
+            case 2: return launch_fwd_fallback<2>(*fb, pr, pa, st);
+            case 4: return launch_fwd_fallback<4>(*fb, pr, pa, st);
+            case 8: return launch_fwd_fallback<8>(*fb, pr, pa, st);
+            default: return launch_fwd_fallback<16>(*fb, pr, pa, st);
         }
     }
     if (er && ea) return launch_fwd_t<ExplicitNoise, ExplicitNoise, 0, true>(a, xr, xa, st);

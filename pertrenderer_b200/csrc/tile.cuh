@@ -15,8 +15,10 @@ namespace pert {
 // ------------------------------------------------------------------------------------------------
 // phase 0: scan pix_to_face of the tile (128-bit loads), build the ascending list of valid entries
 // ------------------------------------------------------------------------------------------------
+// Returns the number of valid entries; only the first `cap` of them are written to vlist (a tile with
+// more is handed to the fallback pass by the caller).
 __device__ __forceinline__ int scan_valid(const int64_t* __restrict__ p2f /* tile base */, int E, bool vec_ok,
-                                          uint16_t* vlist) {
+                                          uint16_t* vlist, int cap) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1u;
     int total = 0;
@@ -48,8 +50,8 @@ __device__ __forceinline__ int scan_valid(const int64_t* __restrict__ p2f /* til
             const bool v0 = a[u] >= 0, v1 = b[u] >= 0;
             const unsigned be = __ballot_sync(FULL, v0), bo = __ballot_sync(FULL, v1);
             const int pos = total + __popc(be & lt) + __popc(bo & lt);
-            if (v0) vlist[pos] = (uint16_t)e0;
-            if (v1) vlist[pos + (v0 ? 1 : 0)] = (uint16_t)(e0 + 1);
+            if (v0 && pos < cap) vlist[pos] = (uint16_t)e0;
+            if (v1 && pos + (v0 ? 1 : 0) < cap) vlist[pos + (v0 ? 1 : 0)] = (uint16_t)(e0 + 1);
             total += __popc(be) + __popc(bo);
         }
     }
@@ -61,14 +63,7 @@ __device__ __forceinline__ void pixel_ranges(const uint16_t* vlist, int nv, int 
     const int lane = threadIdx.x & 31;
 #pragma unroll 1
     for (int p = lane; p <= tp; p += 32) {
-        const int target = p * K;
-        int lo = 0, hi = nv;
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if ((int)vlist[mid] < target) lo = mid + 1;
-            else hi = mid;
-        }
-        vstart[p] = lo;
+        vstart[p] = lower_bound_u16(vlist, 0, nv, p * K);
     }
 }
 
@@ -81,18 +76,18 @@ __device__ __forceinline__ void pixel_ranges(const uint16_t* vlist, int nv, int 
 template <class NoiseT>
 __device__ __forceinline__ void rast_sample_list(const NoiseT& noise, const uint16_t* rlist, int nlist,
                                                  const uint16_t* vlist, const float* xs, uint16_t* cnt, float* rs,
-                                                 int K, float invK, int64_t pix0, float sigma, int s_begin, int s_end,
-                                                 bool gate_ok, int lpe_max /* lanes per entry at most */) {
+                                                 int K, float invK, int64_t pix0, float sigma, float inv_sigma,
+                                                 int s_begin, int s_end, bool gate_ok,
+                                                 int lpe_max /* lanes per entry at most */) {
     const int lane = threadIdx.x & 31;
     const int qb = s_begin >> 2, qe = (s_end + 3) >> 2;
     if (nlist == 0) return;
     // lanes per entry: as many as keep the warp full (few listed entries -> split an entry's samples over
     // more lanes; many -> one lane walks all the quads of its entry and no cross-lane reduction is needed)
-    const int lpe_shift = min(31 - __clz(lpe_max), nlist >= 32 ? 0 : 31 - __clz(32 / nlist));
+    const int lpe_shift = min(31 - __clz(lpe_max), fill_shift(nlist));
     const int lpe = 1 << lpe_shift;
     const int gpw = 32 >> lpe_shift;  // entries per warp pass
     const int lig = lane & (lpe - 1);
-    const float inv_sigma = 1.0f / sigma;
 #pragma unroll 1
     for (int base = 0; base < nlist; base += gpw) {
         const int li = base + (lane >> lpe_shift);
@@ -231,7 +226,7 @@ __device__ __forceinline__ PixPrep prep_pixels(int p, int lig, int G, bool pvali
         const int c = cnt[n];
         float z = -CUDART_INF_F;
         if (c != 0) {
-            const float lg = (c == S_rast) ? 0.0f : logf((float)c / fS);
+            const float lg = (c == S_rast) ? 0.0f : logf_exact((float)c / fS);
             z = __fadd_rn(__fadd_rn(__fmul_rn(gal, lg), zs[n]), -zmax);
         }
         zs[n] = z;

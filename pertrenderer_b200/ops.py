@@ -191,6 +191,7 @@ class ShadeSaved:
     rsum: torch.Tensor  # float (N,H,W,K)
     winners: torch.Tensor  # (N,H,W,S_agg_local) uint8 / int16
     pixstate: torch.Tensor  # int16 storage of uint16 (N,H,W): a0 | 0x8000 * active
+    worklist: Optional[torch.Tensor] = None  # int32 (4 + tiles): sparse-first mode work list (see pertshade.h)
     hist: Optional[torch.Tensor] = None  # int32 (N,H,W,K1), only when requested
 
     def winners_full(self) -> torch.Tensor:
@@ -219,12 +220,13 @@ def shade_forward(pr: ShadeProblem, want_hist: bool = False, phases: int = 0, sa
                 rsum=alloc((N, H, W, K), dtype=torch.float32, device=dev),
                 winners=torch.empty((N, H, W, sa_loc), dtype=pr.winner_dtype(), device=dev),
                 pixstate=torch.empty((N, H, W), dtype=torch.int16, device=dev),
+                worklist=None if phases else torch.empty((4 + pr.num_tiles(),), dtype=torch.int32, device=dev),
                 hist=torch.empty((N, H, W, K + 1), dtype=torch.int32, device=dev) if want_hist else None)
         do_blend = (phases == 0) or bool(phases & PH_BLEND)
         image = torch.empty((N, H, W, 4), dtype=torch.float32, device=dev) if do_blend else None
         pb = pr.c_struct(flags=pr.flags | phases)
         rc = lib.pert_shade_fwd(pb, ptr(image), ptr(saved.counts), ptr(saved.rsum), ptr(saved.winners),
-                                ptr(saved.pixstate), ptr(saved.hist), stream_ptr(dev))
+                                ptr(saved.pixstate), ptr(saved.hist), ptr(saved.worklist), stream_ptr(dev))
     check(rc, "pert_shade_fwd")
     return image, saved
 
@@ -245,12 +247,13 @@ def shade_backward(pr: ShadeProblem, saved: ShadeSaved, grad_image: torch.Tensor
             gc = torch.zeros_like(pr.face_colors) if (finish and need_colors) else None
         else:
             gc = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev) if (finish and need_colors) else None
-        partials = torch.empty((pr.num_tiles(), 4), dtype=torch.float32, device=dev) if finish else None
+        partials = torch.empty((3 * pr.num_tiles(), 4), dtype=torch.float32, device=dev) if finish else None
         scal = torch.empty((3,), dtype=torch.float32, device=dev) if finish else None
         pb = pr.c_struct(flags=pr.flags | phases)
         rc = lib.pert_shade_bwd(pb, ptr(grad_image), ptr(saved.counts), ptr(saved.rsum), ptr(saved.winners),
                                 ptr(saved.pixstate), ptr(gd), ptr(gz), ptr(gc), ptr(partials), ptr(scal), ptr(acc), ptr(pixstat),
-                                ptr(saved.hist) if use_hist else None, stream_ptr(dev))
+                                ptr(saved.hist) if use_hist else None, None if phases else ptr(saved.worklist),
+                                stream_ptr(dev))
     check(rc, "pert_shade_bwd")
     return gd, gz, gc, scal
 
