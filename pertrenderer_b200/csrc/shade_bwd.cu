@@ -53,9 +53,8 @@ void bwd_smem_layout(int tp, int K, int cap, int sc, int nchunks, int win_bytes,
 template <class NoiseA, int GT, bool PHASED, bool FACE, bool COMPACT>
 __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& noise_a, const int64_t tile,
                                                const int64_t prow /* row of the scalar partials */,
-                                               unsigned char* smem_raw) {
+                                               unsigned char* smem_raw, const int lane) {
     const pert_problem& pb = a.pb;
-    const int lane = threadIdx.x;
     const int G = GT ? GT : a.L.G;
     const int gshift = GT ? (GT == 16 ? 4 : GT == 8 ? 3 : GT == 4 ? 2 : GT == 2 ? 1 : 0) : a.L.gshift;
     const int K = pb.K, K1 = K + 1, tp = 32 >> gshift, sc = a.L.sc;
@@ -519,25 +518,26 @@ __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& n
 template <class NoiseA, int GT, bool PHASED, bool FACE, bool COMPACT>
 __global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const NoiseA noise_a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    shade_bwd_tile<NoiseA, GT, PHASED, FACE, COMPACT>(a, noise_a, blockIdx.x, blockIdx.x, smem_raw);
+    shade_bwd_tile<NoiseA, GT, PHASED, FACE, COMPACT>(a, noise_a, blockIdx.x, blockIdx.x, smem_raw, threadIdx.x);
 }
 
 // Fallback pass of the sparse-first mode (see shade_fwd.cu): work-list tiles as half-size tiles with dense
 // per-logit arrays; their scalar partials go to the rows after the main pass's.
 template <class NoiseA, int GT, bool FACE>
-__global__ void __launch_bounds__(FNT) shade_bwd_fallback_kernel(const BwdArgs a, const NoiseA noise_a, int64_t prow0) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(NT, 6) shade_bwd_fallback_kernel(const BwdArgs a, const NoiseA noise_a, int64_t prow0) {
+    extern __shared__ __align__(16) unsigned char smem_all[];
+    unsigned char* smem_raw = smem_all + (threadIdx.x >> 5) * a.L.warp_smem;  // NW independent warps per CTA
     const int n = 2 * a.worklist[0];
 #pragma unroll 1
     for (;;) {  // persistent warps fetch half-tiles dynamically
         int i = 0;
-        if (threadIdx.x == 0) i = n > 0 ? atomicAdd(a.worklist + 1, 1) : 0;
+        if ((threadIdx.x & 31) == 0) i = n > 0 ? atomicAdd(a.worklist + 1, 1) : 0;
         i = __shfl_sync(FULL, i, 0);
         if (i >= n) break;
         const int64_t tile = (int64_t)a.worklist[4 + (i >> 1)] * 2 + (i & 1);
         if (tile < a.L.ntiles) {
-            shade_bwd_tile<NoiseA, GT, false, FACE, false>(a, noise_a, tile, prow0 + i, smem_raw);
-        } else if (threadIdx.x == 0) {
+            shade_bwd_tile<NoiseA, GT, false, FACE, false>(a, noise_a, tile, prow0 + i, smem_raw, threadIdx.x & 31);
+        } else if ((threadIdx.x & 31) == 0) {
             reinterpret_cast<float4*>(a.partials)[prow0 + i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __syncwarp();
@@ -610,9 +610,9 @@ static int launch_bwd_c(const BwdArgs& a, const PhiloxNoise& na, cudaStream_t st
 }
 template <int GT, bool FACE>
 static int launch_bwd_fb(const BwdArgs& a, const PhiloxNoise& na, int64_t prow0, cudaStream_t st) {
-    const size_t smem = (size_t)a.L.warp_smem;
+    const size_t smem = (size_t)a.L.warp_smem * NW;
     if (int rc = set_smem(shade_bwd_fallback_kernel<PhiloxNoise, GT, FACE>, smem)) return rc;
-    shade_bwd_fallback_kernel<PhiloxNoise, GT, FACE><<<148 * 24, FNT, smem, st>>>(a, na, prow0);
+    shade_bwd_fallback_kernel<PhiloxNoise, GT, FACE><<<148 * 6, NT, smem, st>>>(a, na, prow0);
     return (int)cudaGetLastError();
 }
 

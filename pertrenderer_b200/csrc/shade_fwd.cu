@@ -34,9 +34,8 @@ void fwd_smem_layout(int tp, int cap, SmemLayout& L) {
 // kernel is instruction-fetch sensitive, every warp walks the whole body once per tile).
 template <class NoiseR, class NoiseA, int GT, bool PHASED>
 __device__ __forceinline__ void shade_fwd_tile(const FwdArgs& a, const NoiseR& noise_r, const NoiseA& noise_a,
-                                               const int64_t tile, unsigned char* smem_raw) {
+                                               const int64_t tile, unsigned char* smem_raw, const int lane) {
     const pert_problem& pb = a.pb;
-    const int lane = threadIdx.x;
     const int G = GT ? GT : a.L.G;
     const int gshift = GT ? (GT == 16 ? 4 : GT == 8 ? 3 : GT == 4 ? 2 : GT == 2 ? 1 : 0) : a.L.gshift;
     const int K = pb.K, K1 = K + 1, tp = 32 >> gshift;
@@ -345,24 +344,25 @@ __device__ __forceinline__ void shade_fwd_tile(const FwdArgs& a, const NoiseR& n
 template <class NoiseR, class NoiseA, int GT, bool PHASED>
 __global__ void __launch_bounds__(FNT, 32) shade_fwd_kernel(const FwdArgs a, const NoiseR noise_r, const NoiseA noise_a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    shade_fwd_tile<NoiseR, NoiseA, GT, PHASED>(a, noise_r, noise_a, blockIdx.x, smem_raw);
+    shade_fwd_tile<NoiseR, NoiseA, GT, PHASED>(a, noise_r, noise_a, blockIdx.x, smem_raw, threadIdx.x);
 }
 
 // Fallback pass of the sparse-first mode: the tiles whose valid entries did not fit the compact arrays,
 // as half-size tiles (GT lanes per pixel = twice the main pass's) with full capacity.  Few persistent CTAs
 // walk the work list; it is empty for sparse (real) fragments.
 template <class NoiseR, class NoiseA, int GT>
-__global__ void __launch_bounds__(FNT, 32) shade_fwd_fallback_kernel(const FwdArgs a, const NoiseR noise_r, const NoiseA noise_a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+__global__ void __launch_bounds__(NT, 8) shade_fwd_fallback_kernel(const FwdArgs a, const NoiseR noise_r, const NoiseA noise_a) {
+    extern __shared__ __align__(16) unsigned char smem_all[];
+    unsigned char* smem_raw = smem_all + (threadIdx.x >> 5) * a.L.warp_smem;  // NW independent warps per CTA
     const int n = 2 * a.worklist[0];
 #pragma unroll 1
     for (;;) {  // persistent warps fetch half-tiles dynamically
         int i = 0;
-        if (threadIdx.x == 0) i = n > 0 ? atomicAdd(a.worklist + 1, 1) : 0;
+        if ((threadIdx.x & 31) == 0) i = n > 0 ? atomicAdd(a.worklist + 1, 1) : 0;
         i = __shfl_sync(FULL, i, 0);
         if (i >= n) break;
         const int64_t tile = (int64_t)a.worklist[4 + (i >> 1)] * 2 + (i & 1);
-        if (tile < a.L.ntiles) shade_fwd_tile<NoiseR, NoiseA, GT, false>(a, noise_r, noise_a, tile, smem_raw);
+        if (tile < a.L.ntiles) shade_fwd_tile<NoiseR, NoiseA, GT, false>(a, noise_r, noise_a, tile, smem_raw, threadIdx.x & 31);
         __syncwarp();
     }
 }
@@ -381,13 +381,13 @@ static int launch_fwd_t(const FwdArgs& a, const NR& nr, const NA& na, cudaStream
 
 template <int GT>
 static int launch_fwd_fallback(const FwdArgs& a, const PhiloxNoise& nr, const PhiloxNoise& na, cudaStream_t st) {
-    const size_t smem = (size_t)a.L.warp_smem;
+    const size_t smem = (size_t)a.L.warp_smem * NW;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(shade_fwd_fallback_kernel<PhiloxNoise, PhiloxNoise, GT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    shade_fwd_fallback_kernel<PhiloxNoise, PhiloxNoise, GT><<<148 * 32, FNT, smem, st>>>(a, nr, na);
+    shade_fwd_fallback_kernel<PhiloxNoise, PhiloxNoise, GT><<<148 * 8, NT, smem, st>>>(a, nr, na);
     return (int)cudaGetLastError();
 }
 
