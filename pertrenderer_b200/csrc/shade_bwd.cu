@@ -516,7 +516,7 @@ __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& n
 }
 
 template <class NoiseA, int GT, bool PHASED, bool FACE, bool COMPACT>
-__global__ void __launch_bounds__(FNT) shade_bwd_kernel(const BwdArgs a, const NoiseA noise_a) {
+__global__ void __launch_bounds__(FNT, 25) shade_bwd_kernel(const BwdArgs a, const NoiseA noise_a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     shade_bwd_tile<NoiseA, GT, PHASED, FACE, COMPACT>(a, noise_a, blockIdx.x, blockIdx.x, smem_raw, threadIdx.x);
 }
