@@ -625,8 +625,12 @@ int launch_shade_bwd(const BwdArgs& a, const BwdArgs* fb, float* grad_scalars, c
         rc = launch_bwd_t<ExplicitNoise, 0, true>(a, xa, st);
     } else {
         PhiloxNoise pa(a.pb.seed_agg, 1, a.pb.pixel_offset);
-        if (phased) {
-            rc = launch_bwd_t<PhiloxNoise, 0, true>(a, pa, st);
+        if (phased) {  // sample-sharded job: compile-time lanes per pixel for the benchmark geometries
+            switch (a.L.G) {
+                case 4: rc = launch_bwd_t<PhiloxNoise, 4, true>(a, pa, st); break;
+                case 8: rc = launch_bwd_t<PhiloxNoise, 8, true>(a, pa, st); break;
+                default: rc = launch_bwd_t<PhiloxNoise, 0, true>(a, pa, st); break;
+            }
         } else if (fb) {  // sparse-first: compact main pass, then half-size tiles for whatever did not fit
             switch (a.L.G) {
                 case 1: rc = launch_bwd_c<1>(a, pa, st); break;

@@ -398,7 +398,13 @@ int launch_shade_fwd(const FwdArgs& a, const FwdArgs* fb, cudaStream_t st) {
     PhiloxNoise pr(a.pb.seed_rast, 0, a.pb.pixel_offset), pa(a.pb.seed_agg, 1, a.pb.pixel_offset);
     ExplicitNoise xr{a.pb.noise_rast, a.L.P, a.pb.K, a.pb.S_rast}, xa{a.pb.noise_agg, a.L.P, a.pb.K + 1, a.pb.S_agg};
     if (!er && !ea) {
-        if (phased) return launch_fwd_t<PhiloxNoise, PhiloxNoise, 0, true>(a, pr, pa, st);
+        if (phased) {  // sample-sharded job: compile-time lanes per pixel for the benchmark geometries
+            switch (a.L.G) {
+                case 4: return launch_fwd_t<PhiloxNoise, PhiloxNoise, 4, true>(a, pr, pa, st);
+                case 8: return launch_fwd_t<PhiloxNoise, PhiloxNoise, 8, true>(a, pr, pa, st);
+                default: return launch_fwd_t<PhiloxNoise, PhiloxNoise, 0, true>(a, pr, pa, st);
+            }
+        }
         int rc;
         switch (a.L.G) {  // production path: lanes per pixel known at compile time
             case 1: rc = launch_fwd_t<PhiloxNoise, PhiloxNoise, 1, false>(a, pr, pa, st); break;

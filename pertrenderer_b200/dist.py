@@ -141,16 +141,25 @@ class _SampleShardedShade(Function):
         group = cfg.get("group")
         world, rank = dist.get_world_size(group), dist.get_rank(group)
         dev = pix_to_face.device
-        # every rank must use the same two seeds: rank 0 draws, everyone receives
-        seeds = torch.zeros(2, dtype=torch.int64)
-        if rank == 0:
-            seeds[0] = ops.draw_seed()
+        if cfg.get("sync_seeds", False):
+            # reproduce the single-GPU sample path: rank 0 draws the two seeds, everyone receives them
+            # (one broadcast and one host read per forward)
+            seeds = torch.zeros(2, dtype=torch.int64)
+            if rank == 0:
+                seeds[0] = ops.draw_seed()
+                if cfg["fixed_noise"]:
+                    torch.manual_seed(1)
+                seeds[1] = ops.draw_seed()
+            seeds = seeds.to(dev)
+            dist.broadcast(seeds, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+            seed_r, seed_a = (int(v) for v in seeds.cpu())
+        else:
+            # every rank draws its own seeds from its own torch generator: the shards own disjoint sample
+            # indices, so whatever the seeds are the union is S independent samples (no communication)
+            seed_r = ops.draw_seed()
             if cfg["fixed_noise"]:
                 torch.manual_seed(1)
-            seeds[1] = ops.draw_seed()
-        seeds = seeds.to(dev)
-        dist.broadcast(seeds, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
-        seed_r, seed_a = (int(v) for v in seeds.cpu())
+            seed_a = ops.draw_seed()
         S_r, S_a = int(cfg["S_rast"]), int(cfg["S_agg"])
         sr, sa = sample_range(S_r, world, rank), sample_range(S_a, world, rank)
         if sr[0] == sr[1] or sa[0] == sa[1]:
@@ -180,16 +189,18 @@ class _SampleShardedShade(Function):
 
 
 def smooth_rgb_blend_sample_sharded(colors, fragments, smoothrast, smoothagg, blend_params, znear=1.0, zfar=100,
-                                    group=None) -> torch.Tensor:
+                                    group=None, sync_seeds=False) -> torch.Tensor:
     """``smooth_rgb_blend`` with the noise samples split over the ranks of ``group`` (inputs
     replicated on every rank; every rank returns the same image and, after backward, the same
-    gradients)."""
+    gradients).  ``sync_seeds=True`` makes rank 0's torch generator drive the noise of every rank, which
+    reproduces the single-GPU sample path exactly (one broadcast + host read per call); by default each
+    rank seeds its own disjoint sample shard from its own generator."""
     from .random_rasterizer import _background_tuple
     from .smoothagg import GaussianAgg
     from .smoothrast import GaussianRast
     if not (isinstance(smoothrast, GaussianRast) and isinstance(smoothagg, GaussianAgg)):
         raise ValueError("sample sharding is implemented for the (GaussianRast, GaussianAgg) pair")
     cfg = dict(background=_background_tuple(blend_params), eps=smoothagg.eps, S_rast=smoothrast.nb_samples,
-               S_agg=smoothagg.nb_samples, fixed_noise=bool(smoothagg.fixed_noise), group=group)
+               S_agg=smoothagg.nb_samples, fixed_noise=bool(smoothagg.fixed_noise), group=group, sync_seeds=sync_seeds)
     return _SampleShardedShade.apply(colors, fragments.dists, fragments.zbuf, smoothrast.sigma, smoothagg.gamma,
                                      smoothagg.alpha, fragments.pix_to_face, znear, zfar, cfg)

@@ -48,7 +48,8 @@ def _render(pb, fr, col, G, dev, S, sharded_group=None, pixel_offset=0):
     with ops.kernel_flags(_cabi.F_PER_SAMPLE_NOISE):  # sample-path comparable across shardings
         if sharded_group is not None:
             from pertrenderer_b200.dist import smooth_rgb_blend_sample_sharded
-            img = smooth_rgb_blend_sample_sharded(c, frag, rast, agg, blend, znear=zn, zfar=zf, group=sharded_group)
+            img = smooth_rgb_blend_sample_sharded(c, frag, rast, agg, blend, znear=zn, zfar=zf, group=sharded_group,
+                                                  sync_seeds=True)
         else:
             from pertrenderer_b200.random_rasterizer import _PerturbedShade, _background_tuple
             cfg = dict(background=_background_tuple(blend), eps=agg.eps, S_rast=S, S_agg=S, fixed_noise=False,
