@@ -87,7 +87,7 @@ static Launch make_launch(const pert_problem* pb, int tp) {
     L.lpe_r_shift = lg2(L.lpe_r);
     L.lpe_a = pow2_ceil(nq_a) < 32 ? pow2_ceil(nq_a) : 32;
     L.lpe_a_shift = lg2(L.lpe_a);
-    L.lpp = pow2_floor(nq_a) < 8 ? pow2_floor(nq_a) : 8;
+    L.lpp = pow2_floor(nq_a) < 32 ? pow2_floor(nq_a) : 32;
     L.lpp_shift = lg2(L.lpp);
     L.cap = L.tp * pb->K;
     L.warp_smem = 0;

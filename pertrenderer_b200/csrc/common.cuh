@@ -197,10 +197,19 @@ static __device__ __noinline__ int lower_bound_u16(const uint16_t* v, int lo, in
 static __device__ __noinline__ void zero_fill(float* dst, int n, bool vec_ok) {
     const int lane = threadIdx.x & 31;
     if (vec_ok && (n & 3) == 0) {
-        float4* d4 = reinterpret_cast<float4*>(dst);
+        float4* d4 = reinterpret_cast<float4*>(dst) + lane;
         const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-        for (int i = lane; i < (n >> 2); i += 32) d4[i] = z;
+        int left = (n >> 2) - lane;  // float4 slots from this lane's first one to the end
+#pragma unroll 1
+        for (; left > 96; left -= 128, d4 += 128) {  // four stores per trip, no per-store bookkeeping
+            d4[0] = z;
+            d4[32] = z;
+            d4[64] = z;
+            d4[96] = z;
+        }
+        if (left > 0) d4[0] = z;
+        if (left > 32) d4[32] = z;
+        if (left > 64) d4[64] = z;
     } else {
 #pragma unroll 1
         for (int i = lane; i < n; i += 32) dst[i] = 0.f;
@@ -209,6 +218,24 @@ static __device__ __noinline__ void zero_fill(float* dst, int n, bool vec_ok) {
 
 // floor(log2(32 / n)) for 1 <= n: lanes per item that keep a warp full (no integer division)
 __device__ __forceinline__ int fill_shift(int n) { return n >= 32 ? 0 : (n <= 1 ? 5 : 5 - (32 - __clz(n - 1))); }
+
+// Lanes per item (log2) for `n` items of `nq` sample quads each: a lane group of 2^k lanes shares one item
+// (each lane takes nq/2^k quads, then a k-level shuffle reduction).  Picks the k <= kmax with the fewest
+// issued instructions: passes * (quads per lane * cost of one quad + reduction).
+__device__ __forceinline__ int best_lane_shift(int n, int nq, int kmax) {
+    int best_k = 0, best_c = 0x7fffffff;
+#pragma unroll 1
+    for (int k = 0; k <= kmax; ++k) {
+        const int passes = ((n << k) + 31) >> 5;
+        const int per_lane = (nq + (1 << k) - 1) >> k;
+        const int c = passes * (per_lane * 100 + 24 + 6 * k);
+        if (c < best_c) {
+            best_c = c;
+            best_k = k;
+        }
+    }
+    return best_k;
+}
 
 // batch element of pixel gp: pixels of a tile span at most two images, so one 32-bit division per tile
 __device__ __forceinline__ int batch_of(int64_t pix0, int p, int64_t HW) {

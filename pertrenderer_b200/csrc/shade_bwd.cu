@@ -259,7 +259,7 @@ __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& n
                 __syncwarp();
             }
             // lanes per pair: as many as keep the warp full, at most a.L.lpp
-            const int lpp_shift = np2 == 0 ? 0 : min(a.L.lpp_shift, fill_shift(np2));
+            const int lpp_shift = np2 == 0 ? 0 : best_lane_shift(np2, (min(sc, sa_loc) + 3) >> 2, a.L.lpp_shift);
             const int LPP = 1 << lpp_shift;
             const int lq = lane & (LPP - 1);
             float C2 = 0.f;

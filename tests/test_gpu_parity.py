@@ -445,8 +445,8 @@ def test_dead_noise_modes_share_forward_and_live_gradients():
     not_argzi = zi < zi.max(-1, keepdim=True).values
     sel = mask & (hist > 0) & not_argzi
     assert sel.any()
-    for r in (b, c):
-        assert torch.allclose(a["grad_zbuf"][sel], r["grad_zbuf"][sel], rtol=1e-6, atol=0)
+    for r in (b, c):  # same terms; the lanes that share one sum (hence its association order) may differ
+        assert rel_err(a["grad_zbuf"][sel], r["grad_zbuf"][sel]) <= 1e-5
 
 
 def test_once_per_logit_noise_has_the_reference_distribution():
