@@ -553,3 +553,40 @@ def test_full_size_properties_config2():
     assert (gc.sum(-2) <= 2 * img[..., :3].abs() + 1e-5).all()
     s, gm, al = shader.get_smoothing()
     assert all(torch.isfinite(t.grad) for t in (s, gm, al))
+
+
+def test_integration_md_ctypes_stub_runs():
+    """The ctypes stub printed in INTEGRATION.md (what a maintainer of the reference would paste into
+    randomras/random_rasterizer.py) is executable as written and reproduces the package's result."""
+    import os
+    import re
+    import pertrenderer_b200 as pb
+    from conftest import ROOT
+    from pertrenderer_b200 import _cabi
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    stub = [b for b in blocks if "class PerturbedShade" in b][0].replace('"libpertshade.so"', repr(_cabi.LIB_PATH))
+    ns = {}
+    exec(stub, ns)
+    dev = "cuda"
+    N, H, W, K, S = 2, 12, 12, 50, 16
+    fr, col = pb.synthetic_fragments(N, H, W, K, kind="realistic", sigma=1e-3, seed=4, device=dev)
+    G = torch.randn((N, H, W, 4), device=dev, generator=torch.Generator(device=dev).manual_seed(8))
+    zn, zf = torch.ones(N, device=dev), torch.full((N,), 100.0, device=dev)
+
+    def leaves():
+        return (col.clone().requires_grad_(True), fr.dists.clone().requires_grad_(True), fr.zbuf.clone().requires_grad_(True))
+
+    c, d, z = leaves()
+    sig, gam, alp = (torch.tensor(v, requires_grad=True) for v in (1e-3, 1e-2, 1.0))
+    torch.manual_seed(21)
+    img = ns["PerturbedShade"].apply(c, d, z, sig, gam, alp, fr.pix_to_face, zn, zf, S, (1.0, 1.0, 1.0), 1e-10)
+    (img * G).sum().backward()
+    c2, d2, z2 = leaves()
+    rast, agg = pb.GaussianRast(nb_samples=S, sigma=1e-3), pb.GaussianAgg(nb_samples=S, gamma=1e-2, alpha=1.0)
+    torch.manual_seed(21)
+    img2 = pb.smooth_rgb_blend(c2, pb.Fragments(fr.pix_to_face, z2, None, d2), rast, agg, pb.BlendParams(), znear=zn, zfar=zf)
+    (img2 * G).sum().backward()
+    assert torch.equal(img, img2)
+    assert torch.equal(d.grad, d2.grad) and torch.equal(z.grad, z2.grad) and torch.equal(c.grad, c2.grad)
+    assert torch.allclose(sig.grad, rast.sigma.grad) and torch.allclose(gam.grad, agg.gamma.grad)
