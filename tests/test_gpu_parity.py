@@ -434,7 +434,10 @@ def test_dead_noise_modes_share_forward_and_live_gradients():
     a, b, c = runs[0], runs[_cabi.F_PER_SAMPLE_NOISE], runs[_cabi.F_SKIP_DEAD_NOISE]
     mask = g["pix_to_face"] >= 0
     for r in (b, c):
-        assert torch.equal(a["image"], r["image"]) and torch.equal(a["winners"], r["winners"])
+        # same winners, hence the same weights; the default mode runs the sparse-first tile geometry, whose
+        # blend sums the (identical) terms with another number of lanes per pixel
+        assert torch.equal(a["winners"], r["winners"]) and torch.equal(a["hist"], r["hist"])
+        assert (a["image"] - r["image"]).abs().max() <= 1e-6
         assert torch.equal(a["grad_colors"], r["grad_colors"])
         assert (r["grad_zbuf"][~mask] == 0).all() and (r["grad_dists"][~mask] == 0).all()
         assert torch.isfinite(r["scalars"]).all()
