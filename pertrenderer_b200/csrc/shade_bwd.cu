@@ -33,7 +33,7 @@ void bwd_smem_layout(int tp, int K, int cap, int sc, int nchunks, int win_bytes,
     cv.take(ns, 2);   // pair_j
     cv.take(ns, 2);   // pair_s
     cv.take(ns, 1);   // pair_p
-    cv.take((size_t)tp * sc, 4);  // cs
+    cv.take((size_t)(tp < NAB ? tp : NAB) * sc, 4);  // cs
     cv.take(tp + 1, 4);           // vstart
     cv.take(tp, 4);               // pa0
     cv.take(tp, 4);               // pg0
@@ -124,18 +124,21 @@ __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& n
         zf = __ldg(pb.zfar + b);
         pstate = a.pixstate[gp];
     }
-    if (do_finish) {
-        zero_fill(a.grad_dists + g0, E, a.L.vec_ok);
-        zero_fill(a.grad_zbuf + g0, E, a.L.vec_ok);
-        if (a.grad_colors && !FACE) zero_fill(a.grad_colors + g0 * 3, E * 3, a.L.vec_ok);
-    } else {
-        zero_fill(a.acc + pix0 * K1, npx * K1, false);
-        if (lane < npx) {
-            a.pixstat[(pix0 + lane) * 2] = 0.f;
-            a.pixstat[(pix0 + lane) * 2 + 1] = 0.f;
+    const int nv = scan_valid(pb.pix_to_face + g0, E, a.L.vec_ok, vlist, cap);
+    if (!(COMPACT && nv > cap)) {
+        // this pass owns the tile: its output rows start as zeros, valid entries are scattered over them later
+        if (do_finish) {
+            zero_fill(a.grad_dists + g0, E, a.L.vec_ok);
+            zero_fill(a.grad_zbuf + g0, E, a.L.vec_ok);
+            if (a.grad_colors && !FACE) zero_fill(a.grad_colors + g0 * 3, E * 3, a.L.vec_ok);
+        } else {
+            zero_fill(a.acc + pix0 * K1, npx * K1, false);
+            if (lane < npx) {
+                a.pixstat[(pix0 + lane) * 2] = 0.f;
+                a.pixstat[(pix0 + lane) * 2 + 1] = 0.f;
+            }
         }
     }
-    const int nv = scan_valid(pb.pix_to_face + g0, E, a.L.vec_ok, vlist, cap);
     if (COMPACT && nv > cap) {
         // more valid entries than the compact arrays hold: the fallback pass redoes this tile
         if (lane == 0) a.worklist[4 + atomicAdd(a.worklist, 1)] = (int32_t)tile;
@@ -193,60 +196,35 @@ __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& n
         const int na = __popc(actb);
         const int my_ai = __popc(actb & ((1u << (p * G)) - 1u));
         if (na > 0) {
-            // g_j of every logit that can win (the saved winners are among them), cleared sums, and the
-            // list of (pixel, logit) pairs that need per-sample noise
-            int np2 = 0;
-            {
-                if (act && lig == 0) {
-                    apx[my_ai] = (uint8_t)p;
-                    pa0[p] = a0;
-                    psb[p] = sb;
-                    pnv[p] = nvp | (prefix ? 0 : 0x10000);
-                }
-                if (act) {
-                    const int ns = COMPACT ? nvp + 2 : K1;
+            // g_j of every logit that can win (the saved winners are among them) and cleared sums
+            if (act && lig == 0) {
+                apx[my_ai] = (uint8_t)p;
+                pa0[p] = a0;
+                psb[p] = sb;
+                pnv[p] = nvp | (prefix ? 0 : 0x10000);
+            }
+            if (act) {
+                const int ns = COMPACT ? nvp + 2 : K1;
 #pragma unroll 1
-                    for (int j = lig; j < ns; j += G) {
-                        hj[sb + j] = 0;
-                        accs[sb + j] = 0.f;
-                    }
+                for (int j = lig; j < ns; j += G) {
+                    hj[sb + j] = 0;
+                    accs[sb + j] = 0.f;
                 }
-                const int span = (!COMPACT && per_sample) ? max(K1, nvp + 1) : nvp + 1;
-                const int iters = warp_max_i(act ? (span + G - 1) / G : 0);
 #pragma unroll 1
-                for (int it = 0; it < iters; ++it) {
-                    const int idx = it * G + lig;
-                    bool want = false;
-                    int j = 0;
-                    if (act && idx <= nvp) {
-                        j = idx < nvp ? (int)vlist[vs + idx] - p * K : K;
-                        const float z = idx < nvp ? zs[vs + idx] : pi.zbg;
-                        const bool live = z > -CUDART_INF_F && z >= floor_v;
-                        if (live) {
-                            float gj;
-                            if (j < K) {
-                                const float* c = fcol ? fcol + 3 * (int)__ldg(p2f_p + j) : colors_p + j * 3;
-                                gj = Gi.x * __ldg(c) + Gi.y * __ldg(c + 1) + Gi.z * __ldg(c + 2);
-                            } else {
-                                gj = Gi.x * pb.background[0] + Gi.y * pb.background[1] + Gi.z * pb.background[2];
-                            }
-                            gsel[COMPACT ? sb + idx : sb + j] = gj;
-                            if (j == a0) pg0[p] = gj;
+                for (int idx = lig; idx <= nvp; idx += G) {
+                    const int j = idx < nvp ? (int)vlist[vs + idx] - p * K : K;
+                    const float z = idx < nvp ? zs[vs + idx] : pi.zbg;
+                    if (z > -CUDART_INF_F && z >= floor_v) {
+                        float gj;
+                        if (j < K) {
+                            const float* c = fcol ? fcol + 3 * (int)__ldg(p2f_p + j) : colors_p + j * 3;
+                            gj = Gi.x * __ldg(c) + Gi.y * __ldg(c + 1) + Gi.z * __ldg(c + 2);
+                        } else {
+                            gj = Gi.x * pb.background[0] + Gi.y * pb.background[1] + Gi.z * pb.background[2];
                         }
-                        want = live && !per_sample;
+                        gsel[COMPACT ? sb + idx : sb + j] = gj;
+                        if (j == a0) pg0[p] = gj;
                     }
-                    if (!COMPACT && per_sample && act && idx < K1) {  // every logit, dense in j
-                        j = idx;
-                        want = true;
-                    }
-                    const unsigned wbal = __ballot_sync(FULL, want);
-                    if (want) {
-                        const int pos = np2 + __popc(wbal & lt);
-                        pair_j[pos] = (uint16_t)j;
-                        pair_s[pos] = (uint16_t)(COMPACT ? sb + idx : sb + j);
-                        pair_p[pos] = (uint8_t)my_ai;
-                    }
-                    np2 += __popc(wbal);
                 }
             }
             __syncwarp();
@@ -258,18 +236,53 @@ __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& n
                 cp_async_wait_all();
                 __syncwarp();
             }
-            // lanes per pair: as many as keep the warp full, at most a.L.lpp
+            float C2 = 0.f;
+            // active pixels are processed NAB at a time: the c_s staging buffer holds NAB rows
+#pragma unroll 1
+            for (int b0 = 0; b0 < na; b0 += NAB) {
+            const int nb = min(NAB, na - b0);
+            const bool mine = act && my_ai >= b0 && my_ai < b0 + NAB;
+            // the (pixel, logit) pairs of this batch that need per-sample noise
+            int np2 = 0;
+            {
+                const int span = (!COMPACT && per_sample) ? K1 : nvp + 1;
+                const int iters = warp_max_i(mine ? (span + G - 1) / G : 0);
+#pragma unroll 1
+                for (int it = 0; it < iters; ++it) {
+                    const int idx = it * G + lig;
+                    bool want = false;
+                    int j = idx;
+                    if (mine && idx < span) {
+                        if (!COMPACT && per_sample) {
+                            want = true;  // every logit, dense in j
+                        } else {
+                            j = idx < nvp ? (int)vlist[vs + idx] - p * K : K;
+                            const float z = idx < nvp ? zs[vs + idx] : pi.zbg;
+                            want = z > -CUDART_INF_F && z >= floor_v;
+                        }
+                    }
+                    const unsigned wbal = __ballot_sync(FULL, want);
+                    if (want) {
+                        const int pos = np2 + __popc(wbal & lt);
+                        pair_j[pos] = (uint16_t)j;
+                        pair_s[pos] = (uint16_t)(COMPACT ? sb + idx : sb + j);
+                        pair_p[pos] = (uint8_t)(my_ai - b0);
+                    }
+                    np2 += __popc(wbal);
+                }
+            }
+            __syncwarp();
+            // lanes per pair: fewest issued instructions (see best_lane_shift), at most a.L.lpp
             const int lpp_shift = np2 == 0 ? 0 : best_lane_shift(np2, (min(sc, sa_loc) + 3) >> 2, a.L.lpp_shift);
             const int LPP = 1 << lpp_shift;
             const int lq = lane & (LPP - 1);
-            float C2 = 0.f;
 #pragma unroll 1
             for (int c0 = 0; c0 < sa_loc; c0 += sc) {  // c0 multiple of 32
                 const int cn = min(sc, sa_loc - c0);
                 const int cn4 = (cn + 3) & ~3;
 #pragma unroll 1
-                for (int ai = 0; ai < na; ++ai) {
-                    const int pp = apx[ai];
+                for (int ai = 0; ai < nb; ++ai) {
+                    const int pp = apx[b0 + ai];
                     const float g0v = pg0[pp];
                     const int ppa0 = pa0[pp];
                     const int64_t wbase = (pix0 + pp) * sa_loc + c0;
@@ -294,7 +307,7 @@ __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& n
                     // pixels of one warp differ in `act`.
                     int others = 0;
                     float c1 = 0.f, c2 = 0.f;
-                    if (act) {
+                    if (mine) {
                         const float g0v = pg0[p];
 #pragma unroll 1
                         for (int idx = lig; idx <= nvp; idx += G) {
@@ -310,9 +323,13 @@ __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& n
                         }
                     }
                     others = group_sum_i(others, G);
-                    csum = group_sum(c1, G);
-                    C2 = group_sum(c2, G);
-                    if (act && lig == 0) hj[slot_of(p, a0)] = sa_loc - others;
+                    c1 = group_sum(c1, G);
+                    c2 = group_sum(c2, G);
+                    if (mine) {
+                        csum = c1;
+                        C2 = c2;
+                        if (lig == 0) hj[slot_of(p, a0)] = sa_loc - others;
+                    }
                     __syncwarp();
                 }
                 const int nqc = cn4 >> 2;
@@ -324,7 +341,7 @@ __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& n
                     const int j = on ? pair_j[pr] : 0;
                     const int ps = on ? pair_s[pr] : 0;
                     const int ai = on ? pair_p[pr] : 0;
-                    const int pp = apx[ai];
+                    const int pp = apx[b0 + ai];
                     float acc = 0.f, t2 = 0.f;
                     if (on) {
                         const float4* c4p = reinterpret_cast<const float4*>(cs + ai * sc);
@@ -356,6 +373,7 @@ __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& n
                 }
                 __syncwarp();
             }
+            }  // batches of active pixels
 
             // ---- logits that can never win: their noise is independent of every a_s, so given c the sum
             //      sum_s c_s V_sj is N(0, sum_s c_s^2) exactly: ONE draw per logit instead of S_agg -------------
