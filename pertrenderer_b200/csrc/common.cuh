@@ -14,6 +14,7 @@ constexpr int NW = NT / 32;
 // CTA only gives its shared memory back when its slowest warp is done; with one-warp CTAs the hardware
 // CTA scheduler balances the load per tile.
 constexpr int FNT = 32;
+constexpr int FBT = 64;  // threads per CTA of the fallback pass: two independent warps
 constexpr int NAB = 8;  // backward: active pixels whose per-sample c_s are staged at a time
 constexpr unsigned FULL = 0xffffffffu;
 

@@ -542,9 +542,9 @@ __global__ void __launch_bounds__(FNT, 25) shade_bwd_kernel(const BwdArgs a, con
 // Fallback pass of the sparse-first mode (see shade_fwd.cu): work-list tiles as half-size tiles with dense
 // per-logit arrays; their scalar partials go to the rows after the main pass's.
 template <class NoiseA, int GT, bool FACE>
-__global__ void __launch_bounds__(NT, 6) shade_bwd_fallback_kernel(const BwdArgs a, const NoiseA noise_a, int64_t prow0) {
+__global__ void __launch_bounds__(FBT, 12) shade_bwd_fallback_kernel(const BwdArgs a, const NoiseA noise_a, int64_t prow0) {
     extern __shared__ __align__(16) unsigned char smem_all[];
-    unsigned char* smem_raw = smem_all + (threadIdx.x >> 5) * a.L.warp_smem;  // NW independent warps per CTA
+    unsigned char* smem_raw = smem_all + (threadIdx.x >> 5) * a.L.warp_smem;  // FBT/32 independent warps per CTA
     const int n = 2 * a.worklist[0];
 #pragma unroll 1
     for (;;) {  // persistent warps fetch half-tiles dynamically
@@ -628,9 +628,9 @@ static int launch_bwd_c(const BwdArgs& a, const PhiloxNoise& na, cudaStream_t st
 }
 template <int GT, bool FACE>
 static int launch_bwd_fb(const BwdArgs& a, const PhiloxNoise& na, int64_t prow0, cudaStream_t st) {
-    const size_t smem = (size_t)a.L.warp_smem * NW;
+    const size_t smem = (size_t)a.L.warp_smem * (FBT / 32);
     if (int rc = set_smem(shade_bwd_fallback_kernel<PhiloxNoise, GT, FACE>, smem)) return rc;
-    shade_bwd_fallback_kernel<PhiloxNoise, GT, FACE><<<148 * 6, NT, smem, st>>>(a, na, prow0);
+    shade_bwd_fallback_kernel<PhiloxNoise, GT, FACE><<<148 * 12, FBT, smem, st>>>(a, na, prow0);
     return (int)cudaGetLastError();
 }
 

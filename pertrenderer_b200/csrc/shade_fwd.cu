@@ -351,9 +351,9 @@ __global__ void __launch_bounds__(FNT, 32) shade_fwd_kernel(const FwdArgs a, con
 // as half-size tiles (GT lanes per pixel = twice the main pass's) with full capacity.  Few persistent CTAs
 // walk the work list; it is empty for sparse (real) fragments.
 template <class NoiseR, class NoiseA, int GT>
-__global__ void __launch_bounds__(NT, 8) shade_fwd_fallback_kernel(const FwdArgs a, const NoiseR noise_r, const NoiseA noise_a) {
+__global__ void __launch_bounds__(FBT, 16) shade_fwd_fallback_kernel(const FwdArgs a, const NoiseR noise_r, const NoiseA noise_a) {
     extern __shared__ __align__(16) unsigned char smem_all[];
-    unsigned char* smem_raw = smem_all + (threadIdx.x >> 5) * a.L.warp_smem;  // NW independent warps per CTA
+    unsigned char* smem_raw = smem_all + (threadIdx.x >> 5) * a.L.warp_smem;  // FBT/32 independent warps per CTA
     const int n = 2 * a.worklist[0];
 #pragma unroll 1
     for (;;) {  // persistent warps fetch half-tiles dynamically
@@ -381,13 +381,13 @@ static int launch_fwd_t(const FwdArgs& a, const NR& nr, const NA& na, cudaStream
 
 template <int GT>
 static int launch_fwd_fallback(const FwdArgs& a, const PhiloxNoise& nr, const PhiloxNoise& na, cudaStream_t st) {
-    const size_t smem = (size_t)a.L.warp_smem * NW;
+    const size_t smem = (size_t)a.L.warp_smem * (FBT / 32);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(shade_fwd_fallback_kernel<PhiloxNoise, PhiloxNoise, GT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    shade_fwd_fallback_kernel<PhiloxNoise, PhiloxNoise, GT><<<148 * 8, NT, smem, st>>>(a, nr, na);
+    shade_fwd_fallback_kernel<PhiloxNoise, PhiloxNoise, GT><<<148 * 16, FBT, smem, st>>>(a, nr, na);
     return (int)cudaGetLastError();
 }
 
