@@ -109,10 +109,15 @@ static Launch make_launch(const pert_problem* pb, int tp) {
 // Sparse-first geometry: the main pass takes tiles of TWICE the pixels (fewer per-tile fixed costs, better
 // lane packing in the sampling loops: -10 % instructions) with compact arrays for 40 % of the entries of a
 // normal tile; the fallback pass redoes an overflowing tile as two normal tiles with full capacity.
-static int sparse_tp(int K) { const int tp = 2 * pick_tp(K); return tp > 32 ? 32 : tp; }
-static int sparse_cap(int K) {
-    const int tp = sparse_tp(K);
-    int cap = (tp / 2) * K * 2 / 5;
+static int sparse_tp(int K, int64_t P) {
+    int tp = 2 * pick_tp(K);
+    if (tp > 32) tp = 32;
+    // small jobs: prefer enough tiles to fill the GPU (148 SMs x ~24 resident warps) over double-size tiles
+    if (tp > pick_tp(K) && (P + tp - 1) / tp < 148 * 24) tp = pick_tp(K);
+    return tp;
+}
+static int sparse_cap(int K, int tp) {
+    int cap = tp * K / 5;
     if (const char* e = getenv("PERT_CAP")) cap = atoi(e);  // experiments only
     if (cap < 32) cap = 32;
     if (cap > tp * K) cap = tp * K;
@@ -127,9 +132,10 @@ static bool sparse_first_ok(const pert_problem* pb, const void* worklist, bool a
 
 extern "C" int64_t pert_num_tiles(const pert_problem* pb) {
     if (!pb || pb->K <= 0) return 0;
-    const int tp = pick_tp(pb->K);
     const int64_t P = pb->N * pb->H * pb->W;
-    return (P + tp - 1) / tp;  // one warp tile per CTA
+    const int a = pick_tp(pb->K), b = sparse_tp(pb->K, P);
+    const int tp = a < b ? a : b;  // the finest tile geometry any launch of this problem uses
+    return (P + tp - 1) / tp;
 }
 
 extern "C" int pert_winner_bytes(int32_t K) { return (K + 1 <= 256) ? 1 : 2; }
@@ -155,9 +161,9 @@ extern "C" int pert_shade_fwd(const pert_problem* pb_in, float* image, uint16_t*
     if ((uintptr_t)worklist & 15) return PERT_E_ALIGN;
     const uint32_t all = PERT_PH_RAST | PERT_PH_AGG | PERT_PH_BLEND;
     const bool sparse = sparse_first_ok(&a.pb, worklist, (f & all) == all && !hist);
-    a.L = make_launch(&a.pb, sparse ? sparse_tp(a.pb.K) : pick_tp(a.pb.K));
+    a.L = make_launch(&a.pb, sparse ? sparse_tp(a.pb.K, a.pb.N * a.pb.H * a.pb.W) : pick_tp(a.pb.K));
     a.L.vec_ok = a.L.vec_ok && aligned16(a.pb.pix_to_face);
-    if (sparse) a.L.cap = sparse_cap(a.pb.K);
+    if (sparse) a.L.cap = sparse_cap(a.pb.K, a.L.tp);
     fwd_smem_layout(a.L.tp, a.L.cap, a.L.sm);
     a.L.warp_smem = a.L.sm.bytes;
     if ((size_t)a.L.warp_smem > 200 * 1024) return PERT_E_UNSUPPORTED;
@@ -205,9 +211,9 @@ extern "C" int pert_shade_bwd(const pert_problem* pb_in, const float* grad_image
     const bool sparse = sparse_first_ok(&a.pb, worklist, smp && fin && !hist);
     const bool ptr_ok = aligned16(a.pb.pix_to_face) && aligned16(grad_dists) && aligned16(grad_zbuf) &&
                         (a.pb.face_colors || aligned16(grad_colors));
-    a.L = make_launch(&a.pb, sparse ? sparse_tp(a.pb.K) : pick_tp(a.pb.K));
+    a.L = make_launch(&a.pb, sparse ? sparse_tp(a.pb.K, a.pb.N * a.pb.H * a.pb.W) : pick_tp(a.pb.K));
     a.L.vec_ok = a.L.vec_ok && ptr_ok;
-    if (sparse) a.L.cap = sparse_cap(a.pb.K);
+    if (sparse) a.L.cap = sparse_cap(a.pb.K, a.L.tp);
     if (a.L.win_bytes == 2 && ((uintptr_t)winners & 1)) return PERT_E_ALIGN;
     bwd_smem_layout(a.L.tp, a.pb.K, a.L.cap, a.L.sc, a.L.nchunks, a.L.win_bytes, sparse, a.L.sm);
     a.L.warp_smem = a.L.sm.bytes;

@@ -60,7 +60,7 @@ def test_argument_validation_without_gpu():
     assert lib.pert_shade_fwd(p, None, None, None, None, None, None, None, None) == -1  # null inputs
     assert lib.pert_winner_bytes(50) == 1 and lib.pert_winner_bytes(255) == 1 and lib.pert_winner_bytes(256) == 2
     p.N, p.H, p.W, p.K = 8, 256, 256, 50
-    assert lib.pert_num_tiles(p) == 8 * 256 * 256 // 8  # 8-pixel warp tiles, one per CTA
+    assert lib.pert_num_tiles(p) == 8 * 256 * 256 // 8  # finest geometry of this problem: 8-pixel tiles
     assert lib.pert_rast_fwd(None, 1, 1, 1, 0, 1, 1.0, 0, 0, None, 0, None, None, None) == -1
     assert lib.pert_noise_fill(0, 0, 4, 4, 0, 4, 0, None, None) == -1
 
