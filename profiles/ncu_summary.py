@@ -26,9 +26,15 @@ if len(sys.argv)>2:
     def num(d,name):
         i=hdr.index(name); v=float(d[i].replace(",","")); u=units[i].lower()
         return v*{"byte":1,"kbyte":1e3,"mbyte":1e6,"gbyte":1e9}[u]
+    # a launch of pert_shade_fwd / pert_shade_bwd = main kernel + fallback kernel: sum both, per main launch
+    tot={"pert_shade_fwd":0.0,"pert_shade_bwd":0.0}; n={"pert_shade_fwd":0,"pert_shade_bwd":0}
     for d in data:
         kn=d[hdr.index("Kernel Name")]
         name="pert_shade_fwd" if "shade_fwd" in kn else ("pert_shade_bwd" if "shade_bwd" in kn else None)
-        if name: ent[name]=num(d,"dram__bytes_read.sum")+num(d,"dram__bytes_write.sum")
+        if not name: continue
+        tot[name]+=num(d,"dram__bytes_read.sum")+num(d,"dram__bytes_write.sum")
+        if "fallback" not in kn: n[name]+=1
+    for k in tot:
+        if n[k]: ent[k]=tot[k]/n[k]
     ent["source"]=os.path.basename(rep)
     json.dump(t,open(path,"w"),indent=1)

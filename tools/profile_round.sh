@@ -10,7 +10,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
     python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/ncu_launch_${tag}.log 2>&1
 for kind in realistic dense; do
   python tools/prof_driver.py $kind 3 > gpurun_out/plain_${kind}_${tag}.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:shade_ -s 2 -c 2 -f -o gpurun_out/prof_${tag}_${kind} \
+  ncu --set full --clock-control none --import-source on -k regex:shade_ -s 4 -c 4 -f -o gpurun_out/prof_${tag}_${kind} \
       python tools/prof_driver.py $kind 3 > gpurun_out/ncu_${kind}_${tag}.log 2>&1
 done
 ls -la gpurun_out | tail -20
