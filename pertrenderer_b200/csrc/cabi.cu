@@ -160,7 +160,13 @@ extern "C" int pert_shade_fwd(const pert_problem* pb_in, float* image, uint16_t*
         return PERT_E_ALIGN;
     if ((uintptr_t)worklist & 15) return PERT_E_ALIGN;
     const uint32_t all = PERT_PH_RAST | PERT_PH_AGG | PERT_PH_BLEND;
-    const bool sparse = sparse_first_ok(&a.pb, worklist, (f & all) == all && !hist);
+    bool sparse = sparse_first_ok(&a.pb, worklist, (f & all) == all && !hist);
+    if (sparse) {  // the fallback pass runs FBT/32 warps per CTA: its tiles must fit that many times
+        SmemLayout t;
+        const int tp2 = sparse_tp(a.pb.K, a.pb.N * a.pb.H * a.pb.W) / 2;
+        fwd_smem_layout(tp2, tp2 * a.pb.K, t);
+        if ((size_t)t.bytes * (FBT / 32) > 200 * 1024) sparse = false;
+    }
     a.L = make_launch(&a.pb, sparse ? sparse_tp(a.pb.K, a.pb.N * a.pb.H * a.pb.W) : pick_tp(a.pb.K));
     a.L.vec_ok = a.L.vec_ok && aligned16(a.pb.pix_to_face);
     if (sparse) a.L.cap = sparse_cap(a.pb.K, a.L.tp);
@@ -208,7 +214,14 @@ extern "C" int pert_shade_bwd(const pert_problem* pb_in, const float* grad_image
         ((uintptr_t)scalar_partials & 15) || ((uintptr_t)acc & 3) || ((uintptr_t)pixstat & 3) || ((uintptr_t)hist & 3))
         return PERT_E_ALIGN;
     if ((uintptr_t)worklist & 15) return PERT_E_ALIGN;
-    const bool sparse = sparse_first_ok(&a.pb, worklist, smp && fin && !hist);
+    bool sparse = sparse_first_ok(&a.pb, worklist, smp && fin && !hist);
+    if (sparse) {  // the fallback pass runs FBT/32 warps per CTA: its tiles must fit that many times
+        const int tp2 = sparse_tp(a.pb.K, a.pb.N * a.pb.H * a.pb.W) / 2;
+        const Launch t = make_launch(&a.pb, tp2);
+        SmemLayout sl;
+        bwd_smem_layout(tp2, a.pb.K, t.cap, t.sc, t.nchunks, t.win_bytes, false, sl);
+        if ((size_t)sl.bytes * (FBT / 32) > 200 * 1024) sparse = false;
+    }
     const bool ptr_ok = aligned16(a.pb.pix_to_face) && aligned16(grad_dists) && aligned16(grad_zbuf) &&
                         (a.pb.face_colors || aligned16(grad_colors));
     a.L = make_launch(&a.pb, sparse ? sparse_tp(a.pb.K, a.pb.N * a.pb.H * a.pb.W) : pick_tp(a.pb.K));
