@@ -276,7 +276,9 @@ def device_timed(args, kind, dev, steps, warmup, world, rank, sampler=None, flag
             "bwd": {"ms": bwd_ms, "alg_bytes": bb, "gbs": bb / bwd_ms / 1e6, "frac": bb / bwd_ms / 1e6 / peak},
             "fwd_bwd_frac": (fb + bb) / (fwd_ms + bwd_ms) / 1e6 / peak}
     return {"value": units * world * steps / (total_ms * 1e-3), "ms_per_step": total_ms / steps, "roofline": roof,
-            "launches": 3 * steps}
+            # kernels of libpertshade.so per step: forward main + fallback pass, backward main + fallback pass,
+            # scalar-gradient finalize
+            "launches": 5 * steps}
 
 
 def e2e_timed(args, kind, dev, steps, warmup, world, rank):
