@@ -345,6 +345,71 @@ def shade_fwd_bwd(pix_to_face, zbuf, dists, colors, background, znear, zfar,
 # ----------------------------------------------------------------------------
 # closed-form known answers used by the Philox-mode tests
 # ----------------------------------------------------------------------------
+# ----------------------------------------------------------------------------
+# the SoftRas pair: SoftRast + SoftAgg (the shaders' default operators), deterministic
+# ----------------------------------------------------------------------------
+def soft_shade_fwd_bwd(pix_to_face, zbuf, dists, colors, background, znear, zfar, sigma, gamma, alpha, eps,
+                       grad_image=None):
+    """smooth_rgb_blend (randomras/random_rasterizer.py:34-56) with SoftRast.rasterize
+    (randomras/smoothrast.py:132-134: sigmoid(-dists/sigma)) and SoftAgg.aggregate
+    (randomras/smoothagg.py:172-182: softmax((1/gamma) * logits)), forward and hand-written backward
+    (log_corrected / prod_corrected rules of smoothagg.py:292-337).
+
+    Returns (image, prob, weights) or, with ``grad_image``, also the gradient dict."""
+    N, H, W, K = pix_to_face.shape
+    sig = torch.as_tensor(sigma, dtype=F32)
+    g = torch.as_tensor(gamma, dtype=F32)
+    a = torch.as_tensor(alpha, dtype=F32)
+    bg = _as_background(background)
+    zn, zf = _as_depth_plane(znear, N), _as_depth_plane(zfar, N)
+    mask = pix_to_face >= 0
+    maskf = mask.to(F32)
+    p = torch.sigmoid(-dists / sig)  # smoothrast.py:133
+    prob = p * maskf  # random_rasterizer.py:47
+    alpha_px = 1.0 - torch.prod(1.0 - prob, dim=-1)  # :48, :54
+    zeta, aux = build_logits(zbuf, zf, zn, prob, mask, gamma, alpha, eps)  # smoothagg.py:174-180
+    inv_g = 1.0 / g
+    y = inv_g * zeta  # prod_corrected(1/gamma, z_map), smoothagg.py:181
+    weights = torch.softmax(y, dim=-1)
+    rgb = (weights[..., :K, None] * colors).sum(dim=-2) + weights[..., K:] * bg  # random_rasterizer.py:50-53
+    image = torch.cat((rgb, alpha_px[..., None]), dim=-1)
+    if grad_image is None:
+        return image, prob, weights
+
+    G_rgb, G_a = grad_image[..., :3], grad_image[..., 3]
+    grad_colors = weights[..., :K, None] * G_rgb[..., None, :]
+    gw = _grad_weights(colors, grad_image, bg)  # d/dw_j
+    gy = weights * (gw - (weights * gw).sum(dim=-1, keepdim=True))  # softmax backward
+    # prod_corrected(1/gamma, zeta): scalar side ignores infinite logits, tensor side nan -> 0
+    zeta_fin = torch.where(torch.isinf(zeta), torch.zeros_like(zeta), zeta)
+    g_inv_g = (zeta_fin * gy).nansum()
+    gzeta = inv_g * gy
+    gzeta = torch.where(torch.isnan(gzeta), torch.zeros_like(gzeta), gzeta)
+    grad_gamma = -g_inv_g / (g * g)
+    gz_faces = gzeta[..., :K]
+    g_zmax = -gzeta.sum(dim=-1)
+    passes = (aux["zi_max_raw"] >= eps).to(F32)
+    g_zi = gz_faces.clone()
+    g_zi.scatter_add_(-1, aux["zi_arg"][..., None], (g_zmax * passes)[..., None])
+    grad_zbuf = -(g_zi * maskf) / (zf - zn)
+    logp = aux["logp"]
+    logp_fin = torch.where(torch.isinf(logp), torch.zeros_like(logp), logp)
+    q = (logp_fin * gz_faces).nansum()
+    grad_gamma = grad_gamma + q / a
+    grad_alpha = -q * g / (a * a)
+    g_logp = (g / a) * gz_faces
+    g_logp = torch.where(torch.isnan(g_logp), torch.zeros_like(g_logp), g_logp)
+    inv = 1.0 / prob
+    inv = torch.where(torch.isinf(inv), torch.zeros_like(inv), inv)
+    g_prob = inv * g_logp + G_a[..., None] * _prod_excluding_self(1.0 - prob)
+    g_p = g_prob * maskf
+    g_u = g_p * p * (1.0 - p)  # sigmoid backward, u = -dists / sigma
+    grad_dists = -g_u / sig
+    grad_sigma = (g_u * dists / (sig * sig)).sum()
+    return image, prob, weights, dict(dists=grad_dists, zbuf=grad_zbuf, colors=grad_colors, sigma=grad_sigma,
+                                      gamma=grad_gamma, alpha=grad_alpha)
+
+
 def normal_cdf(t):
     return 0.5 * (1.0 + torch.erf(torch.as_tensor(t, dtype=torch.float64) / 2.0 ** 0.5))
 

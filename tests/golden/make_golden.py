@@ -189,6 +189,46 @@ def run_case(rr, sr, sa, name, *, N, H, W, K, S_r, S_a, sigma, gamma, alpha, see
           f"image mean {image.mean().item():.4f}  |gd| {d_leaf.grad.abs().sum().item():.3e}")
 
 
+def run_soft_case(rr, sr, sa, name, *, N, H, W, K, sigma, gamma, alpha, seed, znear, zfar, background,
+                  p_empty=0.25, mean_valid=3.0, frac_edge=0.6, all_empty_batch=None):
+    """The SoftRas pair (the shaders' DEFAULT operators): SoftRast (smoothrast.py:126-134) + SoftAgg
+    (smoothagg.py:165-182) through smooth_rgb_blend (random_rasterizer.py:34-56); deterministic."""
+    gen = torch.Generator().manual_seed(seed)
+    p2f, zbuf, dists = make_fragments(gen, N, H, W, K, sigma, 12, p_empty, mean_valid, frac_edge)
+    if all_empty_batch is not None:
+        p2f[all_empty_batch] = -1
+        zbuf[all_empty_batch] = -1.0
+        dists[all_empty_batch] = -1.0
+    colors = torch.rand((N, H, W, K, 3), generator=gen) * (p2f >= 0)[..., None]
+    grad_image = torch.randn((N, H, W, 4), generator=gen)
+    zn = torch.tensor(znear, dtype=torch.float32)[:, None, None, None]
+    zf = torch.tensor(zfar, dtype=torch.float32)[:, None, None, None]
+    rast = sr.SoftRast(sigma=sigma)
+    agg = sa.SoftAgg(gamma=gamma, alpha=alpha)
+    d_leaf = dists.clone().requires_grad_(True)
+    z_leaf = zbuf.clone().requires_grad_(True)
+    c_leaf = colors.clone().requires_grad_(True)
+    image = rr.smooth_rgb_blend(c_leaf, Fragments(p2f, z_leaf, None, d_leaf), rast, agg, Blend(sigma, gamma, background),
+                                znear=zn, zfar=zf)
+    (image * grad_image).sum().backward()
+    with torch.no_grad():
+        prob = rast.rasterize(dists) * (p2f >= 0)
+        weights = agg.aggregate(zbuf, zf, zn, prob, p2f >= 0)
+    out = dict(
+        pix_to_face=p2f.numpy(), zbuf=zbuf.numpy(), dists=dists.numpy(), colors=colors.numpy(),
+        grad_image=grad_image.numpy(), znear=np.asarray(znear, np.float32), zfar=np.asarray(zfar, np.float32),
+        background=np.asarray(background, np.float32),
+        sigma=np.float32(sigma), gamma=np.float32(gamma), alpha=np.float32(alpha), eps=np.float64(agg.eps),
+        image=image.detach().numpy(), prob=prob.numpy(), weights=weights.numpy(),
+        grad_dists=d_leaf.grad.numpy(), grad_zbuf=z_leaf.grad.numpy(), grad_colors=c_leaf.grad.numpy(),
+        grad_sigma=rast.sigma.grad.numpy(), grad_gamma=agg.gamma.grad.numpy(), grad_alpha=agg.alpha.grad.numpy(),
+    )
+    path = os.path.join(OUT, f"soft_{name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"soft {name}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)  image mean {image.mean().item():.4f}  "
+          f"grads sigma/gamma/alpha {rast.sigma.grad.item():.4e} {agg.gamma.grad.item():.4e} {agg.alpha.grad.item():.4e}")
+
+
 def run_ops_case(sr, sa, name, *, shape, S, sigma, gamma, seed):
     """Stand-alone autograd Functions with an arbitrary upstream gradient
     (randomHeaviside: smoothrast.py:12-59, randomArgmax: smoothagg.py:10-73)."""
@@ -228,6 +268,8 @@ def run_ops_case(sr, sa, name, *, shape, S, sigma, gamma, seed):
 def main():
     torch.set_num_threads(1)  # reduction order independent of the host
     rr, sr, sa = load_reference()
+    if "--soft-only" in sys.argv:  # leave the committed Gaussian goldens untouched
+        return soft_cases(rr, sr, sa)
     # 1: small, two batch elements with different depth planes, alpha != 1, non-white background
     run_case(rr, sr, sa, "small", N=2, H=6, W=6, K=5, S_r=8, S_a=8, sigma=1e-3, gamma=1e-2, alpha=1.3,
              seed=1, znear=[1.0, 0.5], zfar=[100.0, 50.0], background=(0.2, 0.5, 0.9))
@@ -242,6 +284,18 @@ def main():
              seed=4, znear=[1.0, 1.0], zfar=[100.0, 100.0], background=(0.0, 0.0, 0.0),
              p_empty=0.0, mean_valid=6.0, all_empty_batch=1)
     run_ops_case(sr, sa, "small", shape=(2, 3, 4, 6), S=12, sigma=1e-3, gamma=1e-2, seed=11)
+    if "--soft-only" in sys.argv or True:
+        soft_cases(rr, sr, sa)
+
+
+def soft_cases(rr, sr, sa):
+    run_soft_case(rr, sr, sa, "small", N=2, H=6, W=6, K=5, sigma=1e-3, gamma=1e-2, alpha=1.3, seed=21,
+                  znear=[1.0, 0.5], zfar=[100.0, 50.0], background=(0.2, 0.5, 0.9))
+    run_soft_case(rr, sr, sa, "k50", N=1, H=8, W=8, K=50, sigma=2e-4, gamma=4e-2, alpha=1.0, seed=22,
+                  znear=[1.0], zfar=[100.0], background=(1.0, 1.0, 1.0), mean_valid=6.0)
+    run_soft_case(rr, sr, sa, "empty", N=2, H=4, W=5, K=7, sigma=1e-3, gamma=4e-3, alpha=0.7, seed=23,
+                  znear=[1.0, 1.0], zfar=[100.0, 100.0], background=(0.0, 0.0, 0.0), p_empty=0.0, mean_valid=7.0,
+                  all_empty_batch=1)
 
 
 if __name__ == "__main__":

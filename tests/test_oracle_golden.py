@@ -1,6 +1,7 @@
 """Pin the CPU oracle (oracle/pert_oracle.py) against golden vectors produced by the unmodified
 reference (tests/golden/make_golden.py), and against the closed forms of SURVEY.md Appendix A.4."""
 
+import pytest
 import torch
 
 from conftest import load_golden, rel_err
@@ -86,3 +87,22 @@ def test_closed_forms_monte_carlo():
     w, _, _ = O.random_argmax_fwd(zeta, V, gamma)
     e = O.expected_two_way_weight(0.0, -0.7e-2, gamma).item()
     assert abs(w[0, 0, 0, 0].item() - e) <= 5 * (e * (1 - e) / S) ** 0.5
+
+
+@pytest.mark.parametrize("case", ["small", "k50", "empty"])
+def test_soft_oracle_matches_reference_golden(case):
+    """SoftRast + SoftAgg (the shaders' default operators): the oracle's forward and hand-written backward
+    against vectors produced by the unmodified reference (tests/golden/make_golden.py, soft_*.npz)."""
+    g = load_golden("soft_" + case)
+    zn, zf = g["znear"].reshape(-1, 1, 1, 1), g["zfar"].reshape(-1, 1, 1, 1)
+    image, prob, weights, gr = O.soft_shade_fwd_bwd(g["pix_to_face"], g["zbuf"], g["dists"], g["colors"], g["background"], zn, zf,
+                                                    g["sigma"], g["gamma"], g["alpha"], g["eps"], g["grad_image"])
+    assert torch.equal(prob, g["prob"])
+    assert (weights - g["weights"]).abs().max() <= 1e-6
+    assert (image - g["image"]).abs().max() <= 1e-6
+    assert rel_err(gr["colors"], g["grad_colors"]) <= 1e-6
+    assert rel_err(gr["dists"], g["grad_dists"]) <= 1e-5
+    assert rel_err(gr["zbuf"], g["grad_zbuf"]) <= 1e-5
+    for k in ("sigma", "gamma", "alpha"):
+        ref = float(g["grad_" + k])
+        assert abs(gr[k].item() - ref) <= 2e-5 * max(abs(ref), 1e-12) + 1e-7, (k, gr[k].item(), ref)
