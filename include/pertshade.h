@@ -17,6 +17,8 @@
  *                    randomras/smoothagg.py:45-73          randomArgmax.backward
  *                    randomras/smoothagg.py:303-311,325-337 log_corrected / prod_corrected backward
  *                    randomras/smoothrast.py:40-59         randomHeaviside.backward
+ *   pert_soft_shade_fwd / _bwd        the same blend with SoftRast (smoothrast.py:126-134) + SoftAgg
+ *                                     (smoothagg.py:165-182), the shaders' default operators
  *   pert_rast_fwd / pert_rast_bwd     randomras/smoothrast.py:12-59   (stand-alone randomHeaviside)
  *   pert_argmax_fwd / pert_argmax_bwd randomras/smoothagg.py:10-73    (stand-alone randomArgmax)
  *   pert_noise_fill  the two torch.normal draws, smoothrast.py:21 and smoothagg.py:21 (test aid:
@@ -151,6 +153,18 @@ int pert_shade_bwd(const pert_problem* pb, const float* grad_image, const uint16
                    const float* rsum, const void* winners, const uint16_t* pixstate, float* grad_dists,
                    float* grad_zbuf, float* grad_colors, float* scalar_partials, float* grad_scalars,
                    float* acc, float* pixstat, const int32_t* hist, int32_t* worklist, void* stream);
+
+/*
+ * SoftRas pair: SoftRast + SoftAgg, the DEFAULT operators of RandomSimpleShader
+ * (randomras/random_rasterizer.py:139-140; smoothrast.py:126-134; smoothagg.py:165-182), fused and
+ * deterministic: P = sigmoid(-dists/sigma)*mask, w = softmax(logits/gamma), same logits, alpha channel and
+ * blend as the perturbed shader.  The sample-count / seed / noise fields of pert_problem are ignored.
+ * Backward recomputes forward (no saved state): outputs as pert_shade_bwd, scalar_partials needs
+ * 4 * pert_num_tiles floats.
+ */
+int pert_soft_shade_fwd(const pert_problem* pb, float* image, void* stream);
+int pert_soft_shade_bwd(const pert_problem* pb, const float* grad_image, float* grad_dists, float* grad_zbuf,
+                        float* grad_colors, float* scalar_partials, float* grad_scalars, void* stream);
 
 /*
  * Stand-alone perturbed Heaviside on x (P,K) (x = -dists in the shader).  prob = counts/S.

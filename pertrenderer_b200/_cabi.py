@@ -26,7 +26,7 @@ PH_BWD_SAMPLE, PH_BWD_FINISH = 0x100, 0x200
 
 EXPORTS = [
     "pert_version", "pert_strerror", "pert_last_cuda_error", "pert_num_tiles", "pert_winner_bytes",
-    "pert_shade_fwd", "pert_shade_bwd", "pert_rast_fwd", "pert_rast_bwd", "pert_argmax_fwd",
+    "pert_shade_fwd", "pert_shade_bwd", "pert_soft_shade_fwd", "pert_soft_shade_bwd", "pert_rast_fwd", "pert_rast_bwd", "pert_argmax_fwd",
     "pert_argmax_bwd", "pert_noise_fill",
 ]
 
@@ -89,6 +89,10 @@ def load():
         lib.pert_shade_fwd.argtypes = [pp] + [vp] * 8
         lib.pert_shade_bwd.restype = C.c_int
         lib.pert_shade_bwd.argtypes = [pp] + [vp] * 15
+        lib.pert_soft_shade_fwd.restype = C.c_int
+        lib.pert_soft_shade_fwd.argtypes = [pp, vp, vp]
+        lib.pert_soft_shade_bwd.restype = C.c_int
+        lib.pert_soft_shade_bwd.argtypes = [pp] + [vp] * 7
         lib.pert_rast_fwd.restype = C.c_int
         lib.pert_rast_fwd.argtypes = [vp, i64, i32, i32, i32, i32, f32, u64, i64, vp, u32, vp, vp, vp]
         lib.pert_rast_bwd.restype = C.c_int

@@ -99,6 +99,7 @@ static Launch make_launch(const pert_problem* pb, int tp) {
     L.invSg = 1.0f / ((float)pb->S_agg * pb->gamma);
     L.inv_sr = 1.0f / ((float)pb->S_rast * pb->sigma);
     L.invS = 1.0f / (float)pb->S_agg;
+    L.inv_gamma = 1.0f / pb->gamma;
     return L;
 }
 
@@ -255,6 +256,48 @@ extern "C" int pert_shade_bwd(const pert_problem* pb_in, const float* grad_image
     cudaError_t e = cudaMemsetAsync(worklist, 0, 16, st);
     if (e != cudaSuccess) return cuda_fail((int)e);
     return cuda_rc(launch_shade_bwd(a, &fb, grad_scalars, st));
+}
+
+// ---- SoftRas pair (SoftRast + SoftAgg), deterministic -----------------------------------------------
+static int soft_launch_record(pert_problem& pb, Launch& L, bool bwd, bool ptr_ok) {
+    // sample counts are unused on this path; make the shared validation happy
+    pb.S_rast = pb.S_agg = 4;
+    pb.s_rast_begin = pb.s_agg_begin = 0;
+    pb.s_rast_end = pb.s_agg_end = 4;
+    pb.noise_rast = pb.noise_agg = nullptr;
+    pb.face_colors = nullptr;
+    int rc = check_problem(&pb);
+    if (rc) return rc;
+    if (!pb.colors) return PERT_E_NULL;
+    L = make_launch(&pb, pick_tp(pb.K));
+    L.vec_ok = L.vec_ok && ptr_ok;
+    soft_smem_layout(L.tp, pb.K, bwd, L.sm);
+    L.warp_smem = L.sm.bytes;
+    if ((size_t)L.warp_smem > 200 * 1024) return PERT_E_UNSUPPORTED;
+    return PERT_OK;
+}
+
+extern "C" int pert_soft_shade_fwd(const pert_problem* pb_in, float* image, void* stream) {
+    if (!pb_in || !image) return PERT_E_NULL;
+    if ((uintptr_t)image & 15) return PERT_E_ALIGN;
+    pert_problem pb = *pb_in;
+    Launch L;
+    if (int rc = soft_launch_record(pb, L, false, aligned16(pb.pix_to_face))) return rc;
+    return cuda_rc(launch_soft_fwd(pb, L, image, (cudaStream_t)stream));
+}
+
+extern "C" int pert_soft_shade_bwd(const pert_problem* pb_in, const float* grad_image, float* grad_dists, float* grad_zbuf,
+                                   float* grad_colors, float* scalar_partials, float* grad_scalars, void* stream) {
+    if (!pb_in || !grad_image || !grad_dists || !grad_zbuf || !scalar_partials || !grad_scalars) return PERT_E_NULL;
+    if (((uintptr_t)grad_image & 15) || ((uintptr_t)scalar_partials & 15) || ((uintptr_t)grad_dists & 3) ||
+        ((uintptr_t)grad_zbuf & 3) || ((uintptr_t)grad_colors & 3))
+        return PERT_E_ALIGN;
+    pert_problem pb = *pb_in;
+    Launch L;
+    const bool ptr_ok = aligned16(pb.pix_to_face) && aligned16(grad_dists) && aligned16(grad_zbuf) && aligned16(grad_colors);
+    if (int rc = soft_launch_record(pb, L, true, ptr_ok)) return rc;
+    return cuda_rc(launch_soft_bwd(pb, L, grad_image, grad_dists, grad_zbuf, grad_colors, scalar_partials, grad_scalars,
+                                   (cudaStream_t)stream));
 }
 
 extern "C" int pert_rast_fwd(const float* x, int64_t P, int32_t K, int32_t S, int32_t s_begin, int32_t s_end,

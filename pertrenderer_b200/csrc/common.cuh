@@ -175,6 +175,7 @@ struct Launch {
     // launch constants computed once on the host (IEEE fp32, the same values the kernels used to derive)
     float gal;      // gamma / alpha (smoothagg.py:201)
     float inv_sigma, invSg, inv_sr, invS;  // 1/sigma, 1/(S_agg gamma), 1/(S_rast sigma), 1/S_agg
+    float inv_gamma;  // 1/gamma (SoftAgg, smoothagg.py:181)
 };
 
 // 16-byte asynchronous global -> shared copy (LDGSTS) and its completion wait

@@ -42,6 +42,11 @@ void bwd_smem_layout(int tp, int K, int cap, int sc, int nchunks, int win_bytes,
 int launch_shade_fwd(const FwdArgs& a, const FwdArgs* fb, cudaStream_t st);
 int launch_shade_bwd(const BwdArgs& a, const BwdArgs* fb, float* grad_scalars, cudaStream_t st);
 
+void soft_smem_layout(int tp, int K, bool bwd, SmemLayout& L);
+int launch_soft_fwd(const pert_problem& pb, const Launch& L, float* image, cudaStream_t st);
+int launch_soft_bwd(const pert_problem& pb, const Launch& L, const float* grad_image, float* grad_dists, float* grad_zbuf,
+                    float* grad_colors, float* partials, float* grad_scalars, cudaStream_t st);
+
 int launch_rast_fwd(const float* x, int64_t P, int K, int S, int s_begin, int s_end, float sigma, uint64_t seed,
                     int64_t pixel_offset, const float* noise, uint32_t flags, float* prob, float* rsum, cudaStream_t st);
 int launch_rast_bwd(const float* grad_l, const float* rsum, int64_t n, int S, float sigma, float* grad_x,

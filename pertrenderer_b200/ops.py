@@ -259,6 +259,40 @@ def shade_backward(pr: ShadeProblem, saved: ShadeSaved, grad_image: torch.Tensor
 
 
 # ---------------------------------------------------------------------------------------------
+# SoftRas pair (SoftRast + SoftAgg): deterministic fused kernels, nothing saved between the passes
+# ---------------------------------------------------------------------------------------------
+def soft_shade_forward(pr: ShadeProblem):
+    """Launch pert_soft_shade_fwd.  Returns the image (N,H,W,4)."""
+    lib = _cabi.load()
+    N, H, W, K = pr.shape
+    dev = pr.device
+    with torch.cuda.device(dev):
+        image = torch.empty((N, H, W, 4), dtype=torch.float32, device=dev)
+        rc = lib.pert_soft_shade_fwd(pr.c_struct(), ptr(image), stream_ptr(dev))
+    check(rc, "pert_soft_shade_fwd")
+    return image
+
+
+def soft_shade_backward(pr: ShadeProblem, grad_image: torch.Tensor, need_colors: bool = True):
+    """Launch pert_soft_shade_bwd.  Returns (grad_dists, grad_zbuf, grad_colors | None, grad_scalars(3))."""
+    lib = _cabi.load()
+    N, H, W, K = pr.shape
+    dev = pr.device
+    require_cuda(grad_image)
+    grad_image = _f32c(grad_image)
+    with torch.cuda.device(dev):
+        gd = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+        gz = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
+        gc = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev) if need_colors else None
+        partials = torch.empty((pr.num_tiles(), 4), dtype=torch.float32, device=dev)
+        scal = torch.empty((3,), dtype=torch.float32, device=dev)
+        rc = lib.pert_soft_shade_bwd(pr.c_struct(), ptr(grad_image), ptr(gd), ptr(gz), ptr(gc), ptr(partials), ptr(scal),
+                                     stream_ptr(dev))
+    check(rc, "pert_soft_shade_bwd")
+    return gd, gz, gc, scal
+
+
+# ---------------------------------------------------------------------------------------------
 # stand-alone operators
 # ---------------------------------------------------------------------------------------------
 def rast_forward(x, S, sigma, seed=0, noise=None, pixel_offset=0, flags=0, s_range=None):

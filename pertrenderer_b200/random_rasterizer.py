@@ -75,6 +75,35 @@ class _PerturbedShade(Function):
                 out_scal[0], out_scal[1], out_scal[2], None, None, None, None)
 
 
+class _SoftShade(Function):
+    """Fused SoftRast -> mask/alpha -> SoftAgg -> blend (the shaders' DEFAULT operator pair;
+    smoothrast.py:126-134, smoothagg.py:165-182): one deterministic streaming kernel per pass,
+    backward recomputes forward instead of saving it."""
+
+    @staticmethod
+    def forward(ctx, colors, dists, zbuf, sigma, gamma, alpha, pix_to_face, znear, zfar, cfg):
+        pr = ops.ShadeProblem(
+            pix_to_face=pix_to_face, zbuf=zbuf, dists=dists, colors=colors, znear=znear, zfar=zfar,
+            background=cfg["background"], sigma=float(sigma), gamma=float(gamma), alpha=float(alpha),
+            eps=float(cfg["eps"]), S_rast=4, S_agg=4)
+        ctx.pr = pr
+        ctx.scalars = (sigma, gamma, alpha)
+        return ops.soft_shade_forward(pr)
+
+    @staticmethod
+    def backward(ctx, grad_image):
+        need = ctx.needs_input_grad
+        gd, gz, gc, scal = ops.soft_shade_backward(ctx.pr, grad_image, need_colors=need[0])
+        out_scal = [None, None, None]
+        if any(need[3:6]):
+            host = scal.cpu()
+            for i, t in enumerate(ctx.scalars):
+                if need[3 + i] and torch.is_tensor(t):
+                    out_scal[i] = host[i].to(dtype=t.dtype).reshape(t.shape).to(t.device)
+        return (gc if need[0] else None, gd if need[1] else None, gz if need[2] else None,
+                out_scal[0], out_scal[1], out_scal[2], None, None, None, None)
+
+
 def smooth_rgb_blend(colors, fragments, smoothrast, smoothagg, blend_params, znear: float = 1.0,
                      zfar: float = 100) -> torch.Tensor:
     """random_rasterizer.py:34-56.  Returns the (N,H,W,4) RGBA image.
@@ -89,6 +118,11 @@ def smooth_rgb_blend(colors, fragments, smoothrast, smoothagg, blend_params, zne
                    fixed_noise=bool(smoothagg.fixed_noise), face_colors=face)
         return _PerturbedShade.apply(colors.face_colors if face else colors, fragments.dists, fragments.zbuf, smoothrast.sigma,
                                      smoothagg.gamma, smoothagg.alpha, fragments.pix_to_face, znear, zfar, cfg)
+
+    if type(smoothrast) is SoftRast and type(smoothagg) is SoftAgg and not face:
+        cfg = dict(background=_background_tuple(blend_params), eps=smoothagg.eps)
+        return _SoftShade.apply(colors, fragments.dists, fragments.zbuf, smoothrast.sigma, smoothagg.gamma,
+                                smoothagg.alpha, fragments.pix_to_face, znear, zfar, cfg)
 
     # operator-by-operator composition for every other pair (e.g. GaussianRast + SoftAgg)
     if face:
