@@ -201,7 +201,7 @@ def workload_config(args, world):
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
-def device_timed(args, kind, dev, steps, warmup, world, rank, sampler=None, flags=0, face=False):
+def device_timed(args, kind, dev, steps, warmup, world, rank, sampler=None, flags=0, face=False, soft=False):
     """Inputs resident in HBM; K steps of pert_shade_fwd + pert_shade_bwd through the C ABI."""
     import torch.distributed as dist
     from pertrenderer_b200 import ops, synthetic_fragments
@@ -228,10 +228,13 @@ def device_timed(args, kind, dev, steps, warmup, world, rank, sampler=None, flag
         pr = problem()
         if i is not None:
             ev[i][0].record()
-        image, saved = ops.shade_forward(pr)
+        if soft:  # SoftRast + SoftAgg (deterministic): the shaders' default operator pair
+            image = ops.soft_shade_forward(pr)
+        else:
+            image, saved = ops.shade_forward(pr)
         if i is not None:
             ev[i][1].record()
-        gd, gz, gc, scal = ops.shade_backward(pr, saved, G)
+        gd, gz, gc, scal = ops.soft_shade_backward(pr, G) if soft else ops.shade_backward(pr, saved, G)
         if i is not None:
             ev[i][2].record()
         if world > 1:
@@ -381,7 +384,14 @@ def run_b200_arm(args):
         o = device_timed(args, other_kind, dev, max(3, args.steps // 4), 3, world, rank)
         ps = device_timed(args, args.fragments, dev, max(3, args.steps // 2), 3, world, rank, flags=_cabi.F_PER_SAMPLE_NOISE)
         fc = device_timed(args, args.fragments, dev, max(3, args.steps // 2), 3, world, rank, face=True)
-        also = {"face_colour_gather": {"fragments": args.fragments,
+        sf = device_timed(args, args.fragments, dev, max(3, args.steps // 2), 3, world, rank, soft=True)
+        also = {"softras_pair": {"fragments": args.fragments,
+                                 "note": "SoftRast + SoftAgg (the shaders' DEFAULT operators, deterministic) through the "
+                                         "fused soft kernels; same algorithmic bytes; 'units' counts nb_samples like the "
+                                         "headline although this pair draws no samples",
+                                 "value": sf["value"], "unit": UNIT, "ms_per_step": sf["ms_per_step"],
+                                 "roofline": sf["roofline"]},
+                "face_colour_gather": {"fragments": args.fragments,
                                        "note": "texel colours gathered through pix_to_face inside the kernels (per-face "
                                                "colour table of 1280 faces), gradient scattered by atomics; algorithmic "
                                                "bytes 40 PF + 32 P + 24 F",

@@ -10,6 +10,8 @@ print("dense     ms/step %.4f fwd %.4f (%.3f) bwd %.4f (%.3f)" % (d["also"]["fra
 print("persample ms/step %.4f bwd %.4f (%.3f)" % (ps["ms_per_step"], ps["roofline"]["bwd"]["ms"], ps["roofline"]["bwd"]["frac"]))
 fc=d["also"]["face_colour_gather"]
 print("facecol   ms/step %.4f fwd %.4f (%.3f) bwd %.4f (%.3f)" % (fc["ms_per_step"], fc["roofline"]["fwd"]["ms"], fc["roofline"]["fwd"]["frac"], fc["roofline"]["bwd"]["ms"], fc["roofline"]["bwd"]["frac"]))
+sf=d["also"]["softras_pair"]
+print("softras   ms/step %.4f fwd %.4f (%.3f) bwd %.4f (%.3f)" % (sf["ms_per_step"], sf["roofline"]["fwd"]["ms"], sf["roofline"]["fwd"]["frac"], sf["roofline"]["bwd"]["ms"], sf["roofline"]["bwd"]["frac"]))
 print("clocks", d["clocks"])
 PY
 tail -3 gpurun_out/bench_$1.err
