@@ -75,6 +75,9 @@ extern "C" {
  *     for the squared term): same expectation, lower variance. */
 #define PERT_F_SKIP_DEAD_NOISE 2u
 #define PERT_F_PER_SAMPLE_NOISE 4u
+/* stand-alone operators only: standard Cauchy noise instead of Gaussian (ArctanRast smoothrast.py:162-173,
+ * CauchyAgg smoothagg.py:230-250): noise tan(pi(u-1/2)) clamped to +-1e7, score 2n/(1+n^2) in backward */
+#define PERT_F_CAUCHY 8u
 /* phases of the fused kernels; 0 means "all".  Used for noise-sample sharding where collectives sit
  * between the phases. */
 #define PERT_PH_RAST 0x10u  /* fwd: draw coverage samples -> counts, rsum */
@@ -186,7 +189,7 @@ int pert_argmax_bwd(const float* grad_l, const float* z, const void* winners, in
                     float* scalar_partials, float* grad_gamma, void* stream);
 
 /* Materialise the counter-based noise: out float (s_end-s_begin, P, slots), stage 0 = coverage
- * (slots = K), 1 = aggregation (slots = K1). */
+ * (slots = K), 1 = aggregation (slots = K1); stage | 2 = the Cauchy variant of that stage. */
 int pert_noise_fill(uint64_t seed, int32_t stage, int64_t P, int32_t slots, int32_t s_begin, int32_t s_end,
                     int64_t pixel_offset, float* out, void* stream);
 

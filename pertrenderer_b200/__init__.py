@@ -5,15 +5,16 @@ Drop-in for the hot path of quentinll/pertrenderer (``randomras``): the same pub
 (``include/pertshade.h``).  CUDA only: there is no CPU or PyTorch fallback on this path.
 """
 
-from .random_rasterizer import RandomSimpleShader, smooth_rgb_blend
-from .smoothagg import GaussianAgg, SoftAgg, randomArgmax
-from .smoothrast import GaussianRast, SoftRast, randomHeaviside
+from .random_rasterizer import RandomSimpleShader, SimpleShader, smooth_rgb_blend
+from .smoothagg import CauchyAgg, GaussianAgg, HardAgg, SoftAgg, randomArgmax
+from .smoothrast import AffineRast, ArctanRast, GaussianRast, HardRast, SoftRast, randomHeaviside
 from .structures import (BlendParams, DepthCameras, FaceColorMeshes, FaceTexels, Fragments, TexelMeshes,
                          synthetic_fragments)
 from .ops import explicit_noise, kernel_flags
 
 __all__ = [
-    "RandomSimpleShader", "smooth_rgb_blend", "GaussianAgg", "SoftAgg", "randomArgmax", "GaussianRast",
+    "RandomSimpleShader", "SimpleShader", "smooth_rgb_blend", "GaussianAgg", "SoftAgg", "CauchyAgg", "HardAgg",
+    "randomArgmax", "GaussianRast", "ArctanRast", "AffineRast", "HardRast",
     "SoftRast", "randomHeaviside", "BlendParams", "DepthCameras", "Fragments", "TexelMeshes",
     "synthetic_fragments", "explicit_noise", "kernel_flags", "FaceColorMeshes", "FaceTexels",
 ]

@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) finalize_single_kernel(const float* parti
 // ------------------------------------------------------------------------------------------------
 constexpr int RAST_TILE = 1024;  // entries per CTA
 
-template <class NoiseT>
+template <class NoiseT, int SCORE>
 __global__ void __launch_bounds__(NT) rast_fwd_kernel(const float* x, int64_t n, int K, int S, int s_begin, int s_end,
                                                       float sigma, uint32_t flags, const NoiseT noise, float* prob,
                                                       float* rsum) {
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(NT) rast_fwd_kernel(const float* x, int64_t n,
                         const bool h = __fadd_rn(v, __fmul_rn(sigma, nz[t])) >= 0.f;
                         if (s >= s_begin && s < s_end) {
                             c += h ? 1 : 0;
-                            if (h != h0) r += h ? nz[t] : -nz[t];
+                            if (h != h0) r += h ? noise_score<SCORE>(nz[t]) : -noise_score<SCORE>(nz[t]);
                         }
                     }
                 }
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(NT) argmax_fwd_kernel(const float* z, int64_t 
     for (int j = lane; j < K1; j += 32) weights[pixel * K1 + j] = (float)hist[j] / (float)S;
 }
 
-template <class NoiseT>
+template <class NoiseT, int SCORE>
 __global__ void __launch_bounds__(NT) argmax_bwd_kernel(const float* grad_l, const float* z, const void* winners,
                                                         int64_t P, int K1, int S, int s_begin, int s_end, float gamma,
                                                         uint32_t flags, int win_bytes, const NoiseT noise, float* grad_z,
@@ -270,7 +270,8 @@ __global__ void __launch_bounds__(NT) argmax_bwd_kernel(const float* grad_l, con
                             }
                             float nz[4];
                             noise.get4((s_begin >> 2) + (c0 >> 2) + ql, j, pixel, nz);
-                            const float v0 = c4.x * nz[0], v1 = c4.y * nz[1], v2 = c4.z * nz[2], v3 = c4.w * nz[3];
+                            const float v0 = c4.x * noise_score<SCORE>(nz[0]), v1 = c4.y * noise_score<SCORE>(nz[1]),
+                                        v2 = c4.z * noise_score<SCORE>(nz[2]), v3 = c4.w * noise_score<SCORE>(nz[3]);
                             acc[u] += (v0 + v1) + (v2 + v3);
                             t2 += (v0 * nz[0] + v1 * nz[1]) + (v2 * nz[2] + v3 * nz[3]);
                         }
@@ -296,6 +297,7 @@ __global__ void __launch_bounds__(NT) argmax_bwd_kernel(const float* grad_l, con
     }
 }
 
+template <class NoiseT>
 __global__ void __launch_bounds__(256) noise_fill_kernel(uint64_t seed, int stage, int64_t P, int slots, int s_begin,
                                                          int s_end, int64_t pixel_offset, float* out) {
     // one thread per (quad, pixel, slot)
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(256) noise_fill_kernel(uint64_t seed, int stag
     const int64_t rem = idx - (int64_t)(q - qb) * per_q;
     const int64_t pixel = rem / slots;
     const int slot = (int)(rem - pixel * slots);
-    PhiloxNoise noise(seed, stage, pixel_offset);
+    NoiseT noise(seed, stage, pixel_offset);
     float n[4];
     noise.get4(q, slot, pixel, n);
     for (int t = 0; t < 4; ++t) {
@@ -320,12 +322,17 @@ int launch_rast_fwd(const float* x, int64_t P, int K, int S, int s_begin, int s_
                     int64_t pixel_offset, const float* noise, uint32_t flags, float* prob, float* rsum, cudaStream_t st) {
     const int64_t n = P * K;
     const unsigned blocks = (unsigned)((n + RAST_TILE - 1) / RAST_TILE);
+    const bool cauchy = flags & PERT_F_CAUCHY;
     if (noise) {
         ExplicitNoise xn{noise, P, K, S};
-        rast_fwd_kernel<ExplicitNoise><<<blocks, NT, 0, st>>>(x, n, K, S, s_begin, s_end, sigma, flags, xn, prob, rsum);
+        if (cauchy) rast_fwd_kernel<ExplicitNoise, 1><<<blocks, NT, 0, st>>>(x, n, K, S, s_begin, s_end, sigma, flags, xn, prob, rsum);
+        else rast_fwd_kernel<ExplicitNoise, 0><<<blocks, NT, 0, st>>>(x, n, K, S, s_begin, s_end, sigma, flags, xn, prob, rsum);
+    } else if (cauchy) {
+        PhiloxCauchy pn(seed, 0, pixel_offset);
+        rast_fwd_kernel<PhiloxCauchy, 1><<<blocks, NT, 0, st>>>(x, n, K, S, s_begin, s_end, sigma, flags, pn, prob, rsum);
     } else {
         PhiloxNoise pn(seed, 0, pixel_offset);
-        rast_fwd_kernel<PhiloxNoise><<<blocks, NT, 0, st>>>(x, n, K, S, s_begin, s_end, sigma, flags, pn, prob, rsum);
+        rast_fwd_kernel<PhiloxNoise, 0><<<blocks, NT, 0, st>>>(x, n, K, S, s_begin, s_end, sigma, flags, pn, prob, rsum);
     }
     return (int)cudaGetLastError();
 }
@@ -347,6 +354,9 @@ int launch_argmax_fwd(const float* z, int64_t P, int K1, int S, int s_begin, int
     if (noise) {
         ExplicitNoise xn{noise, P, K1, S};
         argmax_fwd_kernel<ExplicitNoise><<<blocks, NT, smem, st>>>(z, P, K1, S, s_begin, s_end, gamma, flags, wb, xn, weights, winners);
+    } else if (flags & PERT_F_CAUCHY) {
+        PhiloxCauchy pn(seed, 1, pixel_offset);
+        argmax_fwd_kernel<PhiloxCauchy><<<blocks, NT, smem, st>>>(z, P, K1, S, s_begin, s_end, gamma, flags, wb, pn, weights, winners);
     } else {
         PhiloxNoise pn(seed, 1, pixel_offset);
         argmax_fwd_kernel<PhiloxNoise><<<blocks, NT, smem, st>>>(z, P, K1, S, s_begin, s_end, gamma, flags, wb, pn, weights, winners);
@@ -360,12 +370,17 @@ int launch_argmax_bwd(const float* grad_l, const float* z, const void* winners, 
     const unsigned blocks = (unsigned)((P + NW - 1) / NW);
     const size_t smem = carve((size_t)NW * K1, 4) + carve((size_t)NW * 128, 4);
     const int wb = (K1 <= 256) ? 1 : 2;
+    const bool cauchy = flags & PERT_F_CAUCHY;
     if (noise) {
         ExplicitNoise xn{noise, P, K1, S};
-        argmax_bwd_kernel<ExplicitNoise><<<blocks, NT, smem, st>>>(grad_l, z, winners, P, K1, S, s_begin, s_end, gamma, flags, wb, xn, grad_z, partials);
+        if (cauchy) argmax_bwd_kernel<ExplicitNoise, 1><<<blocks, NT, smem, st>>>(grad_l, z, winners, P, K1, S, s_begin, s_end, gamma, flags, wb, xn, grad_z, partials);
+        else argmax_bwd_kernel<ExplicitNoise, 0><<<blocks, NT, smem, st>>>(grad_l, z, winners, P, K1, S, s_begin, s_end, gamma, flags, wb, xn, grad_z, partials);
+    } else if (cauchy) {
+        PhiloxCauchy pn(seed, 1, pixel_offset);
+        argmax_bwd_kernel<PhiloxCauchy, 1><<<blocks, NT, smem, st>>>(grad_l, z, winners, P, K1, S, s_begin, s_end, gamma, flags, wb, pn, grad_z, partials);
     } else {
         PhiloxNoise pn(seed, 1, pixel_offset);
-        argmax_bwd_kernel<PhiloxNoise><<<blocks, NT, smem, st>>>(grad_l, z, winners, P, K1, S, s_begin, s_end, gamma, flags, wb, pn, grad_z, partials);
+        argmax_bwd_kernel<PhiloxNoise, 0><<<blocks, NT, smem, st>>>(grad_l, z, winners, P, K1, S, s_begin, s_end, gamma, flags, wb, pn, grad_z, partials);
     }
     finalize_single_kernel<<<1, 256, 0, st>>>(partials, blocks, grad_gamma);
     return (int)cudaGetLastError();
@@ -376,7 +391,8 @@ int launch_noise_fill(uint64_t seed, int stage, int64_t P, int slots, int s_begi
     const int qn = ((s_end + 3) >> 2) - (s_begin >> 2);
     const int64_t total = (int64_t)qn * P * slots;
     const unsigned blocks = (unsigned)((total + 255) / 256);
-    noise_fill_kernel<<<blocks, 256, 0, st>>>(seed, stage, P, slots, s_begin, s_end, pixel_offset, out);
+    if (stage & 2) noise_fill_kernel<PhiloxCauchy><<<blocks, 256, 0, st>>>(seed, stage & 1, P, slots, s_begin, s_end, pixel_offset, out);
+    else noise_fill_kernel<PhiloxNoise><<<blocks, 256, 0, st>>>(seed, stage & 1, P, slots, s_begin, s_end, pixel_offset, out);
     return (int)cudaGetLastError();
 }
 

@@ -101,6 +101,30 @@ struct PhiloxNoise {
     static constexpr bool kBounded = true;
 };
 
+// Standard Cauchy noise from the same counters: tan(pi (u - 1/2)), clamped to +-1e7 like the reference
+// (randomras/smoothrast.py:22-24, smoothagg.py:25-27).  Heavy tails: nothing can be skipped (not bounded).
+struct PhiloxCauchy {
+    PhiloxNoise base;
+    __host__ __device__ __forceinline__ PhiloxCauchy(uint64_t seed, int stage, int64_t pixel_off) : base(seed, stage, pixel_off) {}
+    __device__ __forceinline__ void get4(uint32_t q, uint32_t slot, int64_t pixel_local, float (&n)[4]) const {
+        uint32_t r[4];
+        base.words(q, slot, pixel_local, r);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float a = (mant12(r[t]) - 1.5f) * 3.14159265358979f;  // [-pi/2, pi/2)
+            n[t] = fminf(fmaxf(__fdividef(mufu_sin(a), mufu_cos(a)), -1e7f), 1e7f);
+        }
+    }
+    static constexpr bool kBounded = false;
+};
+
+// score of the noise density used by the gradient estimators: -d/dn log p(n)
+//   Gaussian: n   (smoothrast.py:46, smoothagg.py:51-53)     Cauchy: 2n / (1 + n^2)   (smoothrast.py:49, smoothagg.py:58-59)
+template <int SCORE>
+__device__ __forceinline__ float noise_score(float n) {
+    return SCORE == 0 ? n : __fdividef(2.0f * n, 1.0f + n * n);
+}
+
 // Explicit noise tensor (S, P, slots), e.g. the reference's own draws: used for exact-noise parity.
 struct ExplicitNoise {
     const float* base;

@@ -16,7 +16,7 @@ import torch.nn as nn
 from torch.autograd import Function
 
 from . import ops
-from .smoothagg import GaussianAgg, SoftAgg
+from .smoothagg import GaussianAgg, SoftAgg  # noqa: F401
 from .smoothrast import GaussianRast, SoftRast
 from .structures import BlendParams, FaceTexels
 
@@ -149,6 +149,25 @@ def _default_lights_materials(device):
         return PointLights(device=device), Materials(device=device)
     except Exception:
         return None, None
+
+
+class SimpleShader(nn.Module):
+    """random_rasterizer.py:194-203: texels of the closest face, background where the pixel is empty
+    (pytorch3d's hard_rgb_blend: RGB of face k = 0, alpha = coverage)."""
+
+    def __init__(self, device="cpu", blend_params=None):
+        super().__init__()
+        self.blend_params = blend_params if blend_params is not None else BlendParams()
+
+    def forward(self, fragments, meshes, **kwargs) -> torch.Tensor:
+        blend_params = kwargs.get("blend_params", self.blend_params)
+        texels = meshes.sample_textures(fragments)
+        if isinstance(texels, FaceTexels):
+            texels = texels.materialize(fragments.pix_to_face)
+        covered = fragments.pix_to_face[..., 0] >= 0
+        bg = torch.as_tensor(blend_params.background_color, dtype=texels.dtype, device=texels.device)
+        rgb = torch.where(covered[..., None], texels[..., 0, :], bg.expand_as(texels[..., 0, :]))
+        return torch.cat((rgb, covered[..., None].to(texels.dtype)), dim=-1)
 
 
 class RandomSimpleShader(nn.Module):

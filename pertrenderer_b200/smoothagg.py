@@ -15,7 +15,7 @@ from torch.nn import Module
 
 from . import ops
 
-_SUPPORTED = ("gaussian",)
+_SUPPORTED = ("gaussian", "cauchy")
 
 
 def _scalar(v) -> float:
@@ -45,7 +45,7 @@ class randomArgmax(Function):
         gamma = _scalar(noise_intensity)
         _, noise = ops.current_explicit_noise()
         seed = 0 if noise is not None else ops.draw_seed()
-        flags = ops.current_flags()
+        flags = ops.current_flags() | (ops.F_CAUCHY if noise_type == "cauchy" else 0)
         weights, winners = ops.argmax_forward(z, int(nb_samples), gamma, seed=seed, noise=noise, flags=flags)
         ctx.save_for_backward(z.detach(), winners)
         ctx.cfg = (int(nb_samples), gamma, seed, noise, flags)
@@ -151,3 +151,30 @@ class GaussianAgg(SmoothAggBase):
     def aggregate(self, zbuf, zfar, znear, prob_map, mask):
         z_map = self._logits(zbuf, zfar, znear, prob_map, mask)
         return randomArgmax.apply(z_map, self.nb_samples, self.gamma, "gaussian", self.fixed_noise)
+
+
+class CauchyAgg(SmoothAggBase):
+    """Cauchy-perturbed aggregation (smoothagg.py:230-250): the same logits, ``randomArgmax`` with
+    ``"cauchy"`` noise."""
+
+    def __init__(self, nb_samples=16, gamma=4e-2, alpha=1., eps=1e-10, fixed_noise=False):
+        super().__init__(gamma, alpha, eps, nb_samples)
+        self.fixed_noise = fixed_noise
+
+    def aggregate(self, zbuf, zfar, znear, prob_map, mask):
+        z_map = self._logits(zbuf, zfar, znear, prob_map, mask)
+        return randomArgmax.apply(z_map, self.nb_samples, self.gamma, "cauchy", self.fixed_noise)
+
+
+class HardAgg:
+    """No smoothing (smoothagg.py:274-289): one-hot of the arg-max logit, the coverage term weighted by 1e-6."""
+
+    def __init__(self, eps=1e-10):
+        self.eps = eps
+
+    def aggregate(self, zbuf, zfar, znear, prob_map, mask):
+        z_inv = (zfar - zbuf) / (zfar - znear) * mask
+        z_inv_max = z_inv.max(dim=-1, keepdim=True).values.clamp(min=self.eps)
+        faces = 1e-6 * torch.log(prob_map) + z_inv - z_inv_max
+        z_map = torch.cat((faces, self.eps - z_inv_max), dim=-1)
+        return torch.zeros_like(z_map).scatter_(-1, z_map.argmax(dim=-1, keepdim=True), 1.0)

@@ -16,7 +16,7 @@ from torch.nn import Module
 
 from . import ops
 
-_SUPPORTED = ("gaussian",)
+_SUPPORTED = ("gaussian", "cauchy")
 
 
 def _scalar(v) -> float:
@@ -37,15 +37,15 @@ class randomHeaviside(Function):
     def forward(ctx, distances, nb_samples=1, noise_intensity=1e-1, noise_type="gaussian"):
         if noise_type not in _SUPPORTED:
             # the reference prints "noise type not implemented" and then dies on a NameError
-            # (smoothrast.py:30-32); the cauchy / logistic variants are outside the B200 path
+            # (smoothrast.py:30-32); the logistic variant has no backward in the reference either
             raise ValueError(f"noise type {noise_type!r} not implemented (supported: {_SUPPORTED})")
         if distances.dim() != 4:
             raise ValueError("distances must be (N,H,W,K)")
         sigma = _scalar(noise_intensity)
         noise, _ = ops.current_explicit_noise()
         seed = 0 if noise is not None else ops.draw_seed()
-        prob, rsum = ops.rast_forward(distances, int(nb_samples), sigma, seed=seed, noise=noise,
-                                      flags=ops.current_flags())
+        flags = ops.current_flags() | (ops.F_CAUCHY if noise_type == "cauchy" else 0)
+        prob, rsum = ops.rast_forward(distances, int(nb_samples), sigma, seed=seed, noise=noise, flags=flags)
         ctx.save_for_backward(rsum)
         ctx.nb_samples, ctx.sigma = int(nb_samples), sigma
         ctx.sigma_like = noise_intensity if torch.is_tensor(noise_intensity) else None
@@ -99,3 +99,33 @@ class GaussianRast(SmoothRastBase):
 
     def rasterize(self, dists):
         return randomHeaviside.apply(-dists, self.nb_samples, self.sigma)
+
+
+class ArctanRast(SmoothRastBase):
+    """Cauchy-perturbed coverage (smoothrast.py:162-173): ``randomHeaviside`` with ``"cauchy"`` noise, whose
+    expectation is ``arctan(-dists/sigma)/pi + 1/2``."""
+
+    def __init__(self, nb_samples=16, sigma=2e-4):
+        super().__init__(sigma)
+        self.nb_samples = nb_samples
+
+    def rasterize(self, dists):
+        return randomHeaviside.apply(-dists, self.nb_samples, self.sigma, "cauchy")
+
+
+class AffineRast(SmoothRastBase):
+    """Uniform-noise smoothing in closed form (smoothrast.py:175-185): ``clamp(-dists/sigma + 1/2, 0, 1)``."""
+
+    def __init__(self, nb_samples=16, sigma=2e-4):
+        super().__init__(sigma)
+        self.nb_samples = nb_samples
+
+    def rasterize(self, dists):
+        return (dists.neg() / self.sigma + 0.5).clamp(min=0.0, max=1.0)
+
+
+class HardRast:
+    """No smoothing (smoothrast.py:187-194): ``1[-dists >= 0]``."""
+
+    def rasterize(self, dists):
+        return (dists <= 0).to(dists.dtype)

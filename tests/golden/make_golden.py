@@ -265,11 +265,54 @@ def run_ops_case(sr, sa, name, *, shape, S, sigma, gamma, seed):
     print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
 
 
+def run_cauchy_ops_case(sr, sa, name, *, shape, S, sigma, gamma, seed):
+    """Cauchy-perturbed stand-alone Functions (ArctanRast: smoothrast.py:162-173, CauchyAgg: smoothagg.py:230-250;
+    branches of randomHeaviside smoothrast.py:22-24,49-50 and randomArgmax smoothagg.py:25-27,57-63).  The
+    reference draws through torch.distributions.Cauchy: the same draw is repeated after the same manual_seed."""
+    gen = torch.Generator().manual_seed(seed)
+    N, H, W, K = shape
+
+    def cauchy(shape5, s):
+        torch.manual_seed(s)
+        m = torch.distributions.cauchy.Cauchy(torch.tensor([0.]), torch.tensor([1.]))
+        return torch.clamp(m.sample(shape5).squeeze(-1), min=-1e7, max=1e7)
+
+    x = (torch.rand(shape, generator=gen) * 2 - 1) * 3 * sigma
+    x[..., -1] = 1.0
+    x.requires_grad_(True)
+    sig = torch.tensor(sigma, requires_grad=True)
+    gl = torch.randn(shape, generator=gen)
+    U = cauchy((S, N, H, W, K), seed + 7)
+    torch.manual_seed(seed + 7)
+    y = sr.randomHeaviside.apply(x, S, sig, "cauchy")
+    (y * gl).sum().backward()
+    z = torch.randn((N, H, W, K + 1), generator=gen) * 2 * gamma
+    z[..., 0] = float("-inf")
+    z.requires_grad_(True)
+    gam = torch.tensor(gamma, requires_grad=True)
+    gw = torch.randn((N, H, W, K + 1), generator=gen)
+    V = cauchy((S, N, H, W, K + 1), seed + 8)
+    torch.manual_seed(seed + 8)
+    w = sa.randomArgmax.apply(z, S, gam, "cauchy", False)
+    (w * gw).sum().backward()
+    # the recorded draws are the reference's: forward must reproduce from them
+    assert torch.equal(y.detach(), ((x.detach() + sigma * U) >= 0).float().mean(0))
+    out = dict(x=x.detach().numpy(), sigma=np.float32(sigma), S=np.int32(S), U=U.numpy(), grad_l=gl.numpy(),
+               prob=y.detach().numpy(), grad_x=x.grad.numpy(), grad_sigma=sig.grad.numpy(),
+               z=z.detach().numpy(), gamma=np.float32(gamma), V=V.numpy(), grad_w=gw.numpy(),
+               weights=w.detach().numpy(), grad_z=z.grad.numpy(), grad_gamma=gam.grad.numpy())
+    path = os.path.join(OUT, f"ops_{name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
 def main():
     torch.set_num_threads(1)  # reduction order independent of the host
     rr, sr, sa = load_reference()
     if "--soft-only" in sys.argv:  # leave the committed Gaussian goldens untouched
         return soft_cases(rr, sr, sa)
+    if "--cauchy-only" in sys.argv:
+        return run_cauchy_ops_case(sr, sa, "cauchy", shape=(2, 3, 4, 6), S=12, sigma=1e-3, gamma=1e-2, seed=31)
     # 1: small, two batch elements with different depth planes, alpha != 1, non-white background
     run_case(rr, sr, sa, "small", N=2, H=6, W=6, K=5, S_r=8, S_a=8, sigma=1e-3, gamma=1e-2, alpha=1.3,
              seed=1, znear=[1.0, 0.5], zfar=[100.0, 50.0], background=(0.2, 0.5, 0.9))
@@ -284,8 +327,8 @@ def main():
              seed=4, znear=[1.0, 1.0], zfar=[100.0, 100.0], background=(0.0, 0.0, 0.0),
              p_empty=0.0, mean_valid=6.0, all_empty_batch=1)
     run_ops_case(sr, sa, "small", shape=(2, 3, 4, 6), S=12, sigma=1e-3, gamma=1e-2, seed=11)
-    if "--soft-only" in sys.argv or True:
-        soft_cases(rr, sr, sa)
+    soft_cases(rr, sr, sa)
+    run_cauchy_ops_case(sr, sa, "cauchy", shape=(2, 3, 4, 6), S=12, sigma=1e-3, gamma=1e-2, seed=31)
 
 
 def soft_cases(rr, sr, sa):

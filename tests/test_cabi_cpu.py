@@ -118,7 +118,7 @@ def test_operator_surface_matches_reference():
 
 def test_unsupported_noise_type_raises():
     with pytest.raises(ValueError, match="not implemented"):
-        pb.randomHeaviside.apply(torch.zeros(1, 1, 1, 2), 4, torch.tensor(1e-3), "cauchy")
+        pb.randomHeaviside.apply(torch.zeros(1, 1, 1, 2), 4, torch.tensor(1e-3), "logistic")
     with pytest.raises(ValueError, match="not implemented"):
         pb.randomArgmax.apply(torch.zeros(1, 1, 1, 2), 4, torch.tensor(1e-3), "gumbel")
 
@@ -157,3 +157,19 @@ def test_synthetic_fragments_contract():
         dz = fr.zbuf[..., 1:] - fr.zbuf[..., :-1]
         assert (dz[valid[..., 1:]] >= 0).all()
     assert valid.float().mean() < 0.5
+
+
+def test_reference_package_exports_are_present():
+    """Every name randomras/__init__.py:1-3 exports exists here with the reference's constructor arguments."""
+    for name in ("SimpleShader", "RandomSimpleShader", "CauchyAgg", "GaussianAgg", "SoftAgg", "SoftRast", "ArctanRast",
+                 "AffineRast", "GaussianRast"):
+        assert hasattr(pb, name), name
+    assert pb.ArctanRast(nb_samples=8, sigma=1e-3).nb_samples == 8
+    assert pb.CauchyAgg(nb_samples=8, gamma=1e-2, alpha=1.0, eps=1e-10, fixed_noise=True).fixed_noise
+    d = torch.tensor([[[[-1e-3, 0.0, 2e-4, 1e-3]]]])
+    assert torch.allclose(pb.AffineRast(sigma=1e-3).rasterize(d), torch.tensor([[[[1.0, 0.5, 0.3, 0.0]]]]))
+    assert torch.equal(pb.HardRast().rasterize(d), torch.tensor([[[[1.0, 1.0, 0.0, 0.0]]]]))
+    frag = pb.Fragments(torch.tensor([[[[2, -1], [-1, -1]]]]), torch.zeros(1, 1, 2, 2), None, torch.zeros(1, 1, 2, 2))
+    tex = torch.tensor([[[[[0.1, 0.2, 0.3], [0.0, 0.0, 0.0]], [[0.0, 0.0, 0.0], [0.0, 0.0, 0.0]]]]])
+    img = pb.SimpleShader(blend_params=pb.BlendParams(background_color=(1.0, 0.5, 0.0)))(frag, pb.TexelMeshes(tex))
+    assert torch.allclose(img, torch.tensor([[[[0.1, 0.2, 0.3, 1.0], [1.0, 0.5, 0.0, 0.0]]]]))

@@ -666,3 +666,36 @@ def test_softras_pair_matches_oracle_holes(shape):
     assert rel_err(gz.cpu(), gr["zbuf"]) <= RTOL
     for i, k in enumerate(("sigma", "gamma", "alpha")):
         assert abs(scal[i].item() - gr[k].item()) <= 1e-4 * abs(gr[k].item()) + 1e-7, (k, scal[i].item(), gr[k].item())
+
+
+def test_cauchy_operators_match_reference_golden():
+    """ArctanRast / CauchyAgg (exported by randomras/__init__.py): randomHeaviside and randomArgmax with
+    "cauchy" noise, fed the reference's own Cauchy draws."""
+    import pertrenderer_b200 as pb
+    g = load_golden("ops_cauchy")
+    dev = "cuda"
+    x = g["x"].to(dev).requires_grad_(True)
+    sig = torch.tensor(float(g["sigma"]), requires_grad=True)
+    with pb.explicit_noise(g["U"].to(dev), None):
+        y = pb.randomHeaviside.apply(x, int(g["S"]), sig, "cauchy")
+    (y * g["grad_l"].to(dev)).sum().backward()
+    assert torch.equal(y.detach().cpu(), g["prob"])
+    assert rel_err(x.grad.cpu(), g["grad_x"]) <= RTOL
+    _scalars_close(sig.grad.item(), g["grad_sigma"], "sigma")
+    z = g["z"].to(dev).requires_grad_(True)
+    gam = torch.tensor(float(g["gamma"]), requires_grad=True)
+    with pb.explicit_noise(None, g["V"].to(dev)):
+        w = pb.randomArgmax.apply(z, int(g["S"]), gam, "cauchy", False)
+    (w * g["grad_w"].to(dev)).sum().backward()
+    assert torch.equal(w.detach().cpu(), g["weights"])
+    assert rel_err(z.grad.cpu(), g["grad_z"]) <= RTOL
+    _scalars_close(gam.grad.item(), g["grad_gamma"], "gamma")
+    # in-kernel Cauchy stream: E[P] = arctan(x/sigma)/pi + 1/2 (the closed form the reference notes at smoothrast.py:172)
+    S, sigma = 4096, 1e-3
+    d = torch.linspace(-3e-3, 3e-3, 13, device=dev).reshape(1, 1, 13, 1).contiguous()
+    torch.manual_seed(3)
+    p = pb.ArctanRast(nb_samples=S, sigma=sigma).rasterize(d).cpu().double()
+    e = torch.arctan(-d.cpu().double() / sigma) / torch.pi + 0.5
+    assert ((p - e).abs() <= 5 * (e * (1 - e) / S).sqrt() + 1e-4).all()
+    n = pb.ops.noise_fill(9, 1 | 2, (2, 16, 16, 7), 32, dev).flatten().double()
+    assert abs(n.median().item()) < 0.02 and abs((n.abs() < 1).double().mean().item() - 0.5) < 0.01  # quartiles at +-1
