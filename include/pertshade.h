@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define PERT_ABI_VERSION 4
+#define PERT_ABI_VERSION 5
 
 /* error codes */
 #define PERT_OK 0
@@ -134,6 +134,11 @@ const char* pert_last_cuda_error(void);
 int64_t pert_num_tiles(const pert_problem* pb);
 /* element size in bytes of the winners buffer for this K (1 or 2) */
 int pert_winner_bytes(int32_t K);
+/* size in bytes of the optional `tile_blob` buffer (16-byte aligned).  In sparse-first mode forward saves,
+ * per warp tile, the compact list of valid entries and the per-pixel logit summary it computed; backward
+ * then neither re-scans pix_to_face nor recomputes the logits.  Pass the SAME flags / geometry to both
+ * calls.  NULL: backward recomputes (same results). */
+int64_t pert_blob_bytes(const pert_problem* pb);
 
 /*
  * Forward.  Outputs: image (P,4).  Saved state: counts, rsum, winners, pixstate (see top).  `hist` int32
@@ -141,7 +146,7 @@ int pert_winner_bytes(int32_t K);
  * buffers produced by an earlier phase are inputs.
  */
 int pert_shade_fwd(const pert_problem* pb, float* image, uint16_t* counts, float* rsum, void* winners,
-                   uint16_t* pixstate, int32_t* hist, int32_t* worklist, void* stream);
+                   uint16_t* pixstate, int32_t* hist, int32_t* worklist, void* tile_blob, void* stream);
 
 /*
  * Backward.  grad_image (P,4).  Outputs grad_dists, grad_zbuf (P,K), grad_colors (P,K,3; may be
@@ -155,7 +160,8 @@ int pert_shade_fwd(const pert_problem* pb, float* image, uint16_t* counts, float
 int pert_shade_bwd(const pert_problem* pb, const float* grad_image, const uint16_t* counts,
                    const float* rsum, const void* winners, const uint16_t* pixstate, float* grad_dists,
                    float* grad_zbuf, float* grad_colors, float* scalar_partials, float* grad_scalars,
-                   float* acc, float* pixstat, const int32_t* hist, int32_t* worklist, void* stream);
+                   float* acc, float* pixstat, const int32_t* hist, int32_t* worklist, const void* tile_blob,
+                   void* stream);
 
 /*
  * SoftRas pair: SoftRast + SoftAgg, the DEFAULT operators of RandomSimpleShader

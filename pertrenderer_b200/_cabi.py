@@ -15,7 +15,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpertshade.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 # flags (include/pertshade.h)
 F_NO_SKIP = 1
@@ -26,7 +26,7 @@ PH_RAST, PH_AGG, PH_BLEND = 0x10, 0x20, 0x40
 PH_BWD_SAMPLE, PH_BWD_FINISH = 0x100, 0x200
 
 EXPORTS = [
-    "pert_version", "pert_strerror", "pert_last_cuda_error", "pert_num_tiles", "pert_winner_bytes",
+    "pert_version", "pert_strerror", "pert_last_cuda_error", "pert_num_tiles", "pert_winner_bytes", "pert_blob_bytes",
     "pert_shade_fwd", "pert_shade_bwd", "pert_soft_shade_fwd", "pert_soft_shade_bwd", "pert_rast_fwd", "pert_rast_bwd", "pert_argmax_fwd",
     "pert_argmax_bwd", "pert_noise_fill",
 ]
@@ -84,12 +84,14 @@ def load():
         lib.pert_last_cuda_error.argtypes = []
         lib.pert_num_tiles.restype = i64
         lib.pert_num_tiles.argtypes = [pp]
+        lib.pert_blob_bytes.restype = i64
+        lib.pert_blob_bytes.argtypes = [pp]
         lib.pert_winner_bytes.restype = C.c_int
         lib.pert_winner_bytes.argtypes = [i32]
         lib.pert_shade_fwd.restype = C.c_int
-        lib.pert_shade_fwd.argtypes = [pp] + [vp] * 8
+        lib.pert_shade_fwd.argtypes = [pp] + [vp] * 9
         lib.pert_shade_bwd.restype = C.c_int
-        lib.pert_shade_bwd.argtypes = [pp] + [vp] * 15
+        lib.pert_shade_bwd.argtypes = [pp] + [vp] * 16
         lib.pert_soft_shade_fwd.restype = C.c_int
         lib.pert_soft_shade_fwd.argtypes = [pp, vp, vp]
         lib.pert_soft_shade_bwd.restype = C.c_int

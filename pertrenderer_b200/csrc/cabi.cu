@@ -120,8 +120,9 @@ static int sparse_tp(int K, int64_t P) {
 static int sparse_cap(int K, int tp) {
     int cap = tp * K / 5;
     if (const char* e = getenv("PERT_CAP")) cap = atoi(e);  // experiments only
+    cap = (cap + 7) & ~7;  // u16 arrays are copied as 32-bit words
     if (cap < 32) cap = 32;
-    if (cap > tp * K) cap = tp * K;
+    if (cap > tp * K) cap = (tp * K + 1) & ~1;
     return cap;
 }
 
@@ -141,10 +142,17 @@ extern "C" int64_t pert_num_tiles(const pert_problem* pb) {
 
 extern "C" int pert_winner_bytes(int32_t K) { return (K + 1 <= 256) ? 1 : 2; }
 
+extern "C" int64_t pert_blob_bytes(const pert_problem* pb) {
+    if (!pb || pb->K <= 0) return 0;
+    const int64_t P = pb->N * pb->H * pb->W;
+    const int tp = sparse_tp(pb->K, P);
+    return ((P + tp - 1) / tp) * (int64_t)blob_words(tp, sparse_cap(pb->K, tp)) * 4;
+}
+
 static bool aligned16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 extern "C" int pert_shade_fwd(const pert_problem* pb_in, float* image, uint16_t* counts, float* rsum, void* winners,
-                              uint16_t* pixstate, int32_t* hist, int32_t* worklist, void* stream) {
+                              uint16_t* pixstate, int32_t* hist, int32_t* worklist, void* tile_blob, void* stream) {
     int rc = check_problem(pb_in);
     if (rc) return rc;
     FwdArgs a;
@@ -182,9 +190,12 @@ extern "C" int pert_shade_fwd(const pert_problem* pb_in, float* image, uint16_t*
     a.pixstate = pixstate;
     a.hist = hist;
     a.worklist = worklist;
+    if ((uintptr_t)tile_blob & 15) return PERT_E_ALIGN;
+    a.blob = sparse ? (int32_t*)tile_blob : nullptr;
     cudaStream_t st = (cudaStream_t)stream;
     if (!sparse) return cuda_rc(launch_shade_fwd(a, nullptr, st));
     FwdArgs fb = a;  // fallback pass: half-size tiles, full capacity
+    fb.blob = nullptr;
     fb.L = make_launch(&a.pb, a.L.tp / 2);
     fb.L.vec_ok = fb.L.vec_ok && aligned16(a.pb.pix_to_face);
     fwd_smem_layout(fb.L.tp, fb.L.cap, fb.L.sm);
@@ -197,7 +208,8 @@ extern "C" int pert_shade_fwd(const pert_problem* pb_in, float* image, uint16_t*
 extern "C" int pert_shade_bwd(const pert_problem* pb_in, const float* grad_image, const uint16_t* counts,
                               const float* rsum, const void* winners, const uint16_t* pixstate, float* grad_dists,
                               float* grad_zbuf, float* grad_colors, float* scalar_partials, float* grad_scalars,
-                              float* acc, float* pixstat, const int32_t* hist, int32_t* worklist, void* stream) {
+                              float* acc, float* pixstat, const int32_t* hist, int32_t* worklist,
+                              const void* tile_blob, void* stream) {
     int rc = check_problem(pb_in);
     if (rc) return rc;
     BwdArgs a;
@@ -246,9 +258,12 @@ extern "C" int pert_shade_bwd(const pert_problem* pb_in, const float* grad_image
     a.pixstat = pixstat;
     a.hist = hist;
     a.worklist = worklist;
+    if ((uintptr_t)tile_blob & 15) return PERT_E_ALIGN;
+    a.blob = sparse ? (const int32_t*)tile_blob : nullptr;
     cudaStream_t st = (cudaStream_t)stream;
     if (!sparse) return cuda_rc(launch_shade_bwd(a, nullptr, grad_scalars, st));
     BwdArgs fb = a;  // fallback pass: half-size tiles, full capacity, dense per-logit arrays
+    fb.blob = nullptr;
     fb.L = make_launch(&a.pb, a.L.tp / 2);
     fb.L.vec_ok = fb.L.vec_ok && ptr_ok;
     bwd_smem_layout(fb.L.tp, a.pb.K, fb.L.cap, fb.L.sc, fb.L.nchunks, fb.L.win_bytes, false, fb.L.sm);

@@ -253,6 +253,17 @@ __device__ __forceinline__ int batch_of(int64_t pix0, int p, int64_t HW) {
     return (int)b;
 }
 
+// Tile blob (optional saved state of the sparse-first main pass): what backward would otherwise recompute
+// from pix_to_face / zbuf / counts -- the compact valid list and the per-pixel logit summary of forward.
+// 32-bit words per tile:  [0] nv (-1: the tile went to the fallback pass)   [1 .. tp+1] vstart[0..tp]
+//   then 6 per pixel: zmax, zimax, prod_nz, zeta_max, argzi | a0 << 16, nzero | kpad << 16
+//   then vlist (u16 x cap), cnt (u16 x cap), zeta (f32 x cap)
+__host__ __device__ __forceinline__ int blob_words(int tp, int cap) { return ((2 + 7 * tp + 2 * cap) + 3) & ~3; }
+__host__ __device__ __forceinline__ int blob_pix_off(int tp) { return 2 + tp; }
+__host__ __device__ __forceinline__ int blob_vlist_off(int tp) { return 2 + 7 * tp; }
+__host__ __device__ __forceinline__ int blob_cnt_off(int tp, int cap) { return 2 + 7 * tp + cap / 2; }
+__host__ __device__ __forceinline__ int blob_zeta_off(int tp, int cap) { return 2 + 7 * tp + cap; }
+
 // entry index within a tile -> pixel of the tile.  Exact for e < 2^16, K < 2^10: (e + .5)/K is at
 // least .5/K away from an integer, far more than the fp32 rounding of the product.
 __device__ __forceinline__ int entry_pixel(int e, float invK) { return __float2int_rz(((float)e + 0.5f) * invK); }

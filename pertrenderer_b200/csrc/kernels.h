@@ -14,6 +14,7 @@ struct FwdArgs {
     uint16_t* pixstate;
     int32_t* hist;
     int32_t* worklist;  // [0] = number of tiles handed to the fallback pass, [4..] = their indices
+    int32_t* blob;      // tile blobs written by the sparse-first main pass (see common.cuh), or NULL
 };
 
 struct BwdArgs {
@@ -32,6 +33,7 @@ struct BwdArgs {
     float* pixstat;
     const int32_t* hist;
     int32_t* worklist;
+    const int32_t* blob;  // tile blobs of forward, or NULL: backward then rescans and recomputes
 };
 
 void fwd_smem_layout(int tp, int cap, SmemLayout& L);

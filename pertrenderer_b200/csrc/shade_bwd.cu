@@ -50,7 +50,9 @@ void bwd_smem_layout(int tp, int K, int cap, int sc, int nchunks, int win_bytes,
 // COMPACT = true (sparse-first mode): the per-logit arrays are indexed by the position of the logit
 // among the pixel's valid entries (plus a background and a masked-logits slot) instead of densely by j,
 // and every array holds a.L.cap valid entries; tiles with more go to the fallback pass.
-template <class NoiseA, int GT, bool PHASED, bool FACE, bool COMPACT>
+// BLOB = true (only with COMPACT): the compact valid list and the per-pixel logit summary come from the tile
+// blob forward saved (common.cuh) instead of a re-scan of pix_to_face and a recomputation of the logits.
+template <class NoiseA, int GT, bool PHASED, bool FACE, bool COMPACT, bool BLOB>
 __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& noise_a, const int64_t tile,
                                                const int64_t prow /* row of the scalar partials */,
                                                unsigned char* smem_raw, const int lane) {
@@ -124,8 +126,10 @@ __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& n
         zf = __ldg(pb.zfar + b);
         pstate = a.pixstate[gp];
     }
-    const int nv = scan_valid(pb.pix_to_face + g0, E, a.L.vec_ok, vlist, cap);
-    if (!(COMPACT && nv > cap)) {
+    const int32_t* const bl = BLOB ? a.blob + tile * (int64_t)blob_words(tp, cap) : nullptr;
+    const int nv = BLOB ? __ldg(bl) : scan_valid(pb.pix_to_face + g0, E, a.L.vec_ok, vlist, cap);
+    const bool overflow = COMPACT && (BLOB ? nv < 0 : nv > cap);
+    if (!overflow) {
         // this pass owns the tile: its output rows start as zeros, valid entries are scattered over them later
         if (do_finish) {
             zero_fill(a.grad_dists + g0, E, a.L.vec_ok);
@@ -139,32 +143,79 @@ __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& n
             }
         }
     }
-    if (COMPACT && nv > cap) {
+    if (overflow) {
         // more valid entries than the compact arrays hold: the fallback pass redoes this tile
         if (lane == 0) a.worklist[4 + atomicAdd(a.worklist, 1)] = (int32_t)tile;
     } else if (nv > 0) {
-        __syncwarp();
-        pixel_ranges(vlist, nv, K, tp, vstart);
-        {
-            const float* const zbuf_t = pb.zbuf + g0;
-            const uint16_t* const counts_t = a.counts + g0;
+        const float gal = a.L.gal;
+        PixPrep pi;
+        if constexpr (BLOB) {
+            // ---- phase 1 (from forward's blob) -------------------------------------------------------
             const float* const colors_t = pb.colors + g0 * 3;
             const float* const rsum_t = a.rsum + g0;
+            for (int i = lane; i <= tp; i += 32) vstart[i] = __ldg(bl + 1 + i);
+            uint32_t* const vl32 = reinterpret_cast<uint32_t*>(vlist);
+            uint32_t* const cn32 = reinterpret_cast<uint32_t*>(cnt);
+            const int nw = (nv + 1) >> 1;
 #pragma unroll 1
-            for (int n = lane; n < nv; n += 32) {
-                const int e = vlist[n];
-                zs[n] = __ldg(zbuf_t + e);
-                cnt[n] = counts_t[e];
+            for (int i = lane; i < nw; i += 32) {
+                const uint32_t v2 = (uint32_t)__ldg(bl + blob_vlist_off(tp) + i);
+                vl32[i] = v2;
+                cn32[i] = (uint32_t)__ldg(bl + blob_cnt_off(tp, cap) + i);
                 // needed a few round trips later (g_j of the logits that can win; chain rule): start them now
-                if (!FACE) prefetch_l1(colors_t + e * 3);
-                prefetch_l1(rsum_t + e);
+                const int e0 = v2 & 0xffff, e1 = v2 >> 16;
+                if (!FACE) prefetch_l1(colors_t + e0 * 3);
+                prefetch_l1(rsum_t + e0);
+                if (2 * i + 1 < nv) {
+                    if (!FACE) prefetch_l1(colors_t + e1 * 3);
+                    prefetch_l1(rsum_t + e1);
+                }
             }
-        }
-        __syncwarp();
+#pragma unroll 1
+            for (int i = lane; i < nv; i += 32) zs[i] = __int_as_float(__ldg(bl + blob_zeta_off(tp, cap) + i));
+            if (pvalid) {
+                const int32_t* const bp = bl + blob_pix_off(tp) + 6 * p;
+                pi.zmax = __int_as_float(__ldg(bp));
+                pi.zimax = __int_as_float(__ldg(bp + 1));
+                pi.prod_nz = __int_as_float(__ldg(bp + 2));
+                pi.zeta_max = __int_as_float(__ldg(bp + 3));
+                const int w4 = __ldg(bp + 4), w5 = __ldg(bp + 5);
+                pi.argzi = w4 & 0xffff;
+                pi.a0 = w4 >> 16;
+                pi.nzero = w5 & 0xffff;
+                pi.kpad = w5 >> 16;
+            } else {
+                pi.zmax = pb.eps;
+                pi.zimax = 0.f;
+                pi.prod_nz = 1.f;
+                pi.zeta_max = 0.f;
+                pi.argzi = pi.a0 = pi.nzero = pi.kpad = 0;
+            }
+            pi.zbg = __fadd_rn(pb.eps, -pi.zmax);
+            __syncwarp();
+        } else {
+            __syncwarp();
+            pixel_ranges(vlist, nv, K, tp, vstart);
+            {
+                const float* const zbuf_t = pb.zbuf + g0;
+                const uint16_t* const counts_t = a.counts + g0;
+                const float* const colors_t = pb.colors + g0 * 3;
+                const float* const rsum_t = a.rsum + g0;
+#pragma unroll 1
+                for (int n = lane; n < nv; n += 32) {
+                    const int e = vlist[n];
+                    zs[n] = __ldg(zbuf_t + e);
+                    cnt[n] = counts_t[e];
+                    // needed a few round trips later (g_j of the logits that can win; chain rule): start them now
+                    if (!FACE) prefetch_l1(colors_t + e * 3);
+                    prefetch_l1(rsum_t + e);
+                }
+            }
+            __syncwarp();
 
-        // ---- phase 1 -------------------------------------------------------------------------------
-        const float gal = a.L.gal;
-        const PixPrep pi = prep_pixels(p, lig, G, pvalid, K, vstart, vlist, cnt, zs, zn, zf, pb.S_rast, gal, pb.eps);
+            // ---- phase 1 ---------------------------------------------------------------------------
+            pi = prep_pixels(p, lig, G, pvalid, K, vstart, vlist, cnt, zs, zn, zf, pb.S_rast, gal, pb.eps);
+        }
         const int vs = pvalid ? vstart[p] : 0, ve = pvalid ? vstart[p + 1] : 0;
         const int nvp = ve - vs;
         const int a0 = pi.a0;
@@ -533,10 +584,10 @@ __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& n
     }
 }
 
-template <class NoiseA, int GT, bool PHASED, bool FACE, bool COMPACT>
+template <class NoiseA, int GT, bool PHASED, bool FACE, bool COMPACT, bool BLOB>
 __global__ void __launch_bounds__(FNT, 25) shade_bwd_kernel(const BwdArgs a, const NoiseA noise_a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    shade_bwd_tile<NoiseA, GT, PHASED, FACE, COMPACT>(a, noise_a, blockIdx.x, blockIdx.x, smem_raw, threadIdx.x);
+    shade_bwd_tile<NoiseA, GT, PHASED, FACE, COMPACT, BLOB>(a, noise_a, blockIdx.x, blockIdx.x, smem_raw, threadIdx.x);
 }
 
 // Fallback pass of the sparse-first mode (see shade_fwd.cu): work-list tiles as half-size tiles with dense
@@ -554,7 +605,7 @@ __global__ void __launch_bounds__(FBT, 12) shade_bwd_fallback_kernel(const BwdAr
         if (i >= n) break;
         const int64_t tile = (int64_t)a.worklist[4 + (i >> 1)] * 2 + (i & 1);
         if (tile < a.L.ntiles) {
-            shade_bwd_tile<NoiseA, GT, false, FACE, false>(a, noise_a, tile, prow0 + i, smem_raw, threadIdx.x & 31);
+            shade_bwd_tile<NoiseA, GT, false, FACE, false, false>(a, noise_a, tile, prow0 + i, smem_raw, threadIdx.x & 31);
         } else if ((threadIdx.x & 31) == 0) {
             reinterpret_cast<float4*>(a.partials)[prow0 + i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -608,11 +659,11 @@ static int set_smem(K kern, size_t smem) {
     return 0;
 }
 
-template <class NA, int GT, bool PHASED, bool FACE, bool COMPACT>
+template <class NA, int GT, bool PHASED, bool FACE, bool COMPACT, bool BLOB = false>
 static int launch_bwd_f(const BwdArgs& a, const NA& na, cudaStream_t st) {
     const size_t smem = (size_t)a.L.warp_smem;
-    if (int rc = set_smem(shade_bwd_kernel<NA, GT, PHASED, FACE, COMPACT>, smem)) return rc;
-    shade_bwd_kernel<NA, GT, PHASED, FACE, COMPACT><<<(unsigned)a.L.ntiles, FNT, smem, st>>>(a, na);
+    if (int rc = set_smem(shade_bwd_kernel<NA, GT, PHASED, FACE, COMPACT, BLOB>, smem)) return rc;
+    shade_bwd_kernel<NA, GT, PHASED, FACE, COMPACT, BLOB><<<(unsigned)a.L.ntiles, FNT, smem, st>>>(a, na);
     return (int)cudaGetLastError();
 }
 template <class NA, int GT, bool PHASED>
@@ -623,6 +674,12 @@ static int launch_bwd_t(const BwdArgs& a, const NA& na, cudaStream_t st) {
 // sparse-first main pass (compact per-logit arrays)
 template <int GT>
 static int launch_bwd_c(const BwdArgs& a, const PhiloxNoise& na, cudaStream_t st) {
+    if (a.blob) {  // forward left tile blobs: no re-scan, no logit recomputation (the common geometries only)
+        if constexpr (GT == 2 || GT == 4) {
+            return a.pb.face_colors ? launch_bwd_f<PhiloxNoise, GT, false, true, true, true>(a, na, st)
+                                    : launch_bwd_f<PhiloxNoise, GT, false, false, true, true>(a, na, st);
+        }
+    }
     return a.pb.face_colors ? launch_bwd_f<PhiloxNoise, GT, false, true, true>(a, na, st)
                             : launch_bwd_f<PhiloxNoise, GT, false, false, true>(a, na, st);
 }

@@ -78,7 +78,10 @@ __device__ __forceinline__ void shade_fwd_tile(const FwdArgs& a, const NoiseR& n
     if (nv > cap) {
         // sparse-first mode: this tile has more valid entries than the compact arrays hold: hand it to the
         // fallback pass (half-size tiles, full capacity)
-        if (lane == 0) a.worklist[4 + atomicAdd(a.worklist, 1)] = (int32_t)tile;
+        if (lane == 0) {
+            a.worklist[4 + atomicAdd(a.worklist, 1)] = (int32_t)tile;
+            if (a.blob) a.blob[tile * (int64_t)blob_words(tp, cap)] = -1;
+        }
         return;
     }
     if (nv == 0) {
@@ -88,6 +91,7 @@ __device__ __forceinline__ void shade_fwd_tile(const FwdArgs& a, const NoiseR& n
             for (int i = lane; i < npx * K1; i += 32) ghist[pix0 * K1 + i] = ((i % K1) == K) ? sa_loc : 0;
         }
         if (do_agg && lane < npx) a.pixstate[pix0 + lane] = (uint16_t)K;
+        if (!PHASED && a.blob && lane == 0) a.blob[tile * (int64_t)blob_words(tp, a.L.cap)] = 0;
         if (do_blend && lane < npx)
             reinterpret_cast<float4*>(a.image)[pix0 + lane] =
                 make_float4(pb.background[0], pb.background[1], pb.background[2], 0.0f);
@@ -275,6 +279,31 @@ __device__ __forceinline__ void shade_fwd_tile(const FwdArgs& a, const NoiseR& n
         if (pvalid && lig == 0) {
             hl[lb + a0l] = sa_loc - others;
             a.pixstate[gp] = (uint16_t)(pi.a0 | (active ? 0x8000 : 0));
+        }
+        if (!PHASED && a.blob) {
+            // what backward would recompute from pix_to_face / zbuf / counts (layout: common.cuh)
+            int32_t* const bl = a.blob + tile * (int64_t)blob_words(tp, cap);
+            if (lane == 0) bl[0] = nv;
+            for (int i = lane; i <= tp; i += 32) bl[1 + i] = i <= npx ? vstart[i] : nv;
+            if (pvalid && lig == 0) {
+                int32_t* const bp = bl + blob_pix_off(tp) + 6 * p;
+                bp[0] = __float_as_int(pi.zmax);
+                bp[1] = __float_as_int(pi.zimax);
+                bp[2] = __float_as_int(pi.prod_nz);
+                bp[3] = __float_as_int(pi.zeta_max);
+                bp[4] = pi.argzi | (pi.a0 << 16);
+                bp[5] = pi.nzero | (pi.kpad << 16);
+            }
+            const uint32_t* const vl32 = reinterpret_cast<const uint32_t*>(vlist);
+            const uint32_t* const cn32 = reinterpret_cast<const uint32_t*>(cnt);
+            const int nw = (nv + 1) >> 1;
+#pragma unroll 1
+            for (int i = lane; i < nw; i += 32) {
+                bl[blob_vlist_off(tp) + i] = (int32_t)vl32[i];
+                bl[blob_cnt_off(tp, cap) + i] = (int32_t)cn32[i];
+            }
+#pragma unroll 1
+            for (int i = lane; i < nv; i += 32) bl[blob_zeta_off(tp, cap) + i] = __float_as_int(zs[i]);
         }
         __syncwarp();
         if (ghist) {

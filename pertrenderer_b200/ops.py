@@ -192,6 +192,7 @@ class ShadeSaved:
     winners: torch.Tensor  # (N,H,W,S_agg_local) uint8 / int16
     pixstate: torch.Tensor  # int16 storage of uint16 (N,H,W): a0 | 0x8000 * active
     worklist: Optional[torch.Tensor] = None  # int32 (4 + tiles): sparse-first mode work list (see pertshade.h)
+    blob: Optional[torch.Tensor] = None  # uint8 (pert_blob_bytes): per-tile valid lists and logit summaries
     hist: Optional[torch.Tensor] = None  # int32 (N,H,W,K1), only when requested
 
     def winners_full(self) -> torch.Tensor:
@@ -221,12 +222,13 @@ def shade_forward(pr: ShadeProblem, want_hist: bool = False, phases: int = 0, sa
                 winners=torch.empty((N, H, W, sa_loc), dtype=pr.winner_dtype(), device=dev),
                 pixstate=torch.empty((N, H, W), dtype=torch.int16, device=dev),
                 worklist=None if phases else torch.empty((4 + pr.num_tiles(),), dtype=torch.int32, device=dev),
+                blob=None if phases else torch.empty((int(lib.pert_blob_bytes(pr.c_struct())),), dtype=torch.uint8, device=dev),
                 hist=torch.empty((N, H, W, K + 1), dtype=torch.int32, device=dev) if want_hist else None)
         do_blend = (phases == 0) or bool(phases & PH_BLEND)
         image = torch.empty((N, H, W, 4), dtype=torch.float32, device=dev) if do_blend else None
         pb = pr.c_struct(flags=pr.flags | phases)
         rc = lib.pert_shade_fwd(pb, ptr(image), ptr(saved.counts), ptr(saved.rsum), ptr(saved.winners),
-                                ptr(saved.pixstate), ptr(saved.hist), ptr(saved.worklist), stream_ptr(dev))
+                                ptr(saved.pixstate), ptr(saved.hist), ptr(saved.worklist), ptr(saved.blob), stream_ptr(dev))
     check(rc, "pert_shade_fwd")
     return image, saved
 
@@ -253,7 +255,7 @@ def shade_backward(pr: ShadeProblem, saved: ShadeSaved, grad_image: torch.Tensor
         rc = lib.pert_shade_bwd(pb, ptr(grad_image), ptr(saved.counts), ptr(saved.rsum), ptr(saved.winners),
                                 ptr(saved.pixstate), ptr(gd), ptr(gz), ptr(gc), ptr(partials), ptr(scal), ptr(acc), ptr(pixstat),
                                 ptr(saved.hist) if use_hist else None, None if phases else ptr(saved.worklist),
-                                stream_ptr(dev))
+                                None if phases else ptr(saved.blob), stream_ptr(dev))
     check(rc, "pert_shade_bwd")
     return gd, gz, gc, scal
 

@@ -43,21 +43,21 @@ def test_argument_validation_without_gpu():
     """Validation happens before any launch, so it is testable on a CPU-only box."""
     lib = _cabi.load()
     p = _cabi.PertProblem()
-    assert lib.pert_shade_fwd(None, None, None, None, None, None, None, None, None) == -1
+    assert lib.pert_shade_fwd(None, None, None, None, None, None, None, None, None, None) == -1
     p.N, p.H, p.W, p.K = 1, 2, 2, 0
-    assert lib.pert_shade_fwd(p, None, None, None, None, None, None, None, None) == -2  # bad shape
+    assert lib.pert_shade_fwd(p, None, None, None, None, None, None, None, None, None) == -2  # bad shape
     p.K = 5000
-    assert lib.pert_shade_fwd(p, None, None, None, None, None, None, None, None) == -3  # unsupported K
+    assert lib.pert_shade_fwd(p, None, None, None, None, None, None, None, None, None) == -3  # unsupported K
     p.K = 4
     p.S_rast = p.S_agg = 8
     p.depth_len = 1
     p.sigma, p.gamma, p.alpha = 1e-3, 0.0, 1.0
-    assert lib.pert_shade_fwd(p, None, None, None, None, None, None, None, None) == -7  # gamma must be > 0
+    assert lib.pert_shade_fwd(p, None, None, None, None, None, None, None, None, None) == -7  # gamma must be > 0
     p.gamma = 1e-2
     p.s_rast_begin, p.s_rast_end, p.s_agg_begin, p.s_agg_end = 2, 8, 0, 8
-    assert lib.pert_shade_fwd(p, None, None, None, None, None, None, None, None) == -5  # shard begin % 4
+    assert lib.pert_shade_fwd(p, None, None, None, None, None, None, None, None, None) == -5  # shard begin % 4
     p.s_rast_begin = 0
-    assert lib.pert_shade_fwd(p, None, None, None, None, None, None, None, None) == -1  # null inputs
+    assert lib.pert_shade_fwd(p, None, None, None, None, None, None, None, None, None) == -1  # null inputs
     assert lib.pert_winner_bytes(50) == 1 and lib.pert_winner_bytes(255) == 1 and lib.pert_winner_bytes(256) == 2
     p.N, p.H, p.W, p.K = 8, 256, 256, 50
     assert lib.pert_num_tiles(p) == 8 * 256 * 256 // 8  # finest geometry of this problem: 8-pixel tiles
