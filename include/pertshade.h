@@ -21,6 +21,9 @@
  *                                     (smoothagg.py:165-182), the shaders' default operators
  *   pert_rast_fwd / pert_rast_bwd     randomras/smoothrast.py:12-59   (stand-alone randomHeaviside)
  *   pert_argmax_fwd / pert_argmax_bwd randomras/smoothagg.py:10-73    (stand-alone randomArgmax)
+ *   pert_phong_fwd / pert_phong_bwd   pytorch3d.renderer.mesh.shading.phong_shading as called by
+ *                    RandomPhongShader.forward (randomras/random_rasterizer.py:103-110), the shader
+ *                    experiments/eval.py:170-176 uses; its output is the `colors` of pert_shade_fwd
  *   pert_noise_fill  the two torch.normal draws, smoothrast.py:21 and smoothagg.py:21 (test aid:
  *                    materialises the counter-based noise the fused kernels generate in registers)
  *
@@ -48,7 +51,7 @@
 extern "C" {
 #endif
 
-#define PERT_ABI_VERSION 5
+#define PERT_ABI_VERSION 6
 
 /* error codes */
 #define PERT_OK 0
@@ -193,6 +196,53 @@ int pert_argmax_bwd(const float* grad_l, const float* z, const void* winners, in
                     int32_t S, int32_t s_begin, int32_t s_end, float gamma, uint64_t seed,
                     int64_t pixel_offset, const float* noise, uint32_t flags, float* grad_z,
                     float* scalar_partials, float* grad_gamma, void* stream);
+
+/*
+ * Phong lighting of every fragment entry: the `colors` (P,K,3) that RandomPhongShader feeds to
+ * smooth_rgb_blend (randomras/random_rasterizer.py:103-113).  Restates pytorch3d 0.4.0 (requirements.txt:7;
+ * source not part of the reference tree): shading.phong_shading -> interpolate_face_attributes of the face
+ * corners' positions and vertex normals with bary_coords, lighting.diffuse / lighting.specular of a
+ * PointLights or DirectionalLights, Materials, colour = (ambient + diffuse) * texel + specular.
+ *
+ * `lighting`: float (light_rows, PERT_PHONG_STRIDE), one row per batch element (or one row for all):
+ *   [0:3] light location (point) or direction (directional)   [3:6]  materials.ambient * lights.ambient
+ *   [6:9] materials.diffuse * lights.diffuse                  [9:12] materials.specular * lights.specular
+ *   [12]  materials.shininess   [13:16] camera centre (world)  [16]  0 = point light, 1 = directional
+ * Entries with pix_to_face < 0 interpolate to a zero point and normal (pytorch3d's masked interpolation), so
+ * their colour is ambient * texel.  With PERT_PHONG_SPARSE those entries are skipped altogether: forward does
+ * not write their colour (the fused shader kernels never read it), backward neither reads their grad_colors
+ * (the fused shader's is 0 there) nor writes their grad_texels / grad_bary (pre-zero them if they are read).
+ */
+#define PERT_PHONG_STRIDE 20
+#define PERT_PHONG_SPARSE 1u
+
+typedef struct pert_phong {
+    int64_t P;          /* pixels N*H*W */
+    int64_t HW;         /* pixels per batch element: selects the lighting row */
+    int32_t K;
+    int32_t light_rows; /* 1 or N */
+    int64_t num_faces;
+    uint32_t flags;
+    const int64_t* pix_to_face; /* (P,K) */
+    const float* bary;          /* (P,K,3) fragments.bary_coords */
+    const float* face_verts;    /* (F,3,3) verts_packed()[faces_packed()] */
+    const float* face_normals;  /* (F,3,3) verts_normals_packed()[faces_packed()] */
+    const float* texels;        /* (P,K,3) meshes.sample_textures(fragments), or NULL with face_colors */
+    const float* face_colors;   /* (F,3) per-face colours gathered through pix_to_face, or NULL */
+    const float* lighting;      /* (light_rows, PERT_PHONG_STRIDE) */
+} pert_phong;
+
+int pert_phong_fwd(const pert_phong* ph, float* colors, void* stream);
+/*
+ * Backward of pert_phong_fwd.  grad_colors (P,K,3).  Outputs, each optional (NULL: not computed):
+ *   grad_texels        (P,K,3); with ph->face_colors set: (F,3), ZEROED BY THE CALLER, atomic adds
+ *   grad_bary          (P,K,3)
+ *   grad_face_verts    (F,3,3) and grad_face_normals (F,3,3): ZEROED BY THE CALLER, atomic adds (the scatter of
+ *                      interpolate_face_attributes' backward; summation order is not fixed)
+ * Lights, materials and camera centre receive no gradient (constants in experiments/eval.py:233-262).
+ */
+int pert_phong_bwd(const pert_phong* ph, const float* grad_colors, float* grad_texels, float* grad_bary,
+                   float* grad_face_verts, float* grad_face_normals, void* stream);
 
 /* Materialise the counter-based noise: out float (s_end-s_begin, P, slots), stage 0 = coverage
  * (slots = K), 1 = aggregation (slots = K1); stage | 2 = the Cauchy variant of that stage. */

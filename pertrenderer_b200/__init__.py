@@ -5,15 +5,18 @@ Drop-in for the hot path of quentinll/pertrenderer (``randomras``): the same pub
 (``include/pertshade.h``).  CUDA only: there is no CPU or PyTorch fallback on this path.
 """
 
-from .random_rasterizer import RandomSimpleShader, SimpleShader, smooth_rgb_blend
+from .random_rasterizer import RandomPhongShader, RandomSimpleShader, SimpleShader, smooth_rgb_blend
+from .shading import phong_shading
 from .smoothagg import CauchyAgg, GaussianAgg, HardAgg, SoftAgg, randomArgmax
 from .smoothrast import AffineRast, ArctanRast, GaussianRast, HardRast, SoftRast, randomHeaviside
-from .structures import (BlendParams, DepthCameras, FaceColorMeshes, FaceTexels, Fragments, TexelMeshes,
-                         synthetic_fragments)
+from .structures import (BlendParams, DepthCameras, DirectionalLights, FaceColorMeshes, FaceTexels, Fragments, Materials,
+                         PointLights, TexelMeshes, TriMeshes, ViewCameras, synthetic_bary, synthetic_fragments,
+                         synthetic_mesh)
 from .ops import explicit_noise, kernel_flags
 
 __all__ = [
-    "RandomSimpleShader", "SimpleShader", "smooth_rgb_blend", "GaussianAgg", "SoftAgg", "CauchyAgg", "HardAgg",
+    "RandomPhongShader", "RandomSimpleShader", "SimpleShader", "phong_shading", "PointLights", "DirectionalLights",
+    "Materials", "ViewCameras", "TriMeshes", "synthetic_mesh", "synthetic_bary", "smooth_rgb_blend", "GaussianAgg", "SoftAgg", "CauchyAgg", "HardAgg",
     "randomArgmax", "GaussianRast", "ArctanRast", "AffineRast", "HardRast",
     "SoftRast", "randomHeaviside", "BlendParams", "DepthCameras", "Fragments", "TexelMeshes",
     "synthetic_fragments", "explicit_noise", "kernel_flags", "FaceColorMeshes", "FaceTexels",

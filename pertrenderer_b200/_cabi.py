@@ -15,7 +15,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpertshade.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 # flags (include/pertshade.h)
 F_NO_SKIP = 1
@@ -28,8 +28,11 @@ PH_BWD_SAMPLE, PH_BWD_FINISH = 0x100, 0x200
 EXPORTS = [
     "pert_version", "pert_strerror", "pert_last_cuda_error", "pert_num_tiles", "pert_winner_bytes", "pert_blob_bytes",
     "pert_shade_fwd", "pert_shade_bwd", "pert_soft_shade_fwd", "pert_soft_shade_bwd", "pert_rast_fwd", "pert_rast_bwd", "pert_argmax_fwd",
-    "pert_argmax_bwd", "pert_noise_fill",
+    "pert_argmax_bwd", "pert_noise_fill", "pert_phong_fwd", "pert_phong_bwd",
 ]
+
+PHONG_STRIDE = 20  # PERT_PHONG_STRIDE
+PHONG_SPARSE = 1  # PERT_PHONG_SPARSE
 
 
 class PertProblem(C.Structure):
@@ -50,6 +53,18 @@ class PertProblem(C.Structure):
         ("znear", C.c_void_p), ("zfar", C.c_void_p),
         ("noise_rast", C.c_void_p), ("noise_agg", C.c_void_p),
         ("face_colors", C.c_void_p), ("num_faces", C.c_int64),
+    ]
+
+
+class PertPhong(C.Structure):
+    """Mirror of ``struct pert_phong``."""
+    _fields_ = [
+        ("P", C.c_int64), ("HW", C.c_int64),
+        ("K", C.c_int32), ("light_rows", C.c_int32),
+        ("num_faces", C.c_int64),
+        ("flags", C.c_uint32),
+        ("pix_to_face", C.c_void_p), ("bary", C.c_void_p), ("face_verts", C.c_void_p), ("face_normals", C.c_void_p),
+        ("texels", C.c_void_p), ("face_colors", C.c_void_p), ("lighting", C.c_void_p),
     ]
 
 
@@ -106,6 +121,10 @@ def load():
         lib.pert_argmax_bwd.argtypes = [vp, vp, vp, i64, i32, i32, i32, i32, f32, u64, i64, vp, u32, vp, vp, vp, vp]
         lib.pert_noise_fill.restype = C.c_int
         lib.pert_noise_fill.argtypes = [u64, i32, i64, i32, i32, i32, i64, vp, vp]
+        lib.pert_phong_fwd.restype = C.c_int
+        lib.pert_phong_fwd.argtypes = [C.POINTER(PertPhong), vp, vp]
+        lib.pert_phong_bwd.restype = C.c_int
+        lib.pert_phong_bwd.argtypes = [C.POINTER(PertPhong)] + [vp] * 6
         if lib.pert_version() != ABI_VERSION:
             raise PertLibraryError(f"libpertshade.so ABI {lib.pert_version()} != expected {ABI_VERSION}: rebuild")
         _lib = lib

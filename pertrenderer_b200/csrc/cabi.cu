@@ -373,3 +373,35 @@ extern "C" int pert_noise_fill(uint64_t seed, int32_t stage, int64_t P, int32_t 
     if (((int64_t)qn * P * slots + 255) / 256 > 0x7fffffff) return PERT_E_UNSUPPORTED;
     return cuda_rc(launch_noise_fill(seed, stage, P, slots, s_begin, s_end, pixel_offset, out, (cudaStream_t)stream));
 }
+
+static int check_phong(const pert_phong* ph) {
+    if (!ph) return PERT_E_NULL;
+    if (ph->P <= 0 || ph->HW <= 0 || ph->K <= 0 || ph->num_faces <= 0 || ph->P % ph->HW != 0) return PERT_E_SHAPE;
+    if (ph->light_rows != 1 && ph->light_rows != ph->P / ph->HW) return PERT_E_SHAPE;
+    if (ph->num_faces > 0x7fffffff / 21) return PERT_E_UNSUPPORTED;
+    if (!ph->pix_to_face || !ph->bary || !ph->face_verts || !ph->face_normals || !ph->lighting) return PERT_E_NULL;
+    if (!ph->texels && !ph->face_colors) return PERT_E_NULL;
+    if (((uintptr_t)ph->pix_to_face & 7) || ((uintptr_t)ph->bary & 3) || ((uintptr_t)ph->face_verts & 3) ||
+        ((uintptr_t)ph->face_normals & 3) || ((uintptr_t)ph->texels & 3) || ((uintptr_t)ph->face_colors & 3) ||
+        ((uintptr_t)ph->lighting & 3))
+        return PERT_E_ALIGN;
+    return PERT_OK;
+}
+
+extern "C" int pert_phong_fwd(const pert_phong* ph, float* colors, void* stream) {
+    if (int rc = check_phong(ph)) return rc;
+    if (!colors) return PERT_E_NULL;
+    if ((uintptr_t)colors & 3) return PERT_E_ALIGN;
+    return cuda_rc(launch_phong_fwd(*ph, colors, (cudaStream_t)stream));
+}
+
+extern "C" int pert_phong_bwd(const pert_phong* ph, const float* grad_colors, float* grad_texels, float* grad_bary,
+                              float* grad_face_verts, float* grad_face_normals, void* stream) {
+    if (int rc = check_phong(ph)) return rc;
+    if (!grad_colors) return PERT_E_NULL;
+    if (((uintptr_t)grad_colors & 3) || ((uintptr_t)grad_texels & 3) || ((uintptr_t)grad_bary & 3) ||
+        ((uintptr_t)grad_face_verts & 3) || ((uintptr_t)grad_face_normals & 3))
+        return PERT_E_ALIGN;
+    return cuda_rc(launch_phong_bwd(*ph, grad_colors, grad_texels, grad_bary, grad_face_verts, grad_face_normals,
+                                    (cudaStream_t)stream));
+}

@@ -59,6 +59,9 @@ int launch_argmax_fwd(const float* z, int64_t P, int K1, int S, int s_begin, int
 int launch_argmax_bwd(const float* grad_l, const float* z, const void* winners, int64_t P, int K1, int S, int s_begin,
                       int s_end, float gamma, uint64_t seed, int64_t pixel_offset, const float* noise, uint32_t flags,
                       float* grad_z, float* partials, float* grad_gamma, cudaStream_t st);
+int launch_phong_fwd(const pert_phong& ph, float* colors, cudaStream_t st);
+int launch_phong_bwd(const pert_phong& ph, const float* grad_colors, float* grad_texels, float* grad_bary, float* grad_fv,
+                     float* grad_fn, cudaStream_t st);
 int launch_noise_fill(uint64_t seed, int stage, int64_t P, int slots, int s_begin, int s_end, int64_t pixel_offset,
                       float* out, cudaStream_t st);
 

@@ -230,3 +230,44 @@ class RandomSimpleShader(nn.Module):
     def update_nb_samples(self, nb_samples=16):
         self.smoothrast.update_nb_samples(nb_samples)
         self.smoothagg.update_nb_samples(nb_samples)
+
+
+class RandomPhongShader(RandomSimpleShader):
+    """random_rasterizer.py:60-130, the shader experiments/eval.py:170-176 uses: per-pixel Phong lighting of
+    every fragment entry (``phong_shading``, kernels ``pert_phong_fwd/bwd``), then ``smooth_rgb_blend``.
+    Same constructor, ``forward``, ``to`` and smoothing / sample-count accessors as the reference class."""
+
+    def __init__(self, device="cpu", cameras=None, lights=None, materials=None, smoothrast=SoftRast(),
+                 smoothagg=SoftAgg(), blend_params=None):
+        from .structures import Materials, PointLights
+        super().__init__(device=device, cameras=cameras, lights=lights, materials=materials, smoothrast=smoothrast,
+                         smoothagg=smoothagg, blend_params=blend_params)
+        if cameras is None:  # the reference keeps None here and fails in forward (random_rasterizer.py:83,95-99)
+            self.cameras = None
+        if self.lights is None:
+            self.lights = PointLights(device=device)
+        if self.materials is None:
+            self.materials = Materials(device=device)
+
+    def forward(self, fragments, meshes, **kwargs) -> torch.Tensor:
+        from .shading import phong_shading
+        cameras = kwargs.get("cameras", self.cameras)
+        if cameras is None:
+            raise ValueError("Cameras must be specified either at initialization "
+                             "or in the forward pass of SoftPhongShader")
+        texels = meshes.sample_textures(fragments)
+        lights = kwargs.get("lights", self.lights)
+        materials = kwargs.get("materials", self.materials)
+        blend_params = kwargs.get("blend_params", self.blend_params)
+        # every consumer below reads colours of valid entries only when the blend is one of the fused pairs
+        fused = (isinstance(self.smoothrast, GaussianRast) and isinstance(self.smoothagg, GaussianAgg)) or \
+            (type(self.smoothrast) is SoftRast and type(self.smoothagg) is SoftAgg)
+        colors = phong_shading(meshes=meshes, fragments=fragments, texels=texels, lights=lights, cameras=cameras,
+                               materials=materials, sparse=fused)
+        znear = kwargs.get("znear", getattr(cameras, "znear", 1.0))
+        zfar = kwargs.get("zfar", getattr(cameras, "zfar", 100.0))
+        if torch.is_tensor(znear):
+            znear = znear[:, None, None, None]
+        if torch.is_tensor(zfar):
+            zfar = zfar[:, None, None, None]
+        return smooth_rgb_blend(colors, fragments, self.smoothrast, self.smoothagg, blend_params, znear=znear, zfar=zfar)

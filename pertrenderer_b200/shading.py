@@ -1,0 +1,169 @@
+"""Phong lighting of the fragment entries: the ``colors`` RandomPhongShader blends.
+
+``phong_shading`` keeps the signature of ``pytorch3d.renderer.mesh.shading.phong_shading`` as the
+reference calls it (randomras/random_rasterizer.py:103-110) and runs the hand-written kernels
+``pert_phong_fwd`` / ``pert_phong_bwd`` (include/pertshade.h, csrc/phong.cu).  Objects are read by
+attribute only, so pytorch3d's ``Meshes`` / ``PointLights`` / ``DirectionalLights`` / ``Materials`` /
+cameras and the shims of :mod:`pertrenderer_b200.structures` both work:
+
+    meshes.verts_packed() (V,3), meshes.faces_packed() (F,3), meshes.verts_normals_packed() (V,3)
+    lights.location (point) or lights.direction (directional), .ambient_color, .diffuse_color, .specular_color
+    materials.ambient_color, .diffuse_color, .specular_color, .shininess
+    cameras.get_camera_center() (N,3)
+
+Gradients flow to the mesh (vertex positions and vertex normals, through torch's own indexing
+``verts[faces]``), to the texels and to ``fragments.bary_coords``.  Lights, materials and the camera
+centre are constants here, as they are in experiments/eval.py:233-262.
+"""
+
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+from torch.autograd import Function
+
+from . import _cabi
+from ._cabi import PHONG_SPARSE, PHONG_STRIDE, PertPhong, check, ptr, require_cuda, stream_ptr
+from .structures import FaceTexels
+
+
+def _f32c(t):
+    return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.to(torch.float32).contiguous()
+
+
+def _rows(v, n_max, device, width=3):
+    """A light / material attribute as float32 (rows, width) on ``device``, rows = 1 or N."""
+    t = torch.as_tensor(v, dtype=torch.float32, device=device).detach()
+    if t.dim() == 0:
+        t = t.reshape(1, 1).expand(1, width)
+    t = t.reshape(-1, width) if width > 1 else t.reshape(-1, 1)
+    if t.shape[0] not in (1, n_max):
+        raise ValueError(f"lighting attributes must have 1 or N={n_max} rows, got {t.shape[0]}")
+    return t
+
+
+def pack_lighting(lights, materials, cameras, N, device):
+    """(rows, PERT_PHONG_STRIDE) float32 table of include/pertshade.h: one row per batch element, or one
+    row when nothing varies over the batch."""
+    directional = not hasattr(lights, "location")
+    loc = _rows(lights.direction if directional else lights.location, N, device)
+    amb = _rows(materials.ambient_color, N, device) * _rows(lights.ambient_color, N, device)
+    dif = _rows(materials.diffuse_color, N, device) * _rows(lights.diffuse_color, N, device)
+    spc = _rows(materials.specular_color, N, device) * _rows(lights.specular_color, N, device)
+    sh = _rows(materials.shininess, N, device, width=1)
+    cam = _rows(cameras.get_camera_center(), N, device)
+    rows = max(t.shape[0] for t in (loc, amb, dif, spc, sh, cam))
+    table = torch.zeros((rows, PHONG_STRIDE), dtype=torch.float32, device=device)
+    table[:, 0:3], table[:, 3:6], table[:, 6:9], table[:, 9:12] = loc, amb, dif, spc
+    table[:, 12:13] = sh
+    table[:, 13:16] = cam
+    table[:, 16] = 1.0 if directional else 0.0
+    return table
+
+
+def _phong_struct(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting, flags):
+    N, H, W, K = pix_to_face.shape
+    ph = PertPhong()
+    ph.P, ph.HW, ph.K = N * H * W, H * W, K
+    ph.light_rows = lighting.shape[0]
+    ph.num_faces = face_verts.shape[0]
+    ph.flags = flags
+    ph.pix_to_face, ph.bary = pix_to_face.data_ptr(), bary.data_ptr()
+    ph.face_verts, ph.face_normals = face_verts.data_ptr(), face_normals.data_ptr()
+    ph.texels = None if texels is None else texels.data_ptr()
+    ph.face_colors = None if face_colors is None else face_colors.data_ptr()
+    ph.lighting = lighting.data_ptr()
+    return ph
+
+
+def phong_forward(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting, sparse=False):
+    """Launch pert_phong_fwd.  Returns colors (N,H,W,K,3); with ``sparse`` the entries with
+    pix_to_face < 0 are left unwritten (the fused shader kernels never read them)."""
+    lib = _cabi.load()
+    require_cuda(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting)
+    N, H, W, K = pix_to_face.shape
+    dev = pix_to_face.device
+    with torch.cuda.device(dev):
+        colors = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev)
+        ph = _phong_struct(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting,
+                           PHONG_SPARSE if sparse else 0)
+        rc = lib.pert_phong_fwd(ph, ptr(colors), stream_ptr(dev))
+    check(rc, "pert_phong_fwd")
+    return colors
+
+
+def phong_backward(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting, grad_colors,
+                   need_texels=True, need_bary=True, need_verts=True, need_normals=True, sparse=False):
+    """Launch pert_phong_bwd.  Returns (grad_texels | grad_face_colors, grad_bary, grad_face_verts,
+    grad_face_normals), ``None`` where not requested.  Every entry of the dense outputs is defined (they
+    flow on to the caller's own tensors): with ``sparse`` the kernel skips the padded entries, whose
+    gradients are the zeros the buffers are created with."""
+    lib = _cabi.load()
+    require_cuda(grad_colors)
+    grad_colors = _f32c(grad_colors)
+    N, H, W, K = pix_to_face.shape
+    dev = pix_to_face.device
+    with torch.cuda.device(dev):
+        alloc = torch.zeros if sparse else torch.empty
+        if need_texels:
+            g_tex = torch.zeros_like(face_colors) if face_colors is not None else \
+                alloc((N, H, W, K, 3), dtype=torch.float32, device=dev)
+        else:
+            g_tex = None
+        g_bary = alloc((N, H, W, K, 3), dtype=torch.float32, device=dev) if need_bary else None
+        g_fv = torch.zeros_like(face_verts) if need_verts else None
+        g_fn = torch.zeros_like(face_normals) if need_normals else None
+        ph = _phong_struct(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting,
+                           PHONG_SPARSE if sparse else 0)
+        rc = lib.pert_phong_bwd(ph, ptr(grad_colors), ptr(g_tex), ptr(g_bary), ptr(g_fv), ptr(g_fn), stream_ptr(dev))
+    check(rc, "pert_phong_bwd")
+    return g_tex, g_bary, g_fv, g_fn
+
+
+class _PhongShade(Function):
+    """colors = phong(face_verts, face_normals, texels | face_colors, bary); constants: pix_to_face, lighting."""
+
+    @staticmethod
+    def forward(ctx, face_verts, face_normals, texels, bary, pix_to_face, lighting, face_mode, sparse):
+        fv, fn = _f32c(face_verts.detach()), _f32c(face_normals.detach())
+        tx, bc = _f32c(texels.detach()), _f32c(bary.detach())
+        p2f = pix_to_face.contiguous()
+        colors = phong_forward(p2f, bc, fv, fn, None if face_mode else tx, tx if face_mode else None, lighting, sparse)
+        ctx.save_for_backward(fv, fn, tx, bc, p2f, lighting)
+        ctx.face_mode, ctx.sparse = face_mode, sparse
+        return colors
+
+    @staticmethod
+    def backward(ctx, grad_colors):
+        fv, fn, tx, bc, p2f, lighting = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        g_tex, g_bary, g_fv, g_fn = phong_backward(
+            p2f, bc, fv, fn, None if ctx.face_mode else tx, tx if ctx.face_mode else None, lighting, grad_colors,
+            need_texels=need[2], need_bary=need[3], need_verts=need[0], need_normals=need[1], sparse=ctx.sparse)
+        return g_fv, g_fn, g_tex, g_bary, None, None, None, None
+
+
+def phong_shading(meshes, fragments, lights, cameras, materials, texels, sparse: bool = False) -> torch.Tensor:
+    """pytorch3d.renderer.mesh.shading.phong_shading, same arguments (random_rasterizer.py:103-110).
+
+    ``texels`` (N,H,W,K,3), or lazy :class:`FaceTexels` (per-face colours gathered through
+    pix_to_face inside the kernel).  Returns colors (N,H,W,K,3)."""
+    pix_to_face = fragments.pix_to_face
+    if fragments.bary_coords is None:
+        raise ValueError("phong_shading needs fragments.bary_coords (N,H,W,K,3)")
+    require_cuda(pix_to_face, fragments.bary_coords)
+    if pix_to_face.dtype != torch.int64:
+        pix_to_face = pix_to_face.to(torch.int64)
+    N = pix_to_face.shape[0]
+    device = pix_to_face.device
+    verts = meshes.verts_packed()
+    faces = meshes.faces_packed()
+    vertex_normals = meshes.verts_normals_packed()
+    faces_verts = verts[faces]  # (F,3,3); torch's indexing scatters the gradient back to the vertices
+    faces_normals = vertex_normals[faces]
+    lighting = pack_lighting(lights, materials, cameras, N, device)
+    face_mode = isinstance(texels, FaceTexels)
+    tex = texels.face_colors if face_mode else texels
+    return _PhongShade.apply(faces_verts, faces_normals, tex, fragments.bary_coords, pix_to_face, lighting,
+                             face_mode, bool(sparse))

@@ -87,6 +87,137 @@ class FaceColorMeshes:
         return FaceTexels(self.face_colors)
 
 
+def _color_rows(v, device):
+    return torch.as_tensor(v, dtype=torch.float32, device=device).reshape(-1, 3)
+
+
+class PointLights:
+    """pytorch3d.renderer.lighting.PointLights by attribute (same constructor defaults): colours and
+    ``location`` are (1,3) or (N,3) tensors."""
+
+    def __init__(self, ambient_color=((0.5, 0.5, 0.5),), diffuse_color=((0.3, 0.3, 0.3),),
+                 specular_color=((0.2, 0.2, 0.2),), location=((0, 1, 0),), device="cpu"):
+        self.ambient_color = _color_rows(ambient_color, device)
+        self.diffuse_color = _color_rows(diffuse_color, device)
+        self.specular_color = _color_rows(specular_color, device)
+        self.location = _color_rows(location, device)
+
+    def to(self, device):
+        for k in ("ambient_color", "diffuse_color", "specular_color", "location"):
+            setattr(self, k, getattr(self, k).to(device))
+        return self
+
+
+class DirectionalLights:
+    """pytorch3d.renderer.lighting.DirectionalLights by attribute: ``direction`` instead of ``location``."""
+
+    def __init__(self, ambient_color=((0.5, 0.5, 0.5),), diffuse_color=((0.3, 0.3, 0.3),),
+                 specular_color=((0.2, 0.2, 0.2),), direction=((0, 1, 0),), device="cpu"):
+        self.ambient_color = _color_rows(ambient_color, device)
+        self.diffuse_color = _color_rows(diffuse_color, device)
+        self.specular_color = _color_rows(specular_color, device)
+        self.direction = _color_rows(direction, device)
+
+    def to(self, device):
+        for k in ("ambient_color", "diffuse_color", "specular_color", "direction"):
+            setattr(self, k, getattr(self, k).to(device))
+        return self
+
+
+class Materials:
+    """pytorch3d.renderer.materials.Materials by attribute (defaults: white, shininess 64)."""
+
+    def __init__(self, ambient_color=((1, 1, 1),), diffuse_color=((1, 1, 1),), specular_color=((1, 1, 1),),
+                 shininess=64, device="cpu"):
+        self.ambient_color = _color_rows(ambient_color, device)
+        self.diffuse_color = _color_rows(diffuse_color, device)
+        self.specular_color = _color_rows(specular_color, device)
+        self.shininess = torch.as_tensor(shininess, dtype=torch.float32, device=device).reshape(-1)
+
+    def to(self, device):
+        for k in ("ambient_color", "diffuse_color", "specular_color", "shininess"):
+            setattr(self, k, getattr(self, k).to(device))
+        return self
+
+
+class ViewCameras(DepthCameras):
+    """A camera batch with extrinsics: ``R`` (N,3,3), ``T`` (N,3) in pytorch3d's row-vector convention
+    ``X_view = X_world R + T``, so the camera centre is ``-T R^T`` (``get_camera_center``)."""
+
+    def __init__(self, R, T, znear=1.0, zfar=100.0, device="cpu"):
+        self.R = torch.as_tensor(R, dtype=torch.float32, device=device).reshape(-1, 3, 3)
+        self.T = torch.as_tensor(T, dtype=torch.float32, device=device).reshape(-1, 3)
+        super().__init__(znear=znear, zfar=zfar, n=self.R.shape[0], device=device)
+
+    def get_camera_center(self):
+        return -torch.bmm(self.T[:, None, :], self.R.transpose(1, 2))[:, 0, :]
+
+    def to(self, device):
+        super().to(device)
+        self.R, self.T = self.R.to(device), self.T.to(device)
+        return self
+
+
+class TriMeshes:
+    """Stand-in for pytorch3d ``Meshes`` (packed representation only): vertices (V,3), faces (F,3), and
+    either one colour per face (lazy :class:`FaceTexels`) or a preset texel tensor.
+    ``verts_normals_packed`` follows pytorch3d's area-weighted vertex normals (cross products of the
+    face edges summed onto the corners, then normalised with eps 1e-6)."""
+
+    def __init__(self, verts, faces, face_colors=None, texels=None):
+        self._verts, self._faces = verts, faces.to(torch.int64)
+        self.face_colors, self.texels = face_colors, texels
+
+    def verts_packed(self):
+        return self._verts
+
+    def faces_packed(self):
+        return self._faces
+
+    def verts_normals_packed(self):
+        v, f = self._verts, self._faces
+        vf = v[f]
+        n = torch.zeros_like(v)
+        n = n.index_add(0, f[:, 1], torch.cross(vf[:, 2] - vf[:, 1], vf[:, 0] - vf[:, 1], dim=1))
+        n = n.index_add(0, f[:, 2], torch.cross(vf[:, 0] - vf[:, 2], vf[:, 1] - vf[:, 2], dim=1))
+        n = n.index_add(0, f[:, 0], torch.cross(vf[:, 1] - vf[:, 0], vf[:, 2] - vf[:, 0], dim=1))
+        return torch.nn.functional.normalize(n, eps=1e-6, dim=1)
+
+    def sample_textures(self, fragments):
+        if self.texels is not None:
+            return self.texels
+        return FaceTexels(self.face_colors)
+
+    def update_verts(self, verts):
+        return TriMeshes(verts, self._faces, self.face_colors, self.texels)
+
+
+def synthetic_mesh(n_faces=1280, seed=0, device="cuda"):
+    """A closed unit-scale triangle soup with about ``n_faces`` faces for the Phong benchmark: a
+    latitude/longitude sphere (vertex normals are well defined).  Returns (verts (V,3), faces (F,3))."""
+    rows = max(2, int(round(math.sqrt(n_faces / 2.0))))
+    cols = max(3, int(math.ceil(n_faces / (2.0 * rows))))
+    th = torch.linspace(0.0, math.pi, rows + 1, device=device)[:, None]
+    phv = torch.linspace(0.0, 2.0 * math.pi, cols + 1, device=device)[None, :-1]
+    x, y, z = torch.sin(th) * torch.cos(phv), torch.cos(th).expand(rows + 1, cols), torch.sin(th) * torch.sin(phv)
+    verts = torch.stack((x, y, z), dim=-1).reshape(-1, 3).float()
+    r = torch.arange(rows, device=device)[:, None]
+    c = torch.arange(cols, device=device)[None, :]
+    i00, i01 = r * cols + c, r * cols + (c + 1) % cols
+    i10, i11 = (r + 1) * cols + c, (r + 1) * cols + (c + 1) % cols
+    faces = torch.cat((torch.stack((i00, i11, i10), -1).reshape(-1, 3), torch.stack((i00, i01, i11), -1).reshape(-1, 3)))
+    return verts, faces[:n_faces].to(torch.int64)
+
+
+def synthetic_bary(pix_to_face, seed=0):
+    """Random barycentric coordinates (N,H,W,K,3) for the valid entries (positive, summing to 1), -1 at
+    padding like pytorch3d's rasteriser."""
+    g = torch.Generator(device=pix_to_face.device).manual_seed(seed + 17)
+    e = -torch.log(torch.rand(pix_to_face.shape + (3,), generator=g, device=pix_to_face.device).clamp_min(1e-9))
+    b = e / e.sum(dim=-1, keepdim=True)
+    return torch.where((pix_to_face >= 0)[..., None], b, torch.full_like(b, -1.0)).float()
+
+
 def blur_radius(sigma: float) -> float:
     """experiments/eval.py:137: log(1/1e-4 - 1) * sigma."""
     return math.log(1.0 / 1e-4 - 1.0) * sigma

@@ -1,0 +1,215 @@
+"""Parity of the Phong kernels (pert_phong_fwd / pert_phong_bwd, through the C ABI) with the CPU oracle
+(oracle/phong_oracle.py, pytorch3d 0.4.0's phong_shading restated), and of RandomPhongShader end to end
+(random_rasterizer.py:60-130) with the oracle chain Phong -> perturbed blend fed the same noise.
+Tolerance: 1e-5 relative in fp32 (north_star); face-table gradients are summed by atomics in no fixed order."""
+
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import pert_oracle as O
+from oracle import phong_oracle as PO
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def _scene(N, H, W, K, n_faces, light="point", per_batch=False, seed=0, shininess=8.0, kind="realistic"):
+    """Everything on the CPU: fragments with bary, a sphere mesh, lights / materials / cameras shims."""
+    import pertrenderer_b200 as pb
+    fr, _ = pb.synthetic_fragments(N, H, W, K, kind=kind, n_faces=n_faces, seed=seed, device="cpu", mean_valid=3.0)
+    verts, faces = pb.synthetic_mesh(n_faces, device="cpu")
+    fr = pb.Fragments(fr.pix_to_face.clamp(max=faces.shape[0] - 1), fr.zbuf, pb.synthetic_bary(fr.pix_to_face, seed), fr.dists)
+    g = torch.Generator().manual_seed(seed + 3)
+    rows = N if per_batch else 1
+    rnd = lambda *s: torch.rand(*s, generator=g)  # noqa: E731
+    col = dict(ambient_color=0.2 + 0.5 * rnd(rows, 3), diffuse_color=0.2 + 0.5 * rnd(rows, 3), specular_color=0.2 + 0.5 * rnd(rows, 3))
+    if light == "point":
+        lights = pb.PointLights(location=torch.tensor([[0.0, 2.0, -2.0]]) + rnd(rows, 3), **col)
+    else:
+        lights = pb.DirectionalLights(direction=torch.tensor([[0.3, 1.0, -0.5]]) + 0.3 * rnd(rows, 3), **col)
+    mats = pb.Materials(ambient_color=0.5 + 0.5 * rnd(rows, 3), diffuse_color=0.5 + 0.5 * rnd(rows, 3),
+                        specular_color=0.5 + 0.5 * rnd(rows, 3), shininess=torch.full((rows,), shininess))
+    cams = pb.ViewCameras(R=torch.eye(3).expand(N, 3, 3).clone(), T=torch.tensor([[0.0, 0.0, 2.7]]) + 0.2 * rnd(N, 3))
+    face_colors = rnd(faces.shape[0], 3)
+    texels = rnd(N, H, W, K, 3) * (fr.pix_to_face >= 0)[..., None]
+    return fr, verts, faces, lights, mats, cams, face_colors, texels
+
+
+def _to(obj, dev):
+    import copy
+    return copy.deepcopy(obj).to(dev)
+
+
+def _frag_to(fr, dev, bary_grad=False):
+    import pertrenderer_b200 as pb
+    b = fr.bary_coords.to(dev)
+    if bary_grad:
+        b.requires_grad_(True)
+    return pb.Fragments(fr.pix_to_face.to(dev), fr.zbuf.to(dev), b, fr.dists.to(dev))
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(n_faces=40, light="point", per_batch=False, face_mode=False),      # shared-memory face table
+    dict(n_faces=40, light="directional", per_batch=True, face_mode=True),  # per-batch rows, face colours, table
+    dict(n_faces=3000, light="point", per_batch=True, face_mode=False),     # global atomics
+    dict(n_faces=3000, light="directional", per_batch=False, face_mode=True),
+])
+def test_phong_kernels_match_oracle(cfg):
+    import pertrenderer_b200 as pb
+    N, H, W, K = 3, 9, 11, 7
+    fr, verts, faces, lights, mats, cams, face_colors, texels = _scene(N, H, W, K, cfg["n_faces"], cfg["light"], cfg["per_batch"],
+                                                                       seed=cfg["n_faces"])
+    gen = torch.Generator().manual_seed(1)
+    grad_colors = torch.randn(N, H, W, K, 3, generator=gen)
+    grad_colors[torch.rand(N, H, W, K, generator=gen) < 0.5] = 0.0  # entries no sample picked: the kernel's shortcut
+
+    # oracle (autograd over the restatement)
+    v_o, t_o = verts.clone().requires_grad_(True), (face_colors if cfg["face_mode"] else texels).clone().requires_grad_(True)
+    fr_o = pb.Fragments(fr.pix_to_face, fr.zbuf, fr.bary_coords.clone().requires_grad_(True), fr.dists)
+    mesh_o = pb.TriMeshes(v_o, faces, face_colors=t_o) if cfg["face_mode"] else pb.TriMeshes(v_o, faces, texels=t_o)
+    tex_o = pb.FaceTexels(t_o).materialize(fr.pix_to_face) if cfg["face_mode"] else t_o
+    col_o = PO.phong_colors_from(mesh_o, fr_o, lights, cams, mats, tex_o)
+    (col_o * grad_colors).sum().backward()
+
+    # CUDA
+    v_c = verts.to(DEV).requires_grad_(True)
+    t_c = (face_colors if cfg["face_mode"] else texels).to(DEV).requires_grad_(True)
+    fr_c = _frag_to(fr, DEV, bary_grad=True)
+    mesh_c = pb.TriMeshes(v_c, faces.to(DEV), face_colors=t_c) if cfg["face_mode"] else pb.TriMeshes(v_c, faces.to(DEV), texels=t_c)
+    col_c = pb.phong_shading(mesh_c, fr_c, _to(lights, DEV), _to(cams, DEV), _to(mats, DEV), mesh_c.sample_textures(fr_c))
+    (col_c * grad_colors.to(DEV)).sum().backward()
+
+    assert (col_c.detach().cpu() - col_o.detach()).abs().max() <= 2e-6
+    assert rel_err(col_c.detach().cpu(), col_o.detach()) <= RTOL
+    assert rel_err(t_c.grad.cpu(), t_o.grad) <= RTOL
+    assert rel_err(fr_c.bary_coords.grad.cpu(), fr_o.bary_coords.grad) <= RTOL
+    assert rel_err(v_c.grad.cpu(), v_o.grad) <= 2 * RTOL  # thousands of atomic adds per vertex, order not fixed
+    mask = fr.pix_to_face >= 0
+    assert (fr_c.bary_coords.grad.cpu()[~mask] == 0).all()
+
+
+def test_phong_sparse_flag_leaves_padding_alone_and_keeps_valid_entries():
+    import pertrenderer_b200 as pb
+    N, H, W, K = 2, 8, 8, 6
+    fr, verts, faces, lights, mats, cams, face_colors, texels = _scene(N, H, W, K, 60, seed=4)
+    mesh = pb.TriMeshes(verts.to(DEV), faces.to(DEV), texels=texels.to(DEV))
+    args = (mesh, _frag_to(fr, DEV), _to(lights, DEV), _to(cams, DEV), _to(mats, DEV), texels.to(DEV))
+    dense = pb.phong_shading(*args)
+    sparse = pb.phong_shading(*args, sparse=True)
+    mask = (fr.pix_to_face >= 0).to(DEV)
+    assert torch.equal(dense[mask], sparse[mask])
+    assert (dense[~mask] == 0).all()  # zero texels at padded entries -> black
+
+
+def test_degenerate_normals_and_shininess_zero():
+    """Zero interpolated normal (clamped normalisation), light at the shaded point, shininess 0 (0^0 = 1)."""
+    import pertrenderer_b200 as pb
+    fv = torch.tensor([[[-1.0, -1.0, 0.0], [3.0, -1.0, 0.0], [-1.0, 3.0, 0.0]]])
+    verts = fv.reshape(3, 3)
+    faces = torch.tensor([[0, 1, 2]])
+    p2f = torch.zeros(1, 1, 2, 2, dtype=torch.int64)
+    p2f[0, 0, 1, 1] = -1
+    bary = torch.tensor([0.25, 0.25, 0.5]).expand(1, 1, 2, 2, 3).contiguous()
+    fr = pb.Fragments(p2f, torch.ones(1, 1, 2, 2), bary, torch.zeros(1, 1, 2, 2))
+    texels = torch.rand(1, 1, 2, 2, 3)
+
+    class ZeroNormalMesh(pb.TriMeshes):
+        def verts_normals_packed(self):
+            return torch.zeros_like(self.verts_packed())
+
+    for sh in (0.0, 1.0, 64.0):
+        lights = pb.PointLights(location=[[0.0, 0.5, 0.0]])  # ON the shaded point (0, 0.5, 0): zero light direction
+        mats = pb.Materials(shininess=sh)
+        cams = pb.ViewCameras(R=torch.eye(3)[None], T=[[0.0, 0.0, 2.7]])
+        for mesh_cls in (pb.TriMeshes, ZeroNormalMesh):
+            ref = PO.phong_colors_from(mesh_cls(verts, faces, texels=texels), fr, lights, cams, mats, texels)
+            got = pb.phong_shading(mesh_cls(verts.to(DEV), faces.to(DEV), texels=texels.to(DEV)), _frag_to(fr, DEV), _to(lights, DEV),
+                                   _to(cams, DEV), _to(mats, DEV), texels.to(DEV))
+            assert torch.isfinite(got).all()
+            assert (got.cpu() - ref).abs().max() <= 2e-6, (sh, mesh_cls.__name__)
+
+
+@pytest.mark.parametrize("pair", ["gaussian", "softras"])
+def test_random_phong_shader_matches_oracle_chain(pair):
+    """RandomPhongShader.forward + autograd vs oracle Phong colours -> oracle blend, same noise: image, and the
+    gradient that reaches the mesh vertices (the quantity pose optimisation uses, eval.py:343-369)."""
+    import pertrenderer_b200 as pb
+    N, H, W, K, S = 2, 10, 9, 12, 16
+    fr, verts, faces, lights, mats, cams, face_colors, _ = _scene(N, H, W, K, 80, per_batch=True, seed=9)
+    sigma, gamma, alpha = 1e-3, 1e-2, 1.0
+    background = (0.2, 0.4, 0.6)
+    gen = torch.Generator().manual_seed(2)
+    grad_image = torch.randn(N, H, W, 4, generator=gen)
+
+    v_o = verts.clone().requires_grad_(True)
+    mesh_o = pb.TriMeshes(v_o, faces, face_colors=face_colors)
+    col_o = PO.phong_colors_from(mesh_o, fr, lights, cams, mats, pb.FaceTexels(face_colors).materialize(fr.pix_to_face))
+    zn, zf = cams.znear.reshape(-1, 1, 1, 1), cams.zfar.reshape(-1, 1, 1, 1)
+    if pair == "gaussian":
+        U, V = O.draw_noise((N, H, W, K), S, S, generator=torch.Generator().manual_seed(5))
+        st, gr = O.shade_fwd_bwd(fr.pix_to_face, fr.zbuf, fr.dists, col_o.detach(), torch.tensor(background), zn, zf, sigma, gamma,
+                                 alpha, 1e-10, U, V, grad_image)
+        image_o = st.image
+        rast, agg = pb.GaussianRast(nb_samples=S, sigma=sigma), pb.GaussianAgg(nb_samples=S, gamma=gamma, alpha=alpha)
+    else:
+        image_o, _, _, gr = O.soft_shade_fwd_bwd(fr.pix_to_face, fr.zbuf, fr.dists, col_o.detach(), torch.tensor(background), zn, zf, sigma,
+                                           gamma, alpha, 1e-10, grad_image)
+        rast, agg = pb.SoftRast(sigma=sigma), pb.SoftAgg(gamma=gamma, alpha=alpha)
+    col_o.backward(gr["colors"])
+
+    v_c = verts.to(DEV).requires_grad_(True)
+    mesh_c = pb.TriMeshes(v_c, faces.to(DEV), face_colors=face_colors.to(DEV))
+    shader = pb.RandomPhongShader(device=DEV, cameras=_to(cams, DEV), lights=_to(lights, DEV), materials=_to(mats, DEV),
+                                  smoothrast=rast, smoothagg=agg, blend_params=pb.BlendParams(background_color=background))
+    fr_c = _frag_to(fr, DEV)
+    if pair == "gaussian":
+        with pb.explicit_noise(U.to(DEV), V.to(DEV)):
+            img = shader(fr_c, mesh_c)
+            (img * grad_image.to(DEV)).sum().backward()
+    else:
+        img = shader(fr_c, mesh_c)
+        (img * grad_image.to(DEV)).sum().backward()
+    assert (img.detach().cpu() - image_o).abs().max() <= 3e-6
+    assert rel_err(v_c.grad.cpu(), v_o.grad) <= 2 * RTOL
+
+
+def test_phong_full_size_properties_config2():
+    """BASELINE config 2 shapes (8 x 256 x 256, K = 50): size-independent properties of the Phong pass.
+    Linearity of backward in grad_colors; padded entries untouched by sparse mode; the sum of the face-table
+    gradient equals the sum over entries of b_i * g_p (checked through grad_bary's identity
+    sum_i b_i * grad_b_i = g_p . p + g_n . n_raw, i.e. two launches agree on a scalar checksum)."""
+    import pertrenderer_b200 as pb
+    from pertrenderer_b200 import shading
+    N, H, W, K = 8, 256, 256, 50
+    fr, _ = pb.synthetic_fragments(N, H, W, K, kind="realistic", n_faces=1280, device=DEV)
+    verts, faces = pb.synthetic_mesh(1280, device=DEV)
+    p2f = fr.pix_to_face.clamp(max=faces.shape[0] - 1)
+    bary = pb.synthetic_bary(p2f)
+    mesh = pb.TriMeshes(verts, faces)
+    fv, fn = verts[faces].contiguous(), mesh.verts_normals_packed()[faces].contiguous()
+    fc = torch.rand(faces.shape[0], 3, device=DEV)
+    lighting = shading.pack_lighting(pb.PointLights(location=[[0.0, 2.0, -2.0]], device=DEV), pb.Materials(device=DEV),
+                                     pb.ViewCameras(R=torch.eye(3)[None], T=[[0.0, 0.0, 2.7]], device=DEV), N, DEV)
+    colors = shading.phong_forward(p2f, bary, fv, fn, None, fc, lighting)
+    mask = p2f >= 0
+    assert torch.isfinite(colors).all() and (colors[~mask] == 0).all() and (colors[mask] >= 0).all()
+    g1 = torch.randn(N, H, W, K, 3, device=DEV) * mask[..., None]
+    g2 = torch.randn(N, H, W, K, 3, device=DEV) * mask[..., None]
+    a = shading.phong_backward(p2f, bary, fv, fn, None, fc, lighting, g1)
+    b = shading.phong_backward(p2f, bary, fv, fn, None, fc, lighting, g2)
+    c = shading.phong_backward(p2f, bary, fv, fn, None, fc, lighting, 2.0 * g1 - 0.5 * g2)
+    for x, y, z in zip(a, b, c):
+        assert rel_err(z, 2.0 * x - 0.5 * y) <= 1e-4
+    # Euler identity of the interpolation: sum_i b_i * dL/db_i = <dL/dV, V> + <dL/dN, N> entry by entry, summed
+    lhs = (bary * a[1])[mask].double().sum()
+    rhs = (a[2].double() * fv.double()).sum() + (a[3].double() * fn.double()).sum()
+    assert abs(lhs - rhs) <= 1e-4 * max(abs(rhs), 1.0)
