@@ -99,15 +99,24 @@ def test_phong_kernels_match_oracle(cfg):
 
 def test_phong_sparse_flag_leaves_padding_alone_and_keeps_valid_entries():
     import pertrenderer_b200 as pb
+    from pertrenderer_b200 import shading
     N, H, W, K = 2, 8, 8, 6
     fr, verts, faces, lights, mats, cams, face_colors, texels = _scene(N, H, W, K, 60, seed=4)
-    mesh = pb.TriMeshes(verts.to(DEV), faces.to(DEV), texels=texels.to(DEV))
-    args = (mesh, _frag_to(fr, DEV), _to(lights, DEV), _to(cams, DEV), _to(mats, DEV), texels.to(DEV))
-    dense = pb.phong_shading(*args)
-    sparse = pb.phong_shading(*args, sparse=True)
-    mask = (fr.pix_to_face >= 0).to(DEV)
+    mesh = pb.TriMeshes(verts.to(DEV), faces.to(DEV))
+    # one set of face tables for both launches (torch's index_add behind verts_normals_packed sums in no fixed order)
+    fv, fn = mesh.verts_packed()[mesh.faces_packed()].contiguous(), mesh.verts_normals_packed()[mesh.faces_packed()].contiguous()
+    lighting = shading.pack_lighting(_to(lights, DEV), _to(mats, DEV), _to(cams, DEV), N, DEV)
+    p2f, bary, tex = fr.pix_to_face.to(DEV), fr.bary_coords.to(DEV), texels.to(DEV)
+    dense = shading.phong_forward(p2f, bary, fv, fn, tex, None, lighting)
+    sparse = shading.phong_forward(p2f, bary, fv, fn, tex, None, lighting, sparse=True)
+    mask = p2f >= 0
     assert torch.equal(dense[mask], sparse[mask])
     assert (dense[~mask] == 0).all()  # zero texels at padded entries -> black
+    g = torch.randn(N, H, W, K, 3, device=DEV) * mask[..., None]
+    a = shading.phong_backward(p2f, bary, fv, fn, tex, None, lighting, g)
+    b = shading.phong_backward(p2f, bary, fv, fn, tex, None, lighting, g, sparse=True)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    assert rel_err(b[2], a[2]) <= 1e-6 and rel_err(b[3], a[3]) <= 1e-6
 
 
 def test_degenerate_normals_and_shininess_zero():
