@@ -284,6 +284,74 @@ def device_timed(args, kind, dev, steps, warmup, world, rank, sampler=None, flag
             "launches": 5 * steps}
 
 
+def phong_timed(args, kind, dev, steps, warmup, rank):
+    """RandomPhongShader step (random_rasterizer.py:60-130), inputs resident: pert_phong_fwd -> pert_shade_fwd ->
+    pert_shade_bwd -> pert_phong_bwd through the C ABI.  Per-face colours (gathered in the Phong kernel), sphere
+    mesh of 1280 faces, one point light; gradients to the face tables (vertices, normals) and bary_coords."""
+    import pertrenderer_b200 as pb
+    from pertrenderer_b200 import ops, shading
+    N, HW, K, S = args.views, args.image_size, args.faces_per_pixel, args.nb_samples
+    F = 1280
+    fr, _ = pb.synthetic_fragments(N, HW, HW, K, kind=kind, sigma=SIGMA, n_faces=F, seed=rank, device=dev)
+    verts, faces = pb.synthetic_mesh(F, device=dev)
+    F = faces.shape[0]
+    p2f = fr.pix_to_face.clamp(max=F - 1)
+    bary = pb.synthetic_bary(p2f, seed=rank)
+    mesh = pb.TriMeshes(verts, faces)
+    fv, fn = verts[faces].contiguous(), mesh.verts_normals_packed()[faces].contiguous()
+    fc = torch.rand((F, 3), device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+    lighting = shading.pack_lighting(pb.PointLights(location=[[0.0, 2.0, -2.0]], device=dev), pb.Materials(device=dev),
+                                     pb.ViewCameras(R=torch.eye(3)[None], T=[[0.0, 0.0, 6.7]], device=dev), N, dev)
+    G = torch.randn((N, HW, HW, 4), device=dev, generator=torch.Generator(device=dev).manual_seed(1 + rank))
+    P = N * HW * HW
+    torch.manual_seed(4321 + rank)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(5)] for _ in range(steps)]
+
+    def step(i=None):
+        rec = (lambda j: ev[i][j].record()) if i is not None else (lambda j: None)
+        rec(0)
+        colors = shading.phong_forward(p2f, bary, fv, fn, None, fc, lighting, sparse=True)
+        rec(1)
+        pr = ops.ShadeProblem(pix_to_face=p2f, zbuf=fr.zbuf, dists=fr.dists, colors=colors, znear=1.0, zfar=100.0,
+                              background=BACKGROUND, sigma=SIGMA, gamma=GAMMA, alpha=ALPHA, eps=EPS, S_rast=S, S_agg=S,
+                              seed_rast=ops.draw_seed(), seed_agg=ops.draw_seed(), pixel_offset=rank * P)
+        image, saved = ops.shade_forward(pr)
+        rec(2)
+        gd, gz, gc, scal = ops.shade_backward(pr, saved, G)
+        rec(3)
+        out = shading.phong_backward(p2f, bary, fv, fn, None, fc, lighting, gc, need_texels=False, sparse=True)
+        rec(4)
+        return out
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(steps):
+        step(i)
+    t1.record()
+    torch.cuda.synchronize(dev)
+    total_ms = t0.elapsed_time(t1)
+    seg = [sum(e[j].elapsed_time(e[j + 1]) for e in ev) / steps for j in range(4)]
+    peak, peak_src = peaks()
+    PF = P * K
+    # API-faithful bytes of the Phong pass with per-face colours: fwd reads pix_to_face 8 + bary 12 and writes
+    # colors 12 per pixel.face; bwd reads pix_to_face 8 + bary 12 + grad_colors 12 and writes grad_bary 12;
+    # the face tables (84 B per face, read) and their gradients (72 B per face) are noise next to that
+    pf_b, pb_b = 32 * PF + 84 * F, 44 * PF + 156 * F
+    return {"fragments": kind,
+            "note": "RandomPhongShader: pert_phong_fwd -> pert_shade_fwd -> pert_shade_bwd -> pert_phong_bwd; per-face "
+                    "colours, 1280-face sphere, one point light; gradients to face vertices / normals and bary_coords; "
+                    "sparse mode (padded entries of colors are neither written nor read; grad_bary is zero-filled by "
+                    "torch inside the timed region)",
+            "value": P * K * S * steps / (total_ms * 1e-3), "unit": UNIT, "ms_per_step": total_ms / steps,
+            "phong_fwd": {"ms": seg[0], "alg_bytes": pf_b, "gbs": pf_b / seg[0] / 1e6, "frac": pf_b / seg[0] / 1e6 / peak},
+            "shade_fwd_ms": seg[1], "shade_bwd_ms": seg[2],
+            "phong_bwd": {"ms": seg[3], "alg_bytes": pb_b, "gbs": pb_b / seg[3] / 1e6, "frac": pb_b / seg[3] / 1e6 / peak},
+            "peak": peak, "peak_source": peak_src, "launches_per_step": 7}
+
+
 def e2e_timed(args, kind, dev, steps, warmup, world, rank):
     """End to end through the public API (RandomSimpleShader + autograd) with HOST buffers: every
     step copies that step's Fragments and texels from pinned host memory (double-buffered on a copy
@@ -385,7 +453,9 @@ def run_b200_arm(args):
         ps = device_timed(args, args.fragments, dev, max(3, args.steps // 2), 3, world, rank, flags=_cabi.F_PER_SAMPLE_NOISE)
         fc = device_timed(args, args.fragments, dev, max(3, args.steps // 2), 3, world, rank, face=True)
         sf = device_timed(args, args.fragments, dev, max(3, args.steps // 2), 3, world, rank, soft=True)
-        also = {"softras_pair": {"fragments": args.fragments,
+        phg = phong_timed(args, args.fragments, dev, max(3, args.steps // 2), 3, rank)
+        also = {"random_phong_shader": phg,
+                "softras_pair": {"fragments": args.fragments,
                                  "note": "SoftRast + SoftAgg (the shaders' DEFAULT operators, deterministic) through the "
                                          "fused soft kernels; same algorithmic bytes; 'units' counts nb_samples like the "
                                          "headline although this pair draws no samples",

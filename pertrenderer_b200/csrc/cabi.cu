@@ -378,7 +378,7 @@ static int check_phong(const pert_phong* ph) {
     if (!ph) return PERT_E_NULL;
     if (ph->P <= 0 || ph->HW <= 0 || ph->K <= 0 || ph->num_faces <= 0 || ph->P % ph->HW != 0) return PERT_E_SHAPE;
     if (ph->light_rows != 1 && ph->light_rows != ph->P / ph->HW) return PERT_E_SHAPE;
-    if (ph->num_faces > 0x7fffffff / 21) return PERT_E_UNSUPPORTED;
+    if (ph->num_faces > 0x7fffffff / 21 || ph->P >= ((int64_t)1 << 32) / ph->K) return PERT_E_UNSUPPORTED;  // 32-bit entry indices
     if (!ph->pix_to_face || !ph->bary || !ph->face_verts || !ph->face_normals || !ph->lighting) return PERT_E_NULL;
     if (!ph->texels && !ph->face_colors) return PERT_E_NULL;
     if (((uintptr_t)ph->pix_to_face & 7) || ((uintptr_t)ph->bary & 3) || ((uintptr_t)ph->face_verts & 3) ||

@@ -58,7 +58,9 @@ def _frag_to(fr, dev, bary_grad=False):
 
 
 @pytest.mark.parametrize("cfg", [
-    dict(n_faces=40, light="point", per_batch=False, face_mode=False),      # shared-memory face table
+    dict(n_faces=40, light="point", per_batch=False, face_mode=False),      # small shared-memory gradient table
+    dict(n_faces=1200, light="point", per_batch=True, face_mode=True),      # one-CTA-per-SM gradient table
+    dict(n_faces=1200, light="directional", per_batch=False, face_mode=False),
     dict(n_faces=40, light="directional", per_batch=True, face_mode=True),  # per-batch rows, face colours, table
     dict(n_faces=3000, light="point", per_batch=True, face_mode=False),     # global atomics
     dict(n_faces=3000, light="directional", per_batch=False, face_mode=True),

@@ -12,6 +12,8 @@ fc=d["also"]["face_colour_gather"]
 print("facecol   ms/step %.4f fwd %.4f (%.3f) bwd %.4f (%.3f)" % (fc["ms_per_step"], fc["roofline"]["fwd"]["ms"], fc["roofline"]["fwd"]["frac"], fc["roofline"]["bwd"]["ms"], fc["roofline"]["bwd"]["frac"]))
 sf=d["also"]["softras_pair"]
 print("softras   ms/step %.4f fwd %.4f (%.3f) bwd %.4f (%.3f)" % (sf["ms_per_step"], sf["roofline"]["fwd"]["ms"], sf["roofline"]["fwd"]["frac"], sf["roofline"]["bwd"]["ms"], sf["roofline"]["bwd"]["frac"]))
+ph=d["also"]["random_phong_shader"]
+print("phong     ms/step %.4f phong_fwd %.4f (%.3f) shade %.4f + %.4f phong_bwd %.4f (%.3f)" % (ph["ms_per_step"], ph["phong_fwd"]["ms"], ph["phong_fwd"]["frac"], ph["shade_fwd_ms"], ph["shade_bwd_ms"], ph["phong_bwd"]["ms"], ph["phong_bwd"]["frac"]))
 print("clocks", d["clocks"])
 PY
 tail -3 gpurun_out/bench_$1.err
