@@ -223,6 +223,7 @@ def device_timed(args, kind, dev, steps, warmup, world, rank, sampler=None, flag
                                 pixel_offset=rank * P, flags=flags)
 
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    comm = torch.cuda.Stream(device=dev) if world > 1 else None
 
     def step(i=None):
         pr = problem()
@@ -238,7 +239,16 @@ def device_timed(args, kind, dev, steps, warmup, world, rank, sampler=None, flag
         if i is not None:
             ev[i][2].record()
         if world > 1:
-            dist.all_reduce(scal)  # the only collective of batch sharding: d/d(sigma, gamma, alpha)
+            # the only collective of batch sharding: d/d(sigma, gamma, alpha), 3 floats.  Nothing on the GPU waits for
+            # it (the caller reads the scalar gradients on the host after the step, eval.py:386-392), so it runs on
+            # its own stream behind backward and overlaps the next step's forward; the timed region ends only after
+            # the last all-reduce (main stream waits for the side stream before the closing event).
+            done = torch.cuda.Event()
+            done.record()
+            comm.wait_event(done)
+            with torch.cuda.stream(comm):
+                scal.record_stream(comm)
+                dist.all_reduce(scal)
         return image, scal
 
     for _ in range(warmup):
@@ -253,6 +263,8 @@ def device_timed(args, kind, dev, steps, warmup, world, rank, sampler=None, flag
     t0.record()
     for i in range(steps):
         step(i)
+    if world > 1:
+        torch.cuda.current_stream(dev).wait_stream(comm)
     t1.record()
     torch.cuda.synchronize(dev)
     if world > 1:
