@@ -51,7 +51,7 @@
 extern "C" {
 #endif
 
-#define PERT_ABI_VERSION 6
+#define PERT_ABI_VERSION 7
 
 /* error codes */
 #define PERT_OK 0
@@ -215,6 +215,11 @@ int pert_argmax_bwd(const float* grad_l, const float* z, const void* winners, in
  */
 #define PERT_PHONG_STRIDE 20
 #define PERT_PHONG_SPARSE 1u
+/* texture sampling only: colour = texel, no lighting (face_verts / face_normals / lighting may be NULL).  With
+ * face_vert_colors this is TexturesVertex.sample_textures (interpolate_face_attributes of the vertex colours,
+ * experiments/eval.py:450), with face_colors a per-face colour lookup: Meshes.sample_textures at
+ * randomras/random_rasterizer.py:101,170 without leaving the kernels' sparse entry lists. */
+#define PERT_PHONG_UNLIT 2u
 
 typedef struct pert_phong {
     int64_t P;          /* pixels N*H*W */
@@ -230,12 +235,15 @@ typedef struct pert_phong {
     const float* texels;        /* (P,K,3) meshes.sample_textures(fragments), or NULL with face_colors */
     const float* face_colors;   /* (F,3) per-face colours gathered through pix_to_face, or NULL */
     const float* lighting;      /* (light_rows, PERT_PHONG_STRIDE) */
+    const float* face_vert_colors; /* (F,3,3) colours at the face corners, interpolated with bary (TexturesVertex:
+                                      verts_features_packed()[faces_packed()]), or NULL */
 } pert_phong;
 
 int pert_phong_fwd(const pert_phong* ph, float* colors, void* stream);
 /*
  * Backward of pert_phong_fwd.  grad_colors (P,K,3).  Outputs, each optional (NULL: not computed):
- *   grad_texels        (P,K,3); with ph->face_colors set: (F,3), ZEROED BY THE CALLER, atomic adds
+ *   grad_texels        (P,K,3); with ph->face_colors set: (F,3), with ph->face_vert_colors set: (F,3,3), ZEROED BY THE
+ *                      CALLER, atomic adds
  *   grad_bary          (P,K,3)
  *   grad_face_verts    (F,3,3) and grad_face_normals (F,3,3): ZEROED BY THE CALLER, atomic adds (the scatter of
  *                      interpolate_face_attributes' backward; summation order is not fixed)

@@ -6,17 +6,17 @@ Drop-in for the hot path of quentinll/pertrenderer (``randomras``): the same pub
 """
 
 from .random_rasterizer import RandomPhongShader, RandomSimpleShader, SimpleShader, smooth_rgb_blend
-from .shading import phong_shading
+from .shading import phong_shading, sample_lazy_textures
 from .smoothagg import CauchyAgg, GaussianAgg, HardAgg, SoftAgg, randomArgmax
 from .smoothrast import AffineRast, ArctanRast, GaussianRast, HardRast, SoftRast, randomHeaviside
 from .structures import (BlendParams, DepthCameras, DirectionalLights, FaceColorMeshes, FaceTexels, Fragments, Materials,
-                         PointLights, TexelMeshes, TriMeshes, ViewCameras, synthetic_bary, synthetic_fragments,
+                         PointLights, TexelMeshes, TriMeshes, VertexTexels, ViewCameras, synthetic_bary, synthetic_fragments,
                          synthetic_mesh)
 from .ops import explicit_noise, kernel_flags
 
 __all__ = [
     "RandomPhongShader", "RandomSimpleShader", "SimpleShader", "phong_shading", "PointLights", "DirectionalLights",
-    "Materials", "ViewCameras", "TriMeshes", "synthetic_mesh", "synthetic_bary", "smooth_rgb_blend", "GaussianAgg", "SoftAgg", "CauchyAgg", "HardAgg",
+    "Materials", "ViewCameras", "TriMeshes", "VertexTexels", "sample_lazy_textures", "synthetic_mesh", "synthetic_bary", "smooth_rgb_blend", "GaussianAgg", "SoftAgg", "CauchyAgg", "HardAgg",
     "randomArgmax", "GaussianRast", "ArctanRast", "AffineRast", "HardRast",
     "SoftRast", "randomHeaviside", "BlendParams", "DepthCameras", "Fragments", "TexelMeshes",
     "synthetic_fragments", "explicit_noise", "kernel_flags", "FaceColorMeshes", "FaceTexels",

@@ -15,7 +15,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpertshade.so")
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 # flags (include/pertshade.h)
 F_NO_SKIP = 1
@@ -33,6 +33,7 @@ EXPORTS = [
 
 PHONG_STRIDE = 20  # PERT_PHONG_STRIDE
 PHONG_SPARSE = 1  # PERT_PHONG_SPARSE
+PHONG_UNLIT = 2  # PERT_PHONG_UNLIT
 
 
 class PertProblem(C.Structure):
@@ -65,6 +66,7 @@ class PertPhong(C.Structure):
         ("flags", C.c_uint32),
         ("pix_to_face", C.c_void_p), ("bary", C.c_void_p), ("face_verts", C.c_void_p), ("face_normals", C.c_void_p),
         ("texels", C.c_void_p), ("face_colors", C.c_void_p), ("lighting", C.c_void_p),
+        ("face_vert_colors", C.c_void_p),
     ]
 
 

@@ -377,13 +377,15 @@ extern "C" int pert_noise_fill(uint64_t seed, int32_t stage, int64_t P, int32_t 
 static int check_phong(const pert_phong* ph) {
     if (!ph) return PERT_E_NULL;
     if (ph->P <= 0 || ph->HW <= 0 || ph->K <= 0 || ph->num_faces <= 0 || ph->P % ph->HW != 0) return PERT_E_SHAPE;
-    if (ph->light_rows != 1 && ph->light_rows != ph->P / ph->HW) return PERT_E_SHAPE;
-    if (ph->num_faces > 0x7fffffff / 21 || ph->P >= ((int64_t)1 << 32) / ph->K) return PERT_E_UNSUPPORTED;  // 32-bit entry indices
-    if (!ph->pix_to_face || !ph->bary || !ph->face_verts || !ph->face_normals || !ph->lighting) return PERT_E_NULL;
-    if (!ph->texels && !ph->face_colors) return PERT_E_NULL;
+    if (ph->num_faces > 0x7fffffff / 27 || ph->P >= ((int64_t)1 << 32) / ph->K) return PERT_E_UNSUPPORTED;  // 32-bit entry indices
+    const bool unlit = ph->flags & PERT_PHONG_UNLIT;
+    if (!unlit && ph->light_rows != 1 && ph->light_rows != ph->P / ph->HW) return PERT_E_SHAPE;
+    if (!ph->pix_to_face || !ph->bary) return PERT_E_NULL;
+    if (!unlit && (!ph->face_verts || !ph->face_normals || !ph->lighting)) return PERT_E_NULL;
+    if ((ph->texels != nullptr) + (ph->face_colors != nullptr) + (ph->face_vert_colors != nullptr) != 1) return PERT_E_NULL;
     if (((uintptr_t)ph->pix_to_face & 7) || ((uintptr_t)ph->bary & 3) || ((uintptr_t)ph->face_verts & 3) ||
         ((uintptr_t)ph->face_normals & 3) || ((uintptr_t)ph->texels & 3) || ((uintptr_t)ph->face_colors & 3) ||
-        ((uintptr_t)ph->lighting & 3))
+        ((uintptr_t)ph->lighting & 3) || ((uintptr_t)ph->face_vert_colors & 3))
         return PERT_E_ALIGN;
     return PERT_OK;
 }

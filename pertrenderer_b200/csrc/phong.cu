@@ -26,7 +26,7 @@ constexpr int PT = 128;  // threads per CTA (forward, and backward without a sha
 constexpr int PW = PT / 32;
 constexpr int PT_TABLE = 512;  // backward with the gradient table: ONE CTA per SM, 16 warps sharing the table
 constexpr int WCHUNK = 1024;  // entries a warp scans at a time
-constexpr int TABLE_MAX_BYTES = 150 * 1024;  // table of 21 floats per face (F <= 1828) next to 66 KB of warp lists
+constexpr int TABLE_MAX_BYTES = 150 * 1024;  // table of 21..27 floats per face (F <= 1828..1422) next to 66 KB of warp lists
 
 struct V3 {
     float x, y, z;
@@ -92,6 +92,19 @@ __device__ __forceinline__ Lit light_entry(const Row& L, V3 p, V3 n_raw) {
     return o;
 }
 
+
+// Texel of a valid entry from whichever source the call carries: the caller's (P,K,3) tensor, one colour per face
+// (F,3), or colours at the face corners (F,3,3) interpolated with the barycentric coordinates (TexturesVertex).
+__device__ __forceinline__ V3 texel_of(const pert_phong& ph, int64_t e, int64_t face, V3 b) {
+    if (ph.face_vert_colors) {
+        const float* c = ph.face_vert_colors + face * 9;
+        return b.x * ld3(c) + b.y * ld3(c + 3) + b.z * ld3(c + 6);
+    }
+    return ph.face_colors ? ld3(ph.face_colors + face * 3) : ld3(ph.texels + e * 3);
+}
+// floats per face of the texel source's gradient (0: dense (P,K,3) gradient)
+__host__ __device__ __forceinline__ int tex_floats(const pert_phong& ph) { return ph.face_vert_colors ? 9 : (ph.face_colors ? 3 : 0); }
+
 // The lighting rows of the batch elements a chunk of entries can touch: the chunk's first batch element and
 // the next one sit in (per-warp) shared memory, anything further (tiny images) is read from global memory.
 struct RowCache {
@@ -136,7 +149,8 @@ __global__ void __launch_bounds__(PT) phong_fwd_kernel(const pert_phong ph, floa
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint16_t* const vlist = s_vlist[warp];
     float* const srow = s_row[warp];
-    const bool sparse = ph.flags & PERT_PHONG_SPARSE;
+    const bool sparse = ph.flags & PERT_PHONG_SPARSE, unlit = ph.flags & PERT_PHONG_UNLIT;
+    const bool table_tex = ph.face_colors || ph.face_vert_colors;
     const int64_t HWK = ph.HW * ph.K;
     int64_t cached_b0 = -1;
     const int64_t w0 = (int64_t)blockIdx.x * PW + warp, wstride = (int64_t)gridDim.x * PW;
@@ -145,7 +159,7 @@ __global__ void __launch_bounds__(PT) phong_fwd_kernel(const pert_phong ph, floa
         const int64_t e_base = c * WCHUNK;
         const int Ec = (int)min((int64_t)WCHUNK, E - e_base);
         const int64_t b0 = ph.light_rows > 1 ? e_base / HWK : 0;
-        if (b0 != cached_b0) {  // warp-uniform
+        if (b0 != cached_b0 && !unlit) {  // warp-uniform
             __syncwarp();
             fill_rows(ph, b0, srow, lane);
             cached_b0 = b0;
@@ -162,9 +176,9 @@ __global__ void __launch_bounds__(PT) phong_fwd_kernel(const pert_phong ph, floa
                 if (__ldg(p2f + i) >= 0) continue;
                 const int64_t e = e_base + i;
                 const Row L = rows.get(ph.light_rows > 1 ? e / HWK : 0);
-                const V3 t = ph.face_colors ? mk(0.f, 0.f, 0.f) : ld3(ph.texels + e * 3);
+                const V3 t = table_tex ? mk(0.f, 0.f, 0.f) : ld3(ph.texels + e * 3);
                 const float pw = L.sh == 0.0f ? 1.0f : 0.0f;
-                st3(colors + e * 3, mk(L.amb.x * t.x + L.spc.x * pw, L.amb.y * t.y + L.spc.y * pw, L.amb.z * t.z + L.spc.z * pw));
+                st3(colors + e * 3, unlit ? t : mk(L.amb.x * t.x + L.spc.x * pw, L.amb.y * t.y + L.spc.y * pw, L.amb.z * t.z + L.spc.z * pw));
             }
         }
 #pragma unroll 1
@@ -172,11 +186,15 @@ __global__ void __launch_bounds__(PT) phong_fwd_kernel(const pert_phong ph, floa
             const int64_t e = e_base + vlist[i];
             const int64_t face = __ldg(ph.pix_to_face + e);
             const V3 b = ld3(ph.bary + e * 3);
+            const V3 t = texel_of(ph, e, face, b);
+            if (unlit) {  // texture sampling only (Meshes.sample_textures)
+                st3(colors + e * 3, t);
+                continue;
+            }
             const float* fv = ph.face_verts + face * 9;
             const float* fn = ph.face_normals + face * 9;
             const V3 p = b.x * ld3(fv) + b.y * ld3(fv + 3) + b.z * ld3(fv + 6);
             const V3 nr = b.x * ld3(fn) + b.y * ld3(fn + 3) + b.z * ld3(fn + 6);
-            const V3 t = ph.face_colors ? ld3(ph.face_colors + face * 3) : ld3(ph.texels + e * 3);
             const Row L = rows.get(ph.light_rows > 1 ? e / HWK : 0);
             const Lit o = light_entry(L, p, nr);
             st3(colors + e * 3, mk((L.amb.x + L.dif.x * o.ang) * t.x + L.spc.x * o.pw,
@@ -194,7 +212,7 @@ __global__ void __launch_bounds__(NT) phong_bwd_kernel(const pert_phong ph, cons
                                                        float* __restrict__ grad_texels, float* __restrict__ grad_bary,
                                                        float* __restrict__ grad_fv, float* __restrict__ grad_fn, int64_t E,
                                                        int64_t nchunks, int vec_ok) {
-    // dynamic shared memory: [TABLE: F*9 (verts) | F*9 (normals) | F*3 (face colours)] then per warp
+    // dynamic shared memory: [TABLE: F*9 (verts) | F*9 (normals) | F*3 (face colours) or F*9 (corner colours)] then per warp
     // vlist u16[WCHUNK] | hlist u16[WCHUNK] | lighting rows float[2 * PERT_PHONG_STRIDE]
     extern __shared__ __align__(16) float table[];
     constexpr int NWARP = NT / 32;
@@ -202,7 +220,8 @@ __global__ void __launch_bounds__(NT) phong_bwd_kernel(const pert_phong ph, cons
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     unsigned char* const wbase = reinterpret_cast<unsigned char*>(table) +
-                                 (TABLE ? (((size_t)ph.num_faces * 21 * 4 + 15) & ~(size_t)15) : 0) + (size_t)warp * WARP_BYTES;
+                                 (TABLE ? (((size_t)ph.num_faces * (18 + tex_floats(ph)) * 4 + 15) & ~(size_t)15) : 0) +
+                                 (size_t)warp * WARP_BYTES;
     uint16_t* const vlist = reinterpret_cast<uint16_t*>(wbase);
     uint16_t* const hlist = vlist + WCHUNK;
     float* const srow = reinterpret_cast<float*>(hlist + WCHUNK);
@@ -210,9 +229,12 @@ __global__ void __launch_bounds__(NT) phong_bwd_kernel(const pert_phong ph, cons
     float* const t_fv = table;
     float* const t_fn = table + F * 9;
     float* const t_fc = table + F * 18;
-    const bool face_tex = ph.face_colors != nullptr;
+    const bool face_tex = ph.face_colors || ph.face_vert_colors;  // texel gradient scattered to a per-face table
+    const bool vert_tex = ph.face_vert_colors != nullptr;
+    const int TF = tex_floats(ph);
+    const bool unlit = ph.flags & PERT_PHONG_UNLIT;
     if (TABLE) {
-        for (int i = threadIdx.x; i < F * 21; i += NT) table[i] = 0.0f;
+        for (int i = threadIdx.x; i < F * (18 + TF); i += NT) table[i] = 0.0f;
         __syncthreads();
     }
     const bool sparse = ph.flags & PERT_PHONG_SPARSE;
@@ -225,7 +247,7 @@ __global__ void __launch_bounds__(NT) phong_bwd_kernel(const pert_phong ph, cons
         const int64_t e_base = c * WCHUNK;
         const int Ec = (int)min((int64_t)WCHUNK, E - e_base);
         const int64_t b0 = ph.light_rows > 1 ? e_base / HWK : 0;
-        if (b0 != cached_b0) {
+        if (b0 != cached_b0 && !unlit) {
             __syncwarp();
             fill_rows(ph, b0, srow, lane);
             cached_b0 = b0;
@@ -242,7 +264,7 @@ __global__ void __launch_bounds__(NT) phong_bwd_kernel(const pert_phong ph, cons
                 if (grad_texels && !face_tex) {
                     const Row L = rows.get(ph.light_rows > 1 ? e / HWK : 0);
                     const V3 gc = ld3(grad_colors + e * 3);
-                    st3(grad_texels + e * 3, mk(gc.x * L.amb.x, gc.y * L.amb.y, gc.z * L.amb.z));
+                    st3(grad_texels + e * 3, unlit ? gc : mk(gc.x * L.amb.x, gc.y * L.amb.y, gc.z * L.amb.z));
                 }
                 if (grad_bary) st3(grad_bary + e * 3, zero);
             }
@@ -274,21 +296,37 @@ __global__ void __launch_bounds__(NT) phong_bwd_kernel(const pert_phong ph, cons
             const int face = (int)__ldg(ph.pix_to_face + e);
             const V3 gc = ld3(grad_colors + e * 3);
             const V3 b = ld3(ph.bary + e * 3);
-            const float* fv = ph.face_verts + (int64_t)face * 9;
-            const float* fn = ph.face_normals + (int64_t)face * 9;
-            const V3 v0 = ld3(fv), v1 = ld3(fv + 3), v2 = ld3(fv + 6);
-            const V3 n0 = ld3(fn), n1 = ld3(fn + 3), n2 = ld3(fn + 6);
-            const V3 p = b.x * v0 + b.y * v1 + b.z * v2;
-            const V3 nr = b.x * n0 + b.y * n1 + b.z * n2;
-            const V3 t = face_tex ? ld3(ph.face_colors + (int64_t)face * 3) : ld3(ph.texels + e * 3);
-            const Row L = rows.get(ph.light_rows > 1 ? e / HWK : 0);
-            const Lit o = light_entry(L, p, nr);
-
-            // colour = (amb + dif * ang) * t + spc * pw
-            const V3 gt = mk(gc.x * (L.amb.x + L.dif.x * o.ang), gc.y * (L.amb.y + L.dif.y * o.ang),
-                             gc.z * (L.amb.z + L.dif.z * o.ang));
+            const V3 t = texel_of(ph, e, face, b);
+            Row L;
+            Lit o;
+            V3 v0, v1, v2, n0, n1, n2;
+            V3 gt = gc;  // unlit: colour = texel
+            if (!unlit) {
+                const float* fv = ph.face_verts + (int64_t)face * 9;
+                const float* fn = ph.face_normals + (int64_t)face * 9;
+                v0 = ld3(fv), v1 = ld3(fv + 3), v2 = ld3(fv + 6);
+                n0 = ld3(fn), n1 = ld3(fn + 3), n2 = ld3(fn + 6);
+                L = rows.get(ph.light_rows > 1 ? e / HWK : 0);
+                o = light_entry(L, b.x * v0 + b.y * v1 + b.z * v2, b.x * n0 + b.y * n1 + b.z * n2);
+                // colour = (amb + dif * ang) * t + spc * pw
+                gt = mk(gc.x * (L.amb.x + L.dif.x * o.ang), gc.y * (L.amb.y + L.dif.y * o.ang), gc.z * (L.amb.z + L.dif.z * o.ang));
+            }
+            V3 gb = zero;  // gradient of bary_coords
+            if (vert_tex) {  // texel = sum_i b_i C_i
+                const float* c = ph.face_vert_colors + (int64_t)face * 9;
+                gb = mk(dot(gt, ld3(c)), dot(gt, ld3(c + 3)), dot(gt, ld3(c + 6)));
+            }
             if (grad_texels) {
-                if (face_tex) {
+                if (vert_tex) {
+                    float* dst = TABLE ? t_fc + face * 9 : grad_texels + (int64_t)face * 9;
+                    const float bw3[3] = {b.x, b.y, b.z};
+#pragma unroll
+                    for (int i2 = 0; i2 < 3; ++i2) {
+                        atomicAdd(dst + 3 * i2, bw3[i2] * gt.x);
+                        atomicAdd(dst + 3 * i2 + 1, bw3[i2] * gt.y);
+                        atomicAdd(dst + 3 * i2 + 2, bw3[i2] * gt.z);
+                    }
+                } else if (face_tex) {
                     float* dst = TABLE ? t_fc + face * 3 : grad_texels + (int64_t)face * 3;
                     atomicAdd(dst, gt.x);
                     atomicAdd(dst + 1, gt.y);
@@ -296,6 +334,10 @@ __global__ void __launch_bounds__(NT) phong_bwd_kernel(const pert_phong ph, cons
                 } else {
                     st3(grad_texels + e * 3, gt);
                 }
+            }
+            if (unlit) {
+                if (grad_bary) st3(grad_bary + e * 3, gb);
+                continue;
             }
             const float g_ang = gc.x * L.dif.x * t.x + gc.y * L.dif.y * t.y + gc.z * L.dif.z * t.z;
             const float g_pw = gc.x * L.spc.x + gc.y * L.spc.y + gc.z * L.spc.z;
@@ -311,8 +353,8 @@ __global__ void __launch_bounds__(NT) phong_bwd_kernel(const pert_phong ph, cons
             V3 g_p = mk(-g_vraw.x, -g_vraw.y, -g_vraw.z);
             if (!L.directional) g_p = g_p - normalize_bwd(o.d, o.dl, g_d);
             if (grad_bary)
-                st3(grad_bary + e * 3, mk(dot(g_p, v0) + dot(g_nraw, n0), dot(g_p, v1) + dot(g_nraw, n1),
-                                          dot(g_p, v2) + dot(g_nraw, n2)));
+                st3(grad_bary + e * 3, mk(gb.x + dot(g_p, v0) + dot(g_nraw, n0), gb.y + dot(g_p, v1) + dot(g_nraw, n1),
+                                          gb.z + dot(g_p, v2) + dot(g_nraw, n2)));
             const float bw[3] = {b.x, b.y, b.z};
             if (grad_fv) {
                 float* dst = TABLE ? t_fv + face * 9 : grad_fv + (int64_t)face * 9;
@@ -342,7 +384,7 @@ __global__ void __launch_bounds__(NT) phong_bwd_kernel(const pert_phong ph, cons
             if (grad_fn && t_fn[i] != 0.0f) atomicAdd(grad_fn + i, t_fn[i]);
         }
         if (face_tex && grad_texels)
-            for (int i = threadIdx.x; i < F * 3; i += NT)
+            for (int i = threadIdx.x; i < F * TF; i += NT)
                 if (t_fc[i] != 0.0f) atomicAdd(grad_texels + i, t_fc[i]);
     }
 }
@@ -365,7 +407,7 @@ int launch_phong_fwd(const pert_phong& ph, float* colors, cudaStream_t st) {
 template <bool TABLE, int NT>
 static int launch_bwd_t(const pert_phong& ph, const float* grad_colors, float* grad_texels, float* grad_bary, float* grad_fv,
                         float* grad_fn, int64_t E, int64_t nchunks, int ctas_per_sm, cudaStream_t st) {
-    const size_t table = TABLE ? (((size_t)ph.num_faces * 21 * 4 + 15) & ~(size_t)15) : 0;
+    const size_t table = TABLE ? (((size_t)ph.num_faces * (18 + tex_floats(ph)) * 4 + 15) & ~(size_t)15) : 0;
     const size_t smem = table + (size_t)(NT / 32) * (2 * WCHUNK * 2 + 2 * PERT_PHONG_STRIDE * 4);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(phong_bwd_kernel<TABLE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -379,15 +421,16 @@ static int launch_bwd_t(const pert_phong& ph, const float* grad_colors, float* g
 int launch_phong_bwd(const pert_phong& ph, const float* grad_colors, float* grad_texels, float* grad_bary, float* grad_fv,
                      float* grad_fn, cudaStream_t st) {
     const int64_t E = ph.P * ph.K, nchunks = (E + WCHUNK - 1) / WCHUNK;
-    const bool scatter = grad_fv || grad_fn || (ph.face_colors && grad_texels);
+    const bool scatter = grad_fv || grad_fn || (tex_floats(ph) && grad_texels);
+    const size_t table_bytes = (size_t)ph.num_faces * (18 + tex_floats(ph)) * 4;
     // Small meshes: every entry's 18 atomic adds would land on the same few thousand L2 addresses (measured at
     // 1280 faces: 210 us of a 360 us pass); accumulate them in a per-SM shared-memory table instead and flush it
     // once.  Large meshes spread the atomics over enough addresses (100k faces: 58 us).
-    if (scatter && (size_t)ph.num_faces * 21 * 4 <= 16 * 1024)  // tiny table: keep the occupancy of the small CTAs
+    if (scatter && table_bytes <= 16 * 1024)  // tiny table: keep the occupancy of the small CTAs
         return launch_bwd_t<true, PT>(ph, grad_colors, grad_texels, grad_bary, grad_fv, grad_fn, E, nchunks, 4, st);
-    if (scatter && (size_t)ph.num_faces * 21 * 4 <= TABLE_MAX_BYTES)
+    if (scatter && table_bytes <= TABLE_MAX_BYTES)
         return launch_bwd_t<true, PT_TABLE>(ph, grad_colors, grad_texels, grad_bary, grad_fv, grad_fn, E, nchunks, 1, st);
-    return launch_bwd_t<false, PT>(ph, grad_colors, grad_texels, grad_bary, grad_fv, grad_fn, E, nchunks, 6, st);
+    return launch_bwd_t<false, PT>(ph, grad_colors, grad_texels, grad_bary, grad_fv, grad_fn, E, nchunks, 5, st);
 }
 
 }  // namespace pert

@@ -18,7 +18,7 @@ from torch.autograd import Function
 from . import ops
 from .smoothagg import GaussianAgg, SoftAgg  # noqa: F401
 from .smoothrast import GaussianRast, SoftRast
-from .structures import BlendParams, FaceTexels
+from .structures import BlendParams, FaceTexels, VertexTexels
 
 
 def _background_tuple(blend_params):
@@ -110,6 +110,13 @@ def smooth_rgb_blend(colors, fragments, smoothrast, smoothagg, blend_params, zne
 
     ``colors`` (N,H,W,K,3); ``fragments`` with ``pix_to_face`` / ``zbuf`` / ``dists`` (N,H,W,K);
     ``znear`` / ``zfar`` python floats or tensors broadcastable to (N,1,1,1)."""
+    if isinstance(colors, VertexTexels):
+        # TexturesVertex: interpolate the vertex colours with the texture-only mode of the Phong kernel; the fused
+        # pairs read colours of valid entries only, so the padded ones need not be written
+        from .shading import sample_lazy_textures
+        fused = (isinstance(smoothrast, GaussianRast) and isinstance(smoothagg, GaussianAgg)) or \
+            (type(smoothrast) is SoftRast and type(smoothagg) is SoftAgg)
+        colors = sample_lazy_textures(colors, fragments, sparse=fused)
     face = isinstance(colors, FaceTexels)
     ops.require_cuda(colors.face_colors if face else colors, fragments.pix_to_face, fragments.zbuf, fragments.dists)
     if isinstance(smoothrast, GaussianRast) and isinstance(smoothagg, GaussianAgg):
@@ -162,8 +169,9 @@ class SimpleShader(nn.Module):
     def forward(self, fragments, meshes, **kwargs) -> torch.Tensor:
         blend_params = kwargs.get("blend_params", self.blend_params)
         texels = meshes.sample_textures(fragments)
-        if isinstance(texels, FaceTexels):
-            texels = texels.materialize(fragments.pix_to_face)
+        if isinstance(texels, (FaceTexels, VertexTexels)):
+            from .shading import sample_lazy_textures
+            texels = sample_lazy_textures(texels, fragments)
         covered = fragments.pix_to_face[..., 0] >= 0
         bg = torch.as_tensor(blend_params.background_color, dtype=texels.dtype, device=texels.device)
         rgb = torch.where(covered[..., None], texels[..., 0, :], bg.expand_as(texels[..., 0, :]))

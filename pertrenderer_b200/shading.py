@@ -24,8 +24,8 @@ import torch
 from torch.autograd import Function
 
 from . import _cabi
-from ._cabi import PHONG_SPARSE, PHONG_STRIDE, PertPhong, check, ptr, require_cuda, stream_ptr
-from .structures import FaceTexels
+from ._cabi import PHONG_SPARSE, PHONG_STRIDE, PHONG_UNLIT, PertPhong, check, ptr, require_cuda, stream_ptr
+from .structures import FaceTexels, VertexTexels
 
 
 def _f32c(t):
@@ -62,39 +62,46 @@ def pack_lighting(lights, materials, cameras, N, device):
     return table
 
 
-def _phong_struct(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting, flags):
+def _phong_struct(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting, flags, vert_colors=None):
     N, H, W, K = pix_to_face.shape
     ph = PertPhong()
     ph.P, ph.HW, ph.K = N * H * W, H * W, K
-    ph.light_rows = lighting.shape[0]
-    ph.num_faces = face_verts.shape[0]
+    ph.light_rows = 0 if lighting is None else lighting.shape[0]
+    table = face_verts if face_verts is not None else (face_colors if face_colors is not None else vert_colors)
+    ph.num_faces = table.shape[0]
     ph.flags = flags
     ph.pix_to_face, ph.bary = pix_to_face.data_ptr(), bary.data_ptr()
-    ph.face_verts, ph.face_normals = face_verts.data_ptr(), face_normals.data_ptr()
+    ph.face_verts = None if face_verts is None else face_verts.data_ptr()
+    ph.face_normals = None if face_normals is None else face_normals.data_ptr()
     ph.texels = None if texels is None else texels.data_ptr()
     ph.face_colors = None if face_colors is None else face_colors.data_ptr()
-    ph.lighting = lighting.data_ptr()
+    ph.face_vert_colors = None if vert_colors is None else vert_colors.data_ptr()
+    ph.lighting = None if lighting is None else lighting.data_ptr()
     return ph
 
 
-def phong_forward(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting, sparse=False):
+def phong_forward(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting, sparse=False,
+                  vert_colors=None, unlit=False):
     """Launch pert_phong_fwd.  Returns colors (N,H,W,K,3); with ``sparse`` the entries with
-    pix_to_face < 0 are left unwritten (the fused shader kernels never read them)."""
+    pix_to_face < 0 are left unwritten (the fused shader kernels never read them).  Exactly one texel
+    source: ``texels`` (N,H,W,K,3), ``face_colors`` (F,3) or ``vert_colors`` (F,3,3).  ``unlit``: colour =
+    texel (texture sampling only; the face tables and ``lighting`` may be None)."""
     lib = _cabi.load()
-    require_cuda(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting)
+    require_cuda(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting, vert_colors)
     N, H, W, K = pix_to_face.shape
     dev = pix_to_face.device
     with torch.cuda.device(dev):
         colors = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev)
         ph = _phong_struct(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting,
-                           PHONG_SPARSE if sparse else 0)
+                           (PHONG_SPARSE if sparse else 0) | (PHONG_UNLIT if unlit else 0), vert_colors)
         rc = lib.pert_phong_fwd(ph, ptr(colors), stream_ptr(dev))
     check(rc, "pert_phong_fwd")
     return colors
 
 
 def phong_backward(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting, grad_colors,
-                   need_texels=True, need_bary=True, need_verts=True, need_normals=True, sparse=False):
+                   need_texels=True, need_bary=True, need_verts=True, need_normals=True, sparse=False, vert_colors=None,
+                   unlit=False):
     """Launch pert_phong_bwd.  Returns (grad_texels | grad_face_colors, grad_bary, grad_face_verts,
     grad_face_normals), ``None`` where not requested.  Every entry of the dense outputs is defined (they
     flow on to the caller's own tensors): with ``sparse`` the kernel skips the padded entries, whose
@@ -107,48 +114,86 @@ def phong_backward(pix_to_face, bary, face_verts, face_normals, texels, face_col
     with torch.cuda.device(dev):
         alloc = torch.zeros if sparse else torch.empty
         if need_texels:
-            g_tex = torch.zeros_like(face_colors) if face_colors is not None else \
-                alloc((N, H, W, K, 3), dtype=torch.float32, device=dev)
+            table = face_colors if face_colors is not None else vert_colors
+            g_tex = torch.zeros_like(table) if table is not None else alloc((N, H, W, K, 3), dtype=torch.float32, device=dev)
         else:
             g_tex = None
         g_bary = alloc((N, H, W, K, 3), dtype=torch.float32, device=dev) if need_bary else None
-        g_fv = torch.zeros_like(face_verts) if need_verts else None
-        g_fn = torch.zeros_like(face_normals) if need_normals else None
+        g_fv = torch.zeros_like(face_verts) if (need_verts and not unlit) else None
+        g_fn = torch.zeros_like(face_normals) if (need_normals and not unlit) else None
         ph = _phong_struct(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting,
-                           PHONG_SPARSE if sparse else 0)
+                           (PHONG_SPARSE if sparse else 0) | (PHONG_UNLIT if unlit else 0), vert_colors)
         rc = lib.pert_phong_bwd(ph, ptr(grad_colors), ptr(g_tex), ptr(g_bary), ptr(g_fv), ptr(g_fn), stream_ptr(dev))
     check(rc, "pert_phong_bwd")
     return g_tex, g_bary, g_fv, g_fn
 
 
 class _PhongShade(Function):
-    """colors = phong(face_verts, face_normals, texels | face_colors, bary); constants: pix_to_face, lighting."""
+    """colors = phong(face_verts, face_normals, texel source, bary); constants: pix_to_face, lighting.
+    ``tex_mode``: "texels" (N,H,W,K,3), "face" (F,3) or "vert" (F,3,3)."""
 
     @staticmethod
-    def forward(ctx, face_verts, face_normals, texels, bary, pix_to_face, lighting, face_mode, sparse):
-        fv, fn = _f32c(face_verts.detach()), _f32c(face_normals.detach())
+    def forward(ctx, face_verts, face_normals, texels, bary, pix_to_face, lighting, tex_mode, sparse, unlit):
+        fv = None if unlit else _f32c(face_verts.detach())
+        fn = None if unlit else _f32c(face_normals.detach())
         tx, bc = _f32c(texels.detach()), _f32c(bary.detach())
         p2f = pix_to_face.contiguous()
-        colors = phong_forward(p2f, bc, fv, fn, None if face_mode else tx, tx if face_mode else None, lighting, sparse)
-        ctx.save_for_backward(fv, fn, tx, bc, p2f, lighting)
-        ctx.face_mode, ctx.sparse = face_mode, sparse
+        src = dict(texels=tx if tex_mode == "texels" else None, face_colors=tx if tex_mode == "face" else None,
+                   vert_colors=tx if tex_mode == "vert" else None)
+        colors = phong_forward(p2f, bc, fv, fn, lighting=lighting, sparse=sparse, unlit=unlit, **src)
+        ctx.save_for_backward(*[t for t in (fv, fn, tx, bc, p2f, lighting) if t is not None])
+        ctx.tex_mode, ctx.sparse, ctx.unlit = tex_mode, sparse, unlit
         return colors
 
     @staticmethod
     def backward(ctx, grad_colors):
-        fv, fn, tx, bc, p2f, lighting = ctx.saved_tensors
+        if ctx.unlit:
+            tx, bc, p2f = ctx.saved_tensors
+            fv = fn = lighting = None
+        else:
+            fv, fn, tx, bc, p2f, lighting = ctx.saved_tensors
         need = ctx.needs_input_grad
+        src = dict(texels=tx if ctx.tex_mode == "texels" else None, face_colors=tx if ctx.tex_mode == "face" else None,
+                   vert_colors=tx if ctx.tex_mode == "vert" else None)
         g_tex, g_bary, g_fv, g_fn = phong_backward(
-            p2f, bc, fv, fn, None if ctx.face_mode else tx, tx if ctx.face_mode else None, lighting, grad_colors,
-            need_texels=need[2], need_bary=need[3], need_verts=need[0], need_normals=need[1], sparse=ctx.sparse)
-        return g_fv, g_fn, g_tex, g_bary, None, None, None, None
+            p2f, bc, fv, fn, lighting=lighting, grad_colors=grad_colors, need_texels=need[2], need_bary=need[3],
+            need_verts=need[0], need_normals=need[1], sparse=ctx.sparse, unlit=ctx.unlit, **src)
+        return g_fv, g_fn, g_tex, g_bary, None, None, None, None, None
+
+
+def _texel_source(texels):
+    """(tensor, tex_mode) of a texel argument: a dense tensor or one of the lazy per-face sources."""
+    if isinstance(texels, FaceTexels):
+        return texels.face_colors, "face"
+    if isinstance(texels, VertexTexels):
+        return texels.face_vert_colors(), "vert"
+    return texels, "texels"
+
+
+def sample_lazy_textures(texels, fragments, sparse: bool = False) -> torch.Tensor:
+    """Materialise lazy texels (:class:`FaceTexels`, :class:`VertexTexels`) as the (N,H,W,K,3) tensor
+    ``Meshes.sample_textures`` returns (random_rasterizer.py:101,170), with the texture-only mode of the Phong
+    kernel (PERT_PHONG_UNLIT); gradients flow to the colour table and, for vertex colours, to bary_coords."""
+    tex, mode = _texel_source(texels)
+    if mode == "texels":
+        return tex
+    pix_to_face = fragments.pix_to_face
+    if pix_to_face.dtype != torch.int64:
+        pix_to_face = pix_to_face.to(torch.int64)
+    bary = fragments.bary_coords
+    if bary is None:
+        if mode == "vert":
+            raise ValueError("vertex colours need fragments.bary_coords (N,H,W,K,3)")
+        bary = torch.zeros(pix_to_face.shape + (3,), dtype=torch.float32, device=pix_to_face.device)
+    return _PhongShade.apply(None, None, tex, bary, pix_to_face, None, mode, bool(sparse), True)
 
 
 def phong_shading(meshes, fragments, lights, cameras, materials, texels, sparse: bool = False) -> torch.Tensor:
     """pytorch3d.renderer.mesh.shading.phong_shading, same arguments (random_rasterizer.py:103-110).
 
-    ``texels`` (N,H,W,K,3), or lazy :class:`FaceTexels` (per-face colours gathered through
-    pix_to_face inside the kernel).  Returns colors (N,H,W,K,3)."""
+    ``texels`` (N,H,W,K,3), or lazy :class:`FaceTexels` / :class:`VertexTexels` (per-face colours gathered
+    through pix_to_face, vertex colours interpolated with bary_coords, both inside the kernel: the texel
+    tensor of ``sample_textures`` is never materialised).  Returns colors (N,H,W,K,3)."""
     pix_to_face = fragments.pix_to_face
     if fragments.bary_coords is None:
         raise ValueError("phong_shading needs fragments.bary_coords (N,H,W,K,3)")
@@ -163,7 +208,6 @@ def phong_shading(meshes, fragments, lights, cameras, materials, texels, sparse:
     faces_verts = verts[faces]  # (F,3,3); torch's indexing scatters the gradient back to the vertices
     faces_normals = vertex_normals[faces]
     lighting = pack_lighting(lights, materials, cameras, N, device)
-    face_mode = isinstance(texels, FaceTexels)
-    tex = texels.face_colors if face_mode else texels
+    tex, mode = _texel_source(texels)
     return _PhongShade.apply(faces_verts, faces_normals, tex, fragments.bary_coords, pix_to_face, lighting,
-                             face_mode, bool(sparse))
+                             mode, bool(sparse), False)

@@ -76,6 +76,24 @@ class FaceTexels:
         return self.face_colors[pix_to_face.clamp(min=0)] * mask[..., None]
 
 
+class VertexTexels:
+    """Lazy texels of a ``TexturesVertex`` mesh (experiments/eval.py:450): the colour of fragment (n,h,w,k) is the
+    barycentric interpolation of the three vertex colours of face ``pix_to_face[n,h,w,k]``.  The Phong kernel
+    interpolates it in place; ``sample_lazy_textures`` materialises it for the other consumers."""
+
+    def __init__(self, verts_colors: torch.Tensor, faces: torch.Tensor):
+        if verts_colors.dim() != 2 or verts_colors.shape[1] != 3:
+            raise ValueError("verts_colors must be (V,3)")
+        self.verts_colors, self.faces = verts_colors, faces
+
+    def face_vert_colors(self) -> torch.Tensor:
+        return self.verts_colors[self.faces]  # (F,3,3); torch scatters the gradient back to the vertices
+
+    def materialize(self, pix_to_face: torch.Tensor, bary: torch.Tensor) -> torch.Tensor:
+        mask = pix_to_face >= 0
+        return (bary[..., None] * self.face_vert_colors()[pix_to_face.clamp(min=0)]).sum(-2) * mask[..., None]
+
+
 class FaceColorMeshes:
     """Stand-in for ``Meshes`` with one colour per (packed) face: ``sample_textures`` returns lazy
     :class:`FaceTexels` instead of a texel tensor."""
@@ -160,13 +178,14 @@ class ViewCameras(DepthCameras):
 
 class TriMeshes:
     """Stand-in for pytorch3d ``Meshes`` (packed representation only): vertices (V,3), faces (F,3), and
-    either one colour per face (lazy :class:`FaceTexels`) or a preset texel tensor.
+    one colour per face (lazy :class:`FaceTexels`), one colour per vertex (lazy :class:`VertexTexels`) or a preset
+    texel tensor.
     ``verts_normals_packed`` follows pytorch3d's area-weighted vertex normals (cross products of the
     face edges summed onto the corners, then normalised with eps 1e-6)."""
 
-    def __init__(self, verts, faces, face_colors=None, texels=None):
+    def __init__(self, verts, faces, face_colors=None, texels=None, verts_colors=None):
         self._verts, self._faces = verts, faces.to(torch.int64)
-        self.face_colors, self.texels = face_colors, texels
+        self.face_colors, self.texels, self.verts_colors = face_colors, texels, verts_colors
 
     def verts_packed(self):
         return self._verts
@@ -186,10 +205,12 @@ class TriMeshes:
     def sample_textures(self, fragments):
         if self.texels is not None:
             return self.texels
+        if self.verts_colors is not None:
+            return VertexTexels(self.verts_colors, self._faces)
         return FaceTexels(self.face_colors)
 
     def update_verts(self, verts):
-        return TriMeshes(verts, self._faces, self.face_colors, self.texels)
+        return TriMeshes(verts, self._faces, self.face_colors, self.texels, self.verts_colors)
 
 
 def synthetic_mesh(n_faces=1280, seed=0, device="cuda"):

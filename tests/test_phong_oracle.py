@@ -110,7 +110,7 @@ def test_shims_expose_the_pytorch3d_attributes():
 
 
 def test_phong_struct_layout_and_validation_without_gpu():
-    assert ctypes.sizeof(_cabi.PertPhong) == 96
+    assert ctypes.sizeof(_cabi.PertPhong) == 104
     assert _cabi.PertPhong.pix_to_face.offset == 40
     lib = _cabi.load()
     ph = _cabi.PertPhong()
@@ -122,6 +122,9 @@ def test_phong_struct_layout_and_validation_without_gpu():
     assert lib.pert_phong_fwd(ph, None, None) == -2  # rows must be 1 or N
     ph.light_rows = 2
     assert lib.pert_phong_fwd(ph, None, None) == -1  # null inputs
+    ph.flags = _cabi.PHONG_UNLIT
+    ph.light_rows = 0
+    assert lib.pert_phong_fwd(ph, None, None) == -1  # unlit: no lighting rows needed, inputs still NULL
     assert lib.pert_phong_bwd(ph, None, None, None, None, None, None) == -1
 
 
