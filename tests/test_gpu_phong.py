@@ -281,3 +281,39 @@ def test_phong_full_size_properties_config2():
     lhs = (bary * a[1])[mask].double().sum()
     rhs = (a[2].double() * fv.double()).sum() + (a[3].double() * fn.double()).sum()
     assert abs(lhs - rhs) <= 1e-4 * max(abs(rhs), 1.0)
+
+
+def test_integration_md_phong_stub_runs():
+    """The Phong ctypes stub of INTEGRATION.md section 2b is executable as written and reproduces phong_shading."""
+    import os
+    import re
+    import pertrenderer_b200 as pb
+    from conftest import ROOT
+    from pertrenderer_b200 import _cabi
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    base = [b for b in blocks if "class PerturbedShade" in b][0].replace('"libpertshade.so"', repr(_cabi.LIB_PATH))
+    stub = [b for b in blocks if "class PhongColors" in b][0]
+    ns = {}
+    exec(base, ns)
+    exec(stub, ns)
+    N, H, W, K = 1, 10, 10, 8
+    fr, verts, faces, lights, mats, cams, _, texels = _scene(N, H, W, K, 60, seed=11)
+    lights, mats, cams = _to(lights, DEV), _to(mats, DEV), _to(cams, DEV)
+    G = torch.randn(N, H, W, K, 3, device=DEV, generator=torch.Generator(device=DEV).manual_seed(3))
+
+    def run(fn):
+        v = verts.to(DEV).requires_grad_(True)
+        t = texels.to(DEV).requires_grad_(True)
+        frc = _frag_to(fr, DEV, bary_grad=True)
+        mesh = pb.TriMeshes(v, faces.to(DEV), texels=t)
+        col = fn(mesh, frc, t)
+        (col * G).sum().backward()
+        return col.detach(), v.grad, t.grad, frc.bary_coords.grad
+
+    ours = run(lambda mesh, frc, t: pb.phong_shading(mesh, frc, lights, cams, mats, t))
+    theirs = run(lambda mesh, frc, t: ns["PhongColors"].apply(
+        mesh.verts_packed()[mesh.faces_packed()], mesh.verts_normals_packed()[mesh.faces_packed()], t.contiguous(),
+        frc.bary_coords.contiguous(), frc.pix_to_face, ns["lighting_rows"](lights, mats, cams)))
+    for a, b in zip(ours, theirs):
+        assert rel_err(a, b) <= 1e-5
