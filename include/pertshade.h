@@ -24,6 +24,8 @@
  *   pert_phong_fwd / pert_phong_bwd   pytorch3d.renderer.mesh.shading.phong_shading as called by
  *                    RandomPhongShader.forward (randomras/random_rasterizer.py:103-110), the shader
  *                    experiments/eval.py:170-176 uses; its output is the `colors` of pert_shade_fwd
+ *   pert_rasterize_fwd / pert_rasterize_bwd   pytorch3d's MeshRasterizer -> rasterize_meshes as configured at
+ *                    experiments/eval.py:135-141,165-169: the producer of the Fragments this path consumes
  *   pert_noise_fill  the two torch.normal draws, smoothrast.py:21 and smoothagg.py:21 (test aid:
  *                    materialises the counter-based noise the fused kernels generate in registers)
  *
@@ -51,7 +53,7 @@
 extern "C" {
 #endif
 
-#define PERT_ABI_VERSION 7
+#define PERT_ABI_VERSION 8
 
 /* error codes */
 #define PERT_OK 0
@@ -251,6 +253,40 @@ int pert_phong_fwd(const pert_phong* ph, float* colors, void* stream);
  */
 int pert_phong_bwd(const pert_phong* ph, const float* grad_colors, float* grad_texels, float* grad_bary,
                    float* grad_face_verts, float* grad_face_normals, void* stream);
+
+/*
+ * Fragment producer: K-deep rasterisation of packed triangle meshes with a blur radius, the Fragments
+ * (pix_to_face, zbuf, bary_coords, dists) of pytorch3d's MeshRasterizer as the reference configures it
+ * (experiments/eval.py:135-141: blur_radius = log(1/1e-4 - 1) * sigma, faces_per_pixel = 50,
+ * perspective_correct = False, no barycentric clipping).  Restates pytorch3d 0.4.0's naive rasteriser
+ * (rasterize_meshes.cu CheckPixelInsideFace, geometry_utils.cuh, kEpsilon = 1e-8); see csrc/raster.cu.
+ *
+ * face_verts float (F,3,3): per face corner NDC x, NDC y (+X left, +Y up; pixel (0,0) is the top-left corner) and
+ * VIEW-space depth z, as MeshRasterizer.transform produces them.  face_start int64 (N+1), device: the faces
+ * [face_start[n], face_start[n+1]) are rasterised into image n.  Outputs, all written in full (padding -1):
+ * pix_to_face int64 (N,H,W,K) packed face index, zbuf float (N,H,W,K) ascending (ties in face order), bary float
+ * (N,H,W,K,3), dists float (N,H,W,K) signed squared NDC distance to the face (negative inside).
+ */
+#define PERT_RAST_CULL_BACKFACES 1u
+
+typedef struct pert_raster {
+    int64_t N;
+    int32_t H, W, K;
+    uint32_t flags;
+    float blur_radius;
+    int64_t num_faces;
+    const float* face_verts;   /* (F,3,3) */
+    const int64_t* face_start; /* (N+1), device */
+} pert_raster;
+
+int pert_rasterize_fwd(const pert_raster* rs, int64_t* pix_to_face, float* zbuf, float* bary, float* dists, void* stream);
+/*
+ * Backward of pert_rasterize_fwd (rasterize_meshes' autograd backward): gradients of zbuf (N,H,W,K), bary
+ * (N,H,W,K,3) and dists (N,H,W,K), each optional (NULL = zero), to grad_face_verts float (F,3,3), ZEROED BY THE
+ * CALLER, atomic adds.
+ */
+int pert_rasterize_bwd(const pert_raster* rs, const int64_t* pix_to_face, const float* grad_zbuf, const float* grad_bary,
+                       const float* grad_dists, float* grad_face_verts, void* stream);
 
 /* Materialise the counter-based noise: out float (s_end-s_begin, P, slots), stage 0 = coverage
  * (slots = K), 1 = aggregation (slots = K1); stage | 2 = the Cauchy variant of that stage. */

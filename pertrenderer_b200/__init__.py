@@ -6,6 +6,8 @@ Drop-in for the hot path of quentinll/pertrenderer (``randomras``): the same pub
 """
 
 from .random_rasterizer import RandomPhongShader, RandomSimpleShader, SimpleShader, smooth_rgb_blend
+from .rasterizer import (FoVPerspectiveCameras, MeshRasterizer, MeshRenderer, OpenGLPerspectiveCameras,
+                         RasterizationSettings, look_at_view_transform, rasterize_meshes)
 from .shading import phong_shading, sample_lazy_textures
 from .smoothagg import CauchyAgg, GaussianAgg, HardAgg, SoftAgg, randomArgmax
 from .smoothrast import AffineRast, ArctanRast, GaussianRast, HardRast, SoftRast, randomHeaviside
@@ -16,7 +18,8 @@ from .ops import explicit_noise, kernel_flags
 
 __all__ = [
     "RandomPhongShader", "RandomSimpleShader", "SimpleShader", "phong_shading", "PointLights", "DirectionalLights",
-    "Materials", "ViewCameras", "TriMeshes", "VertexTexels", "sample_lazy_textures", "synthetic_mesh", "synthetic_bary", "smooth_rgb_blend", "GaussianAgg", "SoftAgg", "CauchyAgg", "HardAgg",
+    "MeshRasterizer", "MeshRenderer", "RasterizationSettings", "FoVPerspectiveCameras", "OpenGLPerspectiveCameras",
+    "look_at_view_transform", "rasterize_meshes", "Materials", "ViewCameras", "TriMeshes", "VertexTexels", "sample_lazy_textures", "synthetic_mesh", "synthetic_bary", "smooth_rgb_blend", "GaussianAgg", "SoftAgg", "CauchyAgg", "HardAgg",
     "randomArgmax", "GaussianRast", "ArctanRast", "AffineRast", "HardRast",
     "SoftRast", "randomHeaviside", "BlendParams", "DepthCameras", "Fragments", "TexelMeshes",
     "synthetic_fragments", "explicit_noise", "kernel_flags", "FaceColorMeshes", "FaceTexels",

@@ -15,7 +15,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpertshade.so")
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 # flags (include/pertshade.h)
 F_NO_SKIP = 1
@@ -28,8 +28,10 @@ PH_BWD_SAMPLE, PH_BWD_FINISH = 0x100, 0x200
 EXPORTS = [
     "pert_version", "pert_strerror", "pert_last_cuda_error", "pert_num_tiles", "pert_winner_bytes", "pert_blob_bytes",
     "pert_shade_fwd", "pert_shade_bwd", "pert_soft_shade_fwd", "pert_soft_shade_bwd", "pert_rast_fwd", "pert_rast_bwd", "pert_argmax_fwd",
-    "pert_argmax_bwd", "pert_noise_fill", "pert_phong_fwd", "pert_phong_bwd",
+    "pert_argmax_bwd", "pert_noise_fill", "pert_phong_fwd", "pert_phong_bwd", "pert_rasterize_fwd", "pert_rasterize_bwd",
 ]
+
+RAST_CULL_BACKFACES = 1  # PERT_RAST_CULL_BACKFACES
 
 PHONG_STRIDE = 20  # PERT_PHONG_STRIDE
 PHONG_SPARSE = 1  # PERT_PHONG_SPARSE
@@ -67,6 +69,18 @@ class PertPhong(C.Structure):
         ("pix_to_face", C.c_void_p), ("bary", C.c_void_p), ("face_verts", C.c_void_p), ("face_normals", C.c_void_p),
         ("texels", C.c_void_p), ("face_colors", C.c_void_p), ("lighting", C.c_void_p),
         ("face_vert_colors", C.c_void_p),
+    ]
+
+
+class PertRaster(C.Structure):
+    """Mirror of ``struct pert_raster``."""
+    _fields_ = [
+        ("N", C.c_int64),
+        ("H", C.c_int32), ("W", C.c_int32), ("K", C.c_int32),
+        ("flags", C.c_uint32),
+        ("blur_radius", C.c_float),
+        ("num_faces", C.c_int64),
+        ("face_verts", C.c_void_p), ("face_start", C.c_void_p),
     ]
 
 
@@ -127,6 +141,10 @@ def load():
         lib.pert_phong_fwd.argtypes = [C.POINTER(PertPhong), vp, vp]
         lib.pert_phong_bwd.restype = C.c_int
         lib.pert_phong_bwd.argtypes = [C.POINTER(PertPhong)] + [vp] * 6
+        lib.pert_rasterize_fwd.restype = C.c_int
+        lib.pert_rasterize_fwd.argtypes = [C.POINTER(PertRaster)] + [vp] * 5
+        lib.pert_rasterize_bwd.restype = C.c_int
+        lib.pert_rasterize_bwd.argtypes = [C.POINTER(PertRaster)] + [vp] * 6
         if lib.pert_version() != ABI_VERSION:
             raise PertLibraryError(f"libpertshade.so ABI {lib.pert_version()} != expected {ABI_VERSION}: rebuild")
         _lib = lib

@@ -407,3 +407,32 @@ extern "C" int pert_phong_bwd(const pert_phong* ph, const float* grad_colors, fl
     return cuda_rc(launch_phong_bwd(*ph, grad_colors, grad_texels, grad_bary, grad_face_verts, grad_face_normals,
                                     (cudaStream_t)stream));
 }
+
+static int check_raster(const pert_raster* rs) {
+    if (!rs) return PERT_E_NULL;
+    if (rs->N <= 0 || rs->H <= 0 || rs->W <= 0 || rs->K <= 0 || rs->num_faces <= 0) return PERT_E_SHAPE;
+    if (rs->N > 65535 || rs->K > 1023 || rs->num_faces > 0x7fffffff / 9) return PERT_E_UNSUPPORTED;
+    if ((int64_t)rs->N * rs->H * rs->W >= ((int64_t)1 << 32) / rs->K) return PERT_E_UNSUPPORTED;
+    if (!(rs->blur_radius >= 0.0f) || isinf(rs->blur_radius)) return PERT_E_SCALAR;
+    if (!rs->face_verts || !rs->face_start) return PERT_E_NULL;
+    if (((uintptr_t)rs->face_verts & 3) || ((uintptr_t)rs->face_start & 7)) return PERT_E_ALIGN;
+    return PERT_OK;
+}
+
+extern "C" int pert_rasterize_fwd(const pert_raster* rs, int64_t* pix_to_face, float* zbuf, float* bary, float* dists,
+                                  void* stream) {
+    if (int rc = check_raster(rs)) return rc;
+    if (!pix_to_face || !zbuf || !bary || !dists) return PERT_E_NULL;
+    if (((uintptr_t)pix_to_face & 7) || ((uintptr_t)zbuf & 3) || ((uintptr_t)bary & 3) || ((uintptr_t)dists & 3)) return PERT_E_ALIGN;
+    return cuda_rc(launch_rasterize_fwd(*rs, pix_to_face, zbuf, bary, dists, (cudaStream_t)stream));
+}
+
+extern "C" int pert_rasterize_bwd(const pert_raster* rs, const int64_t* pix_to_face, const float* grad_zbuf,
+                                  const float* grad_bary, const float* grad_dists, float* grad_face_verts, void* stream) {
+    if (int rc = check_raster(rs)) return rc;
+    if (!pix_to_face || !grad_face_verts) return PERT_E_NULL;
+    if (((uintptr_t)pix_to_face & 7) || ((uintptr_t)grad_zbuf & 3) || ((uintptr_t)grad_bary & 3) || ((uintptr_t)grad_dists & 3) ||
+        ((uintptr_t)grad_face_verts & 3))
+        return PERT_E_ALIGN;
+    return cuda_rc(launch_rasterize_bwd(*rs, pix_to_face, grad_zbuf, grad_bary, grad_dists, grad_face_verts, (cudaStream_t)stream));
+}

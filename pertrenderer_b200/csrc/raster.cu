@@ -1,0 +1,326 @@
+// Fragment producer (pert_rasterize_fwd / pert_rasterize_bwd in include/pertshade.h): the K-deep Fragments
+// (pix_to_face, zbuf, bary_coords, dists) the perturbed shader consumes.  The reference gets them from pytorch3d's
+// MeshRasterizer (experiments/eval.py:135-141,165-169: blur_radius = log(1/1e-4 - 1) * sigma, faces_per_pixel = 50,
+// perspective_correct = False); pytorch3d 0.4.0 (requirements.txt:7) is not under the reference tree, so this
+// restates its published naive rasteriser (rasterize_meshes.cu CheckPixelInsideFace / RasterizeMeshesNaive,
+// geometry_utils.cuh, kEpsilon = 1e-8) with a B200 work decomposition:
+//
+//   forward   one CTA per 32x8 pixel tile.  Faces are culled against the tile in chunks of 256 (one face per thread:
+//             bounding box grown by sqrt(blur_radius) against the tile's pixel-centre rectangle, zero-area and
+//             behind-camera faces dropped), survivors are compacted IN FACE ORDER into shared memory with their nine
+//             coordinates, and every pixel thread then tests only those.  The K-buffer of a pixel lives in its own
+//             output rows (zbuf / pix_to_face), kept sorted by stable insertion (ascending depth, ties in face
+//             order); bary / dists of the kept faces are recomputed at the end and the padding of each row is
+//             written by the warp as coalesced stores.
+//   backward  a streaming pass over the (P,K) entries, warp-autonomous chunks with compact valid lists (the machinery
+//             of the Phong kernels): every valid entry recomputes its barycentric / distance arithmetic and scatters
+//             d(zbuf, bary, dists)/d(face_verts) with atomics.
+#include "kernels.h"
+#include "tile.cuh"
+
+namespace pert {
+
+namespace {
+
+constexpr float kEps = 1e-8f;  // geometry_utils.cuh kEpsilon
+constexpr int TW = 32, TH = 8, RT = TW * TH;  // pixel tile of the forward kernel
+
+struct P2 {
+    float x, y;
+};
+__device__ __forceinline__ P2 operator-(P2 a, P2 b) { return P2{a.x - b.x, a.y - b.y}; }
+__device__ __forceinline__ float dot2(P2 a, P2 b) { return a.x * b.x + a.y * b.y; }
+
+// rasterize_meshes.cu PixToNonSquareNdc: centre of pixel i along an axis of S1 pixels (other axis S2)
+__device__ __forceinline__ float pix_to_ndc(int i, int S1, int S2) {
+    const float range = S1 > S2 ? (float)S1 / (float)S2 : 1.0f;
+    return -range + (2.0f * (float)i + 1.0f) * range / (float)S1;
+}
+
+// geometry_utils.cuh EdgeFunctionForward
+__device__ __forceinline__ float edge(P2 p, P2 a, P2 b) { return (p.x - a.x) * (b.y - a.y) - (p.y - a.y) * (b.x - a.x); }
+
+// geometry_utils.cuh PointLineDistanceForward: squared distance to the segment a-b; tt = clamped parameter
+__device__ __forceinline__ float point_line(P2 p, P2 a, P2 b, float& tt, bool& degenerate) {
+    const P2 ab = b - a;
+    const float l2 = dot2(ab, ab);
+    degenerate = l2 <= kEps;
+    if (degenerate) {
+        tt = 1.0f;
+        return dot2(p - b, p - b);
+    }
+    const float t = dot2(ab, p - a) / l2;
+    tt = fminf(fmaxf(t, 0.0f), 1.0f);
+    const P2 r = p - P2{a.x + tt * ab.x, a.y + tt * ab.y};
+    return dot2(r, r);
+}
+
+struct FaceEval {
+    float w0, w1, w2, area, pz, dist;
+    int min_edge;  // 0: v0-v1, 1: v0-v2, 2: v1-v2
+    bool inside;
+};
+
+// bary (unclipped, not perspective-corrected), interpolated depth, squared distance to the triangle
+__device__ __forceinline__ FaceEval eval_face(P2 p, const float* v /* 9 floats */) {
+    const P2 v0{v[0], v[1]}, v1{v[3], v[4]}, v2{v[6], v[7]};
+    FaceEval o;
+    o.area = edge(v2, v0, v1) + kEps;  // BarycentricCoordsForward
+    o.w0 = edge(p, v1, v2) / o.area;
+    o.w1 = edge(p, v2, v0) / o.area;
+    o.w2 = edge(p, v0, v1) / o.area;
+    o.pz = o.w0 * v[2] + o.w1 * v[5] + o.w2 * v[8];
+    float tt;
+    bool dg;
+    const float e01 = point_line(p, v0, v1, tt, dg), e02 = point_line(p, v0, v2, tt, dg), e12 = point_line(p, v1, v2, tt, dg);
+    o.dist = e01;
+    o.min_edge = 0;
+    if (e02 < o.dist) {
+        o.dist = e02;
+        o.min_edge = 1;
+    }
+    if (e12 < o.dist) {
+        o.dist = e12;
+        o.min_edge = 2;
+    }
+    o.inside = o.w0 > 0.0f && o.w1 > 0.0f && o.w2 > 0.0f;
+    return o;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// forward
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RT) rasterize_fwd_kernel(const pert_raster rs, int64_t* __restrict__ pix_to_face,
+                                                           float* __restrict__ zbuf, float* __restrict__ bary,
+                                                           float* __restrict__ dists) {
+    __shared__ float s_v[RT][9];
+    __shared__ int s_face[RT];
+    __shared__ int s_wcount[RT / 32];
+    const int H = rs.H, W = rs.W, K = rs.K;
+    const int n = blockIdx.z, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int px = blockIdx.x * TW + lane, py = blockIdx.y * TH + warp;  // column / row of this thread's pixel
+    const bool in_image = px < W && py < H;
+    // pixel (0,0) is the top-left corner; NDC has +X left and +Y up (RasterizeMeshesNaiveCudaKernel)
+    const P2 p{pix_to_ndc(W - 1 - px, W, H), pix_to_ndc(H - 1 - py, H, W)};
+    // pixel-centre rectangle of the tile (clipped to the image)
+    const int px0 = blockIdx.x * TW, px1 = min(px0 + TW, W) - 1, py0 = blockIdx.y * TH, py1 = min(py0 + TH, H) - 1;
+    const float tx_hi = pix_to_ndc(W - 1 - px0, W, H), tx_lo = pix_to_ndc(W - 1 - px1, W, H);
+    const float ty_hi = pix_to_ndc(H - 1 - py0, H, W), ty_lo = pix_to_ndc(H - 1 - py1, H, W);
+    const float blur = rs.blur_radius, r = sqrtf(blur);
+    const int64_t f_begin = __ldg(rs.face_start + n), f_end = __ldg(rs.face_start + n + 1);
+    const int64_t row = (((int64_t)n * H + py) * W + px) * K;  // this pixel's K-buffer = its output rows
+    int cnt = 0;
+
+#pragma unroll 1
+    for (int64_t fc = f_begin; fc < f_end; fc += RT) {
+        // ---- cull one face per thread against the tile --------------------------------------------------
+        const int64_t f = fc + threadIdx.x;
+        bool keep = false;
+        float v[9];
+        if (f < f_end) {
+#pragma unroll
+            for (int i = 0; i < 9; ++i) v[i] = __ldg(rs.face_verts + f * 9 + i);
+            const float xmin = fminf(fminf(v[0], v[3]), v[6]) - r, xmax = fmaxf(fmaxf(v[0], v[3]), v[6]) + r;
+            const float ymin = fminf(fminf(v[1], v[4]), v[7]) - r, ymax = fmaxf(fmaxf(v[1], v[4]), v[7]) + r;
+            const float zmax = fmaxf(fmaxf(v[2], v[5]), v[8]);
+            const float area = edge(P2{v[0], v[1]}, P2{v[3], v[4]}, P2{v[6], v[7]});
+            const bool zero_area = area <= kEps && area >= -kEps;
+            const bool back = (rs.flags & PERT_RAST_CULL_BACKFACES) && area < 0.0f;
+            keep = !(zmax < 0.0f) && !zero_area && !back && !(tx_lo > xmax || tx_hi < xmin || ty_lo > ymax || ty_hi < ymin);
+        }
+        const unsigned b = __ballot_sync(FULL, keep);
+        if (lane == 0) s_wcount[warp] = __popc(b);
+        __syncthreads();  // also: the previous chunk's list has been consumed
+        int base = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < RT / 32; ++w) {
+            const int c = s_wcount[w];
+            base += w < warp ? c : 0;
+            total += c;
+        }
+        if (keep) {  // ordered compaction: faces stay in index order (depth ties are resolved by face order)
+            const int pos = base + __popc(b & ((1u << lane) - 1u));
+            s_face[pos] = (int)(f - f_begin);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) s_v[pos][i] = v[i];
+        }
+        __syncthreads();
+        // ---- every pixel tests the surviving faces (CheckPixelInsideFace) ---------------------------------
+        if (in_image) {
+#pragma unroll 1
+            for (int i = 0; i < total; ++i) {
+                const float* fv = s_v[i];
+                const float xmin = fminf(fminf(fv[0], fv[3]), fv[6]) - r, xmax = fmaxf(fmaxf(fv[0], fv[3]), fv[6]) + r;
+                const float ymin = fminf(fminf(fv[1], fv[4]), fv[7]) - r, ymax = fmaxf(fmaxf(fv[1], fv[4]), fv[7]) + r;
+                if (p.x > xmax || p.x < xmin || p.y > ymax || p.y < ymin) continue;
+                const FaceEval e = eval_face(p, fv);
+                if (e.pz < 0.0f) continue;                      // behind the image plane
+                if (!e.inside && e.dist >= blur) continue;      // outside the blur band
+                if (cnt == K && !(e.pz < zbuf[row + K - 1])) continue;  // farther than everything kept
+                // stable sorted insertion: after every kept entry with depth <= pz
+                int j = cnt < K ? cnt : K - 1;
+                while (j > 0 && zbuf[row + j - 1] > e.pz) {
+                    zbuf[row + j] = zbuf[row + j - 1];
+                    pix_to_face[row + j] = pix_to_face[row + j - 1];
+                    --j;
+                }
+                zbuf[row + j] = e.pz;
+                pix_to_face[row + j] = f_begin + s_face[i];
+                if (cnt < K) ++cnt;
+            }
+        }
+    }
+    // ---- bary / dists of the kept faces, then the padding of the warp's 32 rows as coalesced stores ----------
+    if (in_image) {
+#pragma unroll 1
+        for (int k = 0; k < cnt; ++k) {
+            const int64_t f = pix_to_face[row + k];
+            float v[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) v[i] = __ldg(rs.face_verts + f * 9 + i);
+            const FaceEval e = eval_face(p, v);
+            bary[(row + k) * 3] = e.w0;
+            bary[(row + k) * 3 + 1] = e.w1;
+            bary[(row + k) * 3 + 2] = e.w2;
+            dists[row + k] = e.inside ? -e.dist : e.dist;
+        }
+    }
+    __syncthreads();
+    s_face[threadIdx.x] = in_image ? cnt : K;  // kept count of every pixel of the tile (the face list is done with)
+    __syncwarp();
+    const int* const cnt_w = s_face + warp * 32;
+    const int64_t wrow = (((int64_t)n * H + py) * W + blockIdx.x * TW) * K;  // first entry of the warp's rows
+    if (py < H) {
+        const int npix = min(TW, W - blockIdx.x * TW);
+#pragma unroll 1
+        for (int i = lane; i < npix * K; i += 32) {
+            const int q = i / K, k = i - q * K;
+            if (k >= cnt_w[q]) {
+                pix_to_face[wrow + i] = -1;
+                zbuf[wrow + i] = -1.0f;
+                dists[wrow + i] = -1.0f;
+            }
+        }
+#pragma unroll 1
+        for (int i = lane; i < npix * K * 3; i += 32) {
+            const int q = i / (3 * K), k = (i - q * 3 * K) / 3;
+            if (k >= cnt_w[q]) bary[wrow * 3 + i] = -1.0f;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------------------
+constexpr int BT = 128, BW = BT / 32, BCHUNK = 1024;
+
+// d E(p; a, b) / d(a, b) times g, accumulated (p fixed)
+__device__ __forceinline__ void edge_bwd(P2 p, P2 a, P2 b, float g, P2& ga, P2& gb) {
+    ga.x += g * (p.y - b.y);
+    ga.y += g * (b.x - p.x);
+    gb.x += -g * (p.y - a.y);
+    gb.y += g * (p.x - a.x);
+}
+
+__global__ void __launch_bounds__(BT) rasterize_bwd_kernel(const pert_raster rs, const int64_t* __restrict__ pix_to_face,
+                                                           const float* __restrict__ grad_zbuf,
+                                                           const float* __restrict__ grad_bary,
+                                                           const float* __restrict__ grad_dists,
+                                                           float* __restrict__ grad_face_verts, int64_t E, int64_t nchunks,
+                                                           int vec_ok) {
+    __shared__ __align__(16) uint16_t s_vlist[BW][BCHUNK];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint16_t* const vlist = s_vlist[warp];
+    const int H = rs.H, W = rs.W, K = rs.K;
+    const int64_t w0 = (int64_t)blockIdx.x * BW + warp, wstride = (int64_t)gridDim.x * BW;
+#pragma unroll 1
+    for (int64_t c = w0; c < nchunks; c += wstride) {
+        const int64_t e_base = c * BCHUNK;
+        const int Ec = (int)min((int64_t)BCHUNK, E - e_base);
+        const int nv = scan_valid(pix_to_face + e_base, Ec, vec_ok, vlist, BCHUNK);
+        __syncwarp();
+#pragma unroll 1
+        for (int i = lane; i < nv; i += 32) {
+            const int64_t e = e_base + vlist[i];
+            const float gz = grad_zbuf ? __ldg(grad_zbuf + e) : 0.0f;
+            const float gd_signed = grad_dists ? __ldg(grad_dists + e) : 0.0f;
+            float gb0 = 0.f, gb1 = 0.f, gb2 = 0.f;
+            if (grad_bary) {
+                gb0 = __ldg(grad_bary + e * 3);
+                gb1 = __ldg(grad_bary + e * 3 + 1);
+                gb2 = __ldg(grad_bary + e * 3 + 2);
+            }
+            if (gz == 0.0f && gd_signed == 0.0f && gb0 == 0.0f && gb1 == 0.0f && gb2 == 0.0f) continue;
+            const int64_t f = __ldg(pix_to_face + e);
+            float v[9];
+#pragma unroll
+            for (int j = 0; j < 9; ++j) v[j] = __ldg(rs.face_verts + f * 9 + j);
+            const int64_t pix = e / K;
+            const int x = (int)(pix % W), y = (int)((pix / W) % H);
+            const P2 p{pix_to_ndc(W - 1 - x, W, H), pix_to_ndc(H - 1 - y, H, W)};
+            const P2 v0{v[0], v[1]}, v1{v[3], v[4]}, v2{v[6], v[7]};
+            const FaceEval o = eval_face(p, v);
+            P2 g0{0.f, 0.f}, g1{0.f, 0.f}, g2{0.f, 0.f};
+            // pz = sum w_i z_i; w_i = e_i / area
+            const float gw0 = gb0 + gz * v[2], gw1 = gb1 + gz * v[5], gw2 = gb2 + gz * v[8];
+            const float inv_area = 1.0f / o.area;
+            edge_bwd(p, v1, v2, gw0 * inv_area, g1, g2);  // e0 = E(p; v1, v2)
+            edge_bwd(p, v2, v0, gw1 * inv_area, g2, g0);  // e1 = E(p; v2, v0)
+            edge_bwd(p, v0, v1, gw2 * inv_area, g0, g1);  // e2 = E(p; v0, v1)
+            // area = E(v2; v0, v1) + eps
+            const float g_area = -(gw0 * o.w0 + gw1 * o.w1 + gw2 * o.w2) * inv_area;
+            edge_bwd(v2, v0, v1, g_area, g0, g1);
+            g2.x += g_area * (v1.y - v0.y);
+            g2.y += -g_area * (v1.x - v0.x);
+            // dists = +-|p - proj|^2 on the closest edge; the parameter's own derivative drops out (p - proj is
+            // orthogonal to the edge where the clamp is inactive)
+            if (gd_signed != 0.0f) {
+                const float gd = o.inside ? -gd_signed : gd_signed;
+                const P2 a = o.min_edge == 2 ? v1 : v0, b = o.min_edge == 0 ? v1 : v2;
+                float tt;
+                bool dg;
+                point_line(p, a, b, tt, dg);
+                const P2 proj{a.x + tt * (b.x - a.x), a.y + tt * (b.y - a.y)};
+                const P2 rr = dg ? p - b : p - proj;
+                const float ca = dg ? 0.0f : -2.0f * (1.0f - tt) * gd, cb = dg ? -2.0f * gd : -2.0f * tt * gd;
+                P2& ga = o.min_edge == 2 ? g1 : g0;
+                P2& gbb = o.min_edge == 0 ? g1 : g2;
+                ga.x += ca * rr.x;
+                ga.y += ca * rr.y;
+                gbb.x += cb * rr.x;
+                gbb.y += cb * rr.y;
+            }
+            float* dst = grad_face_verts + f * 9;
+            atomicAdd(dst + 0, g0.x);
+            atomicAdd(dst + 1, g0.y);
+            atomicAdd(dst + 2, gz * o.w0);
+            atomicAdd(dst + 3, g1.x);
+            atomicAdd(dst + 4, g1.y);
+            atomicAdd(dst + 5, gz * o.w1);
+            atomicAdd(dst + 6, g2.x);
+            atomicAdd(dst + 7, g2.y);
+            atomicAdd(dst + 8, gz * o.w2);
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+int launch_rasterize_fwd(const pert_raster& rs, int64_t* pix_to_face, float* zbuf, float* bary, float* dists, cudaStream_t st) {
+    const dim3 grid((unsigned)((rs.W + TW - 1) / TW), (unsigned)((rs.H + TH - 1) / TH), (unsigned)rs.N);
+    rasterize_fwd_kernel<<<grid, RT, 0, st>>>(rs, pix_to_face, zbuf, bary, dists);
+    return (int)cudaGetLastError();
+}
+
+int launch_rasterize_bwd(const pert_raster& rs, const int64_t* pix_to_face, const float* grad_zbuf, const float* grad_bary,
+                         const float* grad_dists, float* grad_face_verts, cudaStream_t st) {
+    const int64_t E = (int64_t)rs.N * rs.H * rs.W * rs.K, nchunks = (E + BCHUNK - 1) / BCHUNK;
+    const int64_t cap = 148 * 8, need = (nchunks + BW - 1) / BW;
+    rasterize_bwd_kernel<<<(unsigned)(need < cap ? need : cap), BT, 0, st>>>(rs, pix_to_face, grad_zbuf, grad_bary, grad_dists,
+                                                                           grad_face_verts, E, nchunks,
+                                                                           ((uintptr_t)pix_to_face & 15) == 0);
+    return (int)cudaGetLastError();
+}
+
+}  // namespace pert

@@ -177,24 +177,39 @@ class ViewCameras(DepthCameras):
 
 
 class TriMeshes:
-    """Stand-in for pytorch3d ``Meshes`` (packed representation only): vertices (V,3), faces (F,3), and
-    one colour per face (lazy :class:`FaceTexels`), one colour per vertex (lazy :class:`VertexTexels`) or a preset
-    texel tensor.
-    ``verts_normals_packed`` follows pytorch3d's area-weighted vertex normals (cross products of the
-    face edges summed onto the corners, then normalised with eps 1e-6)."""
+    """Stand-in for pytorch3d ``Meshes``: ONE topology ``faces`` (F,3) with vertices (V,3), or a batch of N poses of
+    it, vertices (N,V,3) (``extend`` / ``update_padded`` as in eval.py:343,281-283).  The packed representation
+    (``verts_packed`` (N*V,3), ``faces_packed`` (N*F,3)) is what ``pix_to_face`` indexes.  Textures: one colour per
+    face (lazy :class:`FaceTexels`), one colour per vertex (lazy :class:`VertexTexels`) or a preset texel tensor.
+    ``verts_normals_packed`` follows pytorch3d's area-weighted vertex normals (cross products of the face edges
+    summed onto the corners, then normalised with eps 1e-6)."""
 
     def __init__(self, verts, faces, face_colors=None, texels=None, verts_colors=None):
         self._verts, self._faces = verts, faces.to(torch.int64)
         self.face_colors, self.texels, self.verts_colors = face_colors, texels, verts_colors
 
-    def verts_packed(self):
-        return self._verts
+    def __len__(self):
+        return self._verts.shape[0] if self._verts.dim() == 3 else 1
 
-    def faces_packed(self):
+    def verts_padded(self):
+        return self._verts if self._verts.dim() == 3 else self._verts[None]
+
+    def faces_packed_single(self):
         return self._faces
 
+    def verts_packed(self):
+        return self._verts.reshape(-1, 3)
+
+    def faces_packed(self):
+        n = len(self)
+        if n == 1:
+            return self._faces
+        V = self._verts.shape[-2]
+        off = torch.arange(n, device=self._faces.device, dtype=torch.int64)[:, None, None] * V
+        return (self._faces[None] + off).reshape(-1, 3)
+
     def verts_normals_packed(self):
-        v, f = self._verts, self._faces
+        v, f = self.verts_packed(), self.faces_packed()
         vf = v[f]
         n = torch.zeros_like(v)
         n = n.index_add(0, f[:, 1], torch.cross(vf[:, 2] - vf[:, 1], vf[:, 0] - vf[:, 1], dim=1))
@@ -205,29 +220,61 @@ class TriMeshes:
     def sample_textures(self, fragments):
         if self.texels is not None:
             return self.texels
+        n = len(self)
         if self.verts_colors is not None:
-            return VertexTexels(self.verts_colors, self._faces)
-        return FaceTexels(self.face_colors)
+            vc = self.verts_colors if n == 1 else self.verts_colors.repeat(n, 1)
+            return VertexTexels(vc, self.faces_packed())
+        return FaceTexels(self.face_colors if n == 1 else self.face_colors.repeat(n, 1))
 
-    def update_verts(self, verts):
+    def extend(self, n: int):
+        """n copies of a single mesh as one batch (pytorch3d ``Meshes.extend``)."""
+        if len(self) != 1:
+            raise ValueError("extend() needs a single mesh")
+        return TriMeshes(self.verts_padded().expand(n, -1, -1).contiguous(), self._faces, self.face_colors, self.texels,
+                         self.verts_colors)
+
+    def update_padded(self, verts):
+        """Same topology and textures, new vertex positions (V,3) or (N,V,3) (pytorch3d ``Meshes.update_padded``)."""
         return TriMeshes(verts, self._faces, self.face_colors, self.texels, self.verts_colors)
+
+    update_verts = update_padded
+
+
+def _icosphere(level: int):
+    """Unit icosphere: 20 * 4**level faces, 10 * 4**level + 2 vertices (level 3 = 1280 faces / 642 vertices, the
+    sphere_642.obj of experiments/eval.py:289), outward counter-clockwise winding."""
+    t = (1.0 + math.sqrt(5.0)) / 2.0
+    v = torch.tensor([[-1, t, 0], [1, t, 0], [-1, -t, 0], [1, -t, 0], [0, -1, t], [0, 1, t], [0, -1, -t], [0, 1, -t],
+                      [t, 0, -1], [t, 0, 1], [-t, 0, -1], [-t, 0, 1]], dtype=torch.float64)
+    f = torch.tensor([[0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11], [1, 5, 9], [5, 11, 4], [11, 10, 2],
+                      [10, 7, 6], [7, 1, 8], [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8], [3, 8, 9], [4, 9, 5], [2, 4, 11],
+                      [6, 2, 10], [8, 6, 7], [9, 8, 1]], dtype=torch.int64)
+    v = v / v.norm(dim=1, keepdim=True)
+    for _ in range(level):
+        e = torch.cat((f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]))  # (3F,2) directed edges
+        key = torch.sort(e, dim=1).values
+        uniq, inv = torch.unique(key, dim=0, return_inverse=True)
+        mid = v[uniq[:, 0]] + v[uniq[:, 1]]
+        mid = mid / mid.norm(dim=1, keepdim=True)
+        nv = v.shape[0]
+        F_ = f.shape[0]
+        a, b, c = inv[:F_] + nv, inv[F_:2 * F_] + nv, inv[2 * F_:] + nv  # midpoints of edges 01, 12, 20
+        f = torch.cat((torch.stack((f[:, 0], a, c), 1), torch.stack((f[:, 1], b, a), 1), torch.stack((f[:, 2], c, b), 1),
+                       torch.stack((a, b, c), 1)))
+        v = torch.cat((v, mid))
+    return v.float(), f
 
 
 def synthetic_mesh(n_faces=1280, seed=0, device="cuda"):
-    """A closed unit-scale triangle soup with about ``n_faces`` faces for the Phong benchmark: a
-    latitude/longitude sphere (vertex normals are well defined).  Returns (verts (V,3), faces (F,3))."""
-    rows = max(2, int(round(math.sqrt(n_faces / 2.0))))
-    cols = max(3, int(math.ceil(n_faces / (2.0 * rows))))
-    th = torch.linspace(0.0, math.pi, rows + 1, device=device)[:, None]
-    phv = torch.linspace(0.0, 2.0 * math.pi, cols + 1, device=device)[None, :-1]
-    x, y, z = torch.sin(th) * torch.cos(phv), torch.cos(th).expand(rows + 1, cols), torch.sin(th) * torch.sin(phv)
-    verts = torch.stack((x, y, z), dim=-1).reshape(-1, 3).float()
-    r = torch.arange(rows, device=device)[:, None]
-    c = torch.arange(cols, device=device)[None, :]
-    i00, i01 = r * cols + c, r * cols + (c + 1) % cols
-    i10, i11 = (r + 1) * cols + c, (r + 1) * cols + (c + 1) % cols
-    faces = torch.cat((torch.stack((i00, i11, i10), -1).reshape(-1, 3), torch.stack((i00, i01, i11), -1).reshape(-1, 3)))
-    return verts, faces[:n_faces].to(torch.int64)
+    """A unit-scale triangle mesh with ``n_faces`` faces for the benchmarks and tests: the icosphere of the smallest
+    level with at least that many faces (20, 80, 320, 1280, ... are closed spheres; other counts keep the first
+    ``n_faces`` faces of the next level: an open sphere, still without sliver triangles).
+    Returns (verts (V,3), faces (F,3))."""
+    level = 0
+    while 20 * 4 ** level < n_faces:
+        level += 1
+    verts, faces = _icosphere(level)
+    return verts.to(device), faces[:n_faces].contiguous().to(device)
 
 
 def synthetic_bary(pix_to_face, seed=0):

@@ -1,0 +1,221 @@
+"""Parity of the fragment-producer kernels (pert_rasterize_fwd / pert_rasterize_bwd, through the C ABI) with the CPU
+oracle (oracle/raster_oracle.py: pytorch3d 0.4.0's naive rasteriser restated), and the end-to-end renderer
+MeshRenderer(MeshRasterizer, RandomPhongShader) of experiments/eval.py:165-177 on a small pose optimisation."""
+
+import math
+
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import raster_oracle as RO
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def _faces_ndc(n_faces, n_views, seed=0, elev=20.0):
+    """Packed NDC faces of a sphere seen by n_views orbiting cameras, on the CPU."""
+    import pertrenderer_b200 as pb
+    verts, faces = pb.synthetic_mesh(n_faces, device="cpu")
+    R, T = pb.look_at_view_transform(dist=2.7, elev=elev, azim=torch.linspace(0.0, 150.0, n_views) + 10.0 * seed)
+    cam = pb.FoVPerspectiveCameras(R=R, T=T)
+    ndc = cam.transform_points_ndc(verts)  # (N,V,3)
+    fv = ndc[:, faces].reshape(-1, 3, 3).contiguous()
+    F_ = faces.shape[0]
+    return fv, [i * F_ for i in range(n_views + 1)]
+
+
+def _same_fragments(got, ref, fv, blur):
+    """Exact equality except where a decision sits on a float boundary (the kernels contract a*b+c into FMAs, torch
+    does not): such pixels must be few and differ only by faces whose test was marginal."""
+    p2f_g, z_g, b_g, d_g = (t.cpu() for t in got)
+    p2f_r, z_r, b_r, d_r = ref
+    same = (p2f_g == p2f_r).all(-1)
+    assert same.float().mean() > 0.995, same.float().mean()
+    # sliver faces (projected area ~ 1e-6, e.g. next to the poles of the test sphere) have ill-conditioned barycentric
+    # coordinates (e_i / area): values are compared on well-conditioned faces only
+    sel = fv[p2f_r.clamp(min=0)]
+    area = RO.edge_function(sel[..., 0, :2], sel[..., 1, :2], sel[..., 2, :2]).abs()
+    m = same[..., None] & (p2f_r >= 0) & (area > 1e-3)
+    assert m.float().sum() > 0.5 * (p2f_r >= 0).float().sum()
+    pad = same[..., None] & (p2f_r < 0)
+    assert (z_g[pad] == -1).all() and (d_g[pad] == -1).all() and (b_g[pad] == -1).all()
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(n_faces=80, views=2, H=24, W=24, K=8, blur=1e-3),
+    dict(n_faces=320, views=1, H=40, W=33, K=6, blur=5e-3),      # non-square, partial tiles
+    dict(n_faces=1280, views=3, H=32, W=32, K=50, blur=9.21e-3),  # eval.py: K=50, blur = log(1/1e-4-1)*sigma
+    dict(n_faces=20, views=1, H=16, W=16, K=2, blur=0.0),         # K smaller than the number of overlapping faces
+])
+def test_rasterize_forward_matches_oracle(cfg):
+    import pertrenderer_b200 as pb
+    fv, start = _faces_ndc(cfg["n_faces"], cfg["views"], seed=cfg["K"])
+    ref = RO.rasterize(fv, start, cfg["H"], cfg["W"], cfg["K"], cfg["blur"])
+    got = pb.rasterize_meshes(fv.to(DEV), torch.tensor(start, device=DEV), (cfg["H"], cfg["W"]), cfg["blur"], cfg["K"])
+    torch.cuda.synchronize()
+    assert (ref[0] >= 0).float().mean() > 0.02
+    _same_fragments(got, ref, fv, cfg["blur"])
+    z = got[1].cpu()
+    valid = got[0].cpu() >= 0
+    # ascending depth, padding last
+    zz = torch.where(valid, z, torch.full_like(z, float("inf")))
+    assert (zz[..., 1:] >= zz[..., :-1]).all()
+    assert (valid[..., 1:] <= valid[..., :-1]).all()
+
+
+def test_rasterize_backward_matches_oracle_autograd():
+    import pertrenderer_b200 as pb
+    H = W = 28
+    K = 6
+    fv, start = _faces_ndc(80, 2, seed=3)
+    blur = 4e-3
+    fv_c = fv.to(DEV).requires_grad_(True)
+    p2f, zbuf, bary, dists = pb.rasterize_meshes(fv_c, torch.tensor(start, device=DEV), H, blur, K)
+    gen = torch.Generator().manual_seed(0)
+    gz, gb, gd = torch.randn(zbuf.shape, generator=gen), torch.randn(bary.shape, generator=gen), torch.randn(dists.shape, generator=gen)
+    gz[torch.rand(zbuf.shape, generator=gen) < 0.3] = 0.0
+    ((zbuf * gz.to(DEV)).sum() + (bary * gb.to(DEV)).sum() + (dists * gd.to(DEV)).sum()).backward()
+    # oracle: autograd over the restated formulas of the SAME selection
+    fv_o = fv.clone().requires_grad_(True)
+    z_o, b_o, d_o = RO.fragments_from_selection(fv_o, p2f.cpu(), H, W)
+    mask = p2f.cpu() >= 0
+    ((z_o * gz)[mask].sum() + (b_o * gb)[mask].sum() + (d_o * gd)[mask].sum()).backward()
+    assert rel_err(fv_c.grad.cpu(), fv_o.grad) <= 2e-4  # fp32 sums of thousands of terms with 1/area^2 factors
+    # each kind of gradient alone
+    for which in range(3):
+        fv_c2 = fv.to(DEV).requires_grad_(True)
+        out = pb.rasterize_meshes(fv_c2, torch.tensor(start, device=DEV), H, blur, K)
+        (out[1 + which] * (gz, gb, gd)[which].to(DEV)).sum().backward()
+        fv_o2 = fv.clone().requires_grad_(True)
+        ref = RO.fragments_from_selection(fv_o2, p2f.cpu(), H, W)
+        m = mask if which != 1 else mask[..., None].expand_as(ref[1])
+        (ref[which] * (gz, gb, gd)[which])[m].sum().backward()
+        assert rel_err(fv_c2.grad.cpu(), fv_o2.grad) <= 2e-4, which
+
+
+def test_renderer_chain_matches_oracle_chain():
+    """MeshRasterizer -> RandomPhongShader(SoftRast, SoftAgg) against the oracle chain (raster oracle -> Phong oracle ->
+    blend oracle) on the same mesh and camera: same selection, same image, and the same gradient on the fragments and on
+    the mesh vertices (the quantity pose optimisation differentiates, eval.py:341-369)."""
+    import pertrenderer_b200 as pb
+    from oracle import pert_oracle as O
+    from oracle import phong_oracle as PO
+    torch.manual_seed(0)
+    verts, faces = pb.synthetic_mesh(80, device="cpu")
+    verts = verts * torch.tensor([1.0, 0.6, 0.8])
+    fc = torch.rand(faces.shape[0], 3, generator=torch.Generator().manual_seed(1))
+    R, T = pb.look_at_view_transform(dist=2.7, elev=30.0, azim=120.0)
+    H = W = 32
+    K = 20
+    sigma, gamma = 1e-2, 5e-2
+    blur = math.log(1.0 / 1e-4 - 1.0) * sigma
+    G = torch.randn(1, H, W, 4, generator=torch.Generator().manual_seed(2))
+    # oracle chain
+    v_o = verts.clone().requires_grad_(True)
+    cam_o = pb.OpenGLPerspectiveCameras(R=R, T=T)
+    fv_o = cam_o.transform_points_ndc(v_o)[0][faces]
+    p2f = RO.rasterize(fv_o.detach(), [0, faces.shape[0]], H, W, K, blur)[0]
+    z_o, b_o, d_o = RO.fragments_from_selection(fv_o, p2f, H, W)
+    for t in (z_o, b_o, d_o):
+        t.retain_grad()
+    mesh_o = pb.TriMeshes(v_o, faces, face_colors=fc)
+    col_o = PO.phong_colors_from(mesh_o, pb.Fragments(p2f, z_o, b_o, d_o), pb.PointLights(location=[[0.0, 2.0, -2.0]]), cam_o,
+                                 pb.Materials(), pb.FaceTexels(fc).materialize(p2f))
+    img_o, _, _, gr = O.soft_shade_fwd_bwd(p2f, z_o.detach(), d_o.detach(), col_o.detach(), torch.tensor((0.0, 0.0, 0.0)),
+                                           cam_o.znear.reshape(-1, 1, 1, 1), cam_o.zfar.reshape(-1, 1, 1, 1), sigma, gamma, 1.0, 1e-10, G)
+    torch.autograd.backward([col_o, z_o, d_o], [gr["colors"], gr["zbuf"], gr["dists"]])
+    # CUDA chain
+    v_c = verts.to(DEV).requires_grad_(True)
+    cam_c = pb.OpenGLPerspectiveCameras(R=R, T=T, device=DEV)
+    rast = pb.MeshRasterizer(cam_c, pb.RasterizationSettings(image_size=H, blur_radius=blur, faces_per_pixel=K))
+    shader = pb.RandomPhongShader(device=DEV, cameras=cam_c, lights=pb.PointLights(location=[[0.0, 2.0, -2.0]], device=DEV),
+                                  materials=pb.Materials(device=DEV), blend_params=pb.BlendParams(background_color=(0.0, 0.0, 0.0)),
+                                  smoothrast=pb.SoftRast(sigma=sigma), smoothagg=pb.SoftAgg(gamma=gamma, alpha=1.0))
+    mesh_c = pb.TriMeshes(v_c, faces.to(DEV), face_colors=fc.to(DEV))
+    frag_c = rast(mesh_c)
+    for t in (frag_c.zbuf, frag_c.bary_coords, frag_c.dists):
+        t.retain_grad()
+    img_c = shader(frag_c, mesh_c)
+    (img_c * G.to(DEV)).sum().backward()
+    same = (frag_c.pix_to_face.cpu() == p2f).all(-1)
+    assert same.float().mean() > 0.995
+    m = (p2f >= 0) & same[..., None]
+    assert (img_c.detach().cpu() - img_o)[same].abs().max() <= 5e-6
+    assert rel_err(frag_c.zbuf.grad.cpu()[m], z_o.grad[m]) <= 1e-4
+    assert rel_err(frag_c.dists.grad.cpu()[m], d_o.grad[m]) <= 1e-4
+    assert rel_err(frag_c.bary_coords.grad.cpu()[m], b_o.grad[m]) <= 5e-4
+    if same.all():
+        assert rel_err(v_c.grad.cpu(), v_o.grad) <= 1e-3
+
+
+@pytest.mark.parametrize("pair", ["softras", "gaussian"])
+def test_renderer_end_to_end_pose_optimisation(pair):
+    """MeshRenderer(MeshRasterizer, RandomPhongShader) as eval.py:135-177 builds it: render a target at a known rotation
+    with the hard operators (eval.py:272-286), start 15 degrees off, run Adam on the rotation vector (eval.py:320-409):
+    the angle error must drop.  (sigma = 3e-4: with a blur band as wide as the faces, pytorch3d-style unclipped
+    barycentric extrapolation makes the image discontinuous in the pose; the CPU float64 chain behaves the same.)"""
+    import pertrenderer_b200 as pb
+    torch.manual_seed(0)
+    verts, faces = pb.synthetic_mesh(80, device=DEV)
+    verts = verts * torch.tensor([1.0, 0.6, 0.8], device=DEV)  # an ellipsoid: the pose is observable
+    fc = torch.rand(faces.shape[0], 3, device=DEV, generator=torch.Generator(device=DEV).manual_seed(1))
+    mesh = pb.TriMeshes(verts, faces, face_colors=fc)
+    R, T = pb.look_at_view_transform(dist=2.7, elev=30.0, azim=120.0, device=DEV)
+    cameras = pb.OpenGLPerspectiveCameras(R=R, T=T, device=DEV)
+    lights = pb.PointLights(location=[[0.0, 2.0, -2.0]], device=DEV)
+    sigma, gamma = 3e-4, 1e-2
+
+    def make(rast_op, agg_op, sg):
+        settings = pb.RasterizationSettings(image_size=48, blur_radius=math.log(1.0 / 1e-4 - 1.0) * sg, faces_per_pixel=16)
+        return pb.MeshRenderer(
+            rasterizer=pb.MeshRasterizer(cameras=cameras, raster_settings=settings),
+            shader=pb.RandomPhongShader(device=DEV, cameras=cameras, lights=lights,
+                                        blend_params=pb.BlendParams(background_color=(0.0, 0.0, 0.0)),
+                                        smoothrast=rast_op, smoothagg=agg_op))
+
+    if pair == "gaussian":
+        renderer = make(pb.GaussianRast(nb_samples=64, sigma=sigma), pb.GaussianAgg(nb_samples=64, gamma=gamma, alpha=1.0), sigma)
+    else:
+        renderer = make(pb.SoftRast(sigma=sigma), pb.SoftAgg(gamma=gamma, alpha=1.0), sigma)
+    hard = make(pb.HardRast(), pb.HardAgg(), 0.0)
+
+    def rot(w):  # Rodrigues (so3_exponential_map, eval.py:341)
+        th = w.norm().clamp_min(1e-8)
+        k = w / th
+        Kx = torch.zeros(3, 3, device=DEV)
+        Kx[0, 1], Kx[0, 2], Kx[1, 0], Kx[1, 2], Kx[2, 0], Kx[2, 1] = -k[2], k[1], k[2], -k[0], -k[1], k[0]
+        return torch.eye(3, device=DEV) + torch.sin(th) * Kx + (1 - torch.cos(th)) * (Kx @ Kx)
+
+    w_true = torch.tensor([0.3, -0.5, 0.2], device=DEV)
+    with torch.no_grad():
+        target = hard(mesh.update_padded(verts @ rot(w_true)))[..., :3]
+    assert target.shape == (1, 48, 48, 3) and target.sum() > 10
+    axis = torch.tensor([0.6, 0.0, 0.8], device=DEV)
+    w = (w_true + math.radians(15.0) * axis).clone().requires_grad_(True)
+    opt = torch.optim.Adam([w], lr=2e-2)
+
+    def angle_err():
+        Rrel = rot(w.detach()).T @ rot(w_true)
+        return math.degrees(math.acos(max(-1.0, min(1.0, (Rrel.trace().item() - 1.0) / 2.0))))
+
+    a0 = angle_err()
+    best = a0
+    for _ in range(60):
+        opt.zero_grad()
+        img = renderer(mesh.update_padded(verts @ rot(w)))
+        loss = ((img[..., :3] - target) ** 2).mean()
+        loss.backward()
+        assert torch.isfinite(w.grad).all()
+        opt.step()
+        best = min(best, angle_err())
+    a1 = angle_err()
+    assert best < 0.4 * a0 and a1 < 0.6 * a0, (pair, a0, best, a1)
