@@ -198,6 +198,25 @@ def workload_config(args, world):
     }
 
 
+def rasterised_fragments(args, dev, rank=0):
+    """Fragments of an ACTUAL rasterisation at the benchmark shapes: the 1280-face icosphere (sphere_642.obj of
+    experiments/eval.py:289) seen by N orbiting cameras (dist 2.7, fov 60), blur_radius = log(1/1e-4 - 1) * sigma
+    (eval.py:137), produced by pert_rasterize_fwd; texels = per-face colours gathered through pix_to_face."""
+    import math
+    import pertrenderer_b200 as pb
+    N, HW, K = args.views, args.image_size, args.faces_per_pixel
+    verts, faces = pb.synthetic_mesh(1280, device=dev)
+    R, T = pb.look_at_view_transform(dist=2.7, elev=30.0, azim=torch.linspace(0, 315, N) + 7.0 * rank, device=dev)
+    cam = pb.OpenGLPerspectiveCameras(R=R, T=T, device=dev)
+    rast = pb.MeshRasterizer(cam, pb.RasterizationSettings(image_size=HW, blur_radius=math.log(1.0 / 1e-4 - 1.0) * SIGMA,
+                                                           faces_per_pixel=K))
+    with torch.no_grad():
+        fr = rast(pb.TriMeshes(verts, faces).extend(N))
+    fc = torch.rand((N * faces.shape[0], 3), device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+    col = pb.FaceTexels(fc).materialize(fr.pix_to_face)
+    return fr, col.contiguous()
+
+
 # ------------------------------------------------------------------------------------------------
 # B200 arm
 # ------------------------------------------------------------------------------------------------
@@ -206,7 +225,10 @@ def device_timed(args, kind, dev, steps, warmup, world, rank, sampler=None, flag
     import torch.distributed as dist
     from pertrenderer_b200 import ops, synthetic_fragments
     N, HW, K, S = args.views, args.image_size, args.faces_per_pixel, args.nb_samples
-    fr, col = synthetic_fragments(N, HW, HW, K, kind=kind, sigma=SIGMA, seed=rank, device=dev)
+    if kind == "rasterised":
+        fr, col = rasterised_fragments(args, dev, rank)
+    else:
+        fr, col = synthetic_fragments(N, HW, HW, K, kind=kind, sigma=SIGMA, seed=rank, device=dev)
     G = torch.randn((N, HW, HW, 4), device=dev, generator=torch.Generator(device=dev).manual_seed(1 + rank))
     P = N * HW * HW
     torch.manual_seed(1234 + rank)
@@ -364,6 +386,65 @@ def phong_timed(args, kind, dev, steps, warmup, rank):
             "peak": peak, "peak_source": peak_src, "launches_per_step": 7}
 
 
+def renderer_timed(args, dev, steps, warmup, rank):
+    """The whole renderer of experiments/eval.py:165-177 through the public API: MeshRenderer(MeshRasterizer,
+    RandomPhongShader(GaussianRast, GaussianAgg)) forward + autograd backward to the mesh vertices, 1280-face icosphere,
+    N orbiting cameras, config-2 shapes.  Segments timed with CUDA events: rasterise / shade forward / everything
+    backward."""
+    import math
+    import pertrenderer_b200 as pb
+    N, HW, K, S = args.views, args.image_size, args.faces_per_pixel, args.nb_samples
+    verts, faces = pb.synthetic_mesh(1280, device=dev)
+    R, T = pb.look_at_view_transform(dist=2.7, elev=30.0, azim=torch.linspace(0, 315, N) + 7.0 * rank, device=dev)
+    cam = pb.OpenGLPerspectiveCameras(R=R, T=T, device=dev)
+    blur = math.log(1.0 / 1e-4 - 1.0) * SIGMA
+    rast = pb.MeshRasterizer(cam, pb.RasterizationSettings(image_size=HW, blur_radius=blur, faces_per_pixel=K))
+    shader = pb.RandomPhongShader(device=dev, cameras=cam, lights=pb.PointLights(location=[[0.0, 2.0, -2.0]], device=dev),
+                                  blend_params=pb.BlendParams(background_color=BACKGROUND),
+                                  smoothrast=pb.GaussianRast(nb_samples=S, sigma=SIGMA),
+                                  smoothagg=pb.GaussianAgg(nb_samples=S, gamma=GAMMA, alpha=ALPHA))
+    fc = torch.rand((faces.shape[0], 3), device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+    mesh = pb.TriMeshes(verts, faces, face_colors=fc).extend(N)
+    G = torch.randn((N, HW, HW, 4), device=dev, generator=torch.Generator(device=dev).manual_seed(1 + rank))
+    v = mesh.verts_padded().clone().requires_grad_(True)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(steps)]
+    stats = {}
+
+    def step(i=None):
+        rec = (lambda j: ev[i][j].record()) if i is not None else (lambda j: None)
+        v.grad = None
+        m = mesh.update_padded(v)
+        rec(0)
+        frag = rast(m)
+        rec(1)
+        img = shader(frag, m)
+        rec(2)
+        (img * G).sum().backward()
+        rec(3)
+        if i is None and not stats:
+            valid = frag.pix_to_face >= 0
+            stats["coverage"] = valid.any(-1).float().mean().item()
+            stats["valid_per_covered_pixel"] = valid.sum(-1)[valid.any(-1)].float().mean().item()
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize(dev)
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for i in range(steps):
+        step(i)
+    t1.record()
+    torch.cuda.synchronize(dev)
+    total_ms = t0.elapsed_time(t1)
+    seg = [sum(e[j].elapsed_time(e[j + 1]) for e in ev) / steps for j in range(3)]
+    P = N * HW * HW
+    return {"note": "MeshRenderer(MeshRasterizer, RandomPhongShader(GaussianRast, GaussianAgg)), public API + autograd to the "
+                    "mesh vertices; 1280-face icosphere, blur_radius = log(1/1e-4-1)*sigma; includes the host reads of the "
+                    "scalar gradients (sigma, gamma, alpha are CPU leaves)",
+            "value": P * K * S * steps / (total_ms * 1e-3), "unit": UNIT, "ms_per_step": total_ms / steps,
+            "rasterize_ms": seg[0], "shade_fwd_ms": seg[1], "backward_ms": seg[2], **stats}
+
+
 def e2e_timed(args, kind, dev, steps, warmup, world, rank):
     """End to end through the public API (RandomSimpleShader + autograd) with HOST buffers: every
     step copies that step's Fragments and texels from pinned host memory (double-buffered on a copy
@@ -466,7 +547,16 @@ def run_b200_arm(args):
         fc = device_timed(args, args.fragments, dev, max(3, args.steps // 2), 3, world, rank, face=True)
         sf = device_timed(args, args.fragments, dev, max(3, args.steps // 2), 3, world, rank, soft=True)
         phg = phong_timed(args, args.fragments, dev, max(3, args.steps // 2), 3, rank)
+        rz = device_timed(args, "rasterised", dev, max(3, args.steps // 4), 3, world, rank)
+        rnd = renderer_timed(args, dev, max(3, args.steps // 4), 3, rank)
         also = {"random_phong_shader": phg,
+                "renderer": rnd,
+                "fragments_rasterised": {"fragments": "rasterised",
+                                         "note": "fragments of an actual rasterisation (pert_rasterize_fwd) of the 1280-face "
+                                                 "icosphere at the same shapes instead of the SURVEY 8d synthetic sets: "
+                                                 "dozens of faces per covered pixel inside the blur band",
+                                         "value": rz["value"], "unit": UNIT, "ms_per_step": rz["ms_per_step"],
+                                         "roofline": rz["roofline"]},
                 "softras_pair": {"fragments": args.fragments,
                                  "note": "SoftRast + SoftAgg (the shaders' DEFAULT operators, deterministic) through the "
                                          "fused soft kernels; same algorithmic bytes; 'units' counts nb_samples like the "
