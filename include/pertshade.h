@@ -53,7 +53,7 @@
 extern "C" {
 #endif
 
-#define PERT_ABI_VERSION 8
+#define PERT_ABI_VERSION 9
 
 /* error codes */
 #define PERT_OK 0
@@ -277,6 +277,10 @@ typedef struct pert_raster {
     int64_t num_faces;
     const float* face_verts;   /* (F,3,3) */
     const int64_t* face_start; /* (N+1), device */
+    const int64_t* face_order; /* optional (F): a permutation of every range [face_start[n], face_start[n+1]) giving the
+                                  order in which the faces are visited; nearest first (e.g. sorted by centroid depth)
+                                  makes the per-pixel sorted insertion append-only.  The result does not depend on it.
+                                  NULL: index order.  Forward, K <= 64 only */
 } pert_raster;
 
 int pert_rasterize_fwd(const pert_raster* rs, int64_t* pix_to_face, float* zbuf, float* bary, float* dists, void* stream);

@@ -15,7 +15,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpertshade.so")
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 # flags (include/pertshade.h)
 F_NO_SKIP = 1
@@ -80,7 +80,7 @@ class PertRaster(C.Structure):
         ("flags", C.c_uint32),
         ("blur_radius", C.c_float),
         ("num_faces", C.c_int64),
-        ("face_verts", C.c_void_p), ("face_start", C.c_void_p),
+        ("face_verts", C.c_void_p), ("face_start", C.c_void_p), ("face_order", C.c_void_p),
     ]
 
 

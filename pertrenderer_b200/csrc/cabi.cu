@@ -415,7 +415,7 @@ static int check_raster(const pert_raster* rs) {
     if ((int64_t)rs->N * rs->H * rs->W >= ((int64_t)1 << 32) / rs->K) return PERT_E_UNSUPPORTED;
     if (!(rs->blur_radius >= 0.0f) || isinf(rs->blur_radius)) return PERT_E_SCALAR;
     if (!rs->face_verts || !rs->face_start) return PERT_E_NULL;
-    if (((uintptr_t)rs->face_verts & 3) || ((uintptr_t)rs->face_start & 7)) return PERT_E_ALIGN;
+    if (((uintptr_t)rs->face_verts & 3) || ((uintptr_t)rs->face_start & 7) || ((uintptr_t)rs->face_order & 7)) return PERT_E_ALIGN;
     return PERT_OK;
 }
 

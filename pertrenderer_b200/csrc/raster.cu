@@ -8,10 +8,11 @@
 //   forward   one CTA per 32x8 pixel tile.  Faces are culled against the tile in chunks of 256 (one face per thread:
 //             bounding box grown by sqrt(blur_radius) against the tile's pixel-centre rectangle, zero-area and
 //             behind-camera faces dropped), survivors are compacted IN FACE ORDER into shared memory with their nine
-//             coordinates, and every pixel thread then tests only those.  The K-buffer of a pixel lives in its own
-//             output rows (zbuf / pix_to_face), kept sorted by stable insertion (ascending depth, ties in face
-//             order); bary / dists of the kept faces are recomputed at the end and the padding of each row is
-//             written by the warp as coalesced stores.
+//             coordinates, and every pixel thread then tests only those.  The K-buffer of a pixel is a sorted array
+//             of packed keys (depth bits << 32 | face) in local memory for K <= 64, or lives in the pixel's own
+//             output rows for larger K (stable insertion: ascending depth, ties in face order); bary / dists of the
+//             kept faces are recomputed at the end and the padding of each row is written by the warp as coalesced
+//             stores.
 //   backward  a streaming pass over the (P,K) entries, warp-autonomous chunks with compact valid lists (the machinery
 //             of the Phong kernels): every valid entry recomputes its barycentric / distance arithmetic and scatters
 //             d(zbuf, bary, dists)/d(face_verts) with atomics.
@@ -90,7 +91,7 @@ __device__ __forceinline__ FaceEval eval_face(P2 p, const float* v /* 9 floats *
 // ---------------------------------------------------------------------------------------------------------
 // forward
 // ---------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RT) rasterize_fwd_kernel(const pert_raster rs, int64_t* __restrict__ pix_to_face,
+__global__ void __launch_bounds__(RT) rasterize_fwd_rows_kernel(const pert_raster rs, int64_t* __restrict__ pix_to_face,
                                                            float* __restrict__ zbuf, float* __restrict__ bary,
                                                            float* __restrict__ dists) {
     __shared__ float s_v[RT][9];
@@ -193,18 +194,154 @@ __global__ void __launch_bounds__(RT) rasterize_fwd_kernel(const pert_raster rs,
     if (py < H) {
         const int npix = min(TW, W - blockIdx.x * TW);
 #pragma unroll 1
-        for (int i = lane; i < npix * K; i += 32) {
-            const int q = i / K, k = i - q * K;
-            if (k >= cnt_w[q]) {
-                pix_to_face[wrow + i] = -1;
-                zbuf[wrow + i] = -1.0f;
-                dists[wrow + i] = -1.0f;
+        for (int q = 0; q < npix; ++q) {
+            const int c = cnt_w[q];
+            const int64_t r0 = wrow + (int64_t)q * K;
+#pragma unroll 1
+            for (int k = c + lane; k < K; k += 32) {
+                pix_to_face[r0 + k] = -1;
+                zbuf[r0 + k] = -1.0f;
+                dists[r0 + k] = -1.0f;
+            }
+#pragma unroll 1
+            for (int j = 3 * c + lane; j < 3 * K; j += 32) bary[r0 * 3 + j] = -1.0f;
+        }
+    }
+}
+
+
+// Fast path for K <= KMAX: the K-buffer of a pixel is a sorted array of packed 64-bit keys (depth bits << 32 | face)
+// in LOCAL memory.  Depths are >= 0, so the integer order of the keys is the depth order with ties in face order;
+// local memory is interleaved per thread, so the insertion shifts of a warp are coalesced (the per-pixel output rows
+// of the generic kernel are K*4 bytes apart: every shift was its own sector, 2.2 ms at config 2).
+template <int KMAX>
+__global__ void __launch_bounds__(RT) rasterize_fwd_keys_kernel(const pert_raster rs, int64_t* __restrict__ pix_to_face,
+                                                                float* __restrict__ zbuf, float* __restrict__ bary,
+                                                                float* __restrict__ dists) {
+    __shared__ float s_v[RT][9];
+    __shared__ float4 s_bb[RT];  // bounding box grown by sqrt(blur_radius): xmin, xmax, ymin, ymax
+    __shared__ int s_face[RT];
+    __shared__ int s_wcount[RT / 32];
+    const int H = rs.H, W = rs.W, K = rs.K;
+    const int n = blockIdx.z, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int px = blockIdx.x * TW + lane, py = blockIdx.y * TH + warp;
+    const bool in_image = px < W && py < H;
+    const P2 p{pix_to_ndc(W - 1 - px, W, H), pix_to_ndc(H - 1 - py, H, W)};
+    const int px0 = blockIdx.x * TW, px1 = min(px0 + TW, W) - 1, py0 = blockIdx.y * TH, py1 = min(py0 + TH, H) - 1;
+    const float tx_hi = pix_to_ndc(W - 1 - px0, W, H), tx_lo = pix_to_ndc(W - 1 - px1, W, H);
+    const float ty_hi = pix_to_ndc(H - 1 - py0, H, W), ty_lo = pix_to_ndc(H - 1 - py1, H, W);
+    const float blur = rs.blur_radius, r = sqrtf(blur);
+    const int64_t f_begin = __ldg(rs.face_start + n), f_end = __ldg(rs.face_start + n + 1);
+    unsigned long long keys[KMAX];
+    int cnt = 0;
+
+#pragma unroll 1
+    for (int64_t fc = f_begin; fc < f_end; fc += RT) {
+        // faces are visited in the caller's order (nearest first when face_order is given: the sorted insertion
+        // below then appends almost always; the result does not depend on the order, keys are unique)
+        const int64_t fpos = fc + threadIdx.x;
+        int64_t f = fpos;
+        bool keep = false;
+        float v[9];
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (fpos < f_end) {
+            if (rs.face_order) f = __ldg(rs.face_order + fpos);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) v[i] = __ldg(rs.face_verts + f * 9 + i);
+            bb = make_float4(fminf(fminf(v[0], v[3]), v[6]) - r, fmaxf(fmaxf(v[0], v[3]), v[6]) + r,
+                             fminf(fminf(v[1], v[4]), v[7]) - r, fmaxf(fmaxf(v[1], v[4]), v[7]) + r);
+            const float zmax = fmaxf(fmaxf(v[2], v[5]), v[8]);
+            const float area = edge(P2{v[0], v[1]}, P2{v[3], v[4]}, P2{v[6], v[7]});
+            const bool zero_area = area <= kEps && area >= -kEps;
+            const bool back = (rs.flags & PERT_RAST_CULL_BACKFACES) && area < 0.0f;
+            keep = !(zmax < 0.0f) && !zero_area && !back && !(tx_lo > bb.y || tx_hi < bb.x || ty_lo > bb.w || ty_hi < bb.z);
+        }
+        const unsigned b = __ballot_sync(FULL, keep);
+        if (lane == 0) s_wcount[warp] = __popc(b);
+        __syncthreads();
+        int base = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < RT / 32; ++w) {
+            const int c = s_wcount[w];
+            base += w < warp ? c : 0;
+            total += c;
+        }
+        if (keep) {
+            const int pos = base + __popc(b & ((1u << lane) - 1u));
+            s_face[pos] = (int)(f - f_begin);
+            s_bb[pos] = bb;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) s_v[pos][i] = v[i];
+        }
+        __syncthreads();
+        if (in_image) {
+#pragma unroll 1
+            for (int i = 0; i < total; ++i) {
+                const float4 q = s_bb[i];
+                if (p.x > q.y || p.x < q.x || p.y > q.w || p.y < q.z) continue;
+                const float* fv = s_v[i];
+                const P2 v0{fv[0], fv[1]}, v1{fv[3], fv[4]}, v2{fv[6], fv[7]};
+                // the same arithmetic as eval_face, so the values recomputed for the kept faces are these
+                const float area = edge(v2, v0, v1) + kEps;
+                const float w0 = edge(p, v1, v2) / area, w1 = edge(p, v2, v0) / area, w2 = edge(p, v0, v1) / area;
+                float pz = w0 * fv[2] + w1 * fv[5] + w2 * fv[8];
+                if (pz < 0.0f) continue;
+                if (!(w0 > 0.0f && w1 > 0.0f && w2 > 0.0f)) {  // outside the face: inside the blur band?
+                    float tt;
+                    bool dg;
+                    const float d = fminf(fminf(point_line(p, v0, v1, tt, dg), point_line(p, v0, v2, tt, dg)),
+                                          point_line(p, v1, v2, tt, dg));
+                    if (d >= blur) continue;
+                }
+                if (pz == 0.0f) pz = 0.0f;  // -0 would sort last
+                const unsigned long long key = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned)s_face[i];
+                if (cnt == K && key >= keys[K - 1]) continue;
+                int j = cnt < K ? cnt : K - 1;
+                while (j > 0 && keys[j - 1] > key) {
+                    keys[j] = keys[j - 1];
+                    --j;
+                }
+                keys[j] = key;
+                if (cnt < K) ++cnt;
             }
         }
+    }
+    const int64_t row = (((int64_t)n * H + py) * W + px) * K;
+    if (in_image) {
 #pragma unroll 1
-        for (int i = lane; i < npix * K * 3; i += 32) {
-            const int q = i / (3 * K), k = (i - q * 3 * K) / 3;
-            if (k >= cnt_w[q]) bary[wrow * 3 + i] = -1.0f;
+        for (int k = 0; k < cnt; ++k) {
+            const int64_t f = f_begin + (int64_t)(unsigned)(keys[k] & 0xffffffffull);
+            float v[9];
+#pragma unroll
+            for (int i = 0; i < 9; ++i) v[i] = __ldg(rs.face_verts + f * 9 + i);
+            const FaceEval e = eval_face(p, v);
+            pix_to_face[row + k] = f;
+            zbuf[row + k] = e.pz;
+            bary[(row + k) * 3] = e.w0;
+            bary[(row + k) * 3 + 1] = e.w1;
+            bary[(row + k) * 3 + 2] = e.w2;
+            dists[row + k] = e.inside ? -e.dist : e.dist;
+        }
+    }
+    __syncthreads();
+    s_face[threadIdx.x] = in_image ? cnt : K;
+    __syncwarp();
+    const int* const cnt_w = s_face + warp * 32;
+    const int64_t wrow = (((int64_t)n * H + py) * W + blockIdx.x * TW) * K;
+    if (py < H) {
+        const int npix = min(TW, W - blockIdx.x * TW);
+#pragma unroll 1
+        for (int q = 0; q < npix; ++q) {
+            const int c = cnt_w[q];
+            const int64_t r0 = wrow + (int64_t)q * K;
+#pragma unroll 1
+            for (int k = c + lane; k < K; k += 32) {
+                pix_to_face[r0 + k] = -1;
+                zbuf[r0 + k] = -1.0f;
+                dists[r0 + k] = -1.0f;
+            }
+#pragma unroll 1
+            for (int j = 3 * c + lane; j < 3 * K; j += 32) bary[r0 * 3 + j] = -1.0f;
         }
     }
 }
@@ -309,7 +446,12 @@ __global__ void __launch_bounds__(BT) rasterize_bwd_kernel(const pert_raster rs,
 
 int launch_rasterize_fwd(const pert_raster& rs, int64_t* pix_to_face, float* zbuf, float* bary, float* dists, cudaStream_t st) {
     const dim3 grid((unsigned)((rs.W + TW - 1) / TW), (unsigned)((rs.H + TH - 1) / TH), (unsigned)rs.N);
-    rasterize_fwd_kernel<<<grid, RT, 0, st>>>(rs, pix_to_face, zbuf, bary, dists);
+    if (rs.K <= 16)
+        rasterize_fwd_keys_kernel<16><<<grid, RT, 0, st>>>(rs, pix_to_face, zbuf, bary, dists);
+    else if (rs.K <= 64)
+        rasterize_fwd_keys_kernel<64><<<grid, RT, 0, st>>>(rs, pix_to_face, zbuf, bary, dists);
+    else  // K-buffer in the pixel's own output rows
+        rasterize_fwd_rows_kernel<<<grid, RT, 0, st>>>(rs, pix_to_face, zbuf, bary, dists);
     return (int)cudaGetLastError();
 }
 

@@ -38,8 +38,9 @@ class RasterizationSettings:
     cull_backfaces: bool = False
 
 
-def _raster_struct(face_verts, face_start, N, H, W, K, blur_radius, cull_backfaces):
+def _raster_struct(face_verts, face_start, N, H, W, K, blur_radius, cull_backfaces, face_order=None):
     rs = PertRaster()
+    rs.face_order = None if face_order is None else face_order.data_ptr()
     rs.N, rs.H, rs.W, rs.K = N, H, W, K
     rs.flags = RAST_CULL_BACKFACES if cull_backfaces else 0
     rs.blur_radius = float(blur_radius)
@@ -63,7 +64,14 @@ class _Rasterize(Function):
             zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
             bary = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev)
             dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
-            rs = _raster_struct(fv, fs, N, H, W, K, blur_radius, cull_backfaces)
+            # visit the faces of every mesh nearest first (centroid depth): the per-pixel sorted insertion of the kernel
+            # then appends instead of shifting; any order gives the same fragments
+            order = None
+            if K <= 64 and fv.shape[0] > 1:
+                zc = fv[:, :, 2].sum(dim=1)
+                mesh_of = torch.bucketize(torch.arange(fv.shape[0], device=dev), fs[1:], right=True)
+                order = torch.argsort(zc + 4.0 * (zc.abs().max() + 1.0) * mesh_of.to(zc.dtype), stable=True).contiguous()
+            rs = _raster_struct(fv, fs, N, H, W, K, blur_radius, cull_backfaces, order)
             rc = lib.pert_rasterize_fwd(rs, ptr(p2f), ptr(zbuf), ptr(bary), ptr(dists), stream_ptr(dev))
         check(rc, "pert_rasterize_fwd")
         ctx.save_for_backward(fv, fs, p2f)

@@ -55,6 +55,7 @@ def _same_fragments(got, ref, fv, blur):
     dict(n_faces=320, views=1, H=40, W=33, K=6, blur=5e-3),      # non-square, partial tiles
     dict(n_faces=1280, views=3, H=32, W=32, K=50, blur=9.21e-3),  # eval.py: K=50, blur = log(1/1e-4-1)*sigma
     dict(n_faces=20, views=1, H=16, W=16, K=2, blur=0.0),         # K smaller than the number of overlapping faces
+    dict(n_faces=320, views=1, H=24, W=24, K=100, blur=9.21e-3),  # K > 64: K-buffer in the output rows
 ])
 def test_rasterize_forward_matches_oracle(cfg):
     import pertrenderer_b200 as pb
