@@ -31,6 +31,29 @@ SIGMA, GAMMA, ALPHA, EPS = 1e-3, 1e-2, 1.0, 1e-10  # experiments/eval.py:69 defa
 BACKGROUND = (1.0, 1.0, 1.0)
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """stdout must carry exactly ONE JSON line.  Libraries write banners to the C-level stdout (NCCL prints its
+    version there whatever NCCL_DEBUG_FILE says), so file descriptor 1 is pointed at stderr for the whole run and the
+    JSON line goes to a private duplicate of the original stdout."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -183,7 +206,7 @@ def run_reference_arm(args):
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_config(args, world):
@@ -596,11 +619,12 @@ def run_b200_arm(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": main["launches"], "roofline": main["roofline"],
         "cpu_baseline": cpu, "also": also,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
     args = parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:
