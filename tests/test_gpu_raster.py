@@ -220,3 +220,23 @@ def test_renderer_end_to_end_pose_optimisation(pair):
         best = min(best, angle_err())
     a1 = angle_err()
     assert best < 0.4 * a0 and a1 < 0.6 * a0, (pair, a0, best, a1)
+
+
+def test_pose_optimisation_example_and_readme_snippet_run(monkeypatch, capsys):
+    """examples/pose_optimisation.py (eval.py's benchmark loop, incl. the adaptive smoothing schedule) and the renderer
+    snippet of README.md execute as written."""
+    import os
+    import re
+    import runpy
+    import sys
+    from conftest import ROOT
+    monkeypatch.setattr(sys, "argv", ["pose_optimisation.py", "--noise", "gaussian", "cauchy", "--trials", "1", "--niter", "8",
+                                      "--imsize", "32", "--adapt"])
+    mod = runpy.run_path(os.path.join(ROOT, "examples", "pose_optimisation.py"), run_name="pose_example")
+    res = mod["main"]()
+    assert set(res) == {"gaussian", "cauchy"} and all(math.isfinite(r["mean_final"]) for r in res.values())
+    text = open(os.path.join(ROOT, "README.md")).read()
+    snippet = [b for b in re.findall(r"```python\n(.*?)```", text, flags=re.S) if "MeshRenderer" in b][0]
+    ns = {}
+    exec(snippet, ns)
+    assert ns["image"].shape == (1, 256, 256, 4) and torch.isfinite(ns["verts"].grad).all() and ns["verts"].grad.abs().sum() > 0
