@@ -53,7 +53,7 @@
 extern "C" {
 #endif
 
-#define PERT_ABI_VERSION 9
+#define PERT_ABI_VERSION 10
 
 /* error codes */
 #define PERT_OK 0
@@ -239,6 +239,9 @@ typedef struct pert_phong {
     const float* lighting;      /* (light_rows, PERT_PHONG_STRIDE) */
     const float* face_vert_colors; /* (F,3,3) colours at the face corners, interpolated with bary (TexturesVertex:
                                       verts_features_packed()[faces_packed()]), or NULL */
+    int64_t faces_per_mesh; /* optional hint, 0 = none: the faces are N equal ranges, image n using only faces
+                               [n * faces_per_mesh, (n+1) * faces_per_mesh) (a batch of poses of one topology); lets
+                               backward keep one shared-memory gradient table per image.  Results do not depend on it */
 } pert_phong;
 
 int pert_phong_fwd(const pert_phong* ph, float* colors, void* stream);

@@ -15,7 +15,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpertshade.so")
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 # flags (include/pertshade.h)
 F_NO_SKIP = 1
@@ -69,6 +69,7 @@ class PertPhong(C.Structure):
         ("pix_to_face", C.c_void_p), ("bary", C.c_void_p), ("face_verts", C.c_void_p), ("face_normals", C.c_void_p),
         ("texels", C.c_void_p), ("face_colors", C.c_void_p), ("lighting", C.c_void_p),
         ("face_vert_colors", C.c_void_p),
+        ("faces_per_mesh", C.c_int64),
     ]
 
 

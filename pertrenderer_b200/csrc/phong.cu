@@ -211,7 +211,7 @@ template <bool TABLE, int NT>
 __global__ void __launch_bounds__(NT) phong_bwd_kernel(const pert_phong ph, const float* __restrict__ grad_colors,
                                                        float* __restrict__ grad_texels, float* __restrict__ grad_bary,
                                                        float* __restrict__ grad_fv, float* __restrict__ grad_fn, int64_t E,
-                                                       int64_t nchunks, int vec_ok) {
+                                                       int64_t nchunks, int tfaces, int per_image) {
     // dynamic shared memory: [TABLE: F*9 (verts) | F*9 (normals) | F*3 (face colours) or F*9 (corner colours)] then per warp
     // vlist u16[WCHUNK] | hlist u16[WCHUNK] | lighting rows float[2 * PERT_PHONG_STRIDE]
     extern __shared__ __align__(16) float table[];
@@ -220,12 +220,15 @@ __global__ void __launch_bounds__(NT) phong_bwd_kernel(const pert_phong ph, cons
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     unsigned char* const wbase = reinterpret_cast<unsigned char*>(table) +
-                                 (TABLE ? (((size_t)ph.num_faces * (18 + tex_floats(ph)) * 4 + 15) & ~(size_t)15) : 0) +
+                                 (TABLE ? (((size_t)tfaces * (18 + tex_floats(ph)) * 4 + 15) & ~(size_t)15) : 0) +
                                  (size_t)warp * WARP_BYTES;
     uint16_t* const vlist = reinterpret_cast<uint16_t*>(wbase);
     uint16_t* const hlist = vlist + WCHUNK;
     float* const srow = reinterpret_cast<float*>(hlist + WCHUNK);
-    const int F = (int)ph.num_faces;
+    // TABLE: gradients of `tfaces` faces starting at f_begin: the whole mesh, or (per_image) the faces of image
+    // blockIdx.y of a batch of equal-size meshes, whose chunks this grid row of CTAs shares; other faces -> global atomics
+    const int F = tfaces;
+    const int64_t f_begin = (TABLE && per_image) ? (int64_t)blockIdx.y * tfaces : 0;
     float* const t_fv = table;
     float* const t_fn = table + F * 9;
     float* const t_fc = table + F * 18;
@@ -242,10 +245,14 @@ __global__ void __launch_bounds__(NT) phong_bwd_kernel(const pert_phong ph, cons
     int64_t cached_b0 = -1;
     const V3 zero = mk(0.f, 0.f, 0.f);
     const int64_t w0 = (int64_t)blockIdx.x * NWARP + warp, wstride = (int64_t)gridDim.x * NWARP;
+    const int64_t e_first = (TABLE && per_image) ? (int64_t)blockIdx.y * HWK : 0;
+    const int64_t e_last = (TABLE && per_image) ? e_first + HWK : E;
+    const int64_t my_chunks = (TABLE && per_image) ? (HWK + WCHUNK - 1) / WCHUNK : nchunks;
 #pragma unroll 1
-    for (int64_t c = w0; c < nchunks; c += wstride) {
-        const int64_t e_base = c * WCHUNK;
-        const int Ec = (int)min((int64_t)WCHUNK, E - e_base);
+    for (int64_t c = w0; c < my_chunks; c += wstride) {
+        const int64_t e_base = e_first + c * WCHUNK;
+        const int Ec = (int)min((int64_t)WCHUNK, e_last - e_base);
+        const int vec_ok = ((uintptr_t)(ph.pix_to_face + e_base) & 15) == 0;
         const int64_t b0 = ph.light_rows > 1 ? e_base / HWK : 0;
         if (b0 != cached_b0 && !unlit) {
             __syncwarp();
@@ -294,6 +301,8 @@ __global__ void __launch_bounds__(NT) phong_bwd_kernel(const pert_phong ph, cons
         for (int i = lane; i < nh; i += 32) {
             const int64_t e = e_base + hlist[i];
             const int face = (int)__ldg(ph.pix_to_face + e);
+            const int64_t fl = face - f_begin;
+            const bool tab = TABLE && fl >= 0 && fl < F;
             const V3 gc = ld3(grad_colors + e * 3);
             const V3 b = ld3(ph.bary + e * 3);
             const V3 t = texel_of(ph, e, face, b);
@@ -318,7 +327,7 @@ __global__ void __launch_bounds__(NT) phong_bwd_kernel(const pert_phong ph, cons
             }
             if (grad_texels) {
                 if (vert_tex) {
-                    float* dst = TABLE ? t_fc + face * 9 : grad_texels + (int64_t)face * 9;
+                    float* dst = tab ? t_fc + fl * 9 : grad_texels + (int64_t)face * 9;
                     const float bw3[3] = {b.x, b.y, b.z};
 #pragma unroll
                     for (int i2 = 0; i2 < 3; ++i2) {
@@ -327,7 +336,7 @@ __global__ void __launch_bounds__(NT) phong_bwd_kernel(const pert_phong ph, cons
                         atomicAdd(dst + 3 * i2 + 2, bw3[i2] * gt.z);
                     }
                 } else if (face_tex) {
-                    float* dst = TABLE ? t_fc + face * 3 : grad_texels + (int64_t)face * 3;
+                    float* dst = tab ? t_fc + fl * 3 : grad_texels + (int64_t)face * 3;
                     atomicAdd(dst, gt.x);
                     atomicAdd(dst + 1, gt.y);
                     atomicAdd(dst + 2, gt.z);
@@ -357,7 +366,7 @@ __global__ void __launch_bounds__(NT) phong_bwd_kernel(const pert_phong ph, cons
                                           gb.z + dot(g_p, v2) + dot(g_nraw, n2)));
             const float bw[3] = {b.x, b.y, b.z};
             if (grad_fv) {
-                float* dst = TABLE ? t_fv + face * 9 : grad_fv + (int64_t)face * 9;
+                float* dst = tab ? t_fv + fl * 9 : grad_fv + (int64_t)face * 9;
 #pragma unroll
                 for (int i2 = 0; i2 < 3; ++i2) {
                     atomicAdd(dst + 3 * i2, bw[i2] * g_p.x);
@@ -366,7 +375,7 @@ __global__ void __launch_bounds__(NT) phong_bwd_kernel(const pert_phong ph, cons
                 }
             }
             if (grad_fn) {
-                float* dst = TABLE ? t_fn + face * 9 : grad_fn + (int64_t)face * 9;
+                float* dst = tab ? t_fn + fl * 9 : grad_fn + (int64_t)face * 9;
 #pragma unroll
                 for (int i2 = 0; i2 < 3; ++i2) {
                     atomicAdd(dst + 3 * i2, bw[i2] * g_nraw.x);
@@ -380,12 +389,12 @@ __global__ void __launch_bounds__(NT) phong_bwd_kernel(const pert_phong ph, cons
     if (TABLE) {
         __syncthreads();
         for (int i = threadIdx.x; i < F * 9; i += NT) {
-            if (grad_fv && t_fv[i] != 0.0f) atomicAdd(grad_fv + i, t_fv[i]);
-            if (grad_fn && t_fn[i] != 0.0f) atomicAdd(grad_fn + i, t_fn[i]);
+            if (grad_fv && t_fv[i] != 0.0f) atomicAdd(grad_fv + f_begin * 9 + i, t_fv[i]);
+            if (grad_fn && t_fn[i] != 0.0f) atomicAdd(grad_fn + f_begin * 9 + i, t_fn[i]);
         }
         if (face_tex && grad_texels)
             for (int i = threadIdx.x; i < F * TF; i += NT)
-                if (t_fc[i] != 0.0f) atomicAdd(grad_texels + i, t_fc[i]);
+                if (t_fc[i] != 0.0f) atomicAdd(grad_texels + f_begin * TF + i, t_fc[i]);
     }
 }
 
@@ -406,15 +415,22 @@ int launch_phong_fwd(const pert_phong& ph, float* colors, cudaStream_t st) {
 
 template <bool TABLE, int NT>
 static int launch_bwd_t(const pert_phong& ph, const float* grad_colors, float* grad_texels, float* grad_bary, float* grad_fv,
-                        float* grad_fn, int64_t E, int64_t nchunks, int ctas_per_sm, cudaStream_t st) {
-    const size_t table = TABLE ? (((size_t)ph.num_faces * (18 + tex_floats(ph)) * 4 + 15) & ~(size_t)15) : 0;
+                        float* grad_fn, int64_t E, int64_t nchunks, int ctas_per_sm, int tfaces, bool per_image, cudaStream_t st) {
+    const size_t table = TABLE ? (((size_t)tfaces * (18 + tex_floats(ph)) * 4 + 15) & ~(size_t)15) : 0;
     const size_t smem = table + (size_t)(NT / 32) * (2 * WCHUNK * 2 + 2 * PERT_PHONG_STRIDE * 4);
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(phong_bwd_kernel<TABLE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    phong_bwd_kernel<TABLE, NT><<<phong_grid(nchunks, ctas_per_sm, NT / 32), NT, smem, st>>>(
-        ph, grad_colors, grad_texels, grad_bary, grad_fv, grad_fn, E, nchunks, vec_ok_of(ph));
+    dim3 grid(phong_grid(nchunks, ctas_per_sm, NT / 32));
+    if (per_image) {  // one grid row of CTAs per image, about one CTA per SM in total
+        const int64_t n_img = ph.P / ph.HW, img_chunks = (ph.HW * ph.K + WCHUNK - 1) / WCHUNK;
+        int64_t ctas = (148 * (int64_t)ctas_per_sm + n_img - 1) / n_img;
+        const int64_t most = (img_chunks + NT / 32 - 1) / (NT / 32);
+        grid = dim3((unsigned)(ctas < most ? ctas : most), (unsigned)n_img);
+    }
+    phong_bwd_kernel<TABLE, NT><<<grid, NT, smem, st>>>(ph, grad_colors, grad_texels, grad_bary, grad_fv, grad_fn, E, nchunks,
+                                                       tfaces, per_image ? 1 : 0);
     return (int)cudaGetLastError();
 }
 
@@ -422,15 +438,20 @@ int launch_phong_bwd(const pert_phong& ph, const float* grad_colors, float* grad
                      float* grad_fn, cudaStream_t st) {
     const int64_t E = ph.P * ph.K, nchunks = (E + WCHUNK - 1) / WCHUNK;
     const bool scatter = grad_fv || grad_fn || (tex_floats(ph) && grad_texels);
-    const size_t table_bytes = (size_t)ph.num_faces * (18 + tex_floats(ph)) * 4;
+    const size_t per_face = (size_t)(18 + tex_floats(ph)) * 4;
     // Small meshes: every entry's 18 atomic adds would land on the same few thousand L2 addresses (measured at
     // 1280 faces: 210 us of a 360 us pass); accumulate them in a per-SM shared-memory table instead and flush it
-    // once.  Large meshes spread the atomics over enough addresses (100k faces: 58 us).
-    if (scatter && table_bytes <= 16 * 1024)  // tiny table: keep the occupancy of the small CTAs
-        return launch_bwd_t<true, PT>(ph, grad_colors, grad_texels, grad_bary, grad_fv, grad_fn, E, nchunks, 4, st);
-    if (scatter && table_bytes <= TABLE_MAX_BYTES)
-        return launch_bwd_t<true, PT_TABLE>(ph, grad_colors, grad_texels, grad_bary, grad_fv, grad_fn, E, nchunks, 1, st);
-    return launch_bwd_t<false, PT>(ph, grad_colors, grad_texels, grad_bary, grad_fv, grad_fn, E, nchunks, 5, st);
+    // once.  Large meshes spread the atomics over enough addresses (100k faces: 58 us).  A batch of N equal-size
+    // meshes (N poses of one topology: faces_per_mesh) gets one table per image.
+    const int64_t n_img = ph.P / ph.HW;
+    const bool batch = ph.faces_per_mesh > 0 && n_img > 1 && ph.faces_per_mesh * n_img == ph.num_faces && n_img <= 65535 &&
+                       ph.HW * ph.K >= 4 * (int64_t)(PT_TABLE / 32) * WCHUNK;
+    const int64_t tf = batch ? ph.faces_per_mesh : ph.num_faces;
+    if (scatter && tf * per_face <= 16 * 1024 && !batch)  // tiny table: keep the occupancy of the small CTAs
+        return launch_bwd_t<true, PT>(ph, grad_colors, grad_texels, grad_bary, grad_fv, grad_fn, E, nchunks, 4, (int)tf, false, st);
+    if (scatter && tf * per_face <= (size_t)TABLE_MAX_BYTES)
+        return launch_bwd_t<true, PT_TABLE>(ph, grad_colors, grad_texels, grad_bary, grad_fv, grad_fn, E, nchunks, 1, (int)tf, batch, st);
+    return launch_bwd_t<false, PT>(ph, grad_colors, grad_texels, grad_bary, grad_fv, grad_fn, E, nchunks, 5, 0, false, st);
 }
 
 }  // namespace pert

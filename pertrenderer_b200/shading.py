@@ -62,7 +62,8 @@ def pack_lighting(lights, materials, cameras, N, device):
     return table
 
 
-def _phong_struct(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting, flags, vert_colors=None):
+def _phong_struct(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting, flags, vert_colors=None,
+                  faces_per_mesh=0):
     N, H, W, K = pix_to_face.shape
     ph = PertPhong()
     ph.P, ph.HW, ph.K = N * H * W, H * W, K
@@ -70,6 +71,7 @@ def _phong_struct(pix_to_face, bary, face_verts, face_normals, texels, face_colo
     table = face_verts if face_verts is not None else (face_colors if face_colors is not None else vert_colors)
     ph.num_faces = table.shape[0]
     ph.flags = flags
+    ph.faces_per_mesh = int(faces_per_mesh)
     ph.pix_to_face, ph.bary = pix_to_face.data_ptr(), bary.data_ptr()
     ph.face_verts = None if face_verts is None else face_verts.data_ptr()
     ph.face_normals = None if face_normals is None else face_normals.data_ptr()
@@ -101,7 +103,7 @@ def phong_forward(pix_to_face, bary, face_verts, face_normals, texels, face_colo
 
 def phong_backward(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting, grad_colors,
                    need_texels=True, need_bary=True, need_verts=True, need_normals=True, sparse=False, vert_colors=None,
-                   unlit=False):
+                   unlit=False, faces_per_mesh=0):
     """Launch pert_phong_bwd.  Returns (grad_texels | grad_face_colors, grad_bary, grad_face_verts,
     grad_face_normals), ``None`` where not requested.  Every entry of the dense outputs is defined (they
     flow on to the caller's own tensors): with ``sparse`` the kernel skips the padded entries, whose
@@ -122,7 +124,7 @@ def phong_backward(pix_to_face, bary, face_verts, face_normals, texels, face_col
         g_fv = torch.zeros_like(face_verts) if (need_verts and not unlit) else None
         g_fn = torch.zeros_like(face_normals) if (need_normals and not unlit) else None
         ph = _phong_struct(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting,
-                           (PHONG_SPARSE if sparse else 0) | (PHONG_UNLIT if unlit else 0), vert_colors)
+                           (PHONG_SPARSE if sparse else 0) | (PHONG_UNLIT if unlit else 0), vert_colors, faces_per_mesh)
         rc = lib.pert_phong_bwd(ph, ptr(grad_colors), ptr(g_tex), ptr(g_bary), ptr(g_fv), ptr(g_fn), stream_ptr(dev))
     check(rc, "pert_phong_bwd")
     return g_tex, g_bary, g_fv, g_fn
@@ -133,7 +135,7 @@ class _PhongShade(Function):
     ``tex_mode``: "texels" (N,H,W,K,3), "face" (F,3) or "vert" (F,3,3)."""
 
     @staticmethod
-    def forward(ctx, face_verts, face_normals, texels, bary, pix_to_face, lighting, tex_mode, sparse, unlit):
+    def forward(ctx, face_verts, face_normals, texels, bary, pix_to_face, lighting, tex_mode, sparse, unlit, faces_per_mesh=0):
         fv = None if unlit else _f32c(face_verts.detach())
         fn = None if unlit else _f32c(face_normals.detach())
         tx, bc = _f32c(texels.detach()), _f32c(bary.detach())
@@ -142,7 +144,7 @@ class _PhongShade(Function):
                    vert_colors=tx if tex_mode == "vert" else None)
         colors = phong_forward(p2f, bc, fv, fn, lighting=lighting, sparse=sparse, unlit=unlit, **src)
         ctx.save_for_backward(*[t for t in (fv, fn, tx, bc, p2f, lighting) if t is not None])
-        ctx.tex_mode, ctx.sparse, ctx.unlit = tex_mode, sparse, unlit
+        ctx.tex_mode, ctx.sparse, ctx.unlit, ctx.faces_per_mesh = tex_mode, sparse, unlit, faces_per_mesh
         return colors
 
     @staticmethod
@@ -157,8 +159,9 @@ class _PhongShade(Function):
                    vert_colors=tx if ctx.tex_mode == "vert" else None)
         g_tex, g_bary, g_fv, g_fn = phong_backward(
             p2f, bc, fv, fn, lighting=lighting, grad_colors=grad_colors, need_texels=need[2], need_bary=need[3],
-            need_verts=need[0], need_normals=need[1], sparse=ctx.sparse, unlit=ctx.unlit, **src)
-        return g_fv, g_fn, g_tex, g_bary, None, None, None, None, None
+            need_verts=need[0], need_normals=need[1], sparse=ctx.sparse, unlit=ctx.unlit,
+            faces_per_mesh=ctx.faces_per_mesh, **src)
+        return g_fv, g_fn, g_tex, g_bary, None, None, None, None, None, None
 
 
 def _texel_source(texels):
@@ -209,5 +212,8 @@ def phong_shading(meshes, fragments, lights, cameras, materials, texels, sparse:
     faces_normals = vertex_normals[faces]
     lighting = pack_lighting(lights, materials, cameras, N, device)
     tex, mode = _texel_source(texels)
+    # a batch of poses of one topology (TriMeshes.extend / update_padded): image n only sees faces [n F, (n+1) F)
+    n_mesh = len(meshes) if hasattr(meshes, "faces_packed_single") else 1
+    fpm = faces.shape[0] // n_mesh if (n_mesh > 1 and n_mesh == N) else 0
     return _PhongShade.apply(faces_verts, faces_normals, tex, fragments.bary_coords, pix_to_face, lighting,
-                             mode, bool(sparse), False)
+                             mode, bool(sparse), False, fpm)

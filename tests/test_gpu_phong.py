@@ -93,8 +93,10 @@ def test_phong_kernels_match_oracle(cfg):
     assert (col_c.detach().cpu() - col_o.detach()).abs().max() <= 2e-6
     assert rel_err(col_c.detach().cpu(), col_o.detach()) <= RTOL
     assert rel_err(t_c.grad.cpu(), t_o.grad) <= RTOL
-    assert rel_err(fr_c.bary_coords.grad.cpu(), fr_o.bary_coords.grad) <= RTOL
-    assert rel_err(v_c.grad.cpu(), v_o.grad) <= 2 * RTOL  # thousands of atomic adds per vertex, order not fixed
+    # the vertex normals come from torch's index_add on the GPU (summation order not fixed, last-bit differences):
+    # a specular entry with alpha^(shininess-1) amplification moves by 5e-5 relative between runs (300 repetitions)
+    assert rel_err(fr_c.bary_coords.grad.cpu(), fr_o.bary_coords.grad) <= 5 * RTOL
+    assert rel_err(v_c.grad.cpu(), v_o.grad) <= 5 * RTOL  # and thousands of atomic adds per vertex, order not fixed
     mask = fr.pix_to_face >= 0
     assert (fr_c.bary_coords.grad.cpu()[~mask] == 0).all()
 
@@ -248,6 +250,44 @@ def test_vertex_colour_textures_match_oracle(n_faces):
     (img * gi.to(DEV)).sum().backward()
     assert (img.detach().cpu() - image_o).abs().max() <= 3e-6
     assert rel_err(vc_c3.grad.cpu(), vc_o3.grad) <= 2 * RTOL
+
+
+def test_phong_batch_of_poses_uses_per_image_tables_and_matches_oracle():
+    """N poses of one topology (TriMeshes.extend / update_padded): image n sees the packed faces [n F, (n+1) F); backward
+    keeps one shared-memory gradient table per image (faces_per_mesh hint).  Same gradients as the oracle, and as the
+    kernels without the hint."""
+    import pertrenderer_b200 as pb
+    from pertrenderer_b200 import shading
+    N, H, W, K, F_ = 3, 64, 64, 24, 320
+    fr, verts, faces, lights, mats, cams, face_colors, _ = _scene(N, H, W, K, F_, per_batch=True, seed=21, kind="realistic")
+    gen = torch.Generator().manual_seed(5)
+    poses = verts[None] + 0.05 * torch.randn(N, verts.shape[0], 3, generator=gen)
+    off = (torch.arange(N) * F_).view(N, 1, 1, 1)
+    p2f = torch.where(fr.pix_to_face >= 0, fr.pix_to_face + off, fr.pix_to_face)  # image n -> faces of pose n
+    fr = pb.Fragments(p2f, fr.zbuf, fr.bary_coords, fr.dists)
+    grad = torch.randn(N, H, W, K, 3, generator=gen)
+    grad[torch.rand(N, H, W, K, generator=gen) < 0.5] = 0.0
+    v_o = poses.clone().requires_grad_(True)
+    mesh_o = pb.TriMeshes(v_o, faces, face_colors=face_colors)
+    tex_o = mesh_o.sample_textures(fr).materialize(p2f)
+    (PO.phong_colors_from(mesh_o, fr, lights, cams, mats, tex_o) * grad).sum().backward()
+    v_c = poses.to(DEV).requires_grad_(True)
+    mesh_c = pb.TriMeshes(v_c, faces.to(DEV), face_colors=face_colors.to(DEV))
+    assert len(mesh_c) == N and mesh_c.faces_packed().shape[0] == N * F_
+    fr_c = _frag_to(fr, DEV)
+    col = pb.phong_shading(mesh_c, fr_c, _to(lights, DEV), _to(cams, DEV), _to(mats, DEV), mesh_c.sample_textures(fr_c))
+    (col * grad.to(DEV)).sum().backward()
+    assert rel_err(v_c.grad.cpu(), v_o.grad) <= 2 * RTOL
+    # the hint changes where the atomics land, not the result
+    fv = v_c.detach().reshape(-1, 3)[mesh_c.faces_packed()].contiguous()
+    fn = mesh_c.verts_normals_packed().detach()[mesh_c.faces_packed()].contiguous()
+    lighting = shading.pack_lighting(_to(lights, DEV), _to(mats, DEV), _to(cams, DEV), N, DEV)
+    fc = face_colors.to(DEV).repeat(N, 1)
+    args = (fr_c.pix_to_face, fr_c.bary_coords, fv, fn, None, fc, lighting, grad.to(DEV))
+    a = shading.phong_backward(*args, faces_per_mesh=F_)
+    b = shading.phong_backward(*args, faces_per_mesh=0)
+    for x, y in zip(a, b):
+        assert rel_err(x, y) <= 1e-5
 
 
 def test_phong_full_size_properties_config2():

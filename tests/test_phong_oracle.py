@@ -110,7 +110,7 @@ def test_shims_expose_the_pytorch3d_attributes():
 
 
 def test_phong_struct_layout_and_validation_without_gpu():
-    assert ctypes.sizeof(_cabi.PertPhong) == 104
+    assert ctypes.sizeof(_cabi.PertPhong) == 112
     assert _cabi.PertPhong.pix_to_face.offset == 40
     lib = _cabi.load()
     ph = _cabi.PertPhong()
