@@ -53,7 +53,7 @@
 extern "C" {
 #endif
 
-#define PERT_ABI_VERSION 10
+#define PERT_ABI_VERSION 11
 
 /* error codes */
 #define PERT_OK 0
@@ -284,7 +284,25 @@ typedef struct pert_raster {
                                   order in which the faces are visited; nearest first (e.g. sorted by centroid depth)
                                   makes the per-pixel sorted insertion append-only.  The result does not depend on it.
                                   NULL: index order.  Forward, K <= 64 only */
+    /* optional coarse bins (forward, K <= 64): one list of candidate faces per 32x8 pixel tile, built by two
+     * pert_rasterize_bin calls; every tile then walks its own list instead of all faces of its mesh.  For meshes of
+     * thousands of faces.  NULL: off */
+    const int32_t* bin_count;  /* (N * tiles) faces per tile, tiles = ceil(W/32) * ceil(H/8) */
+    const int64_t* bin_offset; /* (N * tiles) start of every tile's list in bin_faces: exclusive prefix sum of bin_count */
+    const int64_t* bin_faces;  /* (sum of bin_count) packed face indices */
 } pert_raster;
+
+/* number of bins of this problem: N * ceil(W/32) * ceil(H/8) */
+int64_t pert_rasterize_num_bins(const pert_raster* rs);
+/*
+ * Coarse binning, two calls around an exclusive prefix sum done by the caller:
+ *   1. bin_faces = NULL: counts the candidate faces of every tile into bin_count (int32, ZEROED BY THE CALLER)
+ *   2. bin_faces != NULL: with bin_offset = exclusive prefix sum of bin_count and bin_cursor (int32, ZEROED BY THE
+ *      CALLER), writes every tile's list; bin_faces holds sum(bin_count) entries.
+ * The rs->bin_* fields are ignored here.
+ */
+int pert_rasterize_bin(const pert_raster* rs, int32_t* bin_count, const int64_t* bin_offset, int32_t* bin_cursor,
+                       int64_t* bin_faces, void* stream);
 
 int pert_rasterize_fwd(const pert_raster* rs, int64_t* pix_to_face, float* zbuf, float* bary, float* dists, void* stream);
 /*

@@ -15,7 +15,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpertshade.so")
-ABI_VERSION = 10
+ABI_VERSION = 11
 
 # flags (include/pertshade.h)
 F_NO_SKIP = 1
@@ -28,7 +28,7 @@ PH_BWD_SAMPLE, PH_BWD_FINISH = 0x100, 0x200
 EXPORTS = [
     "pert_version", "pert_strerror", "pert_last_cuda_error", "pert_num_tiles", "pert_winner_bytes", "pert_blob_bytes",
     "pert_shade_fwd", "pert_shade_bwd", "pert_soft_shade_fwd", "pert_soft_shade_bwd", "pert_rast_fwd", "pert_rast_bwd", "pert_argmax_fwd",
-    "pert_argmax_bwd", "pert_noise_fill", "pert_phong_fwd", "pert_phong_bwd", "pert_rasterize_fwd", "pert_rasterize_bwd",
+    "pert_argmax_bwd", "pert_noise_fill", "pert_phong_fwd", "pert_phong_bwd", "pert_rasterize_fwd", "pert_rasterize_bwd", "pert_rasterize_num_bins", "pert_rasterize_bin",
 ]
 
 RAST_CULL_BACKFACES = 1  # PERT_RAST_CULL_BACKFACES
@@ -82,6 +82,7 @@ class PertRaster(C.Structure):
         ("blur_radius", C.c_float),
         ("num_faces", C.c_int64),
         ("face_verts", C.c_void_p), ("face_start", C.c_void_p), ("face_order", C.c_void_p),
+        ("bin_count", C.c_void_p), ("bin_offset", C.c_void_p), ("bin_faces", C.c_void_p),
     ]
 
 
@@ -144,6 +145,10 @@ def load():
         lib.pert_phong_bwd.argtypes = [C.POINTER(PertPhong)] + [vp] * 6
         lib.pert_rasterize_fwd.restype = C.c_int
         lib.pert_rasterize_fwd.argtypes = [C.POINTER(PertRaster)] + [vp] * 5
+        lib.pert_rasterize_num_bins.restype = i64
+        lib.pert_rasterize_num_bins.argtypes = [C.POINTER(PertRaster)]
+        lib.pert_rasterize_bin.restype = C.c_int
+        lib.pert_rasterize_bin.argtypes = [C.POINTER(PertRaster)] + [vp] * 5
         lib.pert_rasterize_bwd.restype = C.c_int
         lib.pert_rasterize_bwd.argtypes = [C.POINTER(PertRaster)] + [vp] * 6
         if lib.pert_version() != ABI_VERSION:

@@ -234,18 +234,26 @@ __global__ void __launch_bounds__(RT) rasterize_fwd_keys_kernel(const pert_raste
     const int64_t f_begin = __ldg(rs.face_start + n), f_end = __ldg(rs.face_start + n + 1);
     unsigned long long keys[KMAX];
     int cnt = 0;
+    // the faces this tile walks: its own bin (pert_rasterize_bin), or all faces of the mesh, in the caller's order
+    // (nearest first when face_order is given: the sorted insertion below then appends almost always).  The result
+    // does not depend on the order: keys are unique.
+    const int64_t* const fmap = rs.bin_faces ? rs.bin_faces : rs.face_order;
+    int64_t f_lo = f_begin, f_hi = f_end;
+    if (rs.bin_faces) {
+        const int64_t bin = ((int64_t)n * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+        f_lo = __ldg(rs.bin_offset + bin);
+        f_hi = f_lo + __ldg(rs.bin_count + bin);
+    }
 
 #pragma unroll 1
-    for (int64_t fc = f_begin; fc < f_end; fc += RT) {
-        // faces are visited in the caller's order (nearest first when face_order is given: the sorted insertion
-        // below then appends almost always; the result does not depend on the order, keys are unique)
+    for (int64_t fc = f_lo; fc < f_hi; fc += RT) {
         const int64_t fpos = fc + threadIdx.x;
         int64_t f = fpos;
         bool keep = false;
         float v[9];
         float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (fpos < f_end) {
-            if (rs.face_order) f = __ldg(rs.face_order + fpos);
+        if (fpos < f_hi) {
+            if (fmap) f = __ldg(fmap + fpos);
 #pragma unroll
             for (int i = 0; i < 9; ++i) v[i] = __ldg(rs.face_verts + f * 9 + i);
             bb = make_float4(fminf(fminf(v[0], v[3]), v[6]) - r, fmaxf(fmaxf(v[0], v[3]), v[6]) + r,
@@ -344,6 +352,56 @@ __global__ void __launch_bounds__(RT) rasterize_fwd_keys_kernel(const pert_raste
             for (int j = 3 * c + lane; j < 3 * K; j += 32) bary[r0 * 3 + j] = -1.0f;
         }
     }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// coarse binning for large meshes: which faces can touch which 32x8 pixel tile
+// ---------------------------------------------------------------------------------------------------------
+// One thread per face: the tiles overlapped by its bounding box grown by sqrt(blur_radius) (conservative by a pixel).
+// FILL = false counts (atomics into bin_count, zeroed by the caller); FILL = true appends the face to every such
+// tile's list at bin_offset[bin] + cursor++ (bin_cursor zeroed by the caller).  The order inside a list is arbitrary;
+// the packed-key K-buffer makes the fragments independent of it.
+template <bool FILL>
+__global__ void __launch_bounds__(256) rasterize_bin_kernel(const pert_raster rs, int32_t* __restrict__ bin_count,
+                                                            const int64_t* __restrict__ bin_offset, int32_t* __restrict__ bin_cursor,
+                                                            int64_t* __restrict__ bin_faces) {
+    const int64_t f = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    if (f >= rs.num_faces) return;
+    // image of this face: last n with face_start[n] <= f
+    int lo = 0, hi = (int)rs.N;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(rs.face_start + mid) <= f) lo = mid; else hi = mid;
+    }
+    const int n = lo;
+    if (f < __ldg(rs.face_start + n) || f >= __ldg(rs.face_start + n + 1)) return;
+    float v[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) v[i] = __ldg(rs.face_verts + f * 9 + i);
+    const float r = sqrtf(rs.blur_radius);
+    const float xmin = fminf(fminf(v[0], v[3]), v[6]) - r, xmax = fmaxf(fmaxf(v[0], v[3]), v[6]) + r;
+    const float ymin = fminf(fminf(v[1], v[4]), v[7]) - r, ymax = fmaxf(fmaxf(v[1], v[4]), v[7]) + r;
+    const float zmax = fmaxf(fmaxf(v[2], v[5]), v[8]);
+    const float area = edge(P2{v[0], v[1]}, P2{v[3], v[4]}, P2{v[6], v[7]});
+    if (zmax < 0.0f || (area <= kEps && area >= -kEps) || ((rs.flags & PERT_RAST_CULL_BACKFACES) && area < 0.0f)) return;
+    const int H = rs.H, W = rs.W;
+    // pixel index i (from the -X / -Y side) whose centre is x: x = -range + (2 i + 1) range / S
+    const float rx = W > H ? (float)W / (float)H : 1.0f, ry = H > W ? (float)H / (float)W : 1.0f;
+    const int ix0 = (int)floorf(((xmin + rx) * (float)W / rx - 1.0f) * 0.5f) - 1, ix1 = (int)ceilf(((xmax + rx) * (float)W / rx - 1.0f) * 0.5f) + 1;
+    const int iy0 = (int)floorf(((ymin + ry) * (float)H / ry - 1.0f) * 0.5f) - 1, iy1 = (int)ceilf(((ymax + ry) * (float)H / ry - 1.0f) * 0.5f) + 1;
+    if (ix1 < 0 || iy1 < 0 || ix0 > W - 1 || iy0 > H - 1) return;
+    // image column = W-1-i, row = H-1-i
+    const int cx0 = W - 1 - min(ix1, W - 1), cx1 = W - 1 - max(ix0, 0), cy0 = H - 1 - min(iy1, H - 1), cy1 = H - 1 - max(iy0, 0);
+    const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
+    for (int ty = cy0 / TH; ty <= cy1 / TH; ++ty)
+        for (int tx = cx0 / TW; tx <= cx1 / TW; ++tx) {
+            const int64_t bin = ((int64_t)n * tiles_y + ty) * tiles_x + tx;
+            if (FILL)
+                bin_faces[__ldg(bin_offset + bin) + atomicAdd(bin_cursor + bin, 1)] = f;
+            else
+                atomicAdd(bin_count + bin, 1);
+        }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -467,6 +525,16 @@ __global__ void __launch_bounds__(NT) rasterize_bwd_kernel(const pert_raster rs,
 }
 
 }  // namespace
+
+int launch_rasterize_bin(const pert_raster& rs, int32_t* bin_count, const int64_t* bin_offset, int32_t* bin_cursor,
+                         int64_t* bin_faces, cudaStream_t st) {
+    const unsigned grid = (unsigned)((rs.num_faces + 255) / 256);
+    if (bin_faces)
+        rasterize_bin_kernel<true><<<grid, 256, 0, st>>>(rs, bin_count, bin_offset, bin_cursor, bin_faces);
+    else
+        rasterize_bin_kernel<false><<<grid, 256, 0, st>>>(rs, bin_count, bin_offset, bin_cursor, bin_faces);
+    return (int)cudaGetLastError();
+}
 
 int launch_rasterize_fwd(const pert_raster& rs, int64_t* pix_to_face, float* zbuf, float* bary, float* dists, cudaStream_t st) {
     const dim3 grid((unsigned)((rs.W + TW - 1) / TW), (unsigned)((rs.H + TH - 1) / TH), (unsigned)rs.N);

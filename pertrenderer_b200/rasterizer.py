@@ -23,6 +23,9 @@ from ._cabi import RAST_CULL_BACKFACES, PertRaster, check, ptr, require_cuda, st
 from .structures import DepthCameras, Fragments
 
 
+BIN_MIN_FACES = 8192  # faces per mesh from which the forward builds coarse bins (measured: 5 k faces are faster without)
+
+
 @dataclass
 class RasterizationSettings:
     """pytorch3d.renderer.mesh.rasterizer.RasterizationSettings (same field names and defaults).  ``bin_size`` /
@@ -64,15 +67,31 @@ class _Rasterize(Function):
             zbuf = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
             bary = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev)
             dists = torch.empty((N, H, W, K), dtype=torch.float32, device=dev)
-            # visit the faces of every mesh nearest first (centroid depth): the per-pixel sorted insertion of the kernel
-            # then appends instead of shifting; any order gives the same fragments
-            order = None
-            if K <= 64 and fv.shape[0] > 1:
+            rs = _raster_struct(fv, fs, N, H, W, K, blur_radius, cull_backfaces)
+            keep = []
+            if K <= 64 and fv.shape[0] >= BIN_MIN_FACES * N:
+                # large meshes: coarse bins, one candidate list per 32x8 pixel tile (two kernel passes around a prefix
+                # sum; the total length of the lists is read back to size the buffer: the one host sync of this path)
+                nb = int(lib.pert_rasterize_num_bins(rs))
+                count = torch.zeros((nb,), dtype=torch.int32, device=dev)
+                check(lib.pert_rasterize_bin(rs, ptr(count), None, None, None, stream_ptr(dev)), "pert_rasterize_bin")
+                ends = torch.cumsum(count, 0, dtype=torch.int64)
+                offset = (ends - count).contiguous()
+                lists = torch.empty((max(int(ends[-1].item()), 1),), dtype=torch.int64, device=dev)
+                cursor = torch.zeros((nb,), dtype=torch.int32, device=dev)
+                check(lib.pert_rasterize_bin(rs, ptr(count), ptr(offset), ptr(cursor), ptr(lists), stream_ptr(dev)), "pert_rasterize_bin")
+                rs.bin_count, rs.bin_offset, rs.bin_faces = count.data_ptr(), offset.data_ptr(), lists.data_ptr()
+                keep = [count, offset, lists]
+            elif K <= 64 and fv.shape[0] > 1:
+                # visit the faces of every mesh nearest first (centroid depth): the per-pixel sorted insertion of the
+                # kernel then appends instead of shifting; any order gives the same fragments
                 zc = fv[:, :, 2].sum(dim=1)
                 mesh_of = torch.bucketize(torch.arange(fv.shape[0], device=dev), fs[1:], right=True)
                 order = torch.argsort(zc + 4.0 * (zc.abs().max() + 1.0) * mesh_of.to(zc.dtype), stable=True).contiguous()
-            rs = _raster_struct(fv, fs, N, H, W, K, blur_radius, cull_backfaces, order)
+                rs.face_order = order.data_ptr()
+                keep = [order]
             rc = lib.pert_rasterize_fwd(rs, ptr(p2f), ptr(zbuf), ptr(bary), ptr(dists), stream_ptr(dev))
+            del keep
         check(rc, "pert_rasterize_fwd")
         ctx.save_for_backward(fv, fs, p2f)
         ctx.cfg = (N, H, W, K, blur_radius, cull_backfaces)

@@ -73,6 +73,29 @@ def test_rasterize_forward_matches_oracle(cfg):
     assert (valid[..., 1:] <= valid[..., :-1]).all()
 
 
+def test_coarse_bins_give_the_same_fragments(monkeypatch):
+    """Meshes of thousands of faces go through per-tile candidate lists (pert_rasterize_bin); the fragments are those of
+    the walk over all faces, and of the oracle."""
+    import pertrenderer_b200 as pb
+    from pertrenderer_b200 import rasterizer
+    fv, start = _faces_ndc(5120, 2, seed=1)
+    H, W, K, blur = 40, 72, 8, 2e-3
+    fs = torch.tensor(start, device=DEV)
+    monkeypatch.setattr(rasterizer, "BIN_MIN_FACES", 1024)
+    binned = pb.rasterize_meshes(fv.to(DEV), fs, (H, W), blur, K)
+    monkeypatch.setattr(rasterizer, "BIN_MIN_FACES", 10 ** 9)
+    plain = pb.rasterize_meshes(fv.to(DEV), fs, (H, W), blur, K)
+    for a, b in zip(binned, plain):
+        assert torch.equal(a, b)
+    _same_fragments(binned, RO.rasterize(fv, start, H, W, K, blur), fv, blur)
+    # gradients flow through the binned forward as well
+    fvg = fv.to(DEV).requires_grad_(True)
+    monkeypatch.setattr(rasterizer, "BIN_MIN_FACES", 1024)
+    out = pb.rasterize_meshes(fvg, fs, (H, W), blur, K)
+    (out[1].sum() + out[3].sum()).backward()
+    assert torch.isfinite(fvg.grad).all() and fvg.grad.abs().sum() > 0
+
+
 def test_rasterize_backward_matches_oracle_autograd():
     import pertrenderer_b200 as pb
     H = W = 28

@@ -100,7 +100,7 @@ def test_camera_shims_match_the_oracle_restatement():
 
 
 def test_raster_struct_layout_and_validation_without_gpu():
-    assert ctypes.sizeof(_cabi.PertRaster) == 64
+    assert ctypes.sizeof(_cabi.PertRaster) == 88
     assert _cabi.PertRaster.face_verts.offset == 40
     lib = _cabi.load()
     rs = _cabi.PertRaster()
