@@ -264,3 +264,30 @@ def test_pose_optimisation_example_and_readme_snippet_run(monkeypatch, capsys):
     ns = {}
     exec(snippet, ns)
     assert ns["image"].shape == (1, 256, 256, 4) and torch.isfinite(ns["verts"].grad).all() and ns["verts"].grad.abs().sum() > 0
+
+
+def test_integration_md_raster_stub_runs():
+    """The rasteriser ctypes stub of INTEGRATION.md section 2c is executable as written and reproduces rasterize_meshes."""
+    import os
+    import re
+    import pertrenderer_b200 as pb
+    from conftest import ROOT
+    from pertrenderer_b200 import _cabi
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    blocks = re.findall(r"```python\n(.*?)```", text, flags=re.S)
+    base = [b for b in blocks if "class PerturbedShade" in b][0].replace('"libpertshade.so"', repr(_cabi.LIB_PATH))
+    stub = [b for b in blocks if "class Rasterize(" in b][0]
+    ns = {}
+    exec(base, ns)
+    exec(stub, ns)
+    fv, start = _faces_ndc(80, 2, seed=2)
+    fs = torch.tensor(start, device=DEV)
+    a_in, b_in = fv.to(DEV).requires_grad_(True), fv.to(DEV).requires_grad_(True)
+    a = ns["Rasterize"].apply(a_in, fs, 24, 3e-3, 6)
+    b = pb.rasterize_meshes(b_in, fs, 24, 3e-3, 6)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    g = torch.randn_like(a[1])
+    (a[1] * g).sum().backward()
+    (b[1] * g).sum().backward()
+    assert rel_err(a_in.grad, b_in.grad) <= 1e-5
