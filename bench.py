@@ -67,6 +67,8 @@ def parse_args():
     ap.add_argument("--nb-samples", type=int, default=64)
     ap.add_argument("--no-also", action="store_true", help="skip the secondary fragment set")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-renderer-legs", action="store_true",
+                    help="skip the Phong / rasteriser / renderer legs of `also` (tools/bench_configs.sh: the large configs)")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
@@ -569,17 +571,20 @@ def run_b200_arm(args):
         ps = device_timed(args, args.fragments, dev, max(3, args.steps // 2), 3, world, rank, flags=_cabi.F_PER_SAMPLE_NOISE)
         fc = device_timed(args, args.fragments, dev, max(3, args.steps // 2), 3, world, rank, face=True)
         sf = device_timed(args, args.fragments, dev, max(3, args.steps // 2), 3, world, rank, soft=True)
-        phg = phong_timed(args, args.fragments, dev, max(3, args.steps // 2), 3, rank)
-        rz = device_timed(args, "rasterised", dev, max(3, args.steps // 4), 3, world, rank)
-        rnd = renderer_timed(args, dev, max(3, args.steps // 4), 3, rank)
-        also = {"random_phong_shader": phg,
-                "renderer": rnd,
-                "fragments_rasterised": {"fragments": "rasterised",
-                                         "note": "fragments of an actual rasterisation (pert_rasterize_fwd) of the 1280-face "
-                                                 "icosphere at the same shapes instead of the SURVEY 8d synthetic sets: "
-                                                 "dozens of faces per covered pixel inside the blur band",
-                                         "value": rz["value"], "unit": UNIT, "ms_per_step": rz["ms_per_step"],
-                                         "roofline": rz["roofline"]},
+        extra = {}
+        if not args.no_renderer_legs:
+            phg = phong_timed(args, args.fragments, dev, max(3, args.steps // 2), 3, rank)
+            rz = device_timed(args, "rasterised", dev, max(3, args.steps // 4), 3, world, rank)
+            rnd = renderer_timed(args, dev, max(3, args.steps // 4), 3, rank)
+            extra = {"random_phong_shader": phg,
+                     "renderer": rnd,
+                     "fragments_rasterised": {"fragments": "rasterised",
+                                              "note": "fragments of an actual rasterisation (pert_rasterize_fwd) of the 1280-face "
+                                                      "icosphere at the same shapes instead of the SURVEY 8d synthetic sets: "
+                                                      "dozens of faces per covered pixel inside the blur band",
+                                              "value": rz["value"], "unit": UNIT, "ms_per_step": rz["ms_per_step"],
+                                              "roofline": rz["roofline"]}}
+        also = {**extra,
                 "softras_pair": {"fragments": args.fragments,
                                  "note": "SoftRast + SoftAgg (the shaders' DEFAULT operators, deterministic) through the "
                                          "fused soft kernels; same algorithmic bytes; 'units' counts nb_samples like the "

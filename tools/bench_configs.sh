@@ -1,6 +1,6 @@
 #!/bin/bash
 # The five BASELINE configs on one GPU (per-GPU share for the sharded ones); one JSON line each.
-run() { echo "== $1"; shift; python bench.py --no-e2e --no-cpu-baseline --steps 5 --warmup 3 "$@" 2>gpurun_out/cfg.err | python -c "
+run() { echo "== $1"; shift; python bench.py --no-e2e --no-cpu-baseline --no-renderer-legs --steps 5 --warmup 3 "$@" 2>gpurun_out/cfg.err | python -c "
 import json,sys
 d=json.loads(sys.stdin.readlines()[-1]); r=d['roofline']
 print('value %.4g units/s  ms/step %.4f  fwd %.4f ms (%.3f)  bwd %.4f ms (%.3f)  fwd+bwd frac %.3f' % (d['value'], d['ms_per_step'], r['fwd']['ms'], r['fwd']['frac'], r['bwd']['ms'], r['bwd']['frac'], r['fwd_bwd_frac']))
