@@ -70,6 +70,8 @@ def random_rotation(gen, device):
 def make_renderer(noise, cameras, lights, sigma, gamma, nb_samples, imsize, device, K=50):
     pairs = {
         "gaussian": lambda: (pb.GaussianRast(nb_samples=nb_samples, sigma=sigma), pb.GaussianAgg(nb_samples=nb_samples, gamma=gamma, alpha=1.0)),
+        "gaussian_wovr": lambda: (pb.GaussianRast_wovr(nb_samples=nb_samples, sigma=sigma),
+                                  pb.GaussianAgg_wovr(nb_samples=nb_samples, gamma=gamma, alpha=1.0)),
         "cauchy": lambda: (pb.ArctanRast(sigma=sigma), pb.CauchyAgg(nb_samples=nb_samples, gamma=gamma, alpha=1.0)),
         "softras": lambda: (pb.SoftRast(sigma=sigma), pb.SoftAgg(gamma=gamma, alpha=1.0)),
         "hard": lambda: (pb.HardRast(), pb.HardAgg()),
@@ -120,7 +122,7 @@ def optimize_pose(mesh, verts, renderer, target_rgb, w_init, niter, lr, adapt, a
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--noise", nargs="+", default=["softras", "gaussian"], choices=["gaussian", "cauchy", "softras"])
+    ap.add_argument("--noise", nargs="+", default=["softras", "gaussian"], choices=["gaussian", "gaussian_wovr", "cauchy", "softras"])
     ap.add_argument("--trials", type=int, default=10)
     ap.add_argument("--imsize", type=int, default=128)
     ap.add_argument("--init", type=float, default=30.0, help="initial perturbation in degrees (eval.py pert_init_intensity)")

@@ -83,6 +83,10 @@ extern "C" {
 /* stand-alone operators only: standard Cauchy noise instead of Gaussian (ArctanRast smoothrast.py:162-173,
  * CauchyAgg smoothagg.py:230-250): noise tan(pi(u-1/2)) clamped to +-1e7, score 2n/(1+n^2) in backward */
 #define PERT_F_CAUCHY 8u
+/* stand-alone operators only, Gaussian noise: the estimators WITHOUT the control variates, the paper's ablation
+ * (randomHeaviside_wovr smoothrast.py:61-108: sum_s h_s U_s instead of sum_s (h_s - h0) U_s;
+ *  randomArgmax_wovr smoothagg.py:75-141: c_s = <g, onehot(a_s)> instead of <g, onehot(a_s) - onehot(a_0)>) */
+#define PERT_F_NO_VR 0x400u
 /* phases of the fused kernels; 0 means "all".  Used for noise-sample sharding where collectives sit
  * between the phases. */
 #define PERT_PH_RAST 0x10u  /* fwd: draw coverage samples -> counts, rsum */

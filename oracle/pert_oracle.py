@@ -66,15 +66,17 @@ def random_heaviside_fwd(x, U, sigma):
     return prob, h, h0
 
 
-def random_heaviside_bwd(grad_l, h, h0, U, sigma):
-    """randomras/smoothrast.py:40-59 (gaussian branch).
+def random_heaviside_bwd(grad_l, h, h0, U, sigma, control_variate=True):
+    """randomras/smoothrast.py:40-59 (gaussian branch); ``control_variate=False``: randomHeaviside_wovr.backward
+    (smoothrast.py:90-108), the same estimator with ``h`` in place of ``h - h0`` (:95).
 
     grad_x = grad_l * mean_s[(h - h0) * U / sigma]  (:46,53,56).
     grad_sigma = sum(grad_x): the (U^2-1) expression of :47 is computed and then overwritten
     at :57-58, so the value that reaches sigma.grad is the plain sum of grad_x."""
     sig = torch.as_tensor(sigma, dtype=F32)
     S = U.shape[0]
-    score = ((h - h0.unsqueeze(0)) * U / sig).sum(dim=0) / S
+    hh = h - h0.unsqueeze(0) if control_variate else h
+    score = (hh * U / sig).sum(dim=0) / S
     grad_x = score * grad_l
     grad_sigma = grad_x.sum()
     return grad_x, grad_sigma
@@ -119,8 +121,9 @@ def random_argmax_fwd(zeta, V, gamma):
     return weights, a_s, a_0
 
 
-def random_argmax_bwd(grad_l, a_s, a_0, V, gamma):
-    """randomras/smoothagg.py:45-73 (gaussian branch).
+def random_argmax_bwd(grad_l, a_s, a_0, V, gamma, control_variate=True):
+    """randomras/smoothagg.py:45-73 (gaussian branch); ``control_variate=False``: randomArgmax_wovr.backward
+    (smoothagg.py:112-141, gaussian branch :118-123), where c_s = <grad_l, onehot(a_s)> without the a_0 term.
 
     c_s = <grad_l, onehot(a_s) - onehot(a_0)>                      (:51)
     grad_zeta_j = mean_s c_s * V_sj / gamma, for ALL j             (:52,71)
@@ -131,7 +134,7 @@ def random_argmax_bwd(grad_l, a_s, a_0, V, gamma):
     gl_s = grad_l.unsqueeze(0).expand(S, *grad_l.shape)
     g_sel = torch.gather(gl_s, -1, a_s.unsqueeze(-1)).squeeze(-1)  # (S,N,H,W)
     g_ref = torch.gather(grad_l, -1, a_0.unsqueeze(-1)).squeeze(-1)  # (N,H,W)
-    c = g_sel - g_ref.unsqueeze(0)
+    c = g_sel - g_ref.unsqueeze(0) if control_variate else g_sel
     grad_zeta = (c.unsqueeze(-1) * V / g).sum(dim=0) / S
     nsq = (V * V).sum(dim=-1)
     grad_gamma = (c * (nsq - 1.0) / g).sum(dim=(1, 2, 3)).sum() / S

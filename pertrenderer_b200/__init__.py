@@ -9,8 +9,9 @@ from .random_rasterizer import RandomPhongShader, RandomSimpleShader, SimpleShad
 from .rasterizer import (FoVPerspectiveCameras, MeshRasterizer, MeshRenderer, OpenGLPerspectiveCameras,
                          RasterizationSettings, look_at_view_transform, rasterize_meshes)
 from .shading import phong_shading, sample_lazy_textures
-from .smoothagg import CauchyAgg, GaussianAgg, HardAgg, SoftAgg, randomArgmax
-from .smoothrast import AffineRast, ArctanRast, GaussianRast, HardRast, SoftRast, randomHeaviside
+from .smoothagg import CauchyAgg, GaussianAgg, GaussianAgg_wovr, HardAgg, SoftAgg, randomArgmax, randomArgmax_wovr
+from .smoothrast import (AffineRast, ArctanRast, GaussianRast, GaussianRast_wovr, HardRast, SoftRast, randomHeaviside,
+                         randomHeaviside_wovr)
 from .structures import (BlendParams, DepthCameras, DirectionalLights, FaceColorMeshes, FaceTexels, Fragments, Materials,
                          PointLights, TexelMeshes, TriMeshes, VertexTexels, ViewCameras, synthetic_bary, synthetic_fragments,
                          synthetic_mesh)
@@ -20,7 +21,7 @@ __all__ = [
     "RandomPhongShader", "RandomSimpleShader", "SimpleShader", "phong_shading", "PointLights", "DirectionalLights",
     "MeshRasterizer", "MeshRenderer", "RasterizationSettings", "FoVPerspectiveCameras", "OpenGLPerspectiveCameras",
     "look_at_view_transform", "rasterize_meshes", "Materials", "ViewCameras", "TriMeshes", "VertexTexels", "sample_lazy_textures", "synthetic_mesh", "synthetic_bary", "smooth_rgb_blend", "GaussianAgg", "SoftAgg", "CauchyAgg", "HardAgg",
-    "randomArgmax", "GaussianRast", "ArctanRast", "AffineRast", "HardRast",
+    "randomArgmax", "GaussianRast", "GaussianRast_wovr", "GaussianAgg_wovr", "randomHeaviside_wovr", "randomArgmax_wovr", "ArctanRast", "AffineRast", "HardRast",
     "SoftRast", "randomHeaviside", "BlendParams", "DepthCameras", "Fragments", "TexelMeshes",
     "synthetic_fragments", "explicit_noise", "kernel_flags", "FaceColorMeshes", "FaceTexels",
 ]

@@ -22,6 +22,7 @@ F_NO_SKIP = 1
 F_SKIP_DEAD_NOISE = 2
 F_PER_SAMPLE_NOISE = 4
 F_CAUCHY = 8
+F_NO_VR = 0x400
 PH_RAST, PH_AGG, PH_BLEND = 0x10, 0x20, 0x40
 PH_BWD_SAMPLE, PH_BWD_FINISH = 0x100, 0x200
 

@@ -54,7 +54,8 @@ __global__ void __launch_bounds__(NT) rast_fwd_kernel(const float* x, int64_t n,
     if (tid == 0) nlist = 0;
     __syncthreads();
     const float thr = NoiseT::kBounded ? sigma * kNoiseAbsMax * 1.0001f : CUDART_INF_F;
-    const bool no_skip = flags & PERT_F_NO_SKIP;
+    const bool no_vr = flags & PERT_F_NO_VR;  // without the control variate every sample with h = 1 contributes
+    const bool no_skip = (flags & PERT_F_NO_SKIP) || no_vr;
     const int s_loc = s_end - s_begin;
     for (int i = tid; i < RAST_TILE; i += NT) {
         bool need = false;
@@ -99,7 +100,11 @@ __global__ void __launch_bounds__(NT) rast_fwd_kernel(const float* x, int64_t n,
                         const bool h = __fadd_rn(v, __fmul_rn(sigma, nz[t])) >= 0.f;
                         if (s >= s_begin && s < s_end) {
                             c += h ? 1 : 0;
-                            if (h != h0) r += h ? noise_score<SCORE>(nz[t]) : -noise_score<SCORE>(nz[t]);
+                            if (no_vr) {
+                                if (h) r += noise_score<SCORE>(nz[t]);
+                            } else if (h != h0) {
+                                r += h ? noise_score<SCORE>(nz[t]) : -noise_score<SCORE>(nz[t]);
+                            }
                         }
                     }
                 }
@@ -238,7 +243,7 @@ __global__ void __launch_bounds__(NT) argmax_bwd_kernel(const float* grad_l, con
         }
         warp_argmax(best, a0);
         __syncwarp();
-        const float g0 = gl[a0];
+        const float g0 = (flags & PERT_F_NO_VR) ? 0.0f : gl[a0];  // no control variate: c_s = g[a_s]
         const bool skip_dead = flags & PERT_F_SKIP_DEAD_NOISE;
         const bool no_skip = flags & PERT_F_NO_SKIP;
         const int nj = (K1 + 31) / 32;

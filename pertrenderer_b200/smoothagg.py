@@ -34,6 +34,10 @@ class randomArgmax(Function):
 
     @staticmethod
     def forward(ctx, z, nb_samples=1, noise_intensity=1e-1, noise_type="gaussian", fixed_noise=False):
+        return randomArgmax._forward(ctx, z, nb_samples, noise_intensity, noise_type, fixed_noise, 0)
+
+    @staticmethod
+    def _forward(ctx, z, nb_samples, noise_intensity, noise_type, fixed_noise, extra_flags):
         if noise_type not in _SUPPORTED:
             # reference: gumbel / cauchy / uniform exist forward-only or as baselines
             # (smoothagg.py:22-32, 64-69); outside the B200 path
@@ -45,7 +49,7 @@ class randomArgmax(Function):
         gamma = _scalar(noise_intensity)
         _, noise = ops.current_explicit_noise()
         seed = 0 if noise is not None else ops.draw_seed()
-        flags = ops.current_flags() | (ops.F_CAUCHY if noise_type == "cauchy" else 0)
+        flags = ops.current_flags() | (ops.F_CAUCHY if noise_type == "cauchy" else extra_flags)
         weights, winners = ops.argmax_forward(z, int(nb_samples), gamma, seed=seed, noise=noise, flags=flags)
         ctx.save_for_backward(z.detach(), winners)
         ctx.cfg = (int(nb_samples), gamma, seed, noise, flags)
@@ -61,6 +65,16 @@ class randomArgmax(Function):
         if ctx.gamma_like is not None and ctx.needs_input_grad[2]:
             grad_gamma = gg.to(device=ctx.gamma_like.device, dtype=ctx.gamma_like.dtype).reshape(ctx.gamma_like.shape)
         return (gz if ctx.needs_input_grad[0] else None), None, grad_gamma, None, None
+
+
+class randomArgmax_wovr(randomArgmax):
+    """smoothagg.py:75-141: the perturbed argmax WITHOUT variance reduction in backward: ``c_s = <g, onehot(a_s)>``
+    instead of ``<g, onehot(a_s) - onehot(a_0)>`` (Gaussian noise; the reference's Cauchy branch of this class keeps
+    the control variate, smoothagg.py:123-128, i.e. it is the plain operator)."""
+
+    @staticmethod
+    def forward(ctx, z, nb_samples=1, noise_intensity=1e-1, noise_type="gaussian", fixed_noise=False):
+        return randomArgmax._forward(ctx, z, nb_samples, noise_intensity, noise_type, fixed_noise, ops.F_NO_VR)
 
 
 class log_corrected(Function):
@@ -151,6 +165,18 @@ class GaussianAgg(SmoothAggBase):
     def aggregate(self, zbuf, zfar, znear, prob_map, mask):
         z_map = self._logits(zbuf, zfar, znear, prob_map, mask)
         return randomArgmax.apply(z_map, self.nb_samples, self.gamma, "gaussian", self.fixed_noise)
+
+
+class GaussianAgg_wovr(SmoothAggBase):
+    """smoothagg.py:207-228: ``GaussianAgg`` on ``randomArgmax_wovr`` (no variance reduction in backward)."""
+
+    def __init__(self, nb_samples=16, gamma=4e-2, alpha=1., eps=1e-10, fixed_noise=False):
+        super().__init__(gamma, alpha, eps, nb_samples)
+        self.fixed_noise = fixed_noise
+
+    def aggregate(self, zbuf, zfar, znear, prob_map, mask):
+        z_map = self._logits(zbuf, zfar, znear, prob_map, mask)
+        return randomArgmax_wovr.apply(z_map, self.nb_samples, self.gamma, "gaussian", self.fixed_noise)
 
 
 class CauchyAgg(SmoothAggBase):

@@ -35,6 +35,10 @@ class randomHeaviside(Function):
 
     @staticmethod
     def forward(ctx, distances, nb_samples=1, noise_intensity=1e-1, noise_type="gaussian"):
+        return randomHeaviside._forward(ctx, distances, nb_samples, noise_intensity, noise_type, 0)
+
+    @staticmethod
+    def _forward(ctx, distances, nb_samples, noise_intensity, noise_type, extra_flags):
         if noise_type not in _SUPPORTED:
             # the reference prints "noise type not implemented" and then dies on a NameError
             # (smoothrast.py:30-32); the logistic variant has no backward in the reference either
@@ -44,7 +48,7 @@ class randomHeaviside(Function):
         sigma = _scalar(noise_intensity)
         noise, _ = ops.current_explicit_noise()
         seed = 0 if noise is not None else ops.draw_seed()
-        flags = ops.current_flags() | (ops.F_CAUCHY if noise_type == "cauchy" else 0)
+        flags = ops.current_flags() | (ops.F_CAUCHY if noise_type == "cauchy" else extra_flags)
         prob, rsum = ops.rast_forward(distances, int(nb_samples), sigma, seed=seed, noise=noise, flags=flags)
         ctx.save_for_backward(rsum)
         ctx.nb_samples, ctx.sigma = int(nb_samples), sigma
@@ -60,6 +64,16 @@ class randomHeaviside(Function):
         if ctx.sigma_like is not None and ctx.needs_input_grad[2]:
             gs = grad_sigma.to(device=ctx.sigma_like.device, dtype=ctx.sigma_like.dtype).reshape(ctx.sigma_like.shape)
         return grad_dist, None, gs, None
+
+
+class randomHeaviside_wovr(randomHeaviside):
+    """smoothrast.py:61-108: the same perturbed Heaviside WITHOUT the control variate in backward
+    (``mean_s h_s U_s / sigma`` instead of ``mean_s (h_s - h0) U_s / sigma``): the paper's variance ablation
+    (eval.py:152-154 "gaussian_wovr").  Gaussian noise; with Cauchy noise it is the plain operator."""
+
+    @staticmethod
+    def forward(ctx, distances, nb_samples=1, noise_intensity=1e-1, noise_type="gaussian"):
+        return randomHeaviside._forward(ctx, distances, nb_samples, noise_intensity, noise_type, ops.F_NO_VR)
 
 
 class SmoothRastBase(Module):
@@ -99,6 +113,17 @@ class GaussianRast(SmoothRastBase):
 
     def rasterize(self, dists):
         return randomHeaviside.apply(-dists, self.nb_samples, self.sigma)
+
+
+class GaussianRast_wovr(SmoothRastBase):
+    """smoothrast.py:149-160: ``GaussianRast`` on ``randomHeaviside_wovr``."""
+
+    def __init__(self, nb_samples=16, sigma=2e-4):
+        super().__init__(sigma)
+        self.nb_samples = nb_samples
+
+    def rasterize(self, dists):
+        return randomHeaviside_wovr.apply(-dists, self.nb_samples, self.sigma)
 
 
 class ArctanRast(SmoothRastBase):

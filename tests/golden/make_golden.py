@@ -306,11 +306,47 @@ def run_cauchy_ops_case(sr, sa, name, *, shape, S, sigma, gamma, seed):
     print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
 
 
+def run_wovr_ops_case(sr, sa, name, *, shape, S, sigma, gamma, seed):
+    """The estimators without control variates (randomHeaviside_wovr: smoothrast.py:61-108, randomArgmax_wovr:
+    smoothagg.py:75-141, Gaussian branches) with an arbitrary upstream gradient and recorded noise."""
+    gen = torch.Generator().manual_seed(seed)
+    N, H, W, K = shape
+    x = (torch.rand(shape, generator=gen) * 2 - 1) * 3 * sigma
+    x[..., -1] = 1.0  # a far-inside entry: without the control variate its score sum does not vanish
+    x[..., 0] = -1.0  # a far-outside one
+    x.requires_grad_(True)
+    sig = torch.tensor(sigma, requires_grad=True)
+    gl = torch.randn(shape, generator=gen)
+    torch.manual_seed(seed + 7)
+    with NoiseRecorder() as rec:
+        y = sr.randomHeaviside_wovr.apply(x, S, sig)
+    (y * gl).sum().backward()
+    U = rec.drawn[0]
+    z = torch.randn((N, H, W, K + 1), generator=gen) * 2 * gamma
+    z[..., 0] = float("-inf")
+    z.requires_grad_(True)
+    gam = torch.tensor(gamma, requires_grad=True)
+    gw = torch.randn((N, H, W, K + 1), generator=gen)
+    with NoiseRecorder() as rec:
+        w = sa.randomArgmax_wovr.apply(z, S, gam, "gaussian", False)
+    (w * gw).sum().backward()
+    V = rec.drawn[0]
+    out = dict(x=x.detach().numpy(), sigma=np.float32(sigma), S=np.int32(S), U=U.numpy(), grad_l=gl.numpy(),
+               prob=y.detach().numpy(), grad_x=x.grad.numpy(), grad_sigma=sig.grad.numpy(),
+               z=z.detach().numpy(), gamma=np.float32(gamma), V=V.numpy(), grad_w=gw.numpy(),
+               weights=w.detach().numpy(), grad_z=z.grad.numpy(), grad_gamma=gam.grad.numpy())
+    path = os.path.join(OUT, f"ops_{name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
 def main():
     torch.set_num_threads(1)  # reduction order independent of the host
     rr, sr, sa = load_reference()
     if "--soft-only" in sys.argv:  # leave the committed Gaussian goldens untouched
         return soft_cases(rr, sr, sa)
+    if "--wovr-only" in sys.argv:
+        return run_wovr_ops_case(sr, sa, "wovr", shape=(2, 3, 4, 6), S=12, sigma=1e-3, gamma=1e-2, seed=41)
     if "--cauchy-only" in sys.argv:
         return run_cauchy_ops_case(sr, sa, "cauchy", shape=(2, 3, 4, 6), S=12, sigma=1e-3, gamma=1e-2, seed=31)
     # 1: small, two batch elements with different depth planes, alpha != 1, non-white background
@@ -329,6 +365,7 @@ def main():
     run_ops_case(sr, sa, "small", shape=(2, 3, 4, 6), S=12, sigma=1e-3, gamma=1e-2, seed=11)
     soft_cases(rr, sr, sa)
     run_cauchy_ops_case(sr, sa, "cauchy", shape=(2, 3, 4, 6), S=12, sigma=1e-3, gamma=1e-2, seed=31)
+    run_wovr_ops_case(sr, sa, "wovr", shape=(2, 3, 4, 6), S=12, sigma=1e-3, gamma=1e-2, seed=41)
 
 
 def soft_cases(rr, sr, sa):

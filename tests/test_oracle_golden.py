@@ -67,6 +67,25 @@ def test_standalone_ops():
     assert abs(gg.item() - g["grad_gamma"]) <= 1e-5 * abs(g["grad_gamma"])
 
 
+def test_standalone_ops_without_control_variates():
+    """randomHeaviside_wovr / randomArgmax_wovr (smoothrast.py:61-108, smoothagg.py:75-141): the reference's own
+    outputs with recorded noise."""
+    g = load_golden("ops_wovr")
+    prob, h, h0 = O.random_heaviside_fwd(g["x"], g["U"], g["sigma"])
+    assert torch.equal(prob, g["prob"])
+    gx, gs = O.random_heaviside_bwd(g["grad_l"], h, h0, g["U"], g["sigma"], control_variate=False)
+    assert rel_err(gx, g["grad_x"]) <= 1e-6
+    assert abs(gs.item() - g["grad_sigma"]) <= 1e-5 * abs(g["grad_sigma"])
+    # the control variate matters: the far-inside entry has a non-zero score sum without it
+    gx_vr, _ = O.random_heaviside_bwd(g["grad_l"], h, h0, g["U"], g["sigma"])
+    assert (gx_vr[..., -1] == 0).all() and (gx[..., -1] != 0).any()
+    w, a_s, a_0 = O.random_argmax_fwd(g["z"], g["V"], g["gamma"])
+    assert torch.equal(w, g["weights"])
+    gz, gg = O.random_argmax_bwd(g["grad_w"], a_s, a_0, g["V"], g["gamma"], control_variate=False)
+    assert rel_err(gz, g["grad_z"]) <= 1e-6
+    assert abs(gg.item() - g["grad_gamma"]) <= 1e-5 * abs(g["grad_gamma"])
+
+
 def test_closed_forms_monte_carlo():
     """Appendix A.4 with many samples: E[p_hat] = Phi(x/sigma), E[(h-h0)U]/sigma = phi(x/sigma)/sigma,
     two-way argmax weight = Phi(dzeta / (gamma sqrt 2))."""
