@@ -87,6 +87,11 @@ extern "C" {
  * (randomHeaviside_wovr smoothrast.py:61-108: sum_s h_s U_s instead of sum_s (h_s - h0) U_s;
  *  randomArgmax_wovr smoothagg.py:75-141: c_s = <g, onehot(a_s)> instead of <g, onehot(a_s) - onehot(a_0)>) */
 #define PERT_F_NO_VR 0x400u
+/* pert_argmax_fwd only: uniform noise on [-1/2, 1/2) (UniformAgg, smoothagg.py:252-272) or standard Gumbel noise
+ * (randomArgmax "gumbel", smoothagg.py:22-24).  Forward only, as in the reference (no backward: smoothagg.py:64-67);
+ * pert_argmax_bwd returns PERT_E_UNSUPPORTED with either flag. */
+#define PERT_F_UNIFORM 0x800u
+#define PERT_F_GUMBEL 0x1000u
 /* phases of the fused kernels; 0 means "all".  Used for noise-sample sharding where collectives sit
  * between the phases. */
 #define PERT_PH_RAST 0x10u  /* fwd: draw coverage samples -> counts, rsum */
@@ -318,7 +323,7 @@ int pert_rasterize_bwd(const pert_raster* rs, const int64_t* pix_to_face, const 
                        const float* grad_dists, float* grad_face_verts, void* stream);
 
 /* Materialise the counter-based noise: out float (s_end-s_begin, P, slots), stage 0 = coverage
- * (slots = K), 1 = aggregation (slots = K1); stage | 2 = the Cauchy variant of that stage. */
+ * (slots = K), 1 = aggregation (slots = K1); stage | 2 = the Cauchy variant of that stage, | 4 uniform, | 8 Gumbel. */
 int pert_noise_fill(uint64_t seed, int32_t stage, int64_t P, int32_t slots, int32_t s_begin, int32_t s_end,
                     int64_t pixel_offset, float* out, void* stream);
 

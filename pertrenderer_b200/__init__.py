@@ -5,11 +5,11 @@ Drop-in for the hot path of quentinll/pertrenderer (``randomras``): the same pub
 (``include/pertshade.h``).  CUDA only: there is no CPU or PyTorch fallback on this path.
 """
 
-from .random_rasterizer import RandomPhongShader, RandomSimpleShader, SimpleShader, smooth_rgb_blend
+from .random_rasterizer import RandomPhongShader, RandomSimpleShader, SimpleShader, SoftSimpleShader, smooth_rgb_blend
 from .rasterizer import (FoVPerspectiveCameras, MeshRasterizer, MeshRenderer, OpenGLPerspectiveCameras,
                          RasterizationSettings, look_at_view_transform, rasterize_meshes)
 from .shading import phong_shading, sample_lazy_textures
-from .smoothagg import CauchyAgg, GaussianAgg, GaussianAgg_wovr, HardAgg, SoftAgg, randomArgmax, randomArgmax_wovr
+from .smoothagg import CauchyAgg, GaussianAgg, GaussianAgg_wovr, HardAgg, SoftAgg, UniformAgg, randomArgmax, randomArgmax_wovr
 from .smoothrast import (AffineRast, ArctanRast, GaussianRast, GaussianRast_wovr, HardRast, SoftRast, randomHeaviside,
                          randomHeaviside_wovr)
 from .structures import (BlendParams, DepthCameras, DirectionalLights, FaceColorMeshes, FaceTexels, Fragments, Materials,
@@ -18,7 +18,7 @@ from .structures import (BlendParams, DepthCameras, DirectionalLights, FaceColor
 from .ops import explicit_noise, kernel_flags
 
 __all__ = [
-    "RandomPhongShader", "RandomSimpleShader", "SimpleShader", "phong_shading", "PointLights", "DirectionalLights",
+    "RandomPhongShader", "RandomSimpleShader", "SimpleShader", "SoftSimpleShader", "UniformAgg", "phong_shading", "PointLights", "DirectionalLights",
     "MeshRasterizer", "MeshRenderer", "RasterizationSettings", "FoVPerspectiveCameras", "OpenGLPerspectiveCameras",
     "look_at_view_transform", "rasterize_meshes", "Materials", "ViewCameras", "TriMeshes", "VertexTexels", "sample_lazy_textures", "synthetic_mesh", "synthetic_bary", "smooth_rgb_blend", "GaussianAgg", "SoftAgg", "CauchyAgg", "HardAgg",
     "randomArgmax", "GaussianRast", "GaussianRast_wovr", "GaussianAgg_wovr", "randomHeaviside_wovr", "randomArgmax_wovr", "ArctanRast", "AffineRast", "HardRast",

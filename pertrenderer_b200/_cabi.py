@@ -23,6 +23,8 @@ F_SKIP_DEAD_NOISE = 2
 F_PER_SAMPLE_NOISE = 4
 F_CAUCHY = 8
 F_NO_VR = 0x400
+F_UNIFORM = 0x800
+F_GUMBEL = 0x1000
 PH_RAST, PH_AGG, PH_BLEND = 0x10, 0x20, 0x40
 PH_BWD_SAMPLE, PH_BWD_FINISH = 0x100, 0x200
 

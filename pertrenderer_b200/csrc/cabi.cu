@@ -354,6 +354,7 @@ extern "C" int pert_argmax_bwd(const float* grad_l, const float* z, const void* 
                                int32_t S, int32_t s_begin, int32_t s_end, float gamma, uint64_t seed,
                                int64_t pixel_offset, const float* noise, uint32_t flags, float* grad_z,
                                float* scalar_partials, float* grad_gamma, void* stream) {
+    if (flags & (PERT_F_UNIFORM | PERT_F_GUMBEL)) return PERT_E_UNSUPPORTED;  // forward-only noises (no backward in the reference)
     if (!grad_l || !z || !winners || !grad_z || !scalar_partials || !grad_gamma) return PERT_E_NULL;
     if (P <= 0 || K1 <= 0) return PERT_E_SHAPE;
     if (K1 > 1024 || S <= 0) return PERT_E_UNSUPPORTED;

@@ -362,6 +362,12 @@ int launch_argmax_fwd(const float* z, int64_t P, int K1, int S, int s_begin, int
     } else if (flags & PERT_F_CAUCHY) {
         PhiloxCauchy pn(seed, 1, pixel_offset);
         argmax_fwd_kernel<PhiloxCauchy><<<blocks, NT, smem, st>>>(z, P, K1, S, s_begin, s_end, gamma, flags, wb, pn, weights, winners);
+    } else if (flags & PERT_F_UNIFORM) {
+        PhiloxUniform pn(seed, 1, pixel_offset);
+        argmax_fwd_kernel<PhiloxUniform><<<blocks, NT, smem, st>>>(z, P, K1, S, s_begin, s_end, gamma, flags, wb, pn, weights, winners);
+    } else if (flags & PERT_F_GUMBEL) {
+        PhiloxGumbel pn(seed, 1, pixel_offset);
+        argmax_fwd_kernel<PhiloxGumbel><<<blocks, NT, smem, st>>>(z, P, K1, S, s_begin, s_end, gamma, flags, wb, pn, weights, winners);
     } else {
         PhiloxNoise pn(seed, 1, pixel_offset);
         argmax_fwd_kernel<PhiloxNoise><<<blocks, NT, smem, st>>>(z, P, K1, S, s_begin, s_end, gamma, flags, wb, pn, weights, winners);
@@ -396,7 +402,9 @@ int launch_noise_fill(uint64_t seed, int stage, int64_t P, int slots, int s_begi
     const int qn = ((s_end + 3) >> 2) - (s_begin >> 2);
     const int64_t total = (int64_t)qn * P * slots;
     const unsigned blocks = (unsigned)((total + 255) / 256);
-    if (stage & 2) noise_fill_kernel<PhiloxCauchy><<<blocks, 256, 0, st>>>(seed, stage & 1, P, slots, s_begin, s_end, pixel_offset, out);
+    if (stage & 4) noise_fill_kernel<PhiloxUniform><<<blocks, 256, 0, st>>>(seed, stage & 1, P, slots, s_begin, s_end, pixel_offset, out);
+    else if (stage & 8) noise_fill_kernel<PhiloxGumbel><<<blocks, 256, 0, st>>>(seed, stage & 1, P, slots, s_begin, s_end, pixel_offset, out);
+    else if (stage & 2) noise_fill_kernel<PhiloxCauchy><<<blocks, 256, 0, st>>>(seed, stage & 1, P, slots, s_begin, s_end, pixel_offset, out);
     else noise_fill_kernel<PhiloxNoise><<<blocks, 256, 0, st>>>(seed, stage & 1, P, slots, s_begin, s_end, pixel_offset, out);
     return (int)cudaGetLastError();
 }

@@ -118,6 +118,36 @@ struct PhiloxCauchy {
     static constexpr bool kBounded = false;
 };
 
+// Uniform noise on [-1/2, 1/2) (the reference's UniformAgg: torch.distributions.Uniform(-0.5, 0.5), smoothagg.py:28-30)
+// and standard Gumbel noise -log(-log u) (smoothagg.py:22-24) from the same counters.  Forward only: the reference has
+// no backward for either (smoothagg.py:64-67 prints "noise_type not implemented").  Not treated as bounded by the
+// kernels' skipping rules (those are written for the Gaussian bound).
+struct PhiloxUniform {
+    PhiloxNoise base;
+    __host__ __device__ __forceinline__ PhiloxUniform(uint64_t seed, int stage, int64_t pixel_off) : base(seed, stage, pixel_off) {}
+    __device__ __forceinline__ void get4(uint32_t q, uint32_t slot, int64_t pixel_local, float (&n)[4]) const {
+        uint32_t r[4];
+        base.words(q, slot, pixel_local, r);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) n[t] = mant12(r[t]) - 1.5f;
+    }
+    static constexpr bool kBounded = false;
+};
+struct PhiloxGumbel {
+    PhiloxNoise base;
+    __host__ __device__ __forceinline__ PhiloxGumbel(uint64_t seed, int stage, int64_t pixel_off) : base(seed, stage, pixel_off) {}
+    __device__ __forceinline__ void get4(uint32_t q, uint32_t slot, int64_t pixel_local, float (&n)[4]) const {
+        uint32_t r[4];
+        base.words(q, slot, pixel_local, r);
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            const float u = 2.0f - mant12(r[t]);  // (0, 1]
+            n[t] = -logf(fmaxf(-logf(u), 1e-30f));
+        }
+    }
+    static constexpr bool kBounded = false;
+};
+
 // score of the noise density used by the gradient estimators: -d/dn log p(n)
 //   Gaussian: n   (smoothrast.py:46, smoothagg.py:51-53)     Cauchy: 2n / (1 + n^2)   (smoothrast.py:49, smoothagg.py:58-59)
 template <int SCORE>

@@ -15,7 +15,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _cabi
-from ._cabi import (F_CAUCHY, F_NO_SKIP, F_NO_VR, F_PER_SAMPLE_NOISE, F_SKIP_DEAD_NOISE, PH_AGG, PH_BLEND, PH_BWD_FINISH, PH_BWD_SAMPLE, PH_RAST,
+from ._cabi import (F_CAUCHY, F_GUMBEL, F_NO_SKIP, F_NO_VR, F_UNIFORM, F_PER_SAMPLE_NOISE, F_SKIP_DEAD_NOISE, PH_AGG, PH_BLEND, PH_BWD_FINISH, PH_BWD_SAMPLE, PH_RAST,
                     PertProblem, check, ptr, require_cuda, stream_ptr)
 
 _tls = threading.local()

@@ -178,6 +178,25 @@ class SimpleShader(nn.Module):
         return torch.cat((rgb, covered[..., None].to(texels.dtype)), dim=-1)
 
 
+class SoftSimpleShader(nn.Module):
+    """random_rasterizer.py:205-215: texels blended by pytorch3d's ``softmax_rgb_blend`` with ``blend_params.sigma`` /
+    ``.gamma`` (znear = 1, zfar = 100).  That blend is the SoftRast + SoftAgg pair at alpha = 1 (same probability
+    sigmoid(-dists/sigma), same weights P exp((z_inv - z_max)/gamma) and background term exp((eps - z_max)/gamma), same
+    alpha channel), so it runs on the fused soft kernels; pytorch3d additionally clamps the background term to
+    >= 1e-10, a relative difference of at most 1e-10 in the image."""
+
+    def __init__(self, device="cpu", blend_params=None):
+        super().__init__()
+        self.blend_params = blend_params if blend_params is not None else BlendParams()
+
+    def forward(self, fragments, meshes, **kwargs) -> torch.Tensor:
+        blend_params = kwargs.get("blend_params", self.blend_params)
+        texels = meshes.sample_textures(fragments)
+        return smooth_rgb_blend(texels, fragments, SoftRast(sigma=float(blend_params.sigma)),
+                                SoftAgg(gamma=float(blend_params.gamma), alpha=1.0), blend_params,
+                                znear=kwargs.get("znear", 1.0), zfar=kwargs.get("zfar", 100.0))
+
+
 class RandomSimpleShader(nn.Module):
     """random_rasterizer.py:132-191: texels -> smooth_rgb_blend.  Same constructor, ``forward``,
     ``to``, ``get_smoothing``, ``get_nb_samples``, ``update_smoothing``, ``update_nb_samples``."""

@@ -15,7 +15,8 @@ from torch.nn import Module
 
 from . import ops
 
-_SUPPORTED = ("gaussian", "cauchy")
+_SUPPORTED = ("gaussian", "cauchy", "uniform", "gumbel")
+_FORWARD_ONLY = {"uniform": ops.F_UNIFORM, "gumbel": ops.F_GUMBEL}  # no backward in the reference (smoothagg.py:64-67)
 
 
 def _scalar(v) -> float:
@@ -49,7 +50,8 @@ class randomArgmax(Function):
         gamma = _scalar(noise_intensity)
         _, noise = ops.current_explicit_noise()
         seed = 0 if noise is not None else ops.draw_seed()
-        flags = ops.current_flags() | (ops.F_CAUCHY if noise_type == "cauchy" else extra_flags)
+        flags = ops.current_flags() | (ops.F_CAUCHY if noise_type == "cauchy" else
+                                       _FORWARD_ONLY.get(noise_type, extra_flags))
         weights, winners = ops.argmax_forward(z, int(nb_samples), gamma, seed=seed, noise=noise, flags=flags)
         ctx.save_for_backward(z.detach(), winners)
         ctx.cfg = (int(nb_samples), gamma, seed, noise, flags)
@@ -60,6 +62,9 @@ class randomArgmax(Function):
     def backward(ctx, grad_l):
         z, winners = ctx.saved_tensors
         S, gamma, seed, noise, flags = ctx.cfg
+        if flags & (ops.F_UNIFORM | ops.F_GUMBEL):
+            # the reference prints "noise_type not implemented" and dies on a None (smoothagg.py:64-71)
+            raise RuntimeError("randomArgmax: uniform / gumbel noise has no backward (forward-only in the reference too)")
         gz, gg = ops.argmax_backward(grad_l, z, winners, S, gamma, seed=seed, noise=noise, flags=flags)
         grad_gamma = None
         if ctx.gamma_like is not None and ctx.needs_input_grad[2]:
@@ -190,6 +195,19 @@ class CauchyAgg(SmoothAggBase):
     def aggregate(self, zbuf, zfar, znear, prob_map, mask):
         z_map = self._logits(zbuf, zfar, znear, prob_map, mask)
         return randomArgmax.apply(z_map, self.nb_samples, self.gamma, "cauchy", self.fixed_noise)
+
+
+class UniformAgg(SmoothAggBase):
+    """smoothagg.py:252-272: the same logits, ``randomArgmax`` with uniform noise on [-1/2, 1/2).  Forward only: the
+    reference has no backward for this noise (smoothagg.py:64-65)."""
+
+    def __init__(self, nb_samples=16, gamma=4e-2, alpha=1., eps=1e-10, fixed_noise=False):
+        super().__init__(gamma, alpha, eps, nb_samples)
+        self.fixed_noise = fixed_noise
+
+    def aggregate(self, zbuf, zfar, znear, prob_map, mask):
+        z_map = self._logits(zbuf, zfar, znear, prob_map, mask)
+        return randomArgmax.apply(z_map, self.nb_samples, self.gamma, "uniform", self.fixed_noise)
 
 
 class HardAgg:

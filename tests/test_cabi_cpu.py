@@ -120,7 +120,12 @@ def test_unsupported_noise_type_raises():
     with pytest.raises(ValueError, match="not implemented"):
         pb.randomHeaviside.apply(torch.zeros(1, 1, 1, 2), 4, torch.tensor(1e-3), "logistic")
     with pytest.raises(ValueError, match="not implemented"):
+        pb.randomArgmax.apply(torch.zeros(1, 1, 1, 2), 4, torch.tensor(1e-3), "logistic")
+    # gumbel / uniform exist forward-only (as in the reference): on CPU tensors they hit the CUDA-only guard
+    with pytest.raises(RuntimeError, match="CUDA"):
         pb.randomArgmax.apply(torch.zeros(1, 1, 1, 2), 4, torch.tensor(1e-3), "gumbel")
+    lib = _cabi.load()
+    assert lib.pert_argmax_bwd(None, None, None, 1, 2, 4, 0, 4, 1e-2, 0, 0, None, _cabi.F_UNIFORM, None, None, None, None) == -3
 
 
 def test_soft_operators_cpu():

@@ -743,3 +743,39 @@ def test_wovr_operators_match_reference_golden():
     img = pb.smooth_rgb_blend(col, fr, pb.GaussianRast_wovr(nb_samples=8, sigma=1e-3), pb.GaussianAgg_wovr(nb_samples=8, gamma=1e-2),
                               pb.BlendParams())
     assert img.shape == (1, 8, 8, 4) and torch.isfinite(img).all()
+
+
+def test_forward_only_noises_and_soft_simple_shader():
+    """UniformAgg (smoothagg.py:252-272) and the "gumbel" branch of randomArgmax (smoothagg.py:22-24): forward only, as
+    in the reference; SoftSimpleShader (random_rasterizer.py:205-215) on the fused soft kernels."""
+    import math
+    import pertrenderer_b200 as pb
+    from pertrenderer_b200 import ops
+    dev = "cuda"
+    u = ops.noise_fill(5, 1 | 4, (2, 32, 32, 7), 64, dev).flatten().double()
+    assert u.min() >= -0.5 and u.max() < 0.5 and abs(u.mean().item()) < 2e-3 and abs(u.var().item() - 1 / 12) < 2e-3
+    gmb = ops.noise_fill(5, 1 | 8, (2, 32, 32, 7), 64, dev).flatten().double()
+    assert abs(gmb.mean().item() - 0.5772) < 5e-3 and abs(gmb.var().item() - math.pi ** 2 / 6) < 2e-2
+    # the in-kernel stream equals the explicit-noise kernel fed the materialised stream
+    z = (torch.randn(2, 6, 5, 8, device=dev) * 0.05).requires_grad_(True)
+    for name, bit in (("uniform", 4), ("gumbel", 8)):
+        torch.manual_seed(11)
+        w = pb.randomArgmax.apply(z, 16, torch.tensor(0.05), name, False)
+        torch.manual_seed(11)
+        seed = ops.draw_seed()
+        V = ops.noise_fill(seed, 1 | bit, (2, 6, 5, 7), 16, dev)
+        with pb.explicit_noise(None, V):
+            w2 = pb.randomArgmax.apply(z.detach(), 16, torch.tensor(0.05), "gaussian", False)
+        assert torch.equal(w, w2) and torch.allclose(w.sum(-1), torch.ones_like(w.sum(-1)))
+        with pytest.raises(RuntimeError, match="no backward"):
+            w.sum().backward()
+    fr, col = pb.synthetic_fragments(2, 9, 7, 6, kind="dense", sigma=1e-3, device=dev)
+    agg = pb.UniformAgg(nb_samples=8, gamma=1e-2)
+    wts = agg.aggregate(fr.zbuf, 100.0, 1.0, torch.rand_like(fr.zbuf), fr.pix_to_face >= 0)
+    assert wts.shape == (2, 9, 7, 7) and torch.allclose(wts.sum(-1), torch.ones(2, 9, 7, device=dev))
+    # SoftSimpleShader = softmax_rgb_blend(blend_params.sigma, .gamma) = the SoftRas pair at alpha 1
+    blend = pb.BlendParams(sigma=2e-3, gamma=5e-2, background_color=(0.2, 0.3, 0.4))
+    img = pb.SoftSimpleShader(blend_params=blend)(fr, pb.TexelMeshes(col))
+    ref, _, _ = O.soft_shade_fwd_bwd(fr.pix_to_face.cpu(), fr.zbuf.cpu(), fr.dists.cpu(), col.cpu(), torch.tensor(blend.background_color),
+                                     1.0, 100.0, 2e-3, 5e-2, 1.0, 1e-10)
+    assert (img.cpu() - ref).abs().max() <= 2e-6
