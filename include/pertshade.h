@@ -53,7 +53,7 @@
 extern "C" {
 #endif
 
-#define PERT_ABI_VERSION 11
+#define PERT_ABI_VERSION 12
 
 /* error codes */
 #define PERT_OK 0
@@ -261,10 +261,12 @@ int pert_phong_fwd(const pert_phong* ph, float* colors, void* stream);
  *   grad_bary          (P,K,3)
  *   grad_face_verts    (F,3,3) and grad_face_normals (F,3,3): ZEROED BY THE CALLER, atomic adds (the scatter of
  *                      interpolate_face_attributes' backward; summation order is not fixed)
- * Lights, materials and camera centre receive no gradient (constants in experiments/eval.py:233-262).
+ *   grad_lighting      (light_rows, PERT_PHONG_STRIDE), ZEROED BY THE CALLER: gradient of the lighting table (columns
+ *                      0:16: light location / direction, the three colour products, shininess, camera centre), for
+ *                      callers that optimise lights or cameras (experiments/eval.py:411-470, 693-725); a second sparse pass
  */
 int pert_phong_bwd(const pert_phong* ph, const float* grad_colors, float* grad_texels, float* grad_bary,
-                   float* grad_face_verts, float* grad_face_normals, void* stream);
+                   float* grad_face_verts, float* grad_face_normals, float* grad_lighting, void* stream);
 
 /*
  * Fragment producer: K-deep rasterisation of packed triangle meshes with a blur radius, the Fragments

@@ -15,7 +15,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpertshade.so")
-ABI_VERSION = 11
+ABI_VERSION = 12
 
 # flags (include/pertshade.h)
 F_NO_SKIP = 1
@@ -145,7 +145,7 @@ def load():
         lib.pert_phong_fwd.restype = C.c_int
         lib.pert_phong_fwd.argtypes = [C.POINTER(PertPhong), vp, vp]
         lib.pert_phong_bwd.restype = C.c_int
-        lib.pert_phong_bwd.argtypes = [C.POINTER(PertPhong)] + [vp] * 6
+        lib.pert_phong_bwd.argtypes = [C.POINTER(PertPhong)] + [vp] * 7
         lib.pert_rasterize_fwd.restype = C.c_int
         lib.pert_rasterize_fwd.argtypes = [C.POINTER(PertRaster)] + [vp] * 5
         lib.pert_rasterize_num_bins.restype = i64

@@ -399,14 +399,19 @@ extern "C" int pert_phong_fwd(const pert_phong* ph, float* colors, void* stream)
 }
 
 extern "C" int pert_phong_bwd(const pert_phong* ph, const float* grad_colors, float* grad_texels, float* grad_bary,
-                              float* grad_face_verts, float* grad_face_normals, void* stream) {
+                              float* grad_face_verts, float* grad_face_normals, float* grad_lighting, void* stream) {
     if (int rc = check_phong(ph)) return rc;
     if (!grad_colors) return PERT_E_NULL;
     if (((uintptr_t)grad_colors & 3) || ((uintptr_t)grad_texels & 3) || ((uintptr_t)grad_bary & 3) ||
-        ((uintptr_t)grad_face_verts & 3) || ((uintptr_t)grad_face_normals & 3))
+        ((uintptr_t)grad_face_verts & 3) || ((uintptr_t)grad_face_normals & 3) || ((uintptr_t)grad_lighting & 3))
         return PERT_E_ALIGN;
-    return cuda_rc(launch_phong_bwd(*ph, grad_colors, grad_texels, grad_bary, grad_face_verts, grad_face_normals,
-                                    (cudaStream_t)stream));
+    if (grad_lighting && (ph->flags & PERT_PHONG_UNLIT)) return PERT_E_UNSUPPORTED;
+    if (grad_texels || grad_bary || grad_face_verts || grad_face_normals)
+        if (int rc = cuda_rc(launch_phong_bwd(*ph, grad_colors, grad_texels, grad_bary, grad_face_verts, grad_face_normals,
+                                              (cudaStream_t)stream)))
+            return rc;
+    if (grad_lighting) return cuda_rc(launch_phong_light_bwd(*ph, grad_colors, grad_lighting, (cudaStream_t)stream));
+    return PERT_OK;
 }
 
 static int check_raster(const pert_raster* rs) {

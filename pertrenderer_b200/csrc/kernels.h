@@ -62,6 +62,7 @@ int launch_argmax_bwd(const float* grad_l, const float* z, const void* winners, 
 int launch_phong_fwd(const pert_phong& ph, float* colors, cudaStream_t st);
 int launch_phong_bwd(const pert_phong& ph, const float* grad_colors, float* grad_texels, float* grad_bary, float* grad_fv,
                      float* grad_fn, cudaStream_t st);
+int launch_phong_light_bwd(const pert_phong& ph, const float* grad_colors, float* grad_lighting, cudaStream_t st);
 int launch_rasterize_bin(const pert_raster& rs, int32_t* bin_count, const int64_t* bin_offset, int32_t* bin_cursor,
                          int64_t* bin_faces, cudaStream_t st);
 int launch_rasterize_fwd(const pert_raster& rs, int64_t* pix_to_face, float* zbuf, float* bary, float* dists, cudaStream_t st);

@@ -398,6 +398,97 @@ __global__ void __launch_bounds__(NT) phong_bwd_kernel(const pert_phong ph, cons
     }
 }
 
+
+// Gradient of the lighting table (light location / direction, the three material x light colour products, shininess,
+// camera centre): a second sparse pass launched only when the caller asks for it (lights and cameras are constants in
+// the reference's pose optimisation, eval.py:233-262, but eval.py:411-470 and :693-725 optimise them).  Every lane
+// keeps the sixteen sums of its entries in registers and adds them to grad_lighting once (per row of the table).
+__global__ void __launch_bounds__(PT) phong_light_bwd_kernel(const pert_phong ph, const float* __restrict__ grad_colors,
+                                                             float* __restrict__ grad_lighting, int64_t E, int64_t nchunks) {
+    __shared__ __align__(16) uint16_t s_vlist[PW][WCHUNK];
+    __shared__ float s_row[PW][2 * PERT_PHONG_STRIDE];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint16_t* const vlist = s_vlist[warp];
+    float* const srow = s_row[warp];
+    const int64_t HWK = ph.HW * ph.K;
+    int64_t cached_b0 = -1, acc_row = -1;
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = 0.0f;
+    auto flush = [&]() {
+        if (acc_row < 0) return;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (acc[i] != 0.0f) atomicAdd(grad_lighting + acc_row * PERT_PHONG_STRIDE + i, acc[i]);
+            acc[i] = 0.0f;
+        }
+    };
+    const int64_t w0 = (int64_t)blockIdx.x * PW + warp, wstride = (int64_t)gridDim.x * PW;
+#pragma unroll 1
+    for (int64_t c = w0; c < nchunks; c += wstride) {
+        const int64_t e_base = c * WCHUNK;
+        const int Ec = (int)min((int64_t)WCHUNK, E - e_base);
+        const int vec_ok = ((uintptr_t)(ph.pix_to_face + e_base) & 15) == 0;
+        const int64_t b0 = ph.light_rows > 1 ? e_base / HWK : 0;
+        if (b0 != cached_b0) {
+            __syncwarp();
+            fill_rows(ph, b0, srow, lane);
+            cached_b0 = b0;
+        }
+        const RowCache rows{srow, b0, ph.lighting};
+        const int nv = scan_valid(ph.pix_to_face + e_base, Ec, vec_ok, vlist, WCHUNK);
+        __syncwarp();
+#pragma unroll 1
+        for (int i = lane; i < nv; i += 32) {
+            const int64_t e = e_base + vlist[i];
+            const V3 gc = ld3(grad_colors + e * 3);
+            if (gc.x == 0.0f && gc.y == 0.0f && gc.z == 0.0f) continue;
+            const int64_t face = __ldg(ph.pix_to_face + e);
+            const V3 b = ld3(ph.bary + e * 3);
+            const V3 t = texel_of(ph, e, face, b);
+            const float* fv = ph.face_verts + face * 9;
+            const float* fn = ph.face_normals + face * 9;
+            const V3 p = b.x * ld3(fv) + b.y * ld3(fv + 3) + b.z * ld3(fv + 6);
+            const V3 nr = b.x * ld3(fn) + b.y * ld3(fn + 3) + b.z * ld3(fn + 6);
+            const int64_t row = ph.light_rows > 1 ? e / HWK : 0;
+            const Row L = rows.get(row);
+            const Lit o = light_entry(L, p, nr);
+            if (row != acc_row) {
+                flush();
+                acc_row = row;
+            }
+            // colour = (amb + dif * ang) * t + spc * pw
+            const float g_ang = gc.x * L.dif.x * t.x + gc.y * L.dif.y * t.y + gc.z * L.dif.z * t.z;
+            const float g_pw = gc.x * L.spc.x + gc.y * L.spc.y + gc.z * L.spc.z;
+            const float g_vr = (o.alpha > 0.0f && L.sh != 0.0f) ? g_pw * L.sh * powf(o.alpha, L.sh - 1.0f) : 0.0f;
+            const V3 g_v = g_vr * o.r, g_r = g_vr * o.v;
+            const float g_cos = 2.0f * dot(g_r, o.n) + (o.cosd > 0.0f ? g_ang : 0.0f);
+            const V3 g_d = g_cos * o.n - g_r;
+            const V3 g_loc = normalize_bwd(o.d, o.dl, g_d);   // d_raw = loc - p (point) or loc (directional)
+            const V3 g_cam = normalize_bwd(o.v, o.vl, g_v);   // v_raw = cam - p
+            acc[0] += g_loc.x, acc[1] += g_loc.y, acc[2] += g_loc.z;
+            acc[3] += gc.x * t.x, acc[4] += gc.y * t.y, acc[5] += gc.z * t.z;
+            acc[6] += gc.x * t.x * o.ang, acc[7] += gc.y * t.y * o.ang, acc[8] += gc.z * t.z * o.ang;
+            acc[9] += gc.x * o.pw, acc[10] += gc.y * o.pw, acc[11] += gc.z * o.pw;
+            if (o.alpha > 0.0f) acc[12] += g_pw * o.pw * logf(o.alpha);  // d alpha^sh / d sh
+            acc[13] += g_cam.x, acc[14] += g_cam.y, acc[15] += g_cam.z;
+        }
+        __syncwarp();
+    }
+    // one add per warp when all its lanes hold sums of the same row (the usual case), else one per lane
+    const int64_t rr = (int64_t)warp_max_i((int)acc_row);  // rows fit 32 bits
+    const bool uniform = __all_sync(FULL, acc_row == rr || acc_row < 0);
+    if (uniform) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float v = warp_sum(acc_row >= 0 ? acc[i] : 0.0f);
+            if (lane == 0 && rr >= 0 && v != 0.0f) atomicAdd(grad_lighting + rr * PERT_PHONG_STRIDE + i, v);
+        }
+    } else {
+        flush();
+    }
+}
+
 unsigned phong_grid(int64_t nchunks, int ctas_per_sm, int warps_per_cta = PW) {
     const int64_t cap = 148 * (int64_t)ctas_per_sm, need = (nchunks + warps_per_cta - 1) / warps_per_cta;
     return (unsigned)(need < cap ? need : cap);
@@ -431,6 +522,12 @@ static int launch_bwd_t(const pert_phong& ph, const float* grad_colors, float* g
     }
     phong_bwd_kernel<TABLE, NT><<<grid, NT, smem, st>>>(ph, grad_colors, grad_texels, grad_bary, grad_fv, grad_fn, E, nchunks,
                                                        tfaces, per_image ? 1 : 0);
+    return (int)cudaGetLastError();
+}
+
+int launch_phong_light_bwd(const pert_phong& ph, const float* grad_colors, float* grad_lighting, cudaStream_t st) {
+    const int64_t E = ph.P * ph.K, nchunks = (E + WCHUNK - 1) / WCHUNK;
+    phong_light_bwd_kernel<<<phong_grid(nchunks, 4), PT, 0, st>>>(ph, grad_colors, grad_lighting, E, nchunks);
     return (int)cudaGetLastError();
 }
 

@@ -12,8 +12,9 @@ cameras and the shims of :mod:`pertrenderer_b200.structures` both work:
     cameras.get_camera_center() (N,3)
 
 Gradients flow to the mesh (vertex positions and vertex normals, through torch's own indexing
-``verts[faces]``), to the texels and to ``fragments.bary_coords``.  Lights, materials and the camera
-centre are constants here, as they are in experiments/eval.py:233-262.
+``verts[faces]``), to the texels and to ``fragments.bary_coords``; and, when they require grad, to the light
+location / direction, the light and material colours, the shininess and the camera centre (a second sparse
+pass, only then: experiments/eval.py:411-470 and :693-725 optimise lights and cameras).
 """
 
 from __future__ import annotations
@@ -34,7 +35,7 @@ def _f32c(t):
 
 def _rows(v, n_max, device, width=3):
     """A light / material attribute as float32 (rows, width) on ``device``, rows = 1 or N."""
-    t = torch.as_tensor(v, dtype=torch.float32, device=device).detach()
+    t = torch.as_tensor(v, dtype=torch.float32, device=device)  # differentiable when the caller's tensor requires grad
     if t.dim() == 0:
         t = t.reshape(1, 1).expand(1, width)
     t = t.reshape(-1, width) if width > 1 else t.reshape(-1, 1)
@@ -103,7 +104,7 @@ def phong_forward(pix_to_face, bary, face_verts, face_normals, texels, face_colo
 
 def phong_backward(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting, grad_colors,
                    need_texels=True, need_bary=True, need_verts=True, need_normals=True, sparse=False, vert_colors=None,
-                   unlit=False, faces_per_mesh=0):
+                   unlit=False, faces_per_mesh=0, need_lighting=False):
     """Launch pert_phong_bwd.  Returns (grad_texels | grad_face_colors, grad_bary, grad_face_verts,
     grad_face_normals), ``None`` where not requested.  Every entry of the dense outputs is defined (they
     flow on to the caller's own tensors): with ``sparse`` the kernel skips the padded entries, whose
@@ -123,10 +124,13 @@ def phong_backward(pix_to_face, bary, face_verts, face_normals, texels, face_col
         g_bary = alloc((N, H, W, K, 3), dtype=torch.float32, device=dev) if need_bary else None
         g_fv = torch.zeros_like(face_verts) if (need_verts and not unlit) else None
         g_fn = torch.zeros_like(face_normals) if (need_normals and not unlit) else None
+        g_light = torch.zeros_like(lighting) if (need_lighting and not unlit) else None
         ph = _phong_struct(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting,
                            (PHONG_SPARSE if sparse else 0) | (PHONG_UNLIT if unlit else 0), vert_colors, faces_per_mesh)
-        rc = lib.pert_phong_bwd(ph, ptr(grad_colors), ptr(g_tex), ptr(g_bary), ptr(g_fv), ptr(g_fn), stream_ptr(dev))
+        rc = lib.pert_phong_bwd(ph, ptr(grad_colors), ptr(g_tex), ptr(g_bary), ptr(g_fv), ptr(g_fn), ptr(g_light), stream_ptr(dev))
     check(rc, "pert_phong_bwd")
+    if need_lighting:
+        return g_tex, g_bary, g_fv, g_fn, g_light
     return g_tex, g_bary, g_fv, g_fn
 
 
@@ -142,6 +146,7 @@ class _PhongShade(Function):
         p2f = pix_to_face.contiguous()
         src = dict(texels=tx if tex_mode == "texels" else None, face_colors=tx if tex_mode == "face" else None,
                    vert_colors=tx if tex_mode == "vert" else None)
+        lighting = None if lighting is None else _f32c(lighting.detach())
         colors = phong_forward(p2f, bc, fv, fn, lighting=lighting, sparse=sparse, unlit=unlit, **src)
         ctx.save_for_backward(*[t for t in (fv, fn, tx, bc, p2f, lighting) if t is not None])
         ctx.tex_mode, ctx.sparse, ctx.unlit, ctx.faces_per_mesh = tex_mode, sparse, unlit, faces_per_mesh
@@ -157,11 +162,13 @@ class _PhongShade(Function):
         need = ctx.needs_input_grad
         src = dict(texels=tx if ctx.tex_mode == "texels" else None, face_colors=tx if ctx.tex_mode == "face" else None,
                    vert_colors=tx if ctx.tex_mode == "vert" else None)
-        g_tex, g_bary, g_fv, g_fn = phong_backward(
+        out = phong_backward(
             p2f, bc, fv, fn, lighting=lighting, grad_colors=grad_colors, need_texels=need[2], need_bary=need[3],
             need_verts=need[0], need_normals=need[1], sparse=ctx.sparse, unlit=ctx.unlit,
-            faces_per_mesh=ctx.faces_per_mesh, **src)
-        return g_fv, g_fn, g_tex, g_bary, None, None, None, None, None, None
+            faces_per_mesh=ctx.faces_per_mesh, need_lighting=bool(need[5]) and not ctx.unlit, **src)
+        g_tex, g_bary, g_fv, g_fn = out[:4]
+        g_light = out[4] if len(out) > 4 else None
+        return g_fv, g_fn, g_tex, g_bary, None, g_light, None, None, None, None
 
 
 def _texel_source(texels):

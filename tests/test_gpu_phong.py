@@ -290,6 +290,39 @@ def test_phong_batch_of_poses_uses_per_image_tables_and_matches_oracle():
         assert rel_err(x, y) <= 1e-5
 
 
+@pytest.mark.parametrize("light", ["point", "directional"])
+def test_gradients_reach_lights_materials_and_camera(light):
+    """eval.py:411-470 / :693-725 optimise the light position and the camera: the lighting table is a differentiable
+    input (second sparse pass of pert_phong_bwd), torch carries its gradient back to whichever tensor requires it."""
+    import pertrenderer_b200 as pb
+    N, H, W, K = 2, 12, 10, 6
+    fr, verts, faces, lights, mats, cams, face_colors, _ = _scene(N, H, W, K, 80, light=light, per_batch=(light == "point"), seed=33,
+                                                                  shininess=6.0)
+    gen = torch.Generator().manual_seed(4)
+    grad = torch.randn(N, H, W, K, 3, generator=gen)
+    grad[torch.rand(N, H, W, K, generator=gen) < 0.4] = 0.0
+
+    def leaves(dev):
+        li, ma, ca = _to(lights, dev), _to(mats, dev), _to(cams, dev)
+        t = [getattr(li, "location" if light == "point" else "direction"), li.diffuse_color, li.ambient_color, ma.specular_color,
+             ma.shininess, ca.T]
+        for x in t:
+            x.requires_grad_(True)
+        return li, ma, ca, t
+
+    li_o, ma_o, ca_o, t_o = leaves("cpu")
+    mesh_o = pb.TriMeshes(verts, faces, face_colors=face_colors)
+    col_o = PO.phong_colors_from(mesh_o, fr, li_o, ca_o, ma_o, pb.FaceTexels(face_colors).materialize(fr.pix_to_face))
+    (col_o * grad).sum().backward()
+    li_c, ma_c, ca_c, t_c = leaves(DEV)
+    mesh_c = pb.TriMeshes(verts.to(DEV), faces.to(DEV), face_colors=face_colors.to(DEV))
+    fr_c = _frag_to(fr, DEV)
+    col_c = pb.phong_shading(mesh_c, fr_c, li_c, ca_c, ma_c, mesh_c.sample_textures(fr_c))
+    (col_c * grad.to(DEV)).sum().backward()
+    for name, a, b in zip(("light", "diffuse", "ambient", "specular", "shininess", "camera T"), t_c, t_o):
+        assert a.grad is not None and rel_err(a.grad.cpu(), b.grad) <= 1e-4, (name, a.grad.cpu(), b.grad)
+
+
 def test_phong_full_size_properties_config2():
     """BASELINE config 2 shapes (8 x 256 x 256, K = 50): size-independent properties of the Phong pass.
     Linearity of backward in grad_colors; padded entries untouched by sparse mode; the sum of the face-table

@@ -125,7 +125,7 @@ def test_phong_struct_layout_and_validation_without_gpu():
     ph.flags = _cabi.PHONG_UNLIT
     ph.light_rows = 0
     assert lib.pert_phong_fwd(ph, None, None) == -1  # unlit: no lighting rows needed, inputs still NULL
-    assert lib.pert_phong_bwd(ph, None, None, None, None, None, None) == -1
+    assert lib.pert_phong_bwd(ph, None, None, None, None, None, None, None) == -1
 
 
 def test_phong_cpu_tensors_fail_loudly():
