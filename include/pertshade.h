@@ -53,7 +53,7 @@
 extern "C" {
 #endif
 
-#define PERT_ABI_VERSION 12
+#define PERT_ABI_VERSION 13
 
 /* error codes */
 #define PERT_OK 0
@@ -248,6 +248,11 @@ typedef struct pert_phong {
     const float* lighting;      /* (light_rows, PERT_PHONG_STRIDE) */
     const float* face_vert_colors; /* (F,3,3) colours at the face corners, interpolated with bary (TexturesVertex:
                                       verts_features_packed()[faces_packed()]), or NULL */
+    /* UV texture (TexturesUV / the legacy Textures of experiments/eval.py:750-756), or NULL: the texel is the bilinear
+     * tap (grid_sample: align_corners, border padding, map flipped vertically) of uv_map at sum_i bary_i * face_uvs[f,i] */
+    const float* face_uvs;  /* (F,3,2) verts_uvs[faces_uvs] */
+    const float* uv_map;    /* (map_count, map_h, map_w, 3), map_count = 1 or N (one map per image) */
+    int32_t map_h, map_w, map_count;
     int64_t faces_per_mesh; /* optional hint, 0 = none: the faces are N equal ranges, image n using only faces
                                [n * faces_per_mesh, (n+1) * faces_per_mesh) (a batch of poses of one topology); lets
                                backward keep one shared-memory gradient table per image.  Results do not depend on it */
@@ -256,8 +261,8 @@ typedef struct pert_phong {
 int pert_phong_fwd(const pert_phong* ph, float* colors, void* stream);
 /*
  * Backward of pert_phong_fwd.  grad_colors (P,K,3).  Outputs, each optional (NULL: not computed):
- *   grad_texels        (P,K,3); with ph->face_colors set: (F,3), with ph->face_vert_colors set: (F,3,3), ZEROED BY THE
- *                      CALLER, atomic adds
+ *   grad_texels        (P,K,3); with ph->face_colors set: (F,3), with ph->face_vert_colors set: (F,3,3), with ph->uv_map set:
+ *                      the map's shape; these three ZEROED BY THE CALLER, atomic adds (face_uvs gets no gradient)
  *   grad_bary          (P,K,3)
  *   grad_face_verts    (F,3,3) and grad_face_normals (F,3,3): ZEROED BY THE CALLER, atomic adds (the scatter of
  *                      interpolate_face_attributes' backward; summation order is not fixed)

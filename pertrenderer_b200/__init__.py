@@ -13,14 +13,14 @@ from .smoothagg import CauchyAgg, GaussianAgg, GaussianAgg_wovr, HardAgg, SoftAg
 from .smoothrast import (AffineRast, ArctanRast, GaussianRast, GaussianRast_wovr, HardRast, SoftRast, randomHeaviside,
                          randomHeaviside_wovr)
 from .structures import (BlendParams, DepthCameras, DirectionalLights, FaceColorMeshes, FaceTexels, Fragments, Materials,
-                         PointLights, TexelMeshes, TriMeshes, VertexTexels, ViewCameras, synthetic_bary, synthetic_fragments,
+                         PointLights, TexelMeshes, TriMeshes, UVTexels, VertexTexels, ViewCameras, synthetic_bary, synthetic_fragments,
                          synthetic_mesh)
 from .ops import explicit_noise, kernel_flags
 
 __all__ = [
     "RandomPhongShader", "RandomSimpleShader", "SimpleShader", "SoftSimpleShader", "UniformAgg", "phong_shading", "PointLights", "DirectionalLights",
     "MeshRasterizer", "MeshRenderer", "RasterizationSettings", "FoVPerspectiveCameras", "OpenGLPerspectiveCameras",
-    "look_at_view_transform", "rasterize_meshes", "Materials", "ViewCameras", "TriMeshes", "VertexTexels", "sample_lazy_textures", "synthetic_mesh", "synthetic_bary", "smooth_rgb_blend", "GaussianAgg", "SoftAgg", "CauchyAgg", "HardAgg",
+    "look_at_view_transform", "rasterize_meshes", "Materials", "ViewCameras", "TriMeshes", "VertexTexels", "UVTexels", "sample_lazy_textures", "synthetic_mesh", "synthetic_bary", "smooth_rgb_blend", "GaussianAgg", "SoftAgg", "CauchyAgg", "HardAgg",
     "randomArgmax", "GaussianRast", "GaussianRast_wovr", "GaussianAgg_wovr", "randomHeaviside_wovr", "randomArgmax_wovr", "ArctanRast", "AffineRast", "HardRast",
     "SoftRast", "randomHeaviside", "BlendParams", "DepthCameras", "Fragments", "TexelMeshes",
     "synthetic_fragments", "explicit_noise", "kernel_flags", "FaceColorMeshes", "FaceTexels",

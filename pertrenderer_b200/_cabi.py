@@ -15,7 +15,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpertshade.so")
-ABI_VERSION = 12
+ABI_VERSION = 13
 
 # flags (include/pertshade.h)
 F_NO_SKIP = 1
@@ -72,6 +72,8 @@ class PertPhong(C.Structure):
         ("pix_to_face", C.c_void_p), ("bary", C.c_void_p), ("face_verts", C.c_void_p), ("face_normals", C.c_void_p),
         ("texels", C.c_void_p), ("face_colors", C.c_void_p), ("lighting", C.c_void_p),
         ("face_vert_colors", C.c_void_p),
+        ("face_uvs", C.c_void_p), ("uv_map", C.c_void_p),
+        ("map_h", C.c_int32), ("map_w", C.c_int32), ("map_count", C.c_int32),
         ("faces_per_mesh", C.c_int64),
     ]
 

@@ -383,7 +383,11 @@ static int check_phong(const pert_phong* ph) {
     if (!unlit && ph->light_rows != 1 && ph->light_rows != ph->P / ph->HW) return PERT_E_SHAPE;
     if (!ph->pix_to_face || !ph->bary) return PERT_E_NULL;
     if (!unlit && (!ph->face_verts || !ph->face_normals || !ph->lighting)) return PERT_E_NULL;
-    if ((ph->texels != nullptr) + (ph->face_colors != nullptr) + (ph->face_vert_colors != nullptr) != 1) return PERT_E_NULL;
+    if ((ph->texels != nullptr) + (ph->face_colors != nullptr) + (ph->face_vert_colors != nullptr) + (ph->uv_map != nullptr) != 1)
+        return PERT_E_NULL;
+    if (ph->uv_map && (!ph->face_uvs || ph->map_h <= 0 || ph->map_w <= 0 || (ph->map_count != 1 && ph->map_count != ph->P / ph->HW)))
+        return PERT_E_SHAPE;
+    if (((uintptr_t)ph->uv_map & 3) || ((uintptr_t)ph->face_uvs & 3)) return PERT_E_ALIGN;
     if (((uintptr_t)ph->pix_to_face & 7) || ((uintptr_t)ph->bary & 3) || ((uintptr_t)ph->face_verts & 3) ||
         ((uintptr_t)ph->face_normals & 3) || ((uintptr_t)ph->texels & 3) || ((uintptr_t)ph->face_colors & 3) ||
         ((uintptr_t)ph->lighting & 3) || ((uintptr_t)ph->face_vert_colors & 3))

@@ -24,9 +24,10 @@ namespace {
 
 constexpr int PT = 128;  // threads per CTA (forward, and backward without a shared-memory gradient table)
 constexpr int PW = PT / 32;
-constexpr int PT_TABLE = 512;  // backward with the gradient table: ONE CTA per SM, 16 warps sharing the table
+constexpr int PT_TABLE = 512;  // backward with the gradient table: ONE CTA per SM, 16 warps sharing the table (24 warps at an
+                               // 80-register cap were slower: 273 vs 238 us)
 constexpr int WCHUNK = 1024;  // entries a warp scans at a time
-constexpr int TABLE_MAX_BYTES = 150 * 1024;  // table of 21..27 floats per face (F <= 1828..1422) next to 66 KB of warp lists
+constexpr int TABLE_MAX_BYTES = 150 * 1024;  // table of 18..27 floats per face (F <= 2133..1422) next to 66 KB of warp lists
 
 struct V3 {
     float x, y, z;
@@ -93,17 +94,106 @@ __device__ __forceinline__ Lit light_entry(const Row& L, V3 p, V3 n_raw) {
 }
 
 
+// Bilinear tap of a UV map, torch.nn.functional.grid_sample(mode="bilinear", padding_mode="border",
+// align_corners=True) on the vertically flipped map, as pytorch3d 0.4.0's TexturesUV.sample_textures does:
+// column = u (Wm-1), row = (Hm-1) - v (Hm-1), both clamped to the map.
+// The UV path is rare: it lives in out-of-line functions that take this small record BY VALUE (a reference to the
+// kernel's parameter struct would force a local-memory copy of it in every kernel: measured +60 % on backward).
+struct UvSrc {
+    const float* uv_map;
+    const float* face_uvs;
+    int map_h, map_w, map_count;
+    int64_t HWK;
+};
+__device__ __forceinline__ UvSrc uv_src(const pert_phong& ph) {
+    return UvSrc{ph.uv_map, ph.face_uvs, ph.map_h, ph.map_w, ph.map_count, ph.HW * ph.K};
+}
+struct UvTap {
+    int x0, y0, x1, y1;
+    float fx, fy;   // fractional parts
+    bool cx, cy;    // coordinate clamped by the border rule: its gradient is zero
+};
+__device__ __forceinline__ UvTap uv_tap(const UvSrc& us, float u, float v) {
+    const float wm = (float)(us.map_w - 1), hm = (float)(us.map_h - 1);
+    float ix = u * wm, iy = hm - v * hm;
+    UvTap t;
+    t.cx = !(ix > 0.0f && ix < wm);
+    t.cy = !(iy > 0.0f && iy < hm);
+    ix = fminf(fmaxf(ix, 0.0f), wm);
+    iy = fminf(fmaxf(iy, 0.0f), hm);
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    t.x0 = (int)fx0;
+    t.y0 = (int)fy0;
+    t.x1 = min(t.x0 + 1, us.map_w - 1);
+    t.y1 = min(t.y0 + 1, us.map_h - 1);
+    t.fx = ix - fx0;
+    t.fy = iy - fy0;
+    return t;
+}
+__device__ __forceinline__ int64_t uv_map_offset(const UvSrc& us, int64_t e) {
+    return (us.map_count > 1 ? e / us.HWK : 0) * (int64_t)us.map_h * us.map_w * 3;
+}
+
+__device__ __noinline__ V3 uv_texel(UvSrc us, int64_t e, int64_t face, V3 b) {
+    const float* q = us.face_uvs + face * 6;
+    const float u = b.x * __ldg(q) + b.y * __ldg(q + 2) + b.z * __ldg(q + 4);
+    const float v = b.x * __ldg(q + 1) + b.y * __ldg(q + 3) + b.z * __ldg(q + 5);
+    const UvTap t = uv_tap(us, u, v);
+    const float* m = us.uv_map + uv_map_offset(us, e);
+    const V3 c00 = ld3(m + ((int64_t)t.y0 * us.map_w + t.x0) * 3), c01 = ld3(m + ((int64_t)t.y0 * us.map_w + t.x1) * 3);
+    const V3 c10 = ld3(m + ((int64_t)t.y1 * us.map_w + t.x0) * 3), c11 = ld3(m + ((int64_t)t.y1 * us.map_w + t.x1) * 3);
+    const float w00 = (1.0f - t.fx) * (1.0f - t.fy), w01 = t.fx * (1.0f - t.fy), w10 = (1.0f - t.fx) * t.fy, w11 = t.fx * t.fy;
+    return w00 * c00 + w01 * c01 + w10 * c10 + w11 * c11;
+}
+// gradient of the UV texel: adds w_tap * gt to the four taps of grad_map (may be NULL), returns d/d bary
+__device__ __noinline__ V3 uv_texel_bwd(UvSrc us, int64_t e, int64_t face, V3 b, V3 gt, float* grad_map) {
+    const float* q = us.face_uvs + face * 6;
+    const float u = b.x * __ldg(q) + b.y * __ldg(q + 2) + b.z * __ldg(q + 4);
+    const float v = b.x * __ldg(q + 1) + b.y * __ldg(q + 3) + b.z * __ldg(q + 5);
+    const UvTap tp = uv_tap(us, u, v);
+    const int64_t mo = uv_map_offset(us, e);
+    const float* m = us.uv_map + mo;
+    const int64_t i00 = ((int64_t)tp.y0 * us.map_w + tp.x0) * 3, i01 = ((int64_t)tp.y0 * us.map_w + tp.x1) * 3;
+    const int64_t i10 = ((int64_t)tp.y1 * us.map_w + tp.x0) * 3, i11 = ((int64_t)tp.y1 * us.map_w + tp.x1) * 3;
+    const V3 c00 = ld3(m + i00), c01 = ld3(m + i01), c10 = ld3(m + i10), c11 = ld3(m + i11);
+    // d texel / d column, d texel / d row
+    const V3 dx = (1.0f - tp.fy) * (c01 - c00) + tp.fy * (c11 - c10);
+    const V3 dy = (1.0f - tp.fx) * (c10 - c00) + tp.fx * (c11 - c01);
+    const float g_u = tp.cx ? 0.0f : dot(gt, dx) * (float)(us.map_w - 1);
+    const float g_v = tp.cy ? 0.0f : -dot(gt, dy) * (float)(us.map_h - 1);
+    if (grad_map) {
+        float* gm = grad_map + mo;
+        const float w[4] = {(1.0f - tp.fx) * (1.0f - tp.fy), tp.fx * (1.0f - tp.fy), (1.0f - tp.fx) * tp.fy, tp.fx * tp.fy};
+        const int64_t idx[4] = {i00, i01, i10, i11};
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+            atomicAdd(gm + idx[k4], w[k4] * gt.x);
+            atomicAdd(gm + idx[k4] + 1, w[k4] * gt.y);
+            atomicAdd(gm + idx[k4] + 2, w[k4] * gt.z);
+        }
+    }
+    return mk(g_u * __ldg(q) + g_v * __ldg(q + 1), g_u * __ldg(q + 2) + g_v * __ldg(q + 3), g_u * __ldg(q + 4) + g_v * __ldg(q + 5));
+}
+
 // Texel of a valid entry from whichever source the call carries: the caller's (P,K,3) tensor, one colour per face
-// (F,3), or colours at the face corners (F,3,3) interpolated with the barycentric coordinates (TexturesVertex).
-__device__ __forceinline__ V3 texel_of(const pert_phong& ph, int64_t e, int64_t face, V3 b) {
+// (F,3), colours at the face corners (F,3,3) interpolated with the barycentric coordinates (TexturesVertex), or a UV
+// map sampled at the interpolated corner UVs (TexturesUV; the `Textures(verts_uvs, faces_uvs, maps)` of
+// experiments/eval.py:750-756).
+__device__ __forceinline__ V3 texel_of_plain(const pert_phong& ph, int64_t e, int64_t face, V3 b) {
     if (ph.face_vert_colors) {
         const float* c = ph.face_vert_colors + face * 9;
         return b.x * ld3(c) + b.y * ld3(c + 3) + b.z * ld3(c + 6);
     }
     return ph.face_colors ? ld3(ph.face_colors + face * 3) : ld3(ph.texels + e * 3);
 }
-// floats per face of the texel source's gradient (0: dense (P,K,3) gradient)
-__host__ __device__ __forceinline__ int tex_floats(const pert_phong& ph) { return ph.face_vert_colors ? 9 : (ph.face_colors ? 3 : 0); }
+__device__ __forceinline__ V3 texel_of(const pert_phong& ph, int64_t e, int64_t face, V3 b) {
+    if (ph.uv_map) return uv_texel(uv_src(ph), e, face, b);
+    return texel_of_plain(ph, e, face, b);
+}
+// floats per face of the texel source's gradient table (0: dense (P,K,3) gradient, or the UV map's own gradient)
+__host__ __device__ __forceinline__ int tex_floats(const pert_phong& ph) {
+    return ph.uv_map ? 0 : (ph.face_vert_colors ? 9 : (ph.face_colors ? 3 : 0));
+}
 
 // The lighting rows of the batch elements a chunk of entries can touch: the chunk's first batch element and
 // the next one sit in (per-warp) shared memory, anything further (tiny images) is read from global memory.
@@ -150,7 +240,7 @@ __global__ void __launch_bounds__(PT) phong_fwd_kernel(const pert_phong ph, floa
     uint16_t* const vlist = s_vlist[warp];
     float* const srow = s_row[warp];
     const bool sparse = ph.flags & PERT_PHONG_SPARSE, unlit = ph.flags & PERT_PHONG_UNLIT;
-    const bool table_tex = ph.face_colors || ph.face_vert_colors;
+    const bool table_tex = ph.face_colors || ph.face_vert_colors || ph.uv_map;
     const int64_t HWK = ph.HW * ph.K;
     int64_t cached_b0 = -1;
     const int64_t w0 = (int64_t)blockIdx.x * PW + warp, wstride = (int64_t)gridDim.x * PW;
@@ -207,8 +297,32 @@ __global__ void __launch_bounds__(PT) phong_fwd_kernel(const pert_phong ph, floa
 
 // TABLE: accumulate the (F,3,3) gradients of face_verts / face_normals (and the (F,3) gradient of
 // face_colors) in shared memory and flush once per CTA.
-template <bool TABLE, int NT>
-__global__ void __launch_bounds__(NT) phong_bwd_kernel(const pert_phong ph, const float* __restrict__ grad_colors,
+// dst[3 i + c] += b_i * g_c for the three corners: into the shared-memory table or into global memory.  Two separate
+// code paths so that the compiler emits a shared-memory atomic and a global one (a pointer selected at run time makes
+// it a generic-address atomic: measured 213 -> 238 us on the table variant).
+__device__ __forceinline__ void scatter9(bool in_table, float* sm, float* gl, V3 b, V3 g) {
+    const float bw[3] = {b.x, b.y, b.z};
+    if (in_table) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            atomicAdd(sm + 3 * i, bw[i] * g.x);
+            atomicAdd(sm + 3 * i + 1, bw[i] * g.y);
+            atomicAdd(sm + 3 * i + 2, bw[i] * g.z);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            atomicAdd(gl + 3 * i, bw[i] * g.x);
+            atomicAdd(gl + 3 * i + 1, bw[i] * g.y);
+            atomicAdd(gl + 3 * i + 2, bw[i] * g.z);
+        }
+    }
+}
+
+// the streaming loop is latency-bound: resident warps matter more than a few spills in the rare branches
+// (measured without the cap: 80 -> 120 registers as texel sources were added, 154 -> 224 us)
+template <bool TABLE, int NT, bool UV>
+__global__ void __launch_bounds__(NT, NT <= 128 ? 6 : 1) phong_bwd_kernel(const pert_phong ph, const float* __restrict__ grad_colors,
                                                        float* __restrict__ grad_texels, float* __restrict__ grad_bary,
                                                        float* __restrict__ grad_fv, float* __restrict__ grad_fn, int64_t E,
                                                        int64_t nchunks, int tfaces, int per_image) {
@@ -232,7 +346,9 @@ __global__ void __launch_bounds__(NT) phong_bwd_kernel(const pert_phong ph, cons
     float* const t_fv = table;
     float* const t_fn = table + F * 9;
     float* const t_fc = table + F * 18;
-    const bool face_tex = ph.face_colors || ph.face_vert_colors;  // texel gradient scattered to a per-face table
+    constexpr bool uv_tex = UV;  // UV map: texel gradient scattered into the map (grad_texels = d/d uv_map); its own
+                                 // instantiation, so that the common kernels carry none of its code
+    const bool face_tex = ph.face_colors || ph.face_vert_colors || uv_tex;  // texel gradient not dense
     const bool vert_tex = ph.face_vert_colors != nullptr;
     const int TF = tex_floats(ph);
     const bool unlit = ph.flags & PERT_PHONG_UNLIT;
@@ -305,7 +421,7 @@ __global__ void __launch_bounds__(NT) phong_bwd_kernel(const pert_phong ph, cons
             const bool tab = TABLE && fl >= 0 && fl < F;
             const V3 gc = ld3(grad_colors + e * 3);
             const V3 b = ld3(ph.bary + e * 3);
-            const V3 t = texel_of(ph, e, face, b);
+            const V3 t = UV ? uv_texel(uv_src(ph), e, face, b) : texel_of_plain(ph, e, face, b);
             Row L;
             Lit o;
             V3 v0, v1, v2, n0, n1, n2;
@@ -325,21 +441,22 @@ __global__ void __launch_bounds__(NT) phong_bwd_kernel(const pert_phong ph, cons
                 const float* c = ph.face_vert_colors + (int64_t)face * 9;
                 gb = mk(dot(gt, ld3(c)), dot(gt, ld3(c + 3)), dot(gt, ld3(c + 6)));
             }
-            if (grad_texels) {
+            if (uv_tex) {  // texel = bilinear(map, sum_i b_i uv_i): gradient to the four taps and, through (u, v), to bary
+                gb = uv_texel_bwd(uv_src(ph), e, face, b, gt, grad_texels);
+            } else if (grad_texels) {
                 if (vert_tex) {
-                    float* dst = tab ? t_fc + fl * 9 : grad_texels + (int64_t)face * 9;
-                    const float bw3[3] = {b.x, b.y, b.z};
-#pragma unroll
-                    for (int i2 = 0; i2 < 3; ++i2) {
-                        atomicAdd(dst + 3 * i2, bw3[i2] * gt.x);
-                        atomicAdd(dst + 3 * i2 + 1, bw3[i2] * gt.y);
-                        atomicAdd(dst + 3 * i2 + 2, bw3[i2] * gt.z);
-                    }
+                    scatter9(tab, t_fc + fl * 9, grad_texels + (int64_t)face * 9, b, gt);
                 } else if (face_tex) {
-                    float* dst = tab ? t_fc + fl * 3 : grad_texels + (int64_t)face * 3;
-                    atomicAdd(dst, gt.x);
-                    atomicAdd(dst + 1, gt.y);
-                    atomicAdd(dst + 2, gt.z);
+                    if (tab) {  // separate statements: a shared-memory atomic and a global one, not a generic one
+                        atomicAdd(t_fc + fl * 3, gt.x);
+                        atomicAdd(t_fc + fl * 3 + 1, gt.y);
+                        atomicAdd(t_fc + fl * 3 + 2, gt.z);
+                    } else {
+                        float* dst = grad_texels + (int64_t)face * 3;
+                        atomicAdd(dst, gt.x);
+                        atomicAdd(dst + 1, gt.y);
+                        atomicAdd(dst + 2, gt.z);
+                    }
                 } else {
                     st3(grad_texels + e * 3, gt);
                 }
@@ -364,25 +481,8 @@ __global__ void __launch_bounds__(NT) phong_bwd_kernel(const pert_phong ph, cons
             if (grad_bary)
                 st3(grad_bary + e * 3, mk(gb.x + dot(g_p, v0) + dot(g_nraw, n0), gb.y + dot(g_p, v1) + dot(g_nraw, n1),
                                           gb.z + dot(g_p, v2) + dot(g_nraw, n2)));
-            const float bw[3] = {b.x, b.y, b.z};
-            if (grad_fv) {
-                float* dst = tab ? t_fv + fl * 9 : grad_fv + (int64_t)face * 9;
-#pragma unroll
-                for (int i2 = 0; i2 < 3; ++i2) {
-                    atomicAdd(dst + 3 * i2, bw[i2] * g_p.x);
-                    atomicAdd(dst + 3 * i2 + 1, bw[i2] * g_p.y);
-                    atomicAdd(dst + 3 * i2 + 2, bw[i2] * g_p.z);
-                }
-            }
-            if (grad_fn) {
-                float* dst = tab ? t_fn + fl * 9 : grad_fn + (int64_t)face * 9;
-#pragma unroll
-                for (int i2 = 0; i2 < 3; ++i2) {
-                    atomicAdd(dst + 3 * i2, bw[i2] * g_nraw.x);
-                    atomicAdd(dst + 3 * i2 + 1, bw[i2] * g_nraw.y);
-                    atomicAdd(dst + 3 * i2 + 2, bw[i2] * g_nraw.z);
-                }
-            }
+            if (grad_fv) scatter9(tab, t_fv + fl * 9, grad_fv + (int64_t)face * 9, b, g_p);
+            if (grad_fn) scatter9(tab, t_fn + fl * 9, grad_fn + (int64_t)face * 9, b, g_nraw);
         }
         __syncwarp();
     }
@@ -392,7 +492,7 @@ __global__ void __launch_bounds__(NT) phong_bwd_kernel(const pert_phong ph, cons
             if (grad_fv && t_fv[i] != 0.0f) atomicAdd(grad_fv + f_begin * 9 + i, t_fv[i]);
             if (grad_fn && t_fn[i] != 0.0f) atomicAdd(grad_fn + f_begin * 9 + i, t_fn[i]);
         }
-        if (face_tex && grad_texels)
+        if (face_tex && !uv_tex && grad_texels)
             for (int i = threadIdx.x; i < F * TF; i += NT)
                 if (t_fc[i] != 0.0f) atomicAdd(grad_texels + f_begin * TF + i, t_fc[i]);
     }
@@ -504,13 +604,13 @@ int launch_phong_fwd(const pert_phong& ph, float* colors, cudaStream_t st) {
     return (int)cudaGetLastError();
 }
 
-template <bool TABLE, int NT>
+template <bool TABLE, int NT, bool UV = false>
 static int launch_bwd_t(const pert_phong& ph, const float* grad_colors, float* grad_texels, float* grad_bary, float* grad_fv,
                         float* grad_fn, int64_t E, int64_t nchunks, int ctas_per_sm, int tfaces, bool per_image, cudaStream_t st) {
     const size_t table = TABLE ? (((size_t)tfaces * (18 + tex_floats(ph)) * 4 + 15) & ~(size_t)15) : 0;
     const size_t smem = table + (size_t)(NT / 32) * (2 * WCHUNK * 2 + 2 * PERT_PHONG_STRIDE * 4);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(phong_bwd_kernel<TABLE, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(phong_bwd_kernel<TABLE, NT, UV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
     dim3 grid(phong_grid(nchunks, ctas_per_sm, NT / 32));
@@ -520,7 +620,7 @@ static int launch_bwd_t(const pert_phong& ph, const float* grad_colors, float* g
         const int64_t most = (img_chunks + NT / 32 - 1) / (NT / 32);
         grid = dim3((unsigned)(ctas < most ? ctas : most), (unsigned)n_img);
     }
-    phong_bwd_kernel<TABLE, NT><<<grid, NT, smem, st>>>(ph, grad_colors, grad_texels, grad_bary, grad_fv, grad_fn, E, nchunks,
+    phong_bwd_kernel<TABLE, NT, UV><<<grid, NT, smem, st>>>(ph, grad_colors, grad_texels, grad_bary, grad_fv, grad_fn, E, nchunks,
                                                        tfaces, per_image ? 1 : 0);
     return (int)cudaGetLastError();
 }
@@ -540,6 +640,8 @@ int launch_phong_bwd(const pert_phong& ph, const float* grad_colors, float* grad
     // 1280 faces: 210 us of a 360 us pass); accumulate them in a per-SM shared-memory table instead and flush it
     // once.  Large meshes spread the atomics over enough addresses (100k faces: 58 us).  A batch of N equal-size
     // meshes (N poses of one topology: faces_per_mesh) gets one table per image.
+    if (ph.uv_map)  // rare path: its own instantiation, face-table gradients straight to global memory
+        return launch_bwd_t<false, PT, true>(ph, grad_colors, grad_texels, grad_bary, grad_fv, grad_fn, E, nchunks, 6, 0, false, st);
     const int64_t n_img = ph.P / ph.HW;
     const bool batch = ph.faces_per_mesh > 0 && n_img > 1 && ph.faces_per_mesh * n_img == ph.num_faces && n_img <= 65535 &&
                        ph.HW * ph.K >= 4 * (int64_t)(PT_TABLE / 32) * WCHUNK;
@@ -548,7 +650,7 @@ int launch_phong_bwd(const pert_phong& ph, const float* grad_colors, float* grad
         return launch_bwd_t<true, PT>(ph, grad_colors, grad_texels, grad_bary, grad_fv, grad_fn, E, nchunks, 4, (int)tf, false, st);
     if (scatter && tf * per_face <= (size_t)TABLE_MAX_BYTES)
         return launch_bwd_t<true, PT_TABLE>(ph, grad_colors, grad_texels, grad_bary, grad_fv, grad_fn, E, nchunks, 1, (int)tf, batch, st);
-    return launch_bwd_t<false, PT>(ph, grad_colors, grad_texels, grad_bary, grad_fv, grad_fn, E, nchunks, 5, 0, false, st);
+    return launch_bwd_t<false, PT>(ph, grad_colors, grad_texels, grad_bary, grad_fv, grad_fn, E, nchunks, 6, 0, false, st);
 }
 
 }  // namespace pert

@@ -18,7 +18,7 @@ from torch.autograd import Function
 from . import ops
 from .smoothagg import GaussianAgg, SoftAgg  # noqa: F401
 from .smoothrast import GaussianRast, SoftRast
-from .structures import BlendParams, FaceTexels, VertexTexels
+from .structures import BlendParams, FaceTexels, UVTexels, VertexTexels
 
 
 def _background_tuple(blend_params):
@@ -110,8 +110,8 @@ def smooth_rgb_blend(colors, fragments, smoothrast, smoothagg, blend_params, zne
 
     ``colors`` (N,H,W,K,3); ``fragments`` with ``pix_to_face`` / ``zbuf`` / ``dists`` (N,H,W,K);
     ``znear`` / ``zfar`` python floats or tensors broadcastable to (N,1,1,1)."""
-    if isinstance(colors, VertexTexels):
-        # TexturesVertex: interpolate the vertex colours with the texture-only mode of the Phong kernel; the fused
+    if isinstance(colors, (VertexTexels, UVTexels)):
+        # TexturesVertex / TexturesUV: interpolate the vertex colours with the texture-only mode of the Phong kernel; the fused
         # pairs read colours of valid entries only, so the padded ones need not be written
         from .shading import sample_lazy_textures
         fused = (isinstance(smoothrast, GaussianRast) and isinstance(smoothagg, GaussianAgg)) or \
@@ -169,7 +169,7 @@ class SimpleShader(nn.Module):
     def forward(self, fragments, meshes, **kwargs) -> torch.Tensor:
         blend_params = kwargs.get("blend_params", self.blend_params)
         texels = meshes.sample_textures(fragments)
-        if isinstance(texels, (FaceTexels, VertexTexels)):
+        if isinstance(texels, (FaceTexels, VertexTexels, UVTexels)):
             from .shading import sample_lazy_textures
             texels = sample_lazy_textures(texels, fragments)
         covered = fragments.pix_to_face[..., 0] >= 0

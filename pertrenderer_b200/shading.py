@@ -26,7 +26,7 @@ from torch.autograd import Function
 
 from . import _cabi
 from ._cabi import PHONG_SPARSE, PHONG_STRIDE, PHONG_UNLIT, PertPhong, check, ptr, require_cuda, stream_ptr
-from .structures import FaceTexels, VertexTexels
+from .structures import FaceTexels, UVTexels, VertexTexels
 
 
 def _f32c(t):
@@ -64,12 +64,16 @@ def pack_lighting(lights, materials, cameras, N, device):
 
 
 def _phong_struct(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting, flags, vert_colors=None,
-                  faces_per_mesh=0):
+                  faces_per_mesh=0, uv=None):
     N, H, W, K = pix_to_face.shape
     ph = PertPhong()
     ph.P, ph.HW, ph.K = N * H * W, H * W, K
     ph.light_rows = 0 if lighting is None else lighting.shape[0]
     table = face_verts if face_verts is not None else (face_colors if face_colors is not None else vert_colors)
+    if uv is not None:  # (maps (M,Hm,Wm,3), face_uvs (F,3,2))
+        ph.uv_map, ph.face_uvs = uv[0].data_ptr(), uv[1].data_ptr()
+        ph.map_count, ph.map_h, ph.map_w = uv[0].shape[0], uv[0].shape[1], uv[0].shape[2]
+        table = table if table is not None else uv[1]
     ph.num_faces = table.shape[0]
     ph.flags = flags
     ph.faces_per_mesh = int(faces_per_mesh)
@@ -84,7 +88,7 @@ def _phong_struct(pix_to_face, bary, face_verts, face_normals, texels, face_colo
 
 
 def phong_forward(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting, sparse=False,
-                  vert_colors=None, unlit=False):
+                  vert_colors=None, unlit=False, uv=None):
     """Launch pert_phong_fwd.  Returns colors (N,H,W,K,3); with ``sparse`` the entries with
     pix_to_face < 0 are left unwritten (the fused shader kernels never read them).  Exactly one texel
     source: ``texels`` (N,H,W,K,3), ``face_colors`` (F,3) or ``vert_colors`` (F,3,3).  ``unlit``: colour =
@@ -96,7 +100,7 @@ def phong_forward(pix_to_face, bary, face_verts, face_normals, texels, face_colo
     with torch.cuda.device(dev):
         colors = torch.empty((N, H, W, K, 3), dtype=torch.float32, device=dev)
         ph = _phong_struct(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting,
-                           (PHONG_SPARSE if sparse else 0) | (PHONG_UNLIT if unlit else 0), vert_colors)
+                           (PHONG_SPARSE if sparse else 0) | (PHONG_UNLIT if unlit else 0), vert_colors, uv=uv)
         rc = lib.pert_phong_fwd(ph, ptr(colors), stream_ptr(dev))
     check(rc, "pert_phong_fwd")
     return colors
@@ -104,7 +108,7 @@ def phong_forward(pix_to_face, bary, face_verts, face_normals, texels, face_colo
 
 def phong_backward(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting, grad_colors,
                    need_texels=True, need_bary=True, need_verts=True, need_normals=True, sparse=False, vert_colors=None,
-                   unlit=False, faces_per_mesh=0, need_lighting=False):
+                   unlit=False, faces_per_mesh=0, need_lighting=False, uv=None):
     """Launch pert_phong_bwd.  Returns (grad_texels | grad_face_colors, grad_bary, grad_face_verts,
     grad_face_normals), ``None`` where not requested.  Every entry of the dense outputs is defined (they
     flow on to the caller's own tensors): with ``sparse`` the kernel skips the padded entries, whose
@@ -117,7 +121,8 @@ def phong_backward(pix_to_face, bary, face_verts, face_normals, texels, face_col
     with torch.cuda.device(dev):
         alloc = torch.zeros if sparse else torch.empty
         if need_texels:
-            table = face_colors if face_colors is not None else vert_colors
+            table = face_colors if face_colors is not None else (vert_colors if vert_colors is not None else
+                                                                    (uv[0] if uv is not None else None))
             g_tex = torch.zeros_like(table) if table is not None else alloc((N, H, W, K, 3), dtype=torch.float32, device=dev)
         else:
             g_tex = None
@@ -126,7 +131,7 @@ def phong_backward(pix_to_face, bary, face_verts, face_normals, texels, face_col
         g_fn = torch.zeros_like(face_normals) if (need_normals and not unlit) else None
         g_light = torch.zeros_like(lighting) if (need_lighting and not unlit) else None
         ph = _phong_struct(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting,
-                           (PHONG_SPARSE if sparse else 0) | (PHONG_UNLIT if unlit else 0), vert_colors, faces_per_mesh)
+                           (PHONG_SPARSE if sparse else 0) | (PHONG_UNLIT if unlit else 0), vert_colors, faces_per_mesh, uv=uv)
         rc = lib.pert_phong_bwd(ph, ptr(grad_colors), ptr(g_tex), ptr(g_bary), ptr(g_fv), ptr(g_fn), ptr(g_light), stream_ptr(dev))
     check(rc, "pert_phong_bwd")
     if need_lighting:
@@ -139,13 +144,16 @@ class _PhongShade(Function):
     ``tex_mode``: "texels" (N,H,W,K,3), "face" (F,3) or "vert" (F,3,3)."""
 
     @staticmethod
-    def forward(ctx, face_verts, face_normals, texels, bary, pix_to_face, lighting, tex_mode, sparse, unlit, faces_per_mesh=0):
+    def forward(ctx, face_verts, face_normals, texels, bary, pix_to_face, lighting, tex_mode, sparse, unlit, faces_per_mesh=0,
+                face_uvs=None):
         fv = None if unlit else _f32c(face_verts.detach())
         fn = None if unlit else _f32c(face_normals.detach())
         tx, bc = _f32c(texels.detach()), _f32c(bary.detach())
         p2f = pix_to_face.contiguous()
         src = dict(texels=tx if tex_mode == "texels" else None, face_colors=tx if tex_mode == "face" else None,
-                   vert_colors=tx if tex_mode == "vert" else None)
+                   vert_colors=tx if tex_mode == "vert" else None,
+                   uv=(tx, _f32c(face_uvs.detach())) if tex_mode == "uv" else None)
+        ctx.uv_faces = src["uv"][1] if tex_mode == "uv" else None
         lighting = None if lighting is None else _f32c(lighting.detach())
         colors = phong_forward(p2f, bc, fv, fn, lighting=lighting, sparse=sparse, unlit=unlit, **src)
         ctx.save_for_backward(*[t for t in (fv, fn, tx, bc, p2f, lighting) if t is not None])
@@ -161,14 +169,14 @@ class _PhongShade(Function):
             fv, fn, tx, bc, p2f, lighting = ctx.saved_tensors
         need = ctx.needs_input_grad
         src = dict(texels=tx if ctx.tex_mode == "texels" else None, face_colors=tx if ctx.tex_mode == "face" else None,
-                   vert_colors=tx if ctx.tex_mode == "vert" else None)
+                   vert_colors=tx if ctx.tex_mode == "vert" else None, uv=(tx, ctx.uv_faces) if ctx.tex_mode == "uv" else None)
         out = phong_backward(
             p2f, bc, fv, fn, lighting=lighting, grad_colors=grad_colors, need_texels=need[2], need_bary=need[3],
             need_verts=need[0], need_normals=need[1], sparse=ctx.sparse, unlit=ctx.unlit,
             faces_per_mesh=ctx.faces_per_mesh, need_lighting=bool(need[5]) and not ctx.unlit, **src)
         g_tex, g_bary, g_fv, g_fn = out[:4]
         g_light = out[4] if len(out) > 4 else None
-        return g_fv, g_fn, g_tex, g_bary, None, g_light, None, None, None, None
+        return g_fv, g_fn, g_tex, g_bary, None, g_light, None, None, None, None, None
 
 
 def _texel_source(texels):
@@ -177,6 +185,8 @@ def _texel_source(texels):
         return texels.face_colors, "face"
     if isinstance(texels, VertexTexels):
         return texels.face_vert_colors(), "vert"
+    if isinstance(texels, UVTexels):
+        return texels.maps, "uv"
     return texels, "texels"
 
 
@@ -192,10 +202,11 @@ def sample_lazy_textures(texels, fragments, sparse: bool = False) -> torch.Tenso
         pix_to_face = pix_to_face.to(torch.int64)
     bary = fragments.bary_coords
     if bary is None:
-        if mode == "vert":
-            raise ValueError("vertex colours need fragments.bary_coords (N,H,W,K,3)")
+        if mode in ("vert", "uv"):
+            raise ValueError("vertex colours / UV maps need fragments.bary_coords (N,H,W,K,3)")
         bary = torch.zeros(pix_to_face.shape + (3,), dtype=torch.float32, device=pix_to_face.device)
-    return _PhongShade.apply(None, None, tex, bary, pix_to_face, None, mode, bool(sparse), True)
+    return _PhongShade.apply(None, None, tex, bary, pix_to_face, None, mode, bool(sparse), True, 0,
+                             texels.face_uvs() if mode == "uv" else None)
 
 
 def phong_shading(meshes, fragments, lights, cameras, materials, texels, sparse: bool = False) -> torch.Tensor:
@@ -223,4 +234,4 @@ def phong_shading(meshes, fragments, lights, cameras, materials, texels, sparse:
     n_mesh = len(meshes) if hasattr(meshes, "faces_packed_single") else 1
     fpm = faces.shape[0] // n_mesh if (n_mesh > 1 and n_mesh == N) else 0
     return _PhongShade.apply(faces_verts, faces_normals, tex, fragments.bary_coords, pix_to_face, lighting,
-                             mode, bool(sparse), False, fpm)
+                             mode, bool(sparse), False, fpm, texels.face_uvs() if mode == "uv" else None)

@@ -94,6 +94,37 @@ class VertexTexels:
         return (bary[..., None] * self.face_vert_colors()[pix_to_face.clamp(min=0)]).sum(-2) * mask[..., None]
 
 
+class UVTexels:
+    """Lazy texels of a UV-mapped mesh (pytorch3d ``TexturesUV`` / the legacy ``Textures(verts_uvs, faces_uvs, maps)`` of
+    experiments/eval.py:750-756): the colour of fragment (n,h,w,k) is the bilinear tap of ``maps`` at the barycentric
+    interpolation of the three corner UVs of face ``pix_to_face[n,h,w,k]`` (grid_sample with align_corners and border
+    padding on the vertically flipped map, as pytorch3d 0.4.0 does).  ``maps`` (M,Hm,Wm,3) with M = 1 or N;
+    ``verts_uvs`` (Vt,2); ``faces_uvs`` (F,3) indices into it, F = the PACKED face count."""
+
+    def __init__(self, maps: torch.Tensor, verts_uvs: torch.Tensor, faces_uvs: torch.Tensor):
+        if maps.dim() == 3:
+            maps = maps[None]
+        if maps.dim() != 4 or maps.shape[-1] != 3:
+            raise ValueError("maps must be (M,Hm,Wm,3)")
+        self.maps, self.verts_uvs, self.faces_uvs = maps, verts_uvs, faces_uvs.to(torch.int64)
+
+    def face_uvs(self) -> torch.Tensor:
+        return self.verts_uvs[self.faces_uvs]  # (F,3,2)
+
+    def materialize(self, pix_to_face: torch.Tensor, bary: torch.Tensor) -> torch.Tensor:
+        """The same sampling with torch ops (TexturesUV.sample_textures restated; reference for the tests)."""
+        N, H, W, K = pix_to_face.shape
+        mask = pix_to_face >= 0
+        uv = (bary[..., None] * self.face_uvs()[pix_to_face.clamp(min=0)]).sum(-2)  # (N,H,W,K,2)
+        grid = (uv * 2.0 - 1.0).permute(0, 3, 1, 2, 4).reshape(N * K, H, W, 2)
+        maps = torch.flip(self.maps, [1]).permute(0, 3, 1, 2)  # (M,3,Hm,Wm), flipped vertically
+        maps = maps.expand(N, -1, -1, -1) if maps.shape[0] == 1 else maps
+        maps = maps[:, None].expand(N, K, *maps.shape[1:]).reshape(N * K, *maps.shape[1:])
+        tex = torch.nn.functional.grid_sample(maps, grid, mode="bilinear", padding_mode="border", align_corners=True)
+        tex = tex.reshape(N, K, 3, H, W).permute(0, 3, 4, 1, 2)
+        return tex * mask[..., None]
+
+
 class FaceColorMeshes:
     """Stand-in for ``Meshes`` with one colour per (packed) face: ``sample_textures`` returns lazy
     :class:`FaceTexels` instead of a texel tensor."""
@@ -180,13 +211,15 @@ class TriMeshes:
     """Stand-in for pytorch3d ``Meshes``: ONE topology ``faces`` (F,3) with vertices (V,3), or a batch of N poses of
     it, vertices (N,V,3) (``extend`` / ``update_padded`` as in eval.py:343,281-283).  The packed representation
     (``verts_packed`` (N*V,3), ``faces_packed`` (N*F,3)) is what ``pix_to_face`` indexes.  Textures: one colour per
-    face (lazy :class:`FaceTexels`), one colour per vertex (lazy :class:`VertexTexels`) or a preset texel tensor.
+    face (lazy :class:`FaceTexels`), one colour per vertex (lazy :class:`VertexTexels`), a UV map (lazy
+    :class:`UVTexels`) or a preset texel tensor.
     ``verts_normals_packed`` follows pytorch3d's area-weighted vertex normals (cross products of the face edges
     summed onto the corners, then normalised with eps 1e-6)."""
 
-    def __init__(self, verts, faces, face_colors=None, texels=None, verts_colors=None):
+    def __init__(self, verts, faces, face_colors=None, texels=None, verts_colors=None, uv=None):
         self._verts, self._faces = verts, faces.to(torch.int64)
         self.face_colors, self.texels, self.verts_colors = face_colors, texels, verts_colors
+        self.uv = uv  # (maps (M,Hm,Wm,3), verts_uvs (Vt,2), faces_uvs (F,3)): a UV-mapped mesh
 
     def __len__(self):
         return self._verts.shape[0] if self._verts.dim() == 3 else 1
@@ -221,6 +254,9 @@ class TriMeshes:
         if self.texels is not None:
             return self.texels
         n = len(self)
+        if self.uv is not None:
+            maps, verts_uvs, faces_uvs = self.uv
+            return UVTexels(maps, verts_uvs, faces_uvs if n == 1 else faces_uvs.repeat(n, 1))
         if self.verts_colors is not None:
             vc = self.verts_colors if n == 1 else self.verts_colors.repeat(n, 1)
             return VertexTexels(vc, self.faces_packed())
@@ -231,11 +267,11 @@ class TriMeshes:
         if len(self) != 1:
             raise ValueError("extend() needs a single mesh")
         return TriMeshes(self.verts_padded().expand(n, -1, -1).contiguous(), self._faces, self.face_colors, self.texels,
-                         self.verts_colors)
+                         self.verts_colors, self.uv)
 
     def update_padded(self, verts):
         """Same topology and textures, new vertex positions (V,3) or (N,V,3) (pytorch3d ``Meshes.update_padded``)."""
-        return TriMeshes(verts, self._faces, self.face_colors, self.texels, self.verts_colors)
+        return TriMeshes(verts, self._faces, self.face_colors, self.texels, self.verts_colors, self.uv)
 
     update_verts = update_padded
 

@@ -323,6 +323,55 @@ def test_gradients_reach_lights_materials_and_camera(light):
         assert a.grad is not None and rel_err(a.grad.cpu(), b.grad) <= 1e-4, (name, a.grad.cpu(), b.grad)
 
 
+@pytest.mark.parametrize("n_maps", [1, 2])
+def test_uv_textures_match_grid_sample(n_maps):
+    """TexturesUV / the legacy Textures(verts_uvs, faces_uvs, maps) of eval.py:750-756: bilinear tap of the map at the
+    interpolated corner UVs.  Oracle: UVTexels.materialize = pytorch3d 0.4.0's sample_textures restated on
+    torch.nn.functional.grid_sample (align_corners, border padding, flipped map).  UVs partly outside [0,1]: border."""
+    import pertrenderer_b200 as pb
+    N, H, W, K = 2, 10, 9, 5
+    fr, verts, faces, lights, mats, cams, _, _ = _scene(N, H, W, K, 80, seed=17)
+    gen = torch.Generator().manual_seed(6)
+    maps = torch.rand(n_maps, 7, 11, 3, generator=gen)
+    verts_uvs = torch.rand(40, 2, generator=gen) * 1.3 - 0.15
+    faces_uvs = torch.randint(0, 40, (faces.shape[0], 3), generator=gen)
+    grad = torch.randn(N, H, W, K, 3, generator=gen)
+    grad[torch.rand(N, H, W, K, generator=gen) < 0.3] = 0.0
+    # (a) sampling alone
+    m_o, b_o = maps.clone().requires_grad_(True), fr.bary_coords.clone().requires_grad_(True)
+    tex_o = pb.UVTexels(m_o, verts_uvs, faces_uvs).materialize(fr.pix_to_face, b_o)
+    (tex_o * grad).sum().backward()
+    m_c = maps.to(DEV).requires_grad_(True)
+    fr_c = _frag_to(fr, DEV, bary_grad=True)
+    tex_c = pb.sample_lazy_textures(pb.UVTexels(m_c, verts_uvs.to(DEV), faces_uvs.to(DEV)), fr_c)
+    (tex_c * grad.to(DEV)).sum().backward()
+    assert (tex_c.detach().cpu() - tex_o.detach()).abs().max() <= 2e-6
+    assert rel_err(m_c.grad.cpu(), m_o.grad) <= 5 * RTOL
+    assert rel_err(fr_c.bary_coords.grad.cpu(), b_o.grad) <= 1e-4  # differences of neighbouring texels times (Wm - 1)
+    # (b) inside the Phong kernel, through RandomPhongShader with the SoftRas pair
+    m_o2, v_o = maps.clone().requires_grad_(True), verts.clone().requires_grad_(True)
+    mesh_o = pb.TriMeshes(v_o, faces, uv=(m_o2, verts_uvs, faces_uvs))
+    col_o = PO.phong_colors_from(mesh_o, fr, lights, cams, mats, pb.UVTexels(m_o2, verts_uvs, faces_uvs).materialize(fr.pix_to_face, fr.bary_coords))
+    (col_o * grad).sum().backward()
+    m_c2, v_c = maps.to(DEV).requires_grad_(True), verts.to(DEV).requires_grad_(True)
+    mesh_c = pb.TriMeshes(v_c, faces.to(DEV), uv=(m_c2, verts_uvs.to(DEV), faces_uvs.to(DEV)))
+    fr_c2 = _frag_to(fr, DEV)
+    col_c = pb.phong_shading(mesh_c, fr_c2, _to(lights, DEV), _to(cams, DEV), _to(mats, DEV), mesh_c.sample_textures(fr_c2))
+    (col_c * grad.to(DEV)).sum().backward()
+    assert (col_c.detach().cpu() - col_o.detach()).abs().max() <= 2e-6
+    assert rel_err(m_c2.grad.cpu(), m_o2.grad) <= 5 * RTOL
+    assert rel_err(v_c.grad.cpu(), v_o.grad) <= 5 * RTOL
+    # (c) the reference's cube: one UV point per side -> a constant colour per face, whatever the sampling details
+    strip = torch.tensor([[0.9, 0.1, 0.1], [0.1, 0.7, 0.1], [0.1, 0.2, 0.9]])
+    cmap = strip.repeat_interleave(4, dim=0)[None, None].expand(1, 5, 12, 3).contiguous()  # three vertical strips
+    vt = torch.tensor([[1.5 / 12 * 12 / 11, 0.5], [5.5 / 11, 0.5], [9.5 / 11, 0.5]])  # centres of the strips (align_corners)
+    fuv = (torch.arange(faces.shape[0]) % 3)[:, None].expand(-1, 3).contiguous()
+    tex = pb.sample_lazy_textures(pb.UVTexels(cmap.to(DEV), vt.to(DEV), fuv.to(DEV)), _frag_to(fr, DEV)).cpu()
+    mask = fr.pix_to_face >= 0
+    expect = strip[(fr.pix_to_face.clamp(min=0) % 3)]
+    assert (tex[mask] - expect[mask]).abs().max() <= 1e-6
+
+
 def test_phong_full_size_properties_config2():
     """BASELINE config 2 shapes (8 x 256 x 256, K = 50): size-independent properties of the Phong pass.
     Linearity of backward in grad_colors; padded entries untouched by sparse mode; the sum of the face-table

@@ -110,8 +110,8 @@ def test_shims_expose_the_pytorch3d_attributes():
 
 
 def test_phong_struct_layout_and_validation_without_gpu():
-    assert ctypes.sizeof(_cabi.PertPhong) == 112
-    assert _cabi.PertPhong.pix_to_face.offset == 40
+    assert ctypes.sizeof(_cabi.PertPhong) == 144
+    assert _cabi.PertPhong.pix_to_face.offset == 40 and _cabi.PertPhong.faces_per_mesh.offset == 136
     lib = _cabi.load()
     ph = _cabi.PertPhong()
     assert lib.pert_phong_fwd(None, None, None) == -1
