@@ -422,7 +422,7 @@ __device__ __forceinline__ void edge_bwd(P2 p, P2 a, P2 b, float g, P2& ga, P2& 
 // floats to its face: on a 1280-face mesh that is 79 M atomics on 11 k addresses per 8-view batch, which bound the
 // global-atomics version (0.8 ms at config 2).
 template <bool TABLE, int NT>
-__global__ void __launch_bounds__(NT) rasterize_bwd_kernel(const pert_raster rs, const int64_t* __restrict__ pix_to_face,
+__global__ void __launch_bounds__(NT, NT == 512 ? 2 : 1) rasterize_bwd_kernel(const pert_raster rs, const int64_t* __restrict__ pix_to_face,
                                                            const float* __restrict__ grad_zbuf,
                                                            const float* __restrict__ grad_bary,
                                                            const float* __restrict__ grad_dists,
@@ -503,16 +503,16 @@ __global__ void __launch_bounds__(NT) rasterize_bwd_kernel(const pert_raster rs,
                 gbb.y += cb * rr.y;
             }
             const int64_t fl = f - f_begin;
-            float* dst = (TABLE && fl >= 0 && fl < tcap) ? s_table + fl * 9 : grad_face_verts + f * 9;
-            atomicAdd(dst + 0, g0.x);
-            atomicAdd(dst + 1, g0.y);
-            atomicAdd(dst + 2, gz * o.w0);
-            atomicAdd(dst + 3, g1.x);
-            atomicAdd(dst + 4, g1.y);
-            atomicAdd(dst + 5, gz * o.w1);
-            atomicAdd(dst + 6, g2.x);
-            atomicAdd(dst + 7, g2.y);
-            atomicAdd(dst + 8, gz * o.w2);
+            const float gv[9] = {g0.x, g0.y, gz * o.w0, g1.x, g1.y, gz * o.w1, g2.x, g2.y, gz * o.w2};
+            // two code paths: a shared-memory atomic and a global one (a pointer selected at run time would make
+            // every add a generic-address atomic)
+            if (TABLE && fl >= 0 && fl < tcap) {
+#pragma unroll
+                for (int j = 0; j < 9; ++j) atomicAdd(s_table + fl * 9 + j, gv[j]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 9; ++j) atomicAdd(grad_face_verts + f * 9 + j, gv[j]);
+            }
         }
         __syncwarp();
     }
