@@ -146,9 +146,11 @@ def main():
     gen = torch.Generator().manual_seed(args.seed)
     torch.manual_seed(args.seed)
     results = {}
-    with torch.no_grad():  # warm-up: module loading and kernel attributes are not part of the timed iterations
-        for noise in args.noise:
-            make_renderer(noise, cameras, lights, args.sigma, args.gamma, args.nb_samples, args.imsize, dev)(mesh)
+    for noise in args.noise:  # warm-up: lazy module loading (forward AND backward) is not part of the timed iterations
+        w = torch.zeros(3, device=dev).add_(0.1).requires_grad_(True)
+        r = make_renderer(noise, cameras, lights, args.sigma, args.gamma, args.nb_samples, args.imsize, dev)
+        for _ in range(3):
+            r(mesh.update_padded(verts @ so3_exp(w)))[..., :3].mean().backward()
     for noise in args.noise:
         errs, inits, t_iter = [], [], []
         for _ in range(args.trials):

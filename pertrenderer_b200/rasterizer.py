@@ -82,7 +82,7 @@ class _Rasterize(Function):
                 check(lib.pert_rasterize_bin(rs, ptr(count), ptr(offset), ptr(cursor), ptr(lists), stream_ptr(dev)), "pert_rasterize_bin")
                 rs.bin_count, rs.bin_offset, rs.bin_faces = count.data_ptr(), offset.data_ptr(), lists.data_ptr()
                 keep = [count, offset, lists]
-            elif K <= 64 and fv.shape[0] > 1:
+            elif K <= 64 and fv.shape[0] > 256 * N:  # up to one chunk of faces per tile the order is irrelevant
                 # visit the faces of every mesh nearest first (centroid depth): the per-pixel sorted insertion of the
                 # kernel then appends instead of shifting; any order gives the same fragments
                 zc = fv[:, :, 2].sum(dim=1)

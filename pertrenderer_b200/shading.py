@@ -55,12 +55,10 @@ def pack_lighting(lights, materials, cameras, N, device):
     sh = _rows(materials.shininess, N, device, width=1)
     cam = _rows(cameras.get_camera_center(), N, device)
     rows = max(t.shape[0] for t in (loc, amb, dif, spc, sh, cam))
-    table = torch.zeros((rows, PHONG_STRIDE), dtype=torch.float32, device=device)
-    table[:, 0:3], table[:, 3:6], table[:, 6:9], table[:, 9:12] = loc, amb, dif, spc
-    table[:, 12:13] = sh
-    table[:, 13:16] = cam
-    table[:, 16] = 1.0 if directional else 0.0
-    return table
+    kind = torch.full((1, 1), 1.0 if directional else 0.0, dtype=torch.float32, device=device)
+    pad = torch.zeros((1, PHONG_STRIDE - 17), dtype=torch.float32, device=device)
+    # one concatenation (differentiable: the pieces keep their autograd history)
+    return torch.cat([t.expand(rows, -1) for t in (loc, amb, dif, spc, sh, cam, kind, pad)], dim=1)
 
 
 def _phong_struct(pix_to_face, bary, face_verts, face_normals, texels, face_colors, lighting, flags, vert_colors=None,
