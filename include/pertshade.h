@@ -297,18 +297,18 @@ typedef struct pert_raster {
     const float* face_verts;   /* (F,3,3) */
     const int64_t* face_start; /* (N+1), device */
     const int64_t* face_order; /* optional (F): a permutation of every range [face_start[n], face_start[n+1]) giving the
-                                  order in which the faces are visited; nearest first (e.g. sorted by centroid depth)
-                                  makes the per-pixel sorted insertion append-only.  The result does not depend on it.
-                                  NULL: index order.  Forward, K <= 64 only */
-    /* optional coarse bins (forward, K <= 64): one list of candidate faces per 32x8 pixel tile, built by two
+                                  order in which the faces are visited.  The result does not depend on it (the K-buffer
+                                  is ranked at the end); kept for callers that want a traversal order.  NULL: index
+                                  order.  Forward, K <= 64 only */
+    /* optional coarse bins (forward, K <= 64): one list of candidate faces per 32x4 pixel tile, built by two
      * pert_rasterize_bin calls; every tile then walks its own list instead of all faces of its mesh.  For meshes of
      * thousands of faces.  NULL: off */
-    const int32_t* bin_count;  /* (N * tiles) faces per tile, tiles = ceil(W/32) * ceil(H/8) */
+    const int32_t* bin_count;  /* (N * tiles) faces per tile, tiles = ceil(W/32) * ceil(H/4) */
     const int64_t* bin_offset; /* (N * tiles) start of every tile's list in bin_faces: exclusive prefix sum of bin_count */
     const int64_t* bin_faces;  /* (sum of bin_count) packed face indices */
 } pert_raster;
 
-/* number of bins of this problem: N * ceil(W/32) * ceil(H/8) */
+/* number of bins of this problem: N * ceil(W/32) * ceil(H/4) */
 int64_t pert_rasterize_num_bins(const pert_raster* rs);
 /*
  * Coarse binning, two calls around an exclusive prefix sum done by the caller:

@@ -451,7 +451,7 @@ extern "C" int pert_rasterize_bwd(const pert_raster* rs, const int64_t* pix_to_f
 
 extern "C" int64_t pert_rasterize_num_bins(const pert_raster* rs) {
     if (!rs || rs->N <= 0 || rs->H <= 0 || rs->W <= 0) return 0;
-    return rs->N * (int64_t)((rs->W + 31) / 32) * (int64_t)((rs->H + 7) / 8);
+    return rs->N * (int64_t)((rs->W + 31) / 32) * (int64_t)((rs->H + 3) / 4);  // TW x TH tiles of csrc/raster.cu
 }
 
 extern "C" int pert_rasterize_bin(const pert_raster* rs, int32_t* bin_count, const int64_t* bin_offset, int32_t* bin_cursor,

@@ -5,7 +5,7 @@
 // restates its published naive rasteriser (rasterize_meshes.cu CheckPixelInsideFace / RasterizeMeshesNaive,
 // geometry_utils.cuh, kEpsilon = 1e-8) with a B200 work decomposition:
 //
-//   forward   one CTA per 32x8 pixel tile.  Faces are culled against the tile in chunks of 256 (one face per thread:
+//   forward   one CTA per 32x4 pixel tile.  Faces are culled against the tile in chunks of 256 (one face per thread:
 //             bounding box grown by sqrt(blur_radius) against the tile's pixel-centre rectangle, zero-area and
 //             behind-camera faces dropped), survivors are compacted IN FACE ORDER into shared memory with their nine
 //             coordinates, and every pixel thread then tests only those.  The K-buffer of a pixel is a sorted array
@@ -24,7 +24,7 @@ namespace pert {
 namespace {
 
 constexpr float kEps = 1e-8f;  // geometry_utils.cuh kEpsilon
-constexpr int TW = 32, TH = 8, RT = TW * TH;  // pixel tile of the forward kernel
+constexpr int TW = 32, TH = 4, RT = TW * TH;  // pixel tile of the forward kernel (K = 50: 50 KB of K-buffers, 3 CTAs per SM)
 
 struct P2 {
     float x, y;
@@ -210,10 +210,11 @@ __global__ void __launch_bounds__(RT) rasterize_fwd_rows_kernel(const pert_raste
 }
 
 
-// Fast path for K <= KMAX: the K-buffer of a pixel is a sorted array of packed 64-bit keys (depth bits << 32 | face)
-// in LOCAL memory.  Depths are >= 0, so the integer order of the keys is the depth order with ties in face order;
-// local memory is interleaved per thread, so the insertion shifts of a warp are coalesced (the per-pixel output rows
-// of the generic kernel are K*4 bytes apart: every shift was its own sector, 2.2 ms at config 2).
+// Fast path for K <= KMAX: the K-buffer of a pixel is an array of packed 64-bit keys (depth bits << 32 | face)
+// in SHARED memory, unsorted while the faces are walked and ranked at the end.  Depths are >= 0, so the integer order of
+// the keys is the depth order with ties in face order; local memory is interleaved per thread, so the accesses of a warp
+// are coalesced (the per-pixel output rows of the generic kernel are K*4 bytes apart: every shift of its sorted
+// insertion was its own sector, 2.2 ms at config 2).
 template <int KMAX>
 __global__ void __launch_bounds__(RT) rasterize_fwd_keys_kernel(const pert_raster rs, int64_t* __restrict__ pix_to_face,
                                                                 float* __restrict__ zbuf, float* __restrict__ bary,
@@ -232,8 +233,13 @@ __global__ void __launch_bounds__(RT) rasterize_fwd_keys_kernel(const pert_raste
     const float ty_hi = pix_to_ndc(H - 1 - py0, H, W), ty_lo = pix_to_ndc(H - 1 - py1, H, W);
     const float blur = rs.blur_radius, r = sqrtf(blur);
     const int64_t f_begin = __ldg(rs.face_start + n), f_end = __ldg(rs.face_start + n + 1);
-    unsigned long long keys[KMAX];
-    int cnt = 0;
+    // the K-buffers of the tile's pixels live in SHARED memory, key j of thread t at [j * RT + t] (conflict-free).
+    // As per-thread local arrays (512 B x 1024 resident threads per SM) they did not fit the L1 and thrashed to DRAM:
+    // 2.6 GB of traffic for 0.73 GB of output, the rank loop at 46 % of the stall samples.
+    extern __shared__ __align__(16) unsigned long long s_keys[];
+    unsigned long long* const keys = s_keys + threadIdx.x;
+    unsigned long long max_key = 0ull;
+    int cnt = 0, max_idx = 0;
     // the faces this tile walks: its own bin (pert_rasterize_bin), or all faces of the mesh, in the caller's order
     // (nearest first when face_order is given: the sorted insertion below then appends almost always).  The result
     // does not depend on the order: keys are unique.
@@ -303,14 +309,28 @@ __global__ void __launch_bounds__(RT) rasterize_fwd_keys_kernel(const pert_raste
                 }
                 if (pz == 0.0f) pz = 0.0f;  // -0 would sort last
                 const unsigned long long key = ((unsigned long long)__float_as_uint(pz) << 32) | (unsigned)s_face[i];
-                if (cnt == K && key >= keys[K - 1]) continue;
-                int j = cnt < K ? cnt : K - 1;
-                while (j > 0 && keys[j - 1] > key) {
-                    keys[j] = keys[j - 1];
-                    --j;
+                // UNSORTED buffer: appending is one store.  (A sorted insertion is a chain of dependent local-memory
+                // loads, ~17 per candidate at 35 candidates: 43 % of the kernel's stall samples.)  Once the buffer is
+                // full the farthest kept key is tracked and replaced; the order is established at the end by ranks.
+                if (cnt < K) {
+                    keys[(cnt++) * RT] = key;
+                    if (cnt == K) {  // buffer just filled: find the farthest key (independent loads)
+                        max_key = 0ull;
+                        for (int j = 0; j < K; ++j)
+                            if (keys[(j) * RT] > max_key) {
+                                max_key = keys[(j) * RT];
+                                max_idx = j;
+                            }
+                    }
+                } else if (key < max_key) {
+                    keys[(max_idx) * RT] = key;
+                    max_key = 0ull;
+                    for (int j = 0; j < K; ++j)
+                        if (keys[(j) * RT] > max_key) {
+                            max_key = keys[(j) * RT];
+                            max_idx = j;
+                        }
                 }
-                keys[j] = key;
-                if (cnt < K) ++cnt;
             }
         }
     }
@@ -318,17 +338,21 @@ __global__ void __launch_bounds__(RT) rasterize_fwd_keys_kernel(const pert_raste
     if (in_image) {
 #pragma unroll 1
         for (int k = 0; k < cnt; ++k) {
-            const int64_t f = f_begin + (int64_t)(unsigned)(keys[k] & 0xffffffffull);
+            // output slot = rank of the key (keys are unique: depth bits, then face index): cnt independent loads
+            const unsigned long long key = keys[(k) * RT];
+            int rank = 0;
+            for (int j = 0; j < cnt; ++j) rank += keys[(j) * RT] < key ? 1 : 0;
+            const int64_t f = f_begin + (int64_t)(unsigned)(key & 0xffffffffull);
             float v[9];
 #pragma unroll
             for (int i = 0; i < 9; ++i) v[i] = __ldg(rs.face_verts + f * 9 + i);
             const FaceEval e = eval_face(p, v);
-            pix_to_face[row + k] = f;
-            zbuf[row + k] = e.pz;
-            bary[(row + k) * 3] = e.w0;
-            bary[(row + k) * 3 + 1] = e.w1;
-            bary[(row + k) * 3 + 2] = e.w2;
-            dists[row + k] = e.inside ? -e.dist : e.dist;
+            pix_to_face[row + rank] = f;
+            zbuf[row + rank] = e.pz;
+            bary[(row + rank) * 3] = e.w0;
+            bary[(row + rank) * 3 + 1] = e.w1;
+            bary[(row + rank) * 3 + 2] = e.w2;
+            dists[row + rank] = e.inside ? -e.dist : e.dist;
         }
     }
     __syncthreads();
@@ -356,7 +380,7 @@ __global__ void __launch_bounds__(RT) rasterize_fwd_keys_kernel(const pert_raste
 
 
 // ---------------------------------------------------------------------------------------------------------
-// coarse binning for large meshes: which faces can touch which 32x8 pixel tile
+// coarse binning for large meshes: which faces can touch which 32x4 pixel tile
 // ---------------------------------------------------------------------------------------------------------
 // One thread per face: the tiles overlapped by its bounding box grown by sqrt(blur_radius) (conservative by a pixel).
 // FILL = false counts (atomics into bin_count, zeroed by the caller); FILL = true appends the face to every such
@@ -538,11 +562,12 @@ int launch_rasterize_bin(const pert_raster& rs, int32_t* bin_count, const int64_
 
 int launch_rasterize_fwd(const pert_raster& rs, int64_t* pix_to_face, float* zbuf, float* bary, float* dists, cudaStream_t st) {
     const dim3 grid((unsigned)((rs.W + TW - 1) / TW), (unsigned)((rs.H + TH - 1) / TH), (unsigned)rs.N);
-    if (rs.K <= 16)
-        rasterize_fwd_keys_kernel<16><<<grid, RT, 0, st>>>(rs, pix_to_face, zbuf, bary, dists);
-    else if (rs.K <= 64)
-        rasterize_fwd_keys_kernel<64><<<grid, RT, 0, st>>>(rs, pix_to_face, zbuf, bary, dists);
-    else  // K-buffer in the pixel's own output rows
+    if (rs.K <= 64) {
+        const size_t smem = (size_t)rs.K * RT * sizeof(unsigned long long);  // K = 50: 50 KB
+        cudaError_t e = cudaFuncSetAttribute(rasterize_fwd_keys_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        rasterize_fwd_keys_kernel<64><<<grid, RT, smem, st>>>(rs, pix_to_face, zbuf, bary, dists);
+    } else  // K-buffer in the pixel's own output rows
         rasterize_fwd_rows_kernel<<<grid, RT, 0, st>>>(rs, pix_to_face, zbuf, bary, dists);
     return (int)cudaGetLastError();
 }

@@ -82,14 +82,6 @@ class _Rasterize(Function):
                 check(lib.pert_rasterize_bin(rs, ptr(count), ptr(offset), ptr(cursor), ptr(lists), stream_ptr(dev)), "pert_rasterize_bin")
                 rs.bin_count, rs.bin_offset, rs.bin_faces = count.data_ptr(), offset.data_ptr(), lists.data_ptr()
                 keep = [count, offset, lists]
-            elif K <= 64 and fv.shape[0] > 256 * N:  # up to one chunk of faces per tile the order is irrelevant
-                # visit the faces of every mesh nearest first (centroid depth): the per-pixel sorted insertion of the
-                # kernel then appends instead of shifting; any order gives the same fragments
-                zc = fv[:, :, 2].sum(dim=1)
-                mesh_of = torch.bucketize(torch.arange(fv.shape[0], device=dev), fs[1:], right=True)
-                order = torch.argsort(zc + 4.0 * (zc.abs().max() + 1.0) * mesh_of.to(zc.dtype), stable=True).contiguous()
-                rs.face_order = order.data_ptr()
-                keep = [order]
             rc = lib.pert_rasterize_fwd(rs, ptr(p2f), ptr(zbuf), ptr(bary), ptr(dists), stream_ptr(dev))
             del keep
         check(rc, "pert_rasterize_fwd")
