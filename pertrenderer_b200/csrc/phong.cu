@@ -643,8 +643,11 @@ int launch_phong_bwd(const pert_phong& ph, const float* grad_colors, float* grad
     if (ph.uv_map)  // rare path: its own instantiation, face-table gradients straight to global memory
         return launch_bwd_t<false, PT, true>(ph, grad_colors, grad_texels, grad_bary, grad_fv, grad_fn, E, nchunks, 6, 0, false, st);
     const int64_t n_img = ph.P / ph.HW;
-    const bool batch = ph.faces_per_mesh > 0 && n_img > 1 && ph.faces_per_mesh * n_img == ph.num_faces && n_img <= 65535 &&
-                       ph.HW * ph.K >= 4 * (int64_t)(PT_TABLE / 32) * WCHUNK;
+    // per-image tables only for small meshes: measured on a batch of 8 x 1280 faces with real (dense) fragments, the
+    // shared-memory CAS adds of the one-CTA-per-SM table kernel (683 us) lose to plain L2 reductions spread over
+    // 8 x 23 k addresses (427 us); contention on L2 is the problem of SMALL tables only
+    const bool batch = ph.faces_per_mesh > 0 && ph.faces_per_mesh <= 256 && n_img > 1 && ph.faces_per_mesh * n_img == ph.num_faces &&
+                       n_img <= 65535 && ph.HW * ph.K >= 4 * (int64_t)(PT_TABLE / 32) * WCHUNK;
     const int64_t tf = batch ? ph.faces_per_mesh : ph.num_faces;
     if (scatter && tf * per_face <= 16 * 1024 && !batch)  // tiny table: keep the occupancy of the small CTAs
         return launch_bwd_t<true, PT>(ph, grad_colors, grad_texels, grad_bary, grad_fv, grad_fn, E, nchunks, 4, (int)tf, false, st);

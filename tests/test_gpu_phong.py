@@ -258,7 +258,7 @@ def test_phong_batch_of_poses_uses_per_image_tables_and_matches_oracle():
     kernels without the hint."""
     import pertrenderer_b200 as pb
     from pertrenderer_b200 import shading
-    N, H, W, K, F_ = 3, 64, 64, 24, 320
+    N, H, W, K, F_ = 3, 64, 64, 24, 80  # per-image tables are used for meshes of up to 256 faces
     fr, verts, faces, lights, mats, cams, face_colors, _ = _scene(N, H, W, K, F_, per_batch=True, seed=21, kind="realistic")
     gen = torch.Generator().manual_seed(5)
     poses = verts[None] + 0.05 * torch.randn(N, verts.shape[0], 3, generator=gen)
