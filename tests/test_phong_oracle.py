@@ -136,3 +136,55 @@ def test_phong_cpu_tensors_fail_loudly():
     cam = pb.ViewCameras(R=torch.eye(3)[None], T=[[0.0, 0.0, 3.0]])
     with pytest.raises(RuntimeError, match="CUDA"):
         pb.phong_shading(mesh, frag, pb.PointLights(), cam, pb.Materials(), mesh.sample_textures(frag))
+
+
+def test_uv_texels_on_a_striped_map_are_constant_per_face():
+    """The reference's cube (eval.py:727-757): six colour strips in one map, ONE UV point per side, so every face samples a
+    constant colour whatever the bilinear details; and a UV outside [0,1] clamps to the border texel."""
+    strip = torch.tensor([[0.9, 0.1, 0.1], [0.1, 0.7, 0.1], [0.1, 0.2, 0.9]])
+    cmap = strip.repeat_interleave(4, dim=0)[None].expand(5, 12, 3).contiguous()  # (Hm=5, Wm=12, 3)
+    vt = torch.tensor([[1.5 / 11, 0.5], [5.5 / 11, 0.5], [9.5 / 11, 0.5], [-3.0, 0.2], [7.0, 0.9]])
+    fuv = torch.tensor([[0, 0, 0], [1, 1, 1], [2, 2, 2], [3, 3, 3], [4, 4, 4]])
+    p2f = torch.tensor([0, 1, 2, 3, 4, -1]).reshape(1, 1, 1, 6)
+    bary = torch.tensor([0.2, 0.3, 0.5]).expand(1, 1, 1, 6, 3).contiguous()
+    tex = pb.UVTexels(cmap, vt, fuv).materialize(p2f, bary)[0, 0, 0]
+    assert torch.allclose(tex[:3], strip, atol=1e-6)
+    assert torch.allclose(tex[3], strip[0], atol=1e-6) and torch.allclose(tex[4], strip[2], atol=1e-6)  # border clamp
+    assert (tex[5] == 0).all()  # padded entry
+
+
+def test_lighting_table_is_differentiable_and_batches():
+    from pertrenderer_b200 import shading
+    loc = torch.tensor([[0.0, 2.0, -2.0]], requires_grad=True)
+    lights = pb.PointLights(location=loc)
+    mats = pb.Materials(shininess=torch.tensor([8.0, 16.0]))
+    R, T = pb.look_at_view_transform(dist=2.7, elev=[10.0, 20.0], azim=[0.0, 90.0])
+    T.requires_grad_(True)
+    cams = pb.FoVPerspectiveCameras(R=R, T=T)
+    table = shading.pack_lighting(lights, mats, cams, 2, "cpu")
+    assert table.shape == (2, 20) and table[:, 12].tolist() == [8.0, 16.0] and (table[:, 16] == 0).all()
+    assert torch.allclose(table[:, 13:16].norm(dim=1), torch.full((2,), 2.7), atol=1e-5)  # camera centres
+    table[:, :3].sum().backward(retain_graph=True)
+    assert torch.allclose(loc.grad, torch.full((1, 3), 2.0))  # one light row broadcast over two images
+    table[:, 13:16].sum().backward()
+    assert T.grad is not None and T.grad.abs().sum() > 0
+    d = shading.pack_lighting(pb.DirectionalLights(), pb.Materials(), cams, 2, "cpu")
+    assert (d[:, 16] == 1).all()
+
+
+def test_trimeshes_batches_and_textures():
+    verts, faces = pb.synthetic_mesh(20, device="cpu")
+    m = pb.TriMeshes(verts, faces, face_colors=torch.rand(20, 3))
+    assert len(m) == 1 and m.verts_padded().shape == (1, 12, 3)
+    m3 = m.extend(3)
+    assert len(m3) == 3 and m3.verts_packed().shape == (36, 3) and m3.faces_packed().max().item() == 35
+    assert isinstance(m3.sample_textures(None), pb.FaceTexels) and m3.sample_textures(None).face_colors.shape == (60, 3)
+    mv = pb.TriMeshes(verts, faces, verts_colors=torch.rand(12, 3)).extend(2)
+    t = mv.sample_textures(None)
+    assert isinstance(t, pb.VertexTexels) and t.face_vert_colors().shape == (40, 3, 3)
+    mu = pb.TriMeshes(verts, faces, uv=(torch.rand(1, 4, 4, 3), torch.rand(7, 2), torch.randint(0, 7, (20, 3)))).extend(2)
+    assert isinstance(mu.sample_textures(None), pb.UVTexels) and mu.sample_textures(None).face_uvs().shape == (40, 3, 2)
+    moved = m3.update_padded(m3.verts_padded() + 1.0)
+    assert torch.allclose(moved.verts_packed(), m3.verts_packed() + 1.0) and moved.face_colors is m3.face_colors
+    n = m3.verts_normals_packed()
+    assert n.shape == (36, 3) and torch.allclose(n[:12], n[12:24], atol=1e-6)  # same pose, same normals
