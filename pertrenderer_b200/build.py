@@ -43,15 +43,16 @@ def is_stale() -> bool:
     return any(os.path.getmtime(p) > t for p in SOURCES + HEADERS)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile every translation unit (in parallel) and link libpertshade.so in-tree."""
-    if not force and not is_stale():
+def build_library(force: bool = False, verbose: bool = False, experiments: bool = False) -> str:
+    """Compile every translation unit (in parallel) and link libpertshade.so in-tree.  ``experiments`` defines
+    PERT_EXPERIMENTS: tuning knobs read from the environment (PERT_TP, PERT_CAP, ...); never set for the product."""
+    if not force and not experiments and not is_stale():
         return LIB_PATH
     import concurrent.futures
     nvcc = find_nvcc()
     obj_dir = os.path.join(os.path.dirname(HERE), "build")
     os.makedirs(obj_dir, exist_ok=True)
-    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-DPERT_EXPERIMENTS"] if experiments else [])
 
     def compile_one(src):
         obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
@@ -75,4 +76,4 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv, experiments="--experiments" in sys.argv))

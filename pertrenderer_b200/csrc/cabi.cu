@@ -1,5 +1,6 @@
 // C ABI of libpertshade.so (include/pertshade.h): argument validation and launch geometry.  Nothing
 // here allocates, frees, retains or synchronises; every launch goes to the caller's stream.
+#include <math.h>
 #include <stdlib.h>
 
 #include "kernels.h"
@@ -34,14 +35,54 @@ extern "C" const char* pert_strerror(int code) {
 
 // pixels per warp tile: a power of two in [4, 32] with about 512 fragment entries per tile
 static int pick_tp(int K) {
-    if (const char* e = getenv("PERT_TP")) {  // experiments only
+#ifdef PERT_EXPERIMENTS  // tuning builds only (python -m pertrenderer_b200.build --experiments): the product reads no environment
+    if (const char* e = getenv("PERT_TP")) {
         const int v = atoi(e);
         if (v == 4 || v == 8 || v == 16 || v == 32) return v;
     }
+#endif
     if (K <= 16) return 32;
     if (K <= 32) return 16;
     if (K <= 64) return 8;
     return 4;
+}
+
+// Smallest t = |x|/sigma handled by the compound coverage sampler for n local samples: flip probability
+// p = Phi(-t) <= min(0.2 [beyond that the per-sample loop is as cheap], 1 - exp(-80/n) [(1-p)^n must not
+// underflow], 48/n [serial flips per lane]).
+static double tail_quantile(double p) {  // t with Phi(-t) = p, 0 < p <= 0.5
+    double lo = 0.0, hi = 8.0;
+    for (int i = 0; i < 60; ++i) {
+        const double mid = 0.5 * (lo + hi);
+        if (0.5 * erfc(mid * 0.7071067811865476) > p) lo = mid; else hi = mid;
+    }
+    return hi;
+}
+static float compound_threshold(int n) {
+    double pmax = 0.2;
+#ifdef PERT_EXPERIMENTS
+    if (const char* e = getenv("PERT_PCMP")) pmax = atof(e);
+#endif
+    if (n > 0) {
+        pmax = fmin(pmax, 1.0 - exp(-80.0 / n));
+        pmax = fmin(pmax, 48.0 / n);
+    }
+    return (float)tail_quantile(pmax);
+}
+// bucket edges of the compound sampler: expected flips n p = 3 and 0.25
+static void compound_buckets(int n, float t_compound, float* out) {
+    double f0 = 3.0, f1 = 0.25;
+#ifdef PERT_EXPERIMENTS
+    if (const char* e = getenv("PERT_FB0")) f0 = atof(e);
+    if (const char* e = getenv("PERT_FB1")) f1 = atof(e);
+#endif
+    for (int i = 0; i < 2; ++i) {
+        const double p = (i == 0 ? f0 : f1) / (n > 0 ? n : 1);
+        float t = p >= 0.5 ? 0.0f : (float)tail_quantile(p);
+        if (t < t_compound) t = t_compound;
+        out[i] = t;
+    }
+    if (out[1] < out[0]) out[1] = out[0];
 }
 
 static int check_problem(const pert_problem* pb) {
@@ -100,6 +141,8 @@ static Launch make_launch(const pert_problem* pb, int tp) {
     L.inv_sr = 1.0f / ((float)pb->S_rast * pb->sigma);
     L.invS = 1.0f / (float)pb->S_agg;
     L.inv_gamma = 1.0f / pb->gamma;
+    L.t_compound = compound_threshold(pb->s_rast_end - pb->s_rast_begin);
+    compound_buckets(pb->s_rast_end - pb->s_rast_begin, L.t_compound, L.t_bucket);
     return L;
 }
 
@@ -119,7 +162,9 @@ static int sparse_tp(int K, int64_t P) {
 }
 static int sparse_cap(int K, int tp) {
     int cap = tp * K / 5;
-    if (const char* e = getenv("PERT_CAP")) cap = atoi(e);  // experiments only
+#ifdef PERT_EXPERIMENTS
+    if (const char* e = getenv("PERT_CAP")) cap = atoi(e);
+#endif
     cap = (cap + 7) & ~7;  // u16 arrays are copied as 32-bit words
     if (cap < 32) cap = 32;
     if (cap > tp * K) cap = (tp * K + 1) & ~1;

@@ -176,6 +176,8 @@ struct Launch {
     float gal;      // gamma / alpha (smoothagg.py:201)
     float inv_sigma, invSg, inv_sr, invS;  // 1/sigma, 1/(S_agg gamma), 1/(S_rast sigma), 1/S_agg
     float inv_gamma;  // 1/gamma (SoftAgg, smoothagg.py:181)
+    float t_compound; // coverage entries with |x|/sigma >= this are drawn by the compound sampler (tile.cuh)
+    float t_bucket[2]; // ... and bucketed by expected flips: [t_compound, t_bucket[0]) many, [.., t_bucket[1]) some, rest rare
 };
 
 // 16-byte asynchronous global -> shared copy (LDGSTS) and its completion wait

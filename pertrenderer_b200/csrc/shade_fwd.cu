@@ -103,11 +103,18 @@ __device__ __forceinline__ void shade_fwd_tile(const FwdArgs& a, const NoiseR& n
     // ---- phase 1: stage valid entries, coverage samples ---------------------------------------------
     const int sr_loc = pb.s_rast_end - pb.s_rast_begin;
     const float thr = (NoiseR::kBounded && !no_skip) ? pb.sigma * kNoiseAbsMax * 1.0001f : CUDART_INF_F;
-    int nlist = 0;
+    // compound sampler (tile.cuh) for the entries with |x| >= x_cmp: the default with in-kernel noise.  Entries are
+    // bucketed by their expected number of flips (direct | many | some | rare) so that the lanes of a warp pass loop
+    // about equally long
+    const bool compound = NoiseR::kBounded && !no_skip && !(flags & PERT_F_PER_SAMPLE_NOISE);
+    const float x_cmp = compound ? a.L.t_compound * pb.sigma : CUDART_INF_F;
+    const float x_b2 = a.L.t_bucket[0] * pb.sigma, x_b3 = a.L.t_bucket[1] * pb.sigma;
+    int nb0 = 0, nb1 = 0, nb2 = 0, nb3 = 0;
+    auto bucket_of = [&](float ax) -> int { return ax > thr ? -1 : ax < x_cmp ? 0 : ax < x_b2 ? 1 : ax < x_b3 ? 2 : 3; };
 #pragma unroll 1
     for (int n0 = 0; n0 < nv; n0 += 32) {
         const int n = n0 + lane;
-        bool need = false;
+        int bk = -1;
         if (n < nv) {
             const int e = vlist[n];
             zs[n] = __ldg(zbuf_t + e);
@@ -116,8 +123,8 @@ __device__ __forceinline__ void shade_fwd_tile(const FwdArgs& a, const NoiseR& n
                 const float x = -__ldg(dists_t + e);
                 xs[n] = x;
                 // |x| beyond the largest possible sigma*|U| cannot flip: exact, not an approximation
-                need = fabsf(x) <= thr;
-                if (!need) {
+                bk = bucket_of(fabsf(x));
+                if (bk < 0) {
                     cnt[n] = (x >= 0.0f) ? (uint16_t)sr_loc : (uint16_t)0;
                     rs[n] = 0.0f;
                 }
@@ -126,14 +133,45 @@ __device__ __forceinline__ void shade_fwd_tile(const FwdArgs& a, const NoiseR& n
             }
         }
         if (do_rast) {
-            const unsigned b = __ballot_sync(FULL, need);
-            if (need) rlist[nlist + __popc(b & lt)] = (uint16_t)n;
-            nlist += __popc(b);
+            nb0 += __popc(__ballot_sync(FULL, bk == 0));
+            if (compound) {
+                nb1 += __popc(__ballot_sync(FULL, bk == 1));
+                nb2 += __popc(__ballot_sync(FULL, bk == 2));
+                nb3 += __popc(__ballot_sync(FULL, bk == 3));
+            }
         }
     }
     __syncwarp();
     if (do_rast) {
-        rast_sample_list(noise_r, rlist, nlist, vlist, xs, cnt, rs, K, a.L.invK, pix0, pb.sigma, a.L.inv_sigma, pb.s_rast_begin,
+        // place: rlist = [direct | many | some | rare]
+        int o0 = 0, o1 = nb0, o2 = nb0 + nb1, o3 = nb0 + nb1 + nb2;
+        if (nb0 + nb1 + nb2 + nb3 > 0) {
+#pragma unroll 1
+            for (int n0 = 0; n0 < nv; n0 += 32) {
+                const int n = n0 + lane;
+                const int bk = n < nv ? bucket_of(fabsf(xs[n])) : -1;
+                const unsigned b0 = __ballot_sync(FULL, bk == 0);
+                if (bk == 0) rlist[o0 + __popc(b0 & lt)] = (uint16_t)n;
+                o0 += __popc(b0);
+                if (compound) {
+                    const unsigned b1 = __ballot_sync(FULL, bk == 1), b2 = __ballot_sync(FULL, bk == 2),
+                                   b3 = __ballot_sync(FULL, bk == 3);
+                    if (bk == 1) rlist[o1 + __popc(b1 & lt)] = (uint16_t)n;
+                    if (bk == 2) rlist[o2 + __popc(b2 & lt)] = (uint16_t)n;
+                    if (bk == 3) rlist[o3 + __popc(b3 & lt)] = (uint16_t)n;
+                    o1 += __popc(b1);
+                    o2 += __popc(b2);
+                    o3 += __popc(b3);
+                }
+            }
+            __syncwarp();
+        }
+        if constexpr (NoiseR::kBounded) {
+            if (compound)
+                rast_compound_list(noise_r, rlist + nb0, nb1, nb2, nb3, vlist, xs, cnt, rs, K, a.L.invK, pix0, a.L.inv_sigma,
+                                   pb.s_rast_begin, pb.s_rast_end);
+        }
+        rast_sample_list(noise_r, rlist, nb0, vlist, xs, cnt, rs, K, a.L.invK, pix0, pb.sigma, a.L.inv_sigma, pb.s_rast_begin,
                          pb.s_rast_end, !no_skip, a.L.lpe_r);
         __syncwarp();
 #pragma unroll 1

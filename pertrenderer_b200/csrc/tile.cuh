@@ -160,6 +160,87 @@ __device__ __forceinline__ void rast_sample_list(const NoiseT& noise, const uint
 }
 
 // ------------------------------------------------------------------------------------------------
+// stage 1, compound sampler (the default with in-kernel noise).  The pair (cnt, rs) of an entry depends on
+// its samples only through the FLIPPED ones (h != h0).  Their number is F ~ Binomial(n, p) with
+// p = Phi(-t), t = |x| / sigma, and given F each flipped sample contributes (h - h0) U = T, a standard normal
+// conditioned on T > t (x >= 0: flips have U < -t and h - h0 = -1; x < 0: U >= t and h - h0 = +1).  So
+//     cnt = h0 ? n - F : F,      rs = T_1 + ... + T_F
+// drawn with ONE uniform for F (inversion on the survival function) and one per flip (inverse CDF of the
+// tail) has exactly the joint law of the n per-sample draws of randomras/smoothrast.py:32-36,46, at a cost of
+// O(1 + n p) instead of n normals: p = 0.02 two sigma inside a face.  Entries are independent of each other
+// and of the aggregation noise, so every output of the shader keeps the law of the reference estimator; it is
+// not the sample path of pert_noise_fill's tensor (PERT_F_PER_SAMPLE_NOISE restores that).
+// blist holds compact indices in three consecutive segments (n1 entries with many expected flips, n2 with some, n3 with
+// rarely any), each walked in warp passes of its own, so that the lanes of a pass loop about equally long.
+// Counters: (0x40000000 + 2*(s_begin/4) + call, k, pixel, stage 0): disjoint from every sample quad's and,
+// for sample shards, from every other shard's (a shard of nq quads makes at most nq + 1 calls).
+// ------------------------------------------------------------------------------------------------
+template <class NoiseT>
+__device__ __forceinline__ void rast_compound_list(const NoiseT& noise, const uint16_t* blist, int n1, int n2, int n3,
+                                                   const uint16_t* vlist, const float* xs, uint16_t* cnt, float* rs,
+                                                   int K, float invK, int64_t pix0, float inv_sigma, int s_begin,
+                                                   int s_end) {
+    const int lane = threadIdx.x & 31;
+    const int n_loc = s_end - s_begin;
+    const float fn = (float)n_loc;
+    const uint32_t c0 = 0x40000000u + 2u * (uint32_t)(s_begin >> 2);
+    // one lane per entry, no warp collectives inside; a pass never straddles two segments
+    int seg = 0, seg_end = n1, li = lane;
+#pragma unroll 1
+    for (;;) {
+        if (li >= seg_end) {  // this lane is done with the segment: move to its slot in the next one
+            if (seg == 2) break;
+            ++seg;
+            li = seg_end + lane;
+            seg_end = seg == 1 ? n1 + n2 : n1 + n2 + n3;
+            continue;
+        }
+        const int n = blist[li];
+        li += 32;
+        const int e = vlist[n];
+        const int pix = entry_pixel(e, invK), k = e - pix * K;
+        const float x = xs[n];
+        const float t = fabsf(x) * inv_sigma;
+        const float p = 0.5f * erfcf(t * 0.70710678118654752f);
+        const float nl = fn * log1pf(-p);
+        const float sf1 = -expm1f(nl);  // P(F >= 1)
+        uint32_t w[4];
+        noise.words(c0, (uint32_t)k, pix0 + pix, w);
+        const float u = ((float)w[0] + 1.0f) * 2.3283064365386963e-10f;  // (0, 1], 2^-32 resolution near 0
+        int F = 0;
+        float r = 0.0f;
+        if (u <= sf1) {
+            float pmf = __expf(nl), sf = sf1;
+            const float ratio = __fdividef(p, 1.0f - p);
+            // F >= k+1  <=>  u <= sf_k;  past the mode, stop once the terms are below the resolution of the running
+            // difference (an event of probability < 1e-6 whose F is then off by a few)
+            do {
+                ++F;
+                pmf *= ratio * __fdividef((float)(n_loc - F + 1), (float)F);
+                sf -= pmf;
+            } while (u <= sf && F < n_loc && (pmf > 1e-10f || (float)F < fn * p));
+            uint32_t q = c0;
+            int idx = 1;
+#pragma unroll 1
+            for (int i = 0; i < F; ++i) {
+                if (idx == 4) {
+                    ++q;
+                    noise.words(q, (uint32_t)k, pix0 + pix, w);
+                    idx = 0;
+                }
+                const uint32_t word = idx == 0 ? w[0] : idx == 1 ? w[1] : idx == 2 ? w[2] : w[3];
+                ++idx;
+                const float v = ((float)word + 1.0f) * 2.3283064365386963e-10f;  // (0, 1]
+                // T = -Phi^-1(v p) >= t:  Phi(-T) = v p
+                r += fmaxf(1.4142135623730951f * erfcinvf(2.0f * v * p), t);
+            }
+        }
+        cnt[n] = (uint16_t)((x >= 0.0f) ? n_loc - F : F);
+        rs[n] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // per-pixel preparation, G lanes per pixel, all pixels of the tile at once.
 // In:  zs[n] = raw zbuf, cnt[n] = hit count over ALL coverage samples.   Out: zs[n] = zeta_k.
 // Values returned are uniform over the lanes of a pixel's group.

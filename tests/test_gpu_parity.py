@@ -428,16 +428,19 @@ def test_dead_noise_modes_share_forward_and_live_gradients():
     entries stay exactly zero in all of them."""
     from gpu_util import problem_from_case, run_cuda, synthetic_case
     from pertrenderer_b200 import _cabi
+    from pertrenderer_b200 import ops
     g = synthetic_case(1, 12, 12, 20, 32, 32, kind="realistic", seed=51)
-    runs = {f: run_cuda(problem_from_case(g, explicit=False, seed_rast=1, seed_agg=2, flags=f), g["grad_image"])
-            for f in (0, _cabi.F_PER_SAMPLE_NOISE, _cabi.F_SKIP_DEAD_NOISE)}
-    a, b, c = runs[0], runs[_cabi.F_PER_SAMPLE_NOISE], runs[_cabi.F_SKIP_DEAD_NOISE]
+    # ONE forward (the per-sample flag also selects the per-sample coverage draws, which would change the sample
+    # path: the compound sampler of the default mode is tested in test_gpu_compound.py), three backward modes
+    a = run_cuda(problem_from_case(g, explicit=False, seed_rast=1, seed_agg=2, flags=0), g["grad_image"])
+    runs = {0: a}
+    for f in (_cabi.F_PER_SAMPLE_NOISE, _cabi.F_SKIP_DEAD_NOISE):
+        pr = problem_from_case(g, explicit=False, seed_rast=1, seed_agg=2, flags=f)
+        gd, gz, gc, scal = ops.shade_backward(pr, a["saved"], g["grad_image"].cuda())
+        runs[f] = dict(grad_dists=gd.cpu(), grad_zbuf=gz.cpu(), grad_colors=gc.cpu(), scalars=scal.cpu())
+    b, c = runs[_cabi.F_PER_SAMPLE_NOISE], runs[_cabi.F_SKIP_DEAD_NOISE]
     mask = g["pix_to_face"] >= 0
     for r in (b, c):
-        # same winners, hence the same weights; the default mode runs the sparse-first tile geometry, whose
-        # blend sums the (identical) terms with another number of lanes per pixel
-        assert torch.equal(a["winners"], r["winners"]) and torch.equal(a["hist"], r["hist"])
-        assert (a["image"] - r["image"]).abs().max() <= 1e-6
         assert torch.equal(a["grad_colors"], r["grad_colors"])
         assert (r["grad_zbuf"][~mask] == 0).all() and (r["grad_dists"][~mask] == 0).all()
         assert torch.isfinite(r["scalars"]).all()
@@ -475,12 +478,17 @@ def test_once_per_logit_noise_has_the_reference_distribution():
         se = (a.var(0) / reps + b.var(0) / reps).sqrt()
         z = (a.mean(0) - b.mean(0)).abs() / (se + 1e-3 * se.max() + 1e-30)
         assert z.max().item() < 5.5, (k, "mean", z.max().item())
-        # variance: relative standard error of a sample variance of ~Gaussian data is sqrt(2/(reps-1))
+        # variance: z-score with the standard error of a sample variance, sqrt((m4 - var^2) / reps), estimated from the
+        # samples (gradients of rarely flipping coverage entries are heavy tailed: a plain ratio bound fails between two
+        # runs of the SAME mode, tools/diag_law.py)
         va, vb = a.var(0), b.var(0)
-        big = vb > 1e-3 * vb.max()
-        ratio = (va[big] / vb[big])
-        tol = 6.5 * (2 * 2.0 / (reps - 1)) ** 0.5  # heavy-ish tails: allow 6.5 combined standard errors
-        assert (ratio - 1).abs().max().item() < tol, (k, "var", ratio.min().item(), ratio.max().item())
+        m4a, m4b = ((a - a.mean(0)) ** 4).mean(0), ((b - b.mean(0)) ** 4).mean(0)
+        sev = ((m4a - va * va).clamp(min=0) / reps + (m4b - vb * vb).clamp(min=0) / reps).sqrt()
+        zv = (va - vb).abs() / (sev + 1e-3 * sev.max() + 1e-30)
+        assert zv.max().item() < 6.0, (k, "var", zv.max().item())
+        # ... and the bulk of the entries (the well-sampled ones) agree closely
+        big = vb > 0.2 * vb.max()
+        assert abs((va[big] / vb[big]).log().median().item()) < 0.25, (k, "var ratio")
 
 
 def test_face_colour_gather_matches_texel_tensor():

@@ -14,7 +14,12 @@ steps = int(sys.argv[2]) if len(sys.argv) > 2 else 3
 flags = int(sys.argv[3]) if len(sys.argv) > 3 else 0
 N, HW, K, S = 8, 256, 50, 64
 dev = "cuda:0"
-fr, col = synthetic_fragments(N, HW, HW, K, kind=kind, sigma=1e-3, seed=0, device=dev)
+if kind == "rasterised":
+    import types
+    import bench
+    fr, col = bench.rasterised_fragments(types.SimpleNamespace(views=N, image_size=HW, faces_per_pixel=K, nb_samples=S), torch.device(dev))
+else:
+    fr, col = synthetic_fragments(N, HW, HW, K, kind=kind, sigma=1e-3, seed=0, device=dev)
 G = torch.randn((N, HW, HW, 4), device=dev, generator=torch.Generator(device=dev).manual_seed(1))
 for i in range(steps):
     pr = ops.ShadeProblem(pix_to_face=fr.pix_to_face, zbuf=fr.zbuf, dists=fr.dists, colors=col, znear=1.0, zfar=100.0,
