@@ -3,8 +3,10 @@
  *
  * One shared library (libpertshade.so, built for sm_100a from pertrenderer_b200/csrc) exports the
  * functions below.  Plain pointers and sizes only: no torch / C++ types cross this boundary, the
- * library never allocates, frees or retains device memory, holds no global or thread-local state,
- * never synchronises the device and launches on the stream it is given.  Every function returns
+ * library never allocates, frees or retains device memory, never synchronises the device and launches on
+ * the stream it is given.  The only state it keeps is diagnostic or immutable: the name of the calling thread's
+ * last CUDA error (pert_last_cuda_error) and each device's SM count, cached at first use; it reads no environment
+ * variable (tuning builds compiled with -DPERT_EXPERIMENTS do, the product never is).  Every function returns
  * PERT_OK (0) or a negative PERT_E_* code; nothing throws across the ABI.
  *
  * What each entry point replaces in the reference (paths relative to quentinll/pertrenderer):
@@ -92,6 +94,11 @@ extern "C" {
  * pert_argmax_bwd returns PERT_E_UNSUPPORTED with either flag. */
 #define PERT_F_UNIFORM 0x800u
 #define PERT_F_GUMBEL 0x1000u
+/* pert_shade_fwd / pert_shade_bwd with in-kernel noise and all phases in one call: Philox4x32-7 instead of
+ * Philox4x32-10 (7 rounds is the Crush-resistant minimum of Salmon et al., SC'11; 10 is their and cuRAND's default).
+ * Another noise stream of the same law, 30 % fewer multiply / xor pairs per call; pert_noise_fill materialises it with
+ * stage | 16.  Phase-split (sample-sharded) and explicit-noise calls return PERT_E_UNSUPPORTED with this flag. */
+#define PERT_F_PHILOX7 0x2000u
 /* phases of the fused kernels; 0 means "all".  Used for noise-sample sharding where collectives sit
  * between the phases. */
 #define PERT_PH_RAST 0x10u  /* fwd: draw coverage samples -> counts, rsum */
@@ -330,7 +337,8 @@ int pert_rasterize_bwd(const pert_raster* rs, const int64_t* pix_to_face, const 
                        const float* grad_dists, float* grad_face_verts, void* stream);
 
 /* Materialise the counter-based noise: out float (s_end-s_begin, P, slots), stage 0 = coverage
- * (slots = K), 1 = aggregation (slots = K1); stage | 2 = the Cauchy variant of that stage, | 4 uniform, | 8 Gumbel. */
+ * (slots = K), 1 = aggregation (slots = K1); stage | 2 = the Cauchy variant of that stage, | 4 uniform, | 8 Gumbel,
+ * | 16 the Gaussian stream of PERT_F_PHILOX7. */
 int pert_noise_fill(uint64_t seed, int32_t stage, int64_t P, int32_t slots, int32_t s_begin, int32_t s_end,
                     int64_t pixel_offset, float* out, void* stream);
 

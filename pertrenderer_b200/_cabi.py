@@ -25,6 +25,7 @@ F_CAUCHY = 8
 F_NO_VR = 0x400
 F_UNIFORM = 0x800
 F_GUMBEL = 0x1000
+F_PHILOX7 = 0x2000
 PH_RAST, PH_AGG, PH_BLEND = 0x10, 0x20, 0x40
 PH_BWD_SAMPLE, PH_BWD_FINISH = 0x100, 0x200
 

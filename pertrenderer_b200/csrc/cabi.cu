@@ -143,6 +143,11 @@ static Launch make_launch(const pert_problem* pb, int tp) {
     L.inv_gamma = 1.0f / pb->gamma;
     L.t_compound = compound_threshold(pb->s_rast_end - pb->s_rast_begin);
     compound_buckets(pb->s_rast_end - pb->s_rast_begin, L.t_compound, L.t_bucket);
+    L.cmp_min = 12;
+#ifdef PERT_EXPERIMENTS
+    if (const char* e = getenv("PERT_CMP_MIN")) L.cmp_min = atoi(e);
+#endif
+    if (L.cmp_min > 32) L.cmp_min = 32;
     return L;
 }
 
@@ -156,8 +161,8 @@ static Launch make_launch(const pert_problem* pb, int tp) {
 static int sparse_tp(int K, int64_t P) {
     int tp = 2 * pick_tp(K);
     if (tp > 32) tp = 32;
-    // small jobs: prefer enough tiles to fill the GPU (148 SMs x ~24 resident warps) over double-size tiles
-    if (tp > pick_tp(K) && (P + tp - 1) / tp < 148 * 24) tp = pick_tp(K);
+    // small jobs: prefer enough tiles to fill the GPU (SMs x ~24 resident warps) over double-size tiles
+    if (tp > pick_tp(K) && (P + tp - 1) / tp < (int64_t)sm_count() * 24) tp = pick_tp(K);
     return tp;
 }
 static int sparse_cap(int K, int tp) {
@@ -214,6 +219,7 @@ extern "C" int pert_shade_fwd(const pert_problem* pb_in, float* image, uint16_t*
         return PERT_E_ALIGN;
     if ((uintptr_t)worklist & 15) return PERT_E_ALIGN;
     const uint32_t all = PERT_PH_RAST | PERT_PH_AGG | PERT_PH_BLEND;
+    if ((f & PERT_F_PHILOX7) && ((f & all) != all || hist || a.pb.noise_rast || a.pb.noise_agg)) return PERT_E_UNSUPPORTED;
     bool sparse = sparse_first_ok(&a.pb, worklist, (f & all) == all && !hist);
     if (sparse) {  // the fallback pass runs FBT/32 warps per CTA: its tiles must fit that many times
         SmemLayout t;
@@ -272,6 +278,7 @@ extern "C" int pert_shade_bwd(const pert_problem* pb_in, const float* grad_image
         ((uintptr_t)scalar_partials & 15) || ((uintptr_t)acc & 3) || ((uintptr_t)pixstat & 3) || ((uintptr_t)hist & 3))
         return PERT_E_ALIGN;
     if ((uintptr_t)worklist & 15) return PERT_E_ALIGN;
+    if ((f & PERT_F_PHILOX7) && (!(smp && fin) || hist || a.pb.noise_agg)) return PERT_E_UNSUPPORTED;
     bool sparse = sparse_first_ok(&a.pb, worklist, smp && fin && !hist);
     if (sparse) {  // the fallback pass runs FBT/32 warps per CTA: its tiles must fit that many times
         const int tp2 = sparse_tp(a.pb.K, a.pb.N * a.pb.H * a.pb.W) / 2;

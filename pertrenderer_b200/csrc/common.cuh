@@ -112,6 +112,19 @@ __device__ __forceinline__ void list_append(bool flag, uint16_t item, uint16_t* 
     if (flag) list[base + __popc(b & ((1u << lane) - 1u))] = item;
 }
 
+// number of SMs of the current device (persistent grids are sized in multiples of it); cached per device
+static inline int sm_count() {
+    static int cached[64] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (cached[dev] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        cached[dev] = n;
+    }
+    return cached[dev];
+}
+
 // Shared-memory layout of a kernel: computed ONCE on the host (byte offsets in the launch record), so the
 // kernels spend one add per array instead of re-deriving the layout (the fused kernels are instruction-fetch
 // sensitive: every instruction of glue counts).
@@ -177,6 +190,7 @@ struct Launch {
     float inv_sigma, invSg, inv_sr, invS;  // 1/sigma, 1/(S_agg gamma), 1/(S_rast sigma), 1/S_agg
     float inv_gamma;  // 1/gamma (SoftAgg, smoothagg.py:181)
     float t_compound; // coverage entries with |x|/sigma >= this are drawn by the compound sampler (tile.cuh)
+    int cmp_min;       // fewer compound entries than this in a tile are drawn by the per-sample loop instead
     float t_bucket[2]; // ... and bucketed by expected flips: [t_compound, t_bucket[0]) many, [.., t_bucket[1]) some, rest rare
 };
 

@@ -405,6 +405,7 @@ int launch_noise_fill(uint64_t seed, int stage, int64_t P, int slots, int s_begi
     if (stage & 4) noise_fill_kernel<PhiloxUniform><<<blocks, 256, 0, st>>>(seed, stage & 1, P, slots, s_begin, s_end, pixel_offset, out);
     else if (stage & 8) noise_fill_kernel<PhiloxGumbel><<<blocks, 256, 0, st>>>(seed, stage & 1, P, slots, s_begin, s_end, pixel_offset, out);
     else if (stage & 2) noise_fill_kernel<PhiloxCauchy><<<blocks, 256, 0, st>>>(seed, stage & 1, P, slots, s_begin, s_end, pixel_offset, out);
+    else if (stage & 16) noise_fill_kernel<PhiloxNoise7><<<blocks, 256, 0, st>>>(seed, stage & 1, P, slots, s_begin, s_end, pixel_offset, out);
     else noise_fill_kernel<PhiloxNoise><<<blocks, 256, 0, st>>>(seed, stage & 1, P, slots, s_begin, s_end, pixel_offset, out);
     return (int)cudaGetLastError();
 }

@@ -590,7 +590,7 @@ __global__ void __launch_bounds__(PT) phong_light_bwd_kernel(const pert_phong ph
 }
 
 unsigned phong_grid(int64_t nchunks, int ctas_per_sm, int warps_per_cta = PW) {
-    const int64_t cap = 148 * (int64_t)ctas_per_sm, need = (nchunks + warps_per_cta - 1) / warps_per_cta;
+    const int64_t cap = sm_count() * (int64_t)ctas_per_sm, need = (nchunks + warps_per_cta - 1) / warps_per_cta;
     return (unsigned)(need < cap ? need : cap);
 }
 
@@ -616,7 +616,7 @@ static int launch_bwd_t(const pert_phong& ph, const float* grad_colors, float* g
     dim3 grid(phong_grid(nchunks, ctas_per_sm, NT / 32));
     if (per_image) {  // one grid row of CTAs per image, about one CTA per SM in total
         const int64_t n_img = ph.P / ph.HW, img_chunks = (ph.HW * ph.K + WCHUNK - 1) / WCHUNK;
-        int64_t ctas = (148 * (int64_t)ctas_per_sm + n_img - 1) / n_img;
+        int64_t ctas = (sm_count() * (int64_t)ctas_per_sm + n_img - 1) / n_img;
         const int64_t most = (img_chunks + NT / 32 - 1) / (NT / 32);
         grid = dim3((unsigned)(ctas < most ? ctas : most), (unsigned)n_img);
     }

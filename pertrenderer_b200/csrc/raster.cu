@@ -585,13 +585,13 @@ int launch_rasterize_bwd(const pert_raster& rs, const int64_t* pix_to_face, cons
         if (e != cudaSuccess) return (int)e;
         int per_sm = (int)((200 * 1024) / smem);
         per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
-        int64_t ctas = (148 * (int64_t)per_sm + rs.N - 1) / rs.N;
+        int64_t ctas = (sm_count() * (int64_t)per_sm + rs.N - 1) / rs.N;
         const int64_t most = (img_chunks + NT / 32 - 1) / (NT / 32);
         if (ctas > most) ctas = most;
         rasterize_bwd_kernel<true, NT><<<dim3((unsigned)ctas, (unsigned)rs.N), NT, smem, st>>>(
             rs, pix_to_face, grad_zbuf, grad_bary, grad_dists, grad_face_verts, E, nchunks, tcap);
     } else {
-        const int64_t cap = 148 * 8, need = (nchunks + BW - 1) / BW;
+        const int64_t cap = sm_count() * 8, need = (nchunks + BW - 1) / BW;
         rasterize_bwd_kernel<false, BT><<<(unsigned)(need < cap ? need : cap), BT, (size_t)BW * BCHUNK * sizeof(uint16_t), st>>>(
             rs, pix_to_face, grad_zbuf, grad_bary, grad_dists, grad_face_verts, E, nchunks, 0);
     }

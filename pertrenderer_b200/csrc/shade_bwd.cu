@@ -105,7 +105,7 @@ __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& n
     uint8_t* apx = cv.take<uint8_t>();
     // single-chunk jobs: the tile's saved winners (tp rows of sa_loc entries, contiguous) are copied to
     // shared memory asynchronously at the very start, off the critical path
-    const bool early_w = a.L.nchunks == 1 && ((sa_loc * wb) & 15) == 0 && do_sample;
+    const bool early_w = a.L.nchunks == 1 && ((sa_loc * wb) & 15) == 0 && do_sample && (((uintptr_t)a.winners) & 15) == 0;
     unsigned char* wst = cv.take<unsigned char>();
     if (early_w) {
         const unsigned char* src = reinterpret_cast<const unsigned char*>(a.winners) + pix0 * sa_loc * wb;
@@ -671,24 +671,53 @@ static int launch_bwd_t(const BwdArgs& a, const NA& na, cudaStream_t st) {
     return a.pb.face_colors ? launch_bwd_f<NA, GT, PHASED, true, false>(a, na, st)
                             : launch_bwd_f<NA, GT, PHASED, false, false>(a, na, st);
 }
-// sparse-first main pass (compact per-logit arrays)
-template <int GT>
-static int launch_bwd_c(const BwdArgs& a, const PhiloxNoise& na, cudaStream_t st) {
+// sparse-first main pass (compact per-logit arrays); PN = the Philox variant
+template <class PN, int GT>
+static int launch_bwd_c(const BwdArgs& a, const PN& na, cudaStream_t st) {
     if (a.blob) {  // forward left tile blobs: no re-scan, no logit recomputation (the common geometries only)
         if constexpr (GT == 2 || GT == 4) {
-            return a.pb.face_colors ? launch_bwd_f<PhiloxNoise, GT, false, true, true, true>(a, na, st)
-                                    : launch_bwd_f<PhiloxNoise, GT, false, false, true, true>(a, na, st);
+            return a.pb.face_colors ? launch_bwd_f<PN, GT, false, true, true, true>(a, na, st)
+                                    : launch_bwd_f<PN, GT, false, false, true, true>(a, na, st);
         }
     }
-    return a.pb.face_colors ? launch_bwd_f<PhiloxNoise, GT, false, true, true>(a, na, st)
-                            : launch_bwd_f<PhiloxNoise, GT, false, false, true>(a, na, st);
+    return a.pb.face_colors ? launch_bwd_f<PN, GT, false, true, true>(a, na, st)
+                            : launch_bwd_f<PN, GT, false, false, true>(a, na, st);
 }
-template <int GT, bool FACE>
-static int launch_bwd_fb(const BwdArgs& a, const PhiloxNoise& na, int64_t prow0, cudaStream_t st) {
+template <class PN, int GT, bool FACE>
+static int launch_bwd_fb(const BwdArgs& a, const PN& na, int64_t prow0, cudaStream_t st) {
     const size_t smem = (size_t)a.L.warp_smem * (FBT / 32);
-    if (int rc = set_smem(shade_bwd_fallback_kernel<PhiloxNoise, GT, FACE>, smem)) return rc;
-    shade_bwd_fallback_kernel<PhiloxNoise, GT, FACE><<<148 * 12, FBT, smem, st>>>(a, na, prow0);
+    if (int rc = set_smem(shade_bwd_fallback_kernel<PN, GT, FACE>, smem)) return rc;
+    shade_bwd_fallback_kernel<PN, GT, FACE><<<sm_count() * 12, FBT, smem, st>>>(a, na, prow0);
     return (int)cudaGetLastError();
+}
+
+// both phases in one launch, in-kernel noise
+template <class PN>
+static int launch_bwd_production(const BwdArgs& a, const BwdArgs* fb, cudaStream_t st) {
+    const PN pa(a.pb.seed_agg, 1, a.pb.pixel_offset);
+    int rc;
+    if (fb) {  // sparse-first: compact main pass, then half-size tiles for whatever did not fit
+        switch (a.L.G) {
+            case 1: rc = launch_bwd_c<PN, 1>(a, pa, st); break;
+            case 2: rc = launch_bwd_c<PN, 2>(a, pa, st); break;
+            case 4: rc = launch_bwd_c<PN, 4>(a, pa, st); break;
+            default: rc = launch_bwd_c<PN, 8>(a, pa, st); break;
+        }
+        if (rc) return rc;
+        const bool face = a.pb.face_colors != nullptr;
+        switch (fb->L.G) {
+            case 2: return face ? launch_bwd_fb<PN, 2, true>(*fb, pa, a.L.ntiles, st) : launch_bwd_fb<PN, 2, false>(*fb, pa, a.L.ntiles, st);
+            case 4: return face ? launch_bwd_fb<PN, 4, true>(*fb, pa, a.L.ntiles, st) : launch_bwd_fb<PN, 4, false>(*fb, pa, a.L.ntiles, st);
+            case 8: return face ? launch_bwd_fb<PN, 8, true>(*fb, pa, a.L.ntiles, st) : launch_bwd_fb<PN, 8, false>(*fb, pa, a.L.ntiles, st);
+            default: return face ? launch_bwd_fb<PN, 16, true>(*fb, pa, a.L.ntiles, st) : launch_bwd_fb<PN, 16, false>(*fb, pa, a.L.ntiles, st);
+        }
+    }
+    switch (a.L.G) {  // lanes per pixel known at compile time
+        case 1: return launch_bwd_t<PN, 1, false>(a, pa, st);
+        case 2: return launch_bwd_t<PN, 2, false>(a, pa, st);
+        case 4: return launch_bwd_t<PN, 4, false>(a, pa, st);
+        default: return launch_bwd_t<PN, 8, false>(a, pa, st);
+    }
 }
 
 int launch_shade_bwd(const BwdArgs& a, const BwdArgs* fb, float* grad_scalars, cudaStream_t st) {
@@ -698,37 +727,16 @@ int launch_shade_bwd(const BwdArgs& a, const BwdArgs* fb, float* grad_scalars, c
     if (a.pb.noise_agg) {
         ExplicitNoise xa{a.pb.noise_agg, a.L.P, a.pb.K + 1, a.pb.S_agg};
         rc = launch_bwd_t<ExplicitNoise, 0, true>(a, xa, st);
-    } else {
+    } else if (phased) {  // sample-sharded job: compile-time lanes per pixel for the benchmark geometries
         PhiloxNoise pa(a.pb.seed_agg, 1, a.pb.pixel_offset);
-        if (phased) {  // sample-sharded job: compile-time lanes per pixel for the benchmark geometries
-            switch (a.L.G) {
-                case 4: rc = launch_bwd_t<PhiloxNoise, 4, true>(a, pa, st); break;
-                case 8: rc = launch_bwd_t<PhiloxNoise, 8, true>(a, pa, st); break;
-                default: rc = launch_bwd_t<PhiloxNoise, 0, true>(a, pa, st); break;
-            }
-        } else if (fb) {  // sparse-first: compact main pass, then half-size tiles for whatever did not fit
-            switch (a.L.G) {
-                case 1: rc = launch_bwd_c<1>(a, pa, st); break;
-                case 2: rc = launch_bwd_c<2>(a, pa, st); break;
-                case 4: rc = launch_bwd_c<4>(a, pa, st); break;
-                default: rc = launch_bwd_c<8>(a, pa, st); break;
-            }
-            if (rc) return rc;
-            const bool face = a.pb.face_colors != nullptr;
-            switch (fb->L.G) {
-                case 2: rc = face ? launch_bwd_fb<2, true>(*fb, pa, a.L.ntiles, st) : launch_bwd_fb<2, false>(*fb, pa, a.L.ntiles, st); break;
-                case 4: rc = face ? launch_bwd_fb<4, true>(*fb, pa, a.L.ntiles, st) : launch_bwd_fb<4, false>(*fb, pa, a.L.ntiles, st); break;
-                case 8: rc = face ? launch_bwd_fb<8, true>(*fb, pa, a.L.ntiles, st) : launch_bwd_fb<8, false>(*fb, pa, a.L.ntiles, st); break;
-                default: rc = face ? launch_bwd_fb<16, true>(*fb, pa, a.L.ntiles, st) : launch_bwd_fb<16, false>(*fb, pa, a.L.ntiles, st); break;
-            }
-        } else {
-            switch (a.L.G) {  // lanes per pixel known at compile time
-                case 1: rc = launch_bwd_t<PhiloxNoise, 1, false>(a, pa, st); break;
-                case 2: rc = launch_bwd_t<PhiloxNoise, 2, false>(a, pa, st); break;
-                case 4: rc = launch_bwd_t<PhiloxNoise, 4, false>(a, pa, st); break;
-                default: rc = launch_bwd_t<PhiloxNoise, 8, false>(a, pa, st); break;
-            }
+        switch (a.L.G) {
+            case 4: rc = launch_bwd_t<PhiloxNoise, 4, true>(a, pa, st); break;
+            case 8: rc = launch_bwd_t<PhiloxNoise, 8, true>(a, pa, st); break;
+            default: rc = launch_bwd_t<PhiloxNoise, 0, true>(a, pa, st); break;
         }
+    } else {
+        rc = (a.pb.flags & PERT_F_PHILOX7) ? launch_bwd_production<PhiloxNoise7>(a, fb, st)
+                                           : launch_bwd_production<PhiloxNoise>(a, fb, st);
     }
     if (rc) return rc;
     if (a.pb.flags & PERT_PH_BWD_FINISH) {

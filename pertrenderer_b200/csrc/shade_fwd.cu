@@ -26,6 +26,7 @@ void fwd_smem_layout(int tp, int cap, SmemLayout& L) {
     cv.take(tp + 1, 4);    // vstart
     cv.take(tp, 4);        // pinfo
     cv.take(tp, 2);        // plist
+    cv.take(64, 2);        // ring (compound sampler)
 }
 
 // GT = lanes per pixel as a compile-time constant (1, 2, 4, 8), or 0 to read it from the launch record.
@@ -67,6 +68,7 @@ __device__ __forceinline__ void shade_fwd_tile(const FwdArgs& a, const NoiseR& n
     int* vstart = cv.take<int>();
     int* pinfo = cv.take<int>();  // nlive | a0l << 16 of every pixel
     uint16_t* plist = cv.take<uint16_t>();
+    uint16_t* ring = cv.take<uint16_t>();
     const int cap = a.L.cap;
     float* lz = xs;
     int* hl = reinterpret_cast<int*>(rs);
@@ -103,18 +105,15 @@ __device__ __forceinline__ void shade_fwd_tile(const FwdArgs& a, const NoiseR& n
     // ---- phase 1: stage valid entries, coverage samples ---------------------------------------------
     const int sr_loc = pb.s_rast_end - pb.s_rast_begin;
     const float thr = (NoiseR::kBounded && !no_skip) ? pb.sigma * kNoiseAbsMax * 1.0001f : CUDART_INF_F;
-    // compound sampler (tile.cuh) for the entries with |x| >= x_cmp: the default with in-kernel noise.  Entries are
-    // bucketed by their expected number of flips (direct | many | some | rare) so that the lanes of a warp pass loop
-    // about equally long
+    // compound sampler (tile.cuh) for the entries with |x| >= x_cmp: the default with in-kernel noise
     const bool compound = NoiseR::kBounded && !no_skip && !(flags & PERT_F_PER_SAMPLE_NOISE);
     const float x_cmp = compound ? a.L.t_compound * pb.sigma : CUDART_INF_F;
-    const float x_b2 = a.L.t_bucket[0] * pb.sigma, x_b3 = a.L.t_bucket[1] * pb.sigma;
-    int nb0 = 0, nb1 = 0, nb2 = 0, nb3 = 0;
-    auto bucket_of = [&](float ax) -> int { return ax > thr ? -1 : ax < x_cmp ? 0 : ax < x_b2 ? 1 : ax < x_b3 ? 2 : 3; };
+    uint16_t* const blist = rlist + cap - 1;  // stored downwards: the two lists share one array of cap entries
+    int nlist = 0, nblist = 0;
 #pragma unroll 1
     for (int n0 = 0; n0 < nv; n0 += 32) {
         const int n = n0 + lane;
-        int bk = -1;
+        bool need = false, cmp = false;
         if (n < nv) {
             const int e = vlist[n];
             zs[n] = __ldg(zbuf_t + e);
@@ -123,8 +122,9 @@ __device__ __forceinline__ void shade_fwd_tile(const FwdArgs& a, const NoiseR& n
                 const float x = -__ldg(dists_t + e);
                 xs[n] = x;
                 // |x| beyond the largest possible sigma*|U| cannot flip: exact, not an approximation
-                bk = bucket_of(fabsf(x));
-                if (bk < 0) {
+                need = fabsf(x) <= thr;
+                cmp = need && fabsf(x) >= x_cmp;
+                if (!need) {
                     cnt[n] = (x >= 0.0f) ? (uint16_t)sr_loc : (uint16_t)0;
                     rs[n] = 0.0f;
                 }
@@ -133,45 +133,33 @@ __device__ __forceinline__ void shade_fwd_tile(const FwdArgs& a, const NoiseR& n
             }
         }
         if (do_rast) {
-            nb0 += __popc(__ballot_sync(FULL, bk == 0));
-            if (compound) {
-                nb1 += __popc(__ballot_sync(FULL, bk == 1));
-                nb2 += __popc(__ballot_sync(FULL, bk == 2));
-                nb3 += __popc(__ballot_sync(FULL, bk == 3));
-            }
+            const unsigned b = __ballot_sync(FULL, need && !cmp), bc = __ballot_sync(FULL, cmp);
+            if (need && !cmp) rlist[nlist + __popc(b & lt)] = (uint16_t)n;
+            if (cmp) blist[-(nblist + __popc(bc & lt))] = (uint16_t)n;
+            nlist += __popc(b);
+            nblist += __popc(bc);
         }
     }
     __syncwarp();
     if (do_rast) {
-        // place: rlist = [direct | many | some | rare]
-        int o0 = 0, o1 = nb0, o2 = nb0 + nb1, o3 = nb0 + nb1 + nb2;
-        if (nb0 + nb1 + nb2 + nb3 > 0) {
-#pragma unroll 1
-            for (int n0 = 0; n0 < nv; n0 += 32) {
-                const int n = n0 + lane;
-                const int bk = n < nv ? bucket_of(fabsf(xs[n])) : -1;
-                const unsigned b0 = __ballot_sync(FULL, bk == 0);
-                if (bk == 0) rlist[o0 + __popc(b0 & lt)] = (uint16_t)n;
-                o0 += __popc(b0);
-                if (compound) {
-                    const unsigned b1 = __ballot_sync(FULL, bk == 1), b2 = __ballot_sync(FULL, bk == 2),
-                                   b3 = __ballot_sync(FULL, bk == 3);
-                    if (bk == 1) rlist[o1 + __popc(b1 & lt)] = (uint16_t)n;
-                    if (bk == 2) rlist[o2 + __popc(b2 & lt)] = (uint16_t)n;
-                    if (bk == 3) rlist[o3 + __popc(b3 & lt)] = (uint16_t)n;
-                    o1 += __popc(b1);
-                    o2 += __popc(b2);
-                    o3 += __popc(b3);
-                }
-            }
+        if (nblist > 0 && nblist < a.L.cmp_min) {
+            // a handful of entries: the per-sample loop spreads each entry's samples over the idle lanes, which beats
+            // one lane per entry (the lists share one array: the moved entries are read before they can be overwritten)
+            const int moved = lane < nblist ? blist[-lane] : 0;
+            __syncwarp();
+            if (lane < nblist) rlist[nlist + lane] = (uint16_t)moved;
+            nlist += nblist;
+            nblist = 0;
             __syncwarp();
         }
         if constexpr (NoiseR::kBounded) {
-            if (compound)
-                rast_compound_list(noise_r, rlist + nb0, nb1, nb2, nb3, vlist, xs, cnt, rs, K, a.L.invK, pix0, a.L.inv_sigma,
-                                   pb.s_rast_begin, pb.s_rast_end);
+            if (nblist > 0) {
+                const CompoundCtx<NoiseR> cc{noise_r, vlist, xs, cnt, rs, K, a.L.invK, pix0, a.L.inv_sigma, sr_loc,
+                                             0x40000000u + 2u * (uint32_t)(pb.s_rast_begin >> 2)};
+                rast_compound_list(cc, blist, nblist, a.L.t_bucket[0] * pb.sigma, a.L.t_bucket[1] * pb.sigma, ring);
+            }
         }
-        rast_sample_list(noise_r, rlist, nb0, vlist, xs, cnt, rs, K, a.L.invK, pix0, pb.sigma, a.L.inv_sigma, pb.s_rast_begin,
+        rast_sample_list(noise_r, rlist, nlist, vlist, xs, cnt, rs, K, a.L.invK, pix0, pb.sigma, a.L.inv_sigma, pb.s_rast_begin,
                          pb.s_rast_end, !no_skip, a.L.lpe_r);
         __syncwarp();
 #pragma unroll 1
@@ -418,7 +406,7 @@ __global__ void __launch_bounds__(FNT, 32) shade_fwd_kernel(const FwdArgs a, con
 // as half-size tiles (GT lanes per pixel = twice the main pass's) with full capacity.  Few persistent CTAs
 // walk the work list; it is empty for sparse (real) fragments.
 template <class NoiseR, class NoiseA, int GT>
-__global__ void __launch_bounds__(FBT, 16) shade_fwd_fallback_kernel(const FwdArgs a, const NoiseR noise_r, const NoiseA noise_a) {
+__global__ void __launch_bounds__(FBT, 12) shade_fwd_fallback_kernel(const FwdArgs a, const NoiseR noise_r, const NoiseA noise_a) {
     extern __shared__ __align__(16) unsigned char smem_all[];
     unsigned char* smem_raw = smem_all + (threadIdx.x >> 5) * a.L.warp_smem;  // FBT/32 independent warps per CTA
     const int n = 2 * a.worklist[0];
@@ -446,16 +434,36 @@ static int launch_fwd_t(const FwdArgs& a, const NR& nr, const NA& na, cudaStream
     return (int)cudaGetLastError();
 }
 
-template <int GT>
-static int launch_fwd_fallback(const FwdArgs& a, const PhiloxNoise& nr, const PhiloxNoise& na, cudaStream_t st) {
+template <class PN, int GT>
+static int launch_fwd_fallback(const FwdArgs& a, const PN& nr, const PN& na, cudaStream_t st) {
     const size_t smem = (size_t)a.L.warp_smem * (FBT / 32);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(shade_fwd_fallback_kernel<PhiloxNoise, PhiloxNoise, GT>,
+        cudaError_t e = cudaFuncSetAttribute(shade_fwd_fallback_kernel<PN, PN, GT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    shade_fwd_fallback_kernel<PhiloxNoise, PhiloxNoise, GT><<<148 * 16, FBT, smem, st>>>(a, nr, na);
+    shade_fwd_fallback_kernel<PN, PN, GT><<<sm_count() * 12, FBT, smem, st>>>(a, nr, na);
     return (int)cudaGetLastError();
+}
+
+// production path (in-kernel noise in both stages, all phases in one launch); PN = the Philox variant
+template <class PN>
+static int launch_fwd_production(const FwdArgs& a, const FwdArgs* fb, cudaStream_t st) {
+    const PN pr(a.pb.seed_rast, 0, a.pb.pixel_offset), pa(a.pb.seed_agg, 1, a.pb.pixel_offset);
+    int rc;
+    switch (a.L.G) {  // lanes per pixel known at compile time
+        case 1: rc = launch_fwd_t<PN, PN, 1, false>(a, pr, pa, st); break;
+        case 2: rc = launch_fwd_t<PN, PN, 2, false>(a, pr, pa, st); break;
+        case 4: rc = launch_fwd_t<PN, PN, 4, false>(a, pr, pa, st); break;
+        default: rc = launch_fwd_t<PN, PN, 8, false>(a, pr, pa, st); break;
+    }
+    if (rc || !fb) return rc;
+    switch (fb->L.G) {  // sparse-first mode: half-size tiles for whatever did not fit
+        case 2: return launch_fwd_fallback<PN, 2>(*fb, pr, pa, st);
+        case 4: return launch_fwd_fallback<PN, 4>(*fb, pr, pa, st);
+        case 8: return launch_fwd_fallback<PN, 8>(*fb, pr, pa, st);
+        default: return launch_fwd_fallback<PN, 16>(*fb, pr, pa, st);
+    }
 }
 
 int launch_shade_fwd(const FwdArgs& a, const FwdArgs* fb, cudaStream_t st) {
@@ -472,20 +480,8 @@ int launch_shade_fwd(const FwdArgs& a, const FwdArgs* fb, cudaStream_t st) {
                 default: return launch_fwd_t<PhiloxNoise, PhiloxNoise, 0, true>(a, pr, pa, st);
             }
         }
-        int rc;
-        switch (a.L.G) {  // production path: lanes per pixel known at compile time
-            case 1: rc = launch_fwd_t<PhiloxNoise, PhiloxNoise, 1, false>(a, pr, pa, st); break;
-            case 2: rc = launch_fwd_t<PhiloxNoise, PhiloxNoise, 2, false>(a, pr, pa, st); break;
-            case 4: rc = launch_fwd_t<PhiloxNoise, PhiloxNoise, 4, false>(a, pr, pa, st); break;
-            default: rc = launch_fwd_t<PhiloxNoise, PhiloxNoise, 8, false>(a, pr, pa, st); break;
-        }
-        if (rc || !fb) return rc;
-        switch (fb->L.G) {  // sparse-first mode: half-size tiles for whatever did not fit
-            case 2: return launch_fwd_fallback<2>(*fb, pr, pa, st);
-            case 4: return launch_fwd_fallback<4>(*fb, pr, pa, st);
-            case 8: return launch_fwd_fallback<8>(*fb, pr, pa, st);
-            default: return launch_fwd_fallback<16>(*fb, pr, pa, st);
-        }
+        return (a.pb.flags & PERT_F_PHILOX7) ? launch_fwd_production<PhiloxNoise7>(a, fb, st)
+                                             : launch_fwd_production<PhiloxNoise>(a, fb, st);
     }
     if (er && ea) return launch_fwd_t<ExplicitNoise, ExplicitNoise, 0, true>(a, xr, xa, st);
     if (er) return launch_fwd_t<ExplicitNoise, PhiloxNoise, 0, true>(a, xr, pa, st);

@@ -170,73 +170,105 @@ __device__ __forceinline__ void rast_sample_list(const NoiseT& noise, const uint
 // O(1 + n p) instead of n normals: p = 0.02 two sigma inside a face.  Entries are independent of each other
 // and of the aggregation noise, so every output of the shader keeps the law of the reference estimator; it is
 // not the sample path of pert_noise_fill's tensor (PERT_F_PER_SAMPLE_NOISE restores that).
-// blist holds compact indices in three consecutive segments (n1 entries with many expected flips, n2 with some, n3 with
-// rarely any), each walked in warp passes of its own, so that the lanes of a pass loop about equally long.
 // Counters: (0x40000000 + 2*(s_begin/4) + call, k, pixel, stage 0): disjoint from every sample quad's and,
 // for sample shards, from every other shard's (a shard of nq quads makes at most nq + 1 calls).
 // ------------------------------------------------------------------------------------------------
 template <class NoiseT>
-__device__ __forceinline__ void rast_compound_list(const NoiseT& noise, const uint16_t* blist, int n1, int n2, int n3,
-                                                   const uint16_t* vlist, const float* xs, uint16_t* cnt, float* rs,
-                                                   int K, float invK, int64_t pix0, float inv_sigma, int s_begin,
-                                                   int s_end) {
-    const int lane = threadIdx.x & 31;
-    const int n_loc = s_end - s_begin;
-    const float fn = (float)n_loc;
-    const uint32_t c0 = 0x40000000u + 2u * (uint32_t)(s_begin >> 2);
-    // one lane per entry, no warp collectives inside; a pass never straddles two segments
-    int seg = 0, seg_end = n1, li = lane;
+struct CompoundCtx {
+    NoiseT noise;
+    const uint16_t* vlist;
+    const float* xs;
+    uint16_t* cnt;
+    float* rs;
+    int K;
+    float invK;
+    int64_t pix0;
+    float inv_sigma;
+    int n_loc;    // local coverage samples
+    uint32_t c0;  // first counter
+};
+
+// one entry (compact index n) per calling lane; out of line: the body is bulky (erfc, log1p, expm1, erfcinv) and the
+// fused kernels are instruction-fetch sensitive
+template <class NoiseT>
+static __device__ __noinline__ void compound_entry(const CompoundCtx<NoiseT>& c, int n) {
+    const int e = c.vlist[n];
+    const int pix = entry_pixel(e, c.invK), k = e - pix * c.K;
+    const float x = c.xs[n];
+    const float t = fabsf(x) * c.inv_sigma;
+    const float p = 0.5f * erfcf(t * 0.70710678118654752f);
+    const float fn = (float)c.n_loc;
+    const float nl = fn * log1pf(-p);
+    const float sf1 = -expm1f(nl);  // P(F >= 1)
+    uint32_t w[4];
+    c.noise.words(c.c0, (uint32_t)k, c.pix0 + pix, w);
+    const float u = ((float)w[0] + 1.0f) * 2.3283064365386963e-10f;  // (0, 1], 2^-32 resolution near 0
+    int F = 0;
+    float r = 0.0f;
+    if (u <= sf1) {
+        float pmf = __expf(nl), sf = sf1;
+        const float ratio = __fdividef(p, 1.0f - p);
+        // F >= k+1  <=>  u <= sf_k;  past the mode, stop once the terms are below the resolution of the running
+        // difference (an event of probability < 1e-6 whose F is then off by a few)
+        do {
+            ++F;
+            pmf *= ratio * __fdividef((float)(c.n_loc - F + 1), (float)F);
+            sf -= pmf;
+        } while (u <= sf && F < c.n_loc && (pmf > 1e-10f || (float)F < fn * p));
+        uint32_t q = c.c0;
+        int idx = 1;
 #pragma unroll 1
-    for (;;) {
-        if (li >= seg_end) {  // this lane is done with the segment: move to its slot in the next one
-            if (seg == 2) break;
-            ++seg;
-            li = seg_end + lane;
-            seg_end = seg == 1 ? n1 + n2 : n1 + n2 + n3;
-            continue;
+        for (int i = 0; i < F; ++i) {
+            if (idx == 4) {
+                ++q;
+                c.noise.words(q, (uint32_t)k, c.pix0 + pix, w);
+                idx = 0;
+            }
+            const uint32_t word = idx == 0 ? w[0] : idx == 1 ? w[1] : idx == 2 ? w[2] : w[3];
+            ++idx;
+            const float v = ((float)word + 1.0f) * 2.3283064365386963e-10f;  // (0, 1]
+            // T = -Phi^-1(v p) >= t:  Phi(-T) = v p
+            r += fmaxf(1.4142135623730951f * erfcinvf(2.0f * v * p), t);
         }
-        const int n = blist[li];
-        li += 32;
-        const int e = vlist[n];
-        const int pix = entry_pixel(e, invK), k = e - pix * K;
-        const float x = xs[n];
-        const float t = fabsf(x) * inv_sigma;
-        const float p = 0.5f * erfcf(t * 0.70710678118654752f);
-        const float nl = fn * log1pf(-p);
-        const float sf1 = -expm1f(nl);  // P(F >= 1)
-        uint32_t w[4];
-        noise.words(c0, (uint32_t)k, pix0 + pix, w);
-        const float u = ((float)w[0] + 1.0f) * 2.3283064365386963e-10f;  // (0, 1], 2^-32 resolution near 0
-        int F = 0;
-        float r = 0.0f;
-        if (u <= sf1) {
-            float pmf = __expf(nl), sf = sf1;
-            const float ratio = __fdividef(p, 1.0f - p);
-            // F >= k+1  <=>  u <= sf_k;  past the mode, stop once the terms are below the resolution of the running
-            // difference (an event of probability < 1e-6 whose F is then off by a few)
-            do {
-                ++F;
-                pmf *= ratio * __fdividef((float)(n_loc - F + 1), (float)F);
-                sf -= pmf;
-            } while (u <= sf && F < n_loc && (pmf > 1e-10f || (float)F < fn * p));
-            uint32_t q = c0;
-            int idx = 1;
+    }
+    c.cnt[n] = (uint16_t)((x >= 0.0f) ? c.n_loc - F : F);
+    c.rs[n] = r;
+}
+
+// The listed entries (blist[0], blist[-1], ..., blist[-(nb-1)]: compact indices, stored downwards) in warp passes of
+// entries with a similar expected number of flips, so that the lanes of a pass loop about equally long: three sweeps
+// over the list (|x| < x_b2: many flips, < x_b3: some, rest: rarely any), each compacting its entries through a
+// 64-slot ring in shared memory and running a pass whenever 32 are pending.
+template <class NoiseT>
+static __device__ __noinline__ void rast_compound_list(const CompoundCtx<NoiseT>& c, const uint16_t* blist, int nb, float x_b2,
+                                                       float x_b3, uint16_t* ring) {
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1u;
+    if (nb <= 32) {
+        if (lane < nb) compound_entry(c, blist[-lane]);
+        return;
+    }
 #pragma unroll 1
-            for (int i = 0; i < F; ++i) {
-                if (idx == 4) {
-                    ++q;
-                    noise.words(q, (uint32_t)k, pix0 + pix, w);
-                    idx = 0;
-                }
-                const uint32_t word = idx == 0 ? w[0] : idx == 1 ? w[1] : idx == 2 ? w[2] : w[3];
-                ++idx;
-                const float v = ((float)word + 1.0f) * 2.3283064365386963e-10f;  // (0, 1]
-                // T = -Phi^-1(v p) >= t:  Phi(-T) = v p
-                r += fmaxf(1.4142135623730951f * erfcinvf(2.0f * v * p), t);
+    for (int b = 0; b < 3; ++b) {
+        int have = 0, done = 0;
+#pragma unroll 1
+        for (int base = 0; base < nb; base += 32) {
+            const int li = base + lane;
+            const int n = li < nb ? blist[-li] : 0;
+            const float ax = fabsf(c.xs[n]);
+            const bool sel = li < nb && (ax < x_b2 ? 0 : ax < x_b3 ? 1 : 2) == b;
+            const unsigned m = __ballot_sync(FULL, sel);
+            if (sel) ring[(have + __popc(m & lt)) & 63] = (uint16_t)n;
+            have += __popc(m);
+            __syncwarp();
+            if (have - done >= 32) {
+                compound_entry(c, ring[(done + lane) & 63]);
+                done += 32;
+                __syncwarp();
             }
         }
-        cnt[n] = (uint16_t)((x >= 0.0f) ? n_loc - F : F);
-        rs[n] = r;
+        if (lane < have - done) compound_entry(c, ring[(done + lane) & 63]);
+        __syncwarp();
     }
 }
 

@@ -52,6 +52,14 @@ def sample_range(n_samples: int, world: int, rank: int) -> Tuple[int, int]:
     return min(4 * q0, n_samples), min(4 * q1, n_samples)
 
 
+def check_sample_sharding(n_rast: int, n_agg: int, world: int) -> None:
+    """Every rank needs at least one quad of each stage's samples.  Raises the same ValueError on every rank."""
+    for name, n in (("GaussianRast", n_rast), ("GaussianAgg", n_agg)):
+        if (n + 3) // 4 < world:
+            raise ValueError(f"{name}.nb_samples = {n} is too small to shard over {world} ranks "
+                             "(the kernels draw four samples per Philox call: one quad per rank at least)")
+
+
 def all_reduce_scalar_grads(tensors, group=None, device=None):
     """Batch sharding: sum the gradients of the 0-dim CPU leaves (sigma, gamma, alpha) over ranks
     with one 3-float all-reduce."""
@@ -161,9 +169,10 @@ class _SampleShardedShade(Function):
                 torch.manual_seed(1)
             seed_a = ops.draw_seed()
         S_r, S_a = int(cfg["S_rast"]), int(cfg["S_agg"])
+        # decided on data every rank has, so that either all ranks raise or none does (a rank that raised alone would
+        # leave the others blocked in the first all-reduce)
+        check_sample_sharding(S_r, S_a, world)
         sr, sa = sample_range(S_r, world, rank), sample_range(S_a, world, rank)
-        if sr[0] == sr[1] or sa[0] == sa[1]:
-            raise ValueError(f"nb_samples ({S_r}, {S_a}) too small to shard over {world} ranks (4 samples per rank min)")
         pr = ops.ShadeProblem(
             pix_to_face=pix_to_face, zbuf=zbuf, dists=dists, colors=colors, znear=znear, zfar=zfar,
             background=cfg["background"], sigma=float(sigma), gamma=float(gamma), alpha=float(alpha),

@@ -15,7 +15,7 @@ from typing import Optional, Tuple
 import torch
 
 from . import _cabi
-from ._cabi import (F_CAUCHY, F_GUMBEL, F_NO_SKIP, F_NO_VR, F_UNIFORM, F_PER_SAMPLE_NOISE, F_SKIP_DEAD_NOISE, PH_AGG, PH_BLEND, PH_BWD_FINISH, PH_BWD_SAMPLE, PH_RAST,
+from ._cabi import (F_CAUCHY, F_GUMBEL, F_NO_SKIP, F_NO_VR, F_PHILOX7, F_UNIFORM, F_PER_SAMPLE_NOISE, F_SKIP_DEAD_NOISE, PH_AGG, PH_BLEND, PH_BWD_FINISH, PH_BWD_SAMPLE, PH_RAST,
                     PertProblem, check, ptr, require_cuda, stream_ptr)
 
 _tls = threading.local()
@@ -216,13 +216,18 @@ def shade_forward(pr: ShadeProblem, want_hist: bool = False, phases: int = 0, sa
         if saved is None:
             # phase-split (sample-sharded) jobs all-reduce counts / rsum as whole tensors: define every entry
             alloc = torch.zeros if phases else torch.empty
+            # the tile blobs are written by the production path only (in-kernel noise, all phases in one call, no global
+            # histogram, default noise flags: csrc/cabi.cu sparse_first_ok); the buffer only exists then, so that a
+            # backward with other flags can never read what forward did not write
+            prod = not phases and not want_hist and pr.noise_rast is None and pr.noise_agg is None and \
+                not (pr.flags & (F_NO_SKIP | F_PER_SAMPLE_NOISE))
             saved = ShadeSaved(
                 counts=alloc((N, H, W, K), dtype=torch.int16, device=dev),
                 rsum=alloc((N, H, W, K), dtype=torch.float32, device=dev),
                 winners=torch.empty((N, H, W, sa_loc), dtype=pr.winner_dtype(), device=dev),
                 pixstate=torch.empty((N, H, W), dtype=torch.int16, device=dev),
                 worklist=None if phases else torch.empty((4 + pr.num_tiles(),), dtype=torch.int32, device=dev),
-                blob=None if phases else torch.empty((int(lib.pert_blob_bytes(pr.c_struct())),), dtype=torch.uint8, device=dev),
+                blob=torch.empty((int(lib.pert_blob_bytes(pr.c_struct())),), dtype=torch.uint8, device=dev) if prod else None,
                 hist=torch.empty((N, H, W, K + 1), dtype=torch.int32, device=dev) if want_hist else None)
         do_blend = (phases == 0) or bool(phases & PH_BLEND)
         image = torch.empty((N, H, W, 4), dtype=torch.float32, device=dev) if do_blend else None
@@ -385,7 +390,7 @@ def noise_fill(seed, stage, shape4, S, device, pixel_offset=0, s_range=None):
     (S,N,H,W,K+1).  Test aid: the fused kernels never store this tensor."""
     lib = _cabi.load()
     N, H, W, K = shape4
-    slots = K if stage == 0 else K + 1
+    slots = K if (stage & 1) == 0 else K + 1  # bit 0: stage; higher bits: noise variant (pertshade.h pert_noise_fill)
     s0, s1 = s_range if s_range is not None else (0, S)
     dev = torch.device(device)
     with torch.cuda.device(dev):

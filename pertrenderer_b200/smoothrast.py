@@ -48,7 +48,9 @@ class randomHeaviside(Function):
         sigma = _scalar(noise_intensity)
         noise, _ = ops.current_explicit_noise()
         seed = 0 if noise is not None else ops.draw_seed()
-        flags = ops.current_flags() | (ops.F_CAUCHY if noise_type == "cauchy" else extra_flags)
+        # the Cauchy branch of randomHeaviside_wovr drops the control variate too (smoothrast.py:99-101), unlike
+        # randomArgmax_wovr's (smoothagg.py:125-128)
+        flags = ops.current_flags() | extra_flags | (ops.F_CAUCHY if noise_type == "cauchy" else 0)
         prob, rsum = ops.rast_forward(distances, int(nb_samples), sigma, seed=seed, noise=noise, flags=flags)
         ctx.save_for_backward(rsum)
         ctx.nb_samples, ctx.sigma = int(nb_samples), sigma
@@ -69,7 +71,7 @@ class randomHeaviside(Function):
 class randomHeaviside_wovr(randomHeaviside):
     """smoothrast.py:61-108: the same perturbed Heaviside WITHOUT the control variate in backward
     (``mean_s h_s U_s / sigma`` instead of ``mean_s (h_s - h0) U_s / sigma``): the paper's variance ablation
-    (eval.py:152-154 "gaussian_wovr").  Gaussian noise; with Cauchy noise it is the plain operator."""
+    (eval.py:152-154 "gaussian_wovr"), with Gaussian and with Cauchy noise (smoothrast.py:99-101)."""
 
     @staticmethod
     def forward(ctx, distances, nb_samples=1, noise_intensity=1e-1, noise_type="gaussian"):

@@ -44,3 +44,12 @@ def rel_err(a, b):
     a, b = a.double(), b.double()
     denom = b.abs().max().clamp(min=1e-30)
     return ((a - b).abs().max() / denom).item()
+
+
+def elementwise_close(a, b, rtol, floor=0.05):
+    """Element-wise relative agreement |a-b| <= rtol * max(|b|, floor * max|b|): north_star's "1e-5 relative error on images
+    and gradients" entry by entry, with an absolute floor (a fraction of the largest magnitude) so that entries which
+    cancel to nearly zero are not compared at a precision their own terms do not have."""
+    a, b = a.double(), b.double()
+    scale = b.abs().max().clamp(min=1e-30)
+    return bool(((a - b).abs() <= rtol * torch.maximum(b.abs(), floor * scale)).all())

@@ -340,11 +340,38 @@ def run_wovr_ops_case(sr, sa, name, *, shape, S, sigma, gamma, seed):
     print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
 
 
+def run_cauchy_wovr_case(sr, name, *, shape, S, sigma, seed):
+    """randomHeaviside_wovr with Cauchy noise (smoothrast.py:99-101): the Cauchy branch drops the control variate too
+    (`maps * score`), unlike randomArgmax_wovr's (smoothagg.py:125-128, which keeps it: SURVEY B11)."""
+    gen = torch.Generator().manual_seed(seed)
+    N, H, W, K = shape
+    x = (torch.rand(shape, generator=gen) * 2 - 1) * 3 * sigma
+    x[..., -1] = 1.0
+    x[..., 0] = -1.0
+    x.requires_grad_(True)
+    sig = torch.tensor(sigma, requires_grad=True)
+    gl = torch.randn(shape, generator=gen)
+    torch.manual_seed(seed + 7)
+    m = torch.distributions.cauchy.Cauchy(torch.tensor([0.]), torch.tensor([1.]))
+    U = torch.clamp(m.sample((S, N, H, W, K)).squeeze(-1), min=-1e7, max=1e7)
+    torch.manual_seed(seed + 7)
+    y = sr.randomHeaviside_wovr.apply(x, S, sig, "cauchy")
+    (y * gl).sum().backward()
+    assert torch.equal(y.detach(), ((x.detach() + sigma * U) >= 0).float().mean(0))
+    out = dict(x=x.detach().numpy(), sigma=np.float32(sigma), S=np.int32(S), U=U.numpy(), grad_l=gl.numpy(),
+               prob=y.detach().numpy(), grad_x=x.grad.numpy(), grad_sigma=sig.grad.numpy())
+    path = os.path.join(OUT, f"ops_{name}.npz")
+    np.savez_compressed(path, **out)
+    print(f"{name}: wrote {path} ({os.path.getsize(path) / 1024:.0f} KiB)")
+
+
 def main():
     torch.set_num_threads(1)  # reduction order independent of the host
     rr, sr, sa = load_reference()
     if "--soft-only" in sys.argv:  # leave the committed Gaussian goldens untouched
         return soft_cases(rr, sr, sa)
+    if "--cauchy-wovr-only" in sys.argv:
+        return run_cauchy_wovr_case(sr, "cauchy_wovr", shape=(2, 3, 4, 6), S=12, sigma=1e-3, seed=43)
     if "--wovr-only" in sys.argv:
         return run_wovr_ops_case(sr, sa, "wovr", shape=(2, 3, 4, 6), S=12, sigma=1e-3, gamma=1e-2, seed=41)
     if "--cauchy-only" in sys.argv:
@@ -366,6 +393,7 @@ def main():
     soft_cases(rr, sr, sa)
     run_cauchy_ops_case(sr, sa, "cauchy", shape=(2, 3, 4, 6), S=12, sigma=1e-3, gamma=1e-2, seed=31)
     run_wovr_ops_case(sr, sa, "wovr", shape=(2, 3, 4, 6), S=12, sigma=1e-3, gamma=1e-2, seed=41)
+    run_cauchy_wovr_case(sr, "cauchy_wovr", shape=(2, 3, 4, 6), S=12, sigma=1e-3, seed=43)
 
 
 def soft_cases(rr, sr, sa):

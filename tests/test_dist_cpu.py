@@ -124,3 +124,35 @@ def test_sample_sharded_orchestration_gloo_world2(case, tmp_path):
     # every rank ends with identical results
     for k in ("image", "gd", "gz", "gc", "scal"):
         assert torch.equal(outs[0][k], outs[1][k]), k
+
+
+def _small_sample_worker(rank, world, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        # nb_samples = 6 -> two quads for four ranks: sample_range gives ranks 2 and 3 an empty shard.  The check must
+        # raise on EVERY rank (it is decided on data all ranks share); before, only the empty ranks raised and the
+        # others blocked in the first all-reduce
+        try:
+            pdist.check_sample_sharding(6, 6, world)
+            raised = False
+        except ValueError:
+            raised = True
+        empty = pdist.sample_range(6, world, rank)
+        flag = torch.tensor([1.0 if raised else 0.0])
+        dist.all_reduce(flag)  # every rank reaches the collective: nobody raised alone before it
+        torch.save(dict(raised=raised, empty=empty[0] == empty[1], total=flag.item()), os.path.join(out_dir, f"s{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_too_few_samples_raise_on_every_rank(tmp_path):
+    world = 4
+    mp.spawn(_small_sample_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    outs = [torch.load(tmp_path / f"s{r}.pt") for r in range(world)]
+    assert all(o["raised"] for o in outs) and outs[0]["total"] == world
+    assert [o["empty"] for o in outs] == [False, False, True, True]
+    pdist.check_sample_sharding(16, 8, 2)  # enough quads: no error
+    with pytest.raises(ValueError):
+        pdist.check_sample_sharding(16, 4, 2)

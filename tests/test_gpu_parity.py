@@ -5,7 +5,7 @@ reference's exact noise; indices (hit counts, argmax winners) bit-exact."""
 import pytest
 import torch
 
-from conftest import load_golden, rel_err
+from conftest import elementwise_close, load_golden, rel_err
 from oracle import pert_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -256,6 +256,47 @@ def test_philox_equals_explicit_with_materialised_noise(kind):
     assert (a["image"] - st.image).abs().max() <= 2e-6
     assert rel_err(a["grad_dists"], gr["dists"]) <= RTOL
     assert rel_err(a["grad_zbuf"], gr["zbuf"]) <= RTOL
+
+
+@pytest.mark.parametrize("kind", ["realistic", "dense"])
+def test_philox7_stream_is_oracle_checked_too(kind):
+    """PERT_F_PHILOX7: the 7-round stream through the same kernels.  Per-sample mode == the explicit path fed with
+    pert_noise_fill(stage | 16) == the CPU oracle on that tensor; the stream is standard normal and differs from the
+    10-round one."""
+    from gpu_util import problem_from_case, run_cuda, run_oracle, synthetic_case
+    from pertrenderer_b200 import _cabi, ops
+    N, H, W, K, S_r, S_a = 2, 10, 10, 50, 16, 32
+    g = synthetic_case(N, H, W, K, S_r, S_a, kind=kind, seed=8)
+    seed_r, seed_a = 0x1122334455667788, 0x0123456789ABCDEF
+    U = ops.noise_fill(seed_r, 0 | 16, (N, H, W, K), S_r, "cuda")
+    V = ops.noise_fill(seed_a, 1 | 16, (N, H, W, K), S_a, "cuda")
+    assert not torch.equal(V, ops.noise_fill(seed_a, 1, (N, H, W, K), S_a, "cuda"))
+    g["U"], g["V"] = U.cpu(), V.cpu()
+    a = run_cuda(problem_from_case(g, explicit=False, seed_rast=seed_r, seed_agg=seed_a,
+                                   flags=_cabi.F_PER_SAMPLE_NOISE | _cabi.F_PHILOX7), g["grad_image"])
+    st, gr = run_oracle(g, g["U"], g["V"])
+    mask = g["pix_to_face"] >= 0
+    assert torch.equal(a["counts"][mask], st.counts[mask])
+    assert torch.equal(a["winners"].permute(3, 0, 1, 2).long(), st.a_s)
+    assert (a["image"] - st.image).abs().max() <= 2e-6
+    assert rel_err(a["grad_dists"], gr["dists"]) <= RTOL
+    assert rel_err(a["grad_zbuf"], gr["zbuf"]) <= RTOL
+    # default mode with the flag: finite, deterministic, same scene
+    d1 = run_cuda(problem_from_case(g, explicit=False, seed_rast=seed_r, seed_agg=seed_a, flags=_cabi.F_PHILOX7), g["grad_image"])
+    d2 = run_cuda(problem_from_case(g, explicit=False, seed_rast=seed_r, seed_agg=seed_a, flags=_cabi.F_PHILOX7), g["grad_image"])
+    for k in ("image", "grad_dists", "grad_zbuf", "scalars"):
+        assert torch.isfinite(d1[k]).all() and torch.equal(d1[k], d2[k]), k
+    n = ops.noise_fill(77, 1 | 16, (4, 32, 32, 50), 32, "cuda").double().flatten()
+    m = n.numel()
+    assert abs(n.mean().item()) < 5 / m ** 0.5 and abs(n.var().item() - 1) < 5 * (2 / m) ** 0.5
+    assert abs((n ** 3).mean().item()) < 5 * (15 / m) ** 0.5 and abs((n ** 4).mean().item() - 3) < 5 * (96 / m) ** 0.5
+    s = n[:: max(1, m // 200000)].sort().values
+    emp = torch.arange(1, s.numel() + 1, dtype=torch.float64, device=s.device) / s.numel()
+    assert (O.normal_cdf(s).to(s.device) - emp).abs().max().item() < 1.95 / s.numel() ** 0.5
+    # neighbouring counters decorrelate (the avalanche of 7 rounds): samples 4q..4q+3 vs 4q+4..4q+7, slot k vs k+1
+    v = ops.noise_fill(78, 1 | 16, (1, 64, 64, 31), 8, "cuda").double()
+    assert abs(torch.corrcoef(torch.stack((v[0].flatten(), v[4].flatten())))[0, 1].item()) < 5 / v[0].numel() ** 0.5
+    assert abs(torch.corrcoef(torch.stack((v[..., :-1].flatten(), v[..., 1:].flatten())))[0, 1].item()) < 5 / v[..., 1:].numel() ** 0.5
 
 
 @pytest.mark.parametrize("kind", ["realistic", "dense"])
@@ -612,17 +653,20 @@ def test_large_k_many_pixels_default_path():
     g = _holey_case(N, H, W, K, S, S, seed=5)
     a = run_cuda(problem_from_case(g, explicit=False, seed_rast=1, seed_agg=2), g["grad_image"])
     b = run_cuda(problem_from_case(g, explicit=False, seed_rast=1, seed_agg=2, flags=_cabi.F_NO_SKIP), g["grad_image"])
+    c = run_cuda(problem_from_case(g, explicit=False, seed_rast=1, seed_agg=2, flags=_cabi.F_PER_SAMPLE_NOISE), g["grad_image"])
     mask = g["pix_to_face"] >= 0
-    assert torch.equal(a["counts"][mask], b["counts"][mask]) and torch.equal(a["winners"], b["winners"])
-    assert (a["image"] - b["image"]).abs().max() <= 1e-6
-    assert torch.equal(a["grad_colors"], b["grad_colors"])
-    # the default backward draws the never-winning logits' noise once per logit (another sample path than the
-    # brute-force run): same estimator, so here only sanity + determinism; the distributions are compared in
-    # test_once_per_logit_noise_has_the_reference_distribution
+    # the per-sample path is the brute-force run bit for bit
+    assert torch.equal(c["counts"][mask], b["counts"][mask]) and torch.equal(c["winners"], b["winners"])
+    assert (c["image"] - b["image"]).abs().max() <= 1e-6
+    assert torch.equal(c["grad_colors"], b["grad_colors"])
+    # the default mode draws the coverage flips with the compound sampler and the never-winning logits' noise once per
+    # logit (another sample path than the brute-force run): same estimator, so here only sanity + determinism; the
+    # distributions are compared in test_gpu_compound.py and test_once_per_logit_noise_has_the_reference_distribution
     a2 = run_cuda(problem_from_case(g, explicit=False, seed_rast=1, seed_agg=2), g["grad_image"])
-    for k in ("grad_dists", "grad_zbuf", "scalars"):
+    for k in ("image", "grad_dists", "grad_zbuf", "scalars"):
         assert torch.isfinite(a[k]).all() and torch.equal(a[k], a2[k]), k
     assert (a["grad_dists"][~mask] == 0).all() and (a["grad_zbuf"][~mask] == 0).all()
+    assert (a["image"] - b["image"]).abs().mean() < 0.05  # same scene, other noise
 
 
 @pytest.mark.parametrize("case", ["small", "k50", "empty"])
@@ -707,6 +751,27 @@ def test_cauchy_operators_match_reference_golden():
     assert ((p - e).abs() <= 5 * (e * (1 - e) / S).sqrt() + 1e-4).all()
     n = pb.ops.noise_fill(9, 1 | 2, (2, 16, 16, 7), 32, dev).flatten().double()
     assert abs(n.median().item()) < 0.02 and abs((n.abs() < 1).double().mean().item() - 0.5) < 0.01  # quartiles at +-1
+
+
+def test_cauchy_wovr_heaviside_matches_reference_golden():
+    """randomHeaviside_wovr with "cauchy" noise (smoothrast.py:99-101): no control variate in the Cauchy branch either."""
+    import pertrenderer_b200 as pb
+    g = load_golden("ops_cauchy_wovr")
+    dev = "cuda"
+    x = g["x"].to(dev).requires_grad_(True)
+    sig = torch.tensor(float(g["sigma"]), requires_grad=True)
+    with pb.explicit_noise(g["U"].to(dev), None):
+        y = pb.randomHeaviside_wovr.apply(x, int(g["S"]), sig, "cauchy")
+    (y * g["grad_l"].to(dev)).sum().backward()
+    assert torch.equal(y.detach().cpu(), g["prob"])
+    assert rel_err(x.grad.cpu(), g["grad_x"]) <= RTOL
+    _scalars_close(sig.grad.item(), g["grad_sigma"], "sigma")
+    # ... which differs from the variance-reduced Cauchy estimator on the far-inside entry
+    x2 = g["x"].to(dev).requires_grad_(True)
+    with pb.explicit_noise(g["U"].to(dev), None):
+        y2 = pb.randomHeaviside.apply(x2, int(g["S"]), torch.tensor(float(g["sigma"])), "cauchy")
+    (y2 * g["grad_l"].to(dev)).sum().backward()
+    assert (x2.grad[..., -1] == 0).all() and (x.grad[..., -1] != 0).any()
 
 
 def test_wovr_operators_match_reference_golden():

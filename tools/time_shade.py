@@ -18,7 +18,11 @@ ap.add_argument("--flags", type=int, default=0)
 ap.add_argument("--steps", type=int, default=10)
 ap.add_argument("--cfg", default="8,256,50,64")
 ap.add_argument("--tag", default="")
+ap.add_argument("--lib", default=None, help="alternate libpertshade.so (A/B runs of two builds in one GPU call)")
 a = ap.parse_args()
+if a.lib:
+    from pertrenderer_b200 import _cabi
+    _cabi.LIB_PATH = os.path.abspath(a.lib)
 N, HW, K, S = (int(v) for v in a.cfg.split(","))
 dev = torch.device("cuda:0")
 peak = bench.peaks()[0]
