@@ -148,6 +148,10 @@ static Launch make_launch(const pert_problem* pb, int tp) {
     if (const char* e = getenv("PERT_CMP_MIN")) L.cmp_min = atoi(e);
 #endif
     if (L.cmp_min > 32) L.cmp_min = 32;
+    L.defer_min = 48;
+#ifdef PERT_EXPERIMENTS
+    if (const char* e = getenv("PERT_DEFER_MIN")) L.defer_min = atoi(e);
+#endif
     return L;
 }
 

@@ -191,6 +191,7 @@ struct Launch {
     float inv_gamma;  // 1/gamma (SoftAgg, smoothagg.py:181)
     float t_compound; // coverage entries with |x|/sigma >= this are drawn by the compound sampler (tile.cuh)
     int cmp_min;       // fewer compound entries than this in a tile are drawn by the per-sample loop instead
+    int defer_min;     // main pass of the sparse-first mode: tiles with at least this many go to the fallback pass
     float t_bucket[2]; // ... and bucketed by expected flips: [t_compound, t_bucket[0]) many, [.., t_bucket[1]) some, rest rare
 };
 

@@ -622,8 +622,23 @@ __global__ void __launch_bounds__(1024) finalize_scalars_kernel(const float* par
     __shared__ double red[3][32];
     if (worklist) n += 2 * (int64_t)worklist[0];  // rows of the fallback pass
     double s0 = 0, s1 = 0, s2 = 0;
-    for (int64_t t = threadIdx.x; t < n; t += 1024) {
-        const float4 v = reinterpret_cast<const float4*>(partials)[t];
+    // eight independent loads in flight per thread (one CTA walks every row: the loop is latency-bound otherwise);
+    // a thread still adds its rows in increasing order, so the result does not depend on the unrolling
+    const float4* const rows = reinterpret_cast<const float4*>(partials);
+    int64_t t = threadIdx.x;
+    for (; t + 7 * 1024 < n; t += 8 * 1024) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(rows + t + u * 1024);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            s0 += v[u].x;
+            s1 += v[u].y;
+            s2 += v[u].z;
+        }
+    }
+    for (; t < n; t += 1024) {
+        const float4 v = __ldg(rows + t);
         s0 += v.x;
         s1 += v.y;
         s2 += v.z;

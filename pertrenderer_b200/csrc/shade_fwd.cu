@@ -33,7 +33,11 @@ void fwd_smem_layout(int tp, int cap, SmemLayout& L) {
 // PHASED = false is the production instantiation: all three phases in one launch, no global histogram
 // (the phase-split code of the sample-sharded job is compiled out, which keeps the hot code small: the
 // kernel is instruction-fetch sensitive, every warp walks the whole body once per tile).
-template <class NoiseR, class NoiseA, int GT, bool PHASED>
+// DEFER = true (main pass of the sparse-first mode): a tile with enough entries for the compound coverage sampler is
+// handed to the fallback pass like a tile that overflows the compact arrays, so that this instantiation carries no
+// compound-sampler code at all (the kernel is instruction-fetch bound on sparse fragments: every instruction of a
+// path it rarely takes costs the common path)
+template <class NoiseR, class NoiseA, int GT, bool PHASED, bool DEFER = false>
 __device__ __forceinline__ void shade_fwd_tile(const FwdArgs& a, const NoiseR& noise_r, const NoiseA& noise_a,
                                                const int64_t tile, unsigned char* smem_raw, const int lane) {
     const pert_problem& pb = a.pb;
@@ -133,16 +137,32 @@ __device__ __forceinline__ void shade_fwd_tile(const FwdArgs& a, const NoiseR& n
             }
         }
         if (do_rast) {
-            const unsigned b = __ballot_sync(FULL, need && !cmp), bc = __ballot_sync(FULL, cmp);
-            if (need && !cmp) rlist[nlist + __popc(b & lt)] = (uint16_t)n;
-            if (cmp) blist[-(nblist + __popc(bc & lt))] = (uint16_t)n;
-            nlist += __popc(b);
-            nblist += __popc(bc);
+            if constexpr (DEFER) {  // one list; the tile is handed over if enough of it is worth the compound sampler
+                const unsigned b = __ballot_sync(FULL, need);
+                if (need) rlist[nlist + __popc(b & lt)] = (uint16_t)n;
+                nlist += __popc(b);
+                nblist += __popc(__ballot_sync(FULL, cmp));
+            } else {
+                const unsigned b = __ballot_sync(FULL, need && !cmp), bc = __ballot_sync(FULL, cmp);
+                if (need && !cmp) rlist[nlist + __popc(b & lt)] = (uint16_t)n;
+                if (cmp) blist[-(nblist + __popc(bc & lt))] = (uint16_t)n;
+                nlist += __popc(b);
+                nblist += __popc(bc);
+            }
         }
     }
     __syncwarp();
     if (do_rast) {
-        if (nblist > 0 && nblist < a.L.cmp_min) {
+        if constexpr (DEFER) {
+            if (nblist >= a.L.defer_min) {
+                if (lane == 0) {
+                    a.worklist[4 + atomicAdd(a.worklist, 1)] = (int32_t)tile;
+                    if (a.blob) a.blob[tile * (int64_t)blob_words(tp, cap)] = -1;
+                }
+                return;
+            }
+        }
+        if (!DEFER && nblist > 0 && nblist < a.L.cmp_min) {
             // a handful of entries: the per-sample loop spreads each entry's samples over the idle lanes, which beats
             // one lane per entry (the lists share one array: the moved entries are read before they can be overwritten)
             const int moved = lane < nblist ? blist[-lane] : 0;
@@ -152,7 +172,7 @@ __device__ __forceinline__ void shade_fwd_tile(const FwdArgs& a, const NoiseR& n
             nblist = 0;
             __syncwarp();
         }
-        if constexpr (NoiseR::kBounded) {
+        if constexpr (NoiseR::kBounded && !DEFER) {
             if (nblist > 0) {
                 const CompoundCtx<NoiseR> cc{noise_r, vlist, xs, cnt, rs, K, a.L.invK, pix0, a.L.inv_sigma, sr_loc,
                                              0x40000000u + 2u * (uint32_t)(pb.s_rast_begin >> 2)};
@@ -396,10 +416,10 @@ __device__ __forceinline__ void shade_fwd_tile(const FwdArgs& a, const NoiseR& n
     if (pvalid && lig == 0) reinterpret_cast<float4*>(a.image)[gp] = make_float4(r, g, bl, px_alpha);
 }
 
-template <class NoiseR, class NoiseA, int GT, bool PHASED>
+template <class NoiseR, class NoiseA, int GT, bool PHASED, bool DEFER = false>
 __global__ void __launch_bounds__(FNT, 32) shade_fwd_kernel(const FwdArgs a, const NoiseR noise_r, const NoiseA noise_a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    shade_fwd_tile<NoiseR, NoiseA, GT, PHASED>(a, noise_r, noise_a, blockIdx.x, smem_raw, threadIdx.x);
+    shade_fwd_tile<NoiseR, NoiseA, GT, PHASED, DEFER>(a, noise_r, noise_a, blockIdx.x, smem_raw, threadIdx.x);
 }
 
 // Fallback pass of the sparse-first mode: the tiles whose valid entries did not fit the compact arrays,
@@ -422,15 +442,15 @@ __global__ void __launch_bounds__(FBT, 12) shade_fwd_fallback_kernel(const FwdAr
     }
 }
 
-template <class NR, class NA, int GT, bool PHASED>
+template <class NR, class NA, int GT, bool PHASED, bool DEFER = false>
 static int launch_fwd_t(const FwdArgs& a, const NR& nr, const NA& na, cudaStream_t st) {
     const size_t smem = (size_t)a.L.warp_smem;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(shade_fwd_kernel<NR, NA, GT, PHASED>,
+        cudaError_t e = cudaFuncSetAttribute(shade_fwd_kernel<NR, NA, GT, PHASED, DEFER>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    shade_fwd_kernel<NR, NA, GT, PHASED><<<(unsigned)a.L.ntiles, FNT, smem, st>>>(a, nr, na);
+    shade_fwd_kernel<NR, NA, GT, PHASED, DEFER><<<(unsigned)a.L.ntiles, FNT, smem, st>>>(a, nr, na);
     return (int)cudaGetLastError();
 }
 
@@ -451,11 +471,20 @@ template <class PN>
 static int launch_fwd_production(const FwdArgs& a, const FwdArgs* fb, cudaStream_t st) {
     const PN pr(a.pb.seed_rast, 0, a.pb.pixel_offset), pa(a.pb.seed_agg, 1, a.pb.pixel_offset);
     int rc;
-    switch (a.L.G) {  // lanes per pixel known at compile time
-        case 1: rc = launch_fwd_t<PN, PN, 1, false>(a, pr, pa, st); break;
-        case 2: rc = launch_fwd_t<PN, PN, 2, false>(a, pr, pa, st); break;
-        case 4: rc = launch_fwd_t<PN, PN, 4, false>(a, pr, pa, st); break;
-        default: rc = launch_fwd_t<PN, PN, 8, false>(a, pr, pa, st); break;
+    if (fb) {  // sparse-first main pass: defers the tiles the compound sampler is worth running on
+        switch (a.L.G) {  // lanes per pixel known at compile time
+            case 1: rc = launch_fwd_t<PN, PN, 1, false, true>(a, pr, pa, st); break;
+            case 2: rc = launch_fwd_t<PN, PN, 2, false, true>(a, pr, pa, st); break;
+            case 4: rc = launch_fwd_t<PN, PN, 4, false, true>(a, pr, pa, st); break;
+            default: rc = launch_fwd_t<PN, PN, 8, false, true>(a, pr, pa, st); break;
+        }
+    } else {
+        switch (a.L.G) {
+            case 1: rc = launch_fwd_t<PN, PN, 1, false>(a, pr, pa, st); break;
+            case 2: rc = launch_fwd_t<PN, PN, 2, false>(a, pr, pa, st); break;
+            case 4: rc = launch_fwd_t<PN, PN, 4, false>(a, pr, pa, st); break;
+            default: rc = launch_fwd_t<PN, PN, 8, false>(a, pr, pa, st); break;
+        }
     }
     if (rc || !fb) return rc;
     switch (fb->L.G) {  // sparse-first mode: half-size tiles for whatever did not fit

@@ -277,8 +277,21 @@ __global__ void __launch_bounds__(FNT, 24) soft_shade_kernel(const SoftArgs a) {
 __global__ void __launch_bounds__(1024) soft_finalize_kernel(const float* partials, int64_t n, float gamma, float alpha, float* out) {
     __shared__ double red[3][32];
     double s0 = 0, s1 = 0, s2 = 0;
-    for (int64_t t = threadIdx.x; t < n; t += 1024) {
-        const float4 v = reinterpret_cast<const float4*>(partials)[t];
+    const float4* const rows = reinterpret_cast<const float4*>(partials);
+    int64_t t = threadIdx.x;
+    for (; t + 7 * 1024 < n; t += 8 * 1024) {  // eight independent loads in flight per thread (see shade_bwd.cu)
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = __ldg(rows + t + u * 1024);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            s0 += v[u].x;
+            s1 += v[u].y;
+            s2 += v[u].z;
+        }
+    }
+    for (; t < n; t += 1024) {
+        const float4 v = __ldg(rows + t);
         s0 += v.x;
         s1 += v.y;
         s2 += v.z;
