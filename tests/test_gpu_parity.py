@@ -40,6 +40,9 @@ def test_explicit_noise_matches_reference_golden(shade_case):
     assert rel_err(out["grad_colors"], g["grad_colors"]) <= RTOL
     assert rel_err(out["grad_dists"], g["grad_dists"]) <= RTOL
     assert rel_err(out["grad_zbuf"], g["grad_zbuf"]) <= RTOL
+    # ... and entry by entry (north_star: 1e-5 relative on images and gradients), with the floor of conftest.elementwise_close
+    for k in ("image", "grad_colors", "grad_dists", "grad_zbuf"):
+        assert elementwise_close(out[k], g[k], RTOL), k
     _scalars_close(out["scalars"][0].item(), g["grad_sigma"], "sigma")
     _scalars_close(out["scalars"][1].item(), g["grad_gamma"], "gamma")
     _scalars_close(out["scalars"][2].item(), g["grad_alpha"], "alpha")
@@ -143,6 +146,8 @@ def test_explicit_noise_matches_oracle_seeded(shape):
     assert rel_err(out["grad_colors"], gr["colors"]) <= RTOL
     assert rel_err(out["grad_dists"], gr["dists"]) <= RTOL
     assert rel_err(out["grad_zbuf"], gr["zbuf"]) <= RTOL
+    assert elementwise_close(out["grad_colors"], gr["colors"], RTOL) and elementwise_close(out["grad_dists"], gr["dists"], RTOL)
+    assert elementwise_close(out["grad_zbuf"], gr["zbuf"], RTOL) and elementwise_close(out["image"], st.image, RTOL)
     for i, k in enumerate(("sigma", "gamma", "alpha")):
         _scalars_close(out["scalars"][i].item(), gr[k].item(), k)
 
@@ -496,15 +501,17 @@ def test_dead_noise_modes_share_forward_and_live_gradients():
         assert rel_err(a["grad_zbuf"][sel], r["grad_zbuf"][sel]) <= 1e-5
 
 
-def test_once_per_logit_noise_has_the_reference_distribution():
-    """Default backward mode vs PERT_F_PER_SAMPLE_NOISE over many seeds: the gradients have the same
-    mean AND the same variance entry by entry (the once-per-logit draw is the exact conditional law of
-    the per-sample score sum), and so does the gamma gradient."""
+@pytest.mark.parametrize("shape", [(1, 6, 6, 12, 16, 6.0, 400), (1, 5, 5, 50, 16, 9.0, 300)])
+def test_once_per_logit_noise_has_the_reference_distribution(shape):
+    """Default mode (compound coverage draws, one draw per never-winning logit in backward) vs PERT_F_PER_SAMPLE_NOISE
+    over many seeds: the gradients have the same mean AND the same variance entry by entry (both shortcuts are the
+    exact conditional laws of the per-sample sums), and so do the scalar gradients, the gamma gradient included (its
+    squared-noise term keeps mean and variance).  K = 12 and the benchmark's K = 50, both with padded pixels."""
     from gpu_util import problem_from_case, run_cuda, synthetic_case
     from pertrenderer_b200 import _cabi
-    N, H, W, K, S = 1, 6, 6, 12, 16
-    g = synthetic_case(N, H, W, K, S, S, kind="realistic", seed=61, mean_valid=6.0)
-    reps = 400
+    N, H, W, K, S, mean_valid, reps = shape
+    g = synthetic_case(N, H, W, K, S, S, kind="realistic", seed=61, mean_valid=mean_valid)
+    assert (g["pix_to_face"] < 0).any() and (g["pix_to_face"] >= 0).any()
     keys = ("grad_zbuf", "grad_dists", "scalars")
     acc = {m: {k: [] for k in keys} for m in (0, 1)}
     for r in range(reps):
@@ -529,7 +536,8 @@ def test_once_per_logit_noise_has_the_reference_distribution():
         assert zv.max().item() < 6.0, (k, "var", zv.max().item())
         # ... and the bulk of the entries (the well-sampled ones) agree closely
         big = vb > 0.2 * vb.max()
-        assert abs((va[big] / vb[big]).log().median().item()) < 0.25, (k, "var ratio")
+        if big.sum() >= 8:
+            assert abs((va[big] / vb[big]).log().median().item()) < 0.25, (k, "var ratio")
 
 
 def test_face_colour_gather_matches_texel_tensor():
