@@ -480,6 +480,35 @@ def config_legs(dev, rank, steps):
     return out
 
 
+def graph_leg(dev, kind="rasterised", steps=50):
+    """BASELINE config 1 (1 x 64^2, K=50, S=16: launch-bound, 2.4 us at the roofline) with forward + backward captured in ONE
+    CUDA graph (ops.GraphedShadeStep: device-side seeds stepped by a pert_seed_advance node), against the same step
+    launched eagerly."""
+    from pertrenderer_b200 import ops
+    cfg = CONFIGS[1]
+    N, HW, K, S = cfg["N"], cfg["HW"], cfg["K"], cfg["S"]
+    fr, col = make_fragments(kind, N, HW, K, S, dev, 0)
+    G = torch.randn((N, HW, HW, 4), device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    step = ops.GraphedShadeStep(fr.pix_to_face, fr.zbuf.contiguous(), fr.dists.contiguous(), col, G, sigma=SIGMA, gamma=GAMMA,
+                                alpha=ALPHA, eps=EPS, S_rast=S, S_agg=S, background=BACKGROUND)
+    for _ in range(5):
+        step.replay()
+    torch.cuda.synchronize(dev)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step.replay()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1) / steps
+    eager = device_timed(cfg, kind, dev, steps, 5, 1, 0, fragments=(fr, col))
+    units = N * HW * HW * K * S
+    return {"config": cfg["name"], "fragments": kind, "ms_per_step_graph": ms, "ms_per_step_eager": eager["ms_per_step"],
+            "value": units / (ms * 1e-3), "unit": UNIT, "launches_per_step": 8,
+            "note": "one graph replay = seed advance + memsets + forward (main + fallback pass) + backward (main + fallback "
+                    "pass) + scalar finalize"}
+
+
 def sample_sharded_leg(dev, world, rank, steps):
     """BASELINE config 4 (1 x 128^2, K=50, S=4096) with the noise samples split over the ranks
     (dist.smooth_rgb_blend_sample_sharded: three all-reduces over NCCL), against the unsharded job on every rank:
@@ -808,6 +837,10 @@ def run_b200_arm(args):
                                                   "bytes 40 PF + 32 P + 24 F")
             if not args.no_config_legs:
                 also["configs"] = config_legs(dev, rank, args.steps)
+                try:
+                    also["config1_cuda_graph"] = graph_leg(dev)
+                except Exception as e:
+                    also["config1_cuda_graph"] = {"error": repr(e)[:300]}
             if not args.no_renderer_legs:
                 also["random_phong_shader"] = phong_timed(args, "realistic", dev, n2, 3, rank)
                 also["renderer"] = renderer_timed(args, dev, n4, 3, rank)

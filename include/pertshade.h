@@ -55,7 +55,7 @@
 extern "C" {
 #endif
 
-#define PERT_ABI_VERSION 13
+#define PERT_ABI_VERSION 14
 
 /* error codes */
 #define PERT_OK 0
@@ -138,6 +138,11 @@ typedef struct pert_problem {
      * texel tensor of Meshes.sample_textures (random_rasterizer.py:170) is never materialised */
     const float* face_colors;
     int64_t num_faces;
+    /* optional device-side seeds, uint64[2] (device) or NULL: when set the fused kernels draw with seed_rast ^ seed_device[0]
+     * and seed_agg ^ seed_device[1], read at launch.  A forward + backward pair captured in a CUDA graph (together with a
+     * pert_seed_advance node) then draws fresh noise at every replay although every launch parameter is frozen: the
+     * small-problem path, where launch overhead dominates (experiments/eval.py:341-394 loops over 64x64..128x128 images) */
+    const uint64_t* seed_device;
 } pert_problem;
 
 int pert_version(void);
@@ -335,6 +340,10 @@ int pert_rasterize_fwd(const pert_raster* rs, int64_t* pix_to_face, float* zbuf,
  */
 int pert_rasterize_bwd(const pert_raster* rs, const int64_t* pix_to_face, const float* grad_zbuf, const float* grad_bary,
                        const float* grad_dists, float* grad_face_verts, void* stream);
+
+/* Advance device-side seeds (pert_problem.seed_device): seed_device[i] <- splitmix64 step of seed_device[i], i = 0, 1.  One
+ * single-thread launch on `stream`; capturable in a CUDA graph. */
+int pert_seed_advance(uint64_t* seed_device, void* stream);
 
 /* Materialise the counter-based noise: out float (s_end-s_begin, P, slots), stage 0 = coverage
  * (slots = K), 1 = aggregation (slots = K1); stage | 2 = the Cauchy variant of that stage, | 4 uniform, | 8 Gumbel,

@@ -15,7 +15,7 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libpertshade.so")
-ABI_VERSION = 13
+ABI_VERSION = 14
 
 # flags (include/pertshade.h)
 F_NO_SKIP = 1
@@ -32,7 +32,7 @@ PH_BWD_SAMPLE, PH_BWD_FINISH = 0x100, 0x200
 EXPORTS = [
     "pert_version", "pert_strerror", "pert_last_cuda_error", "pert_num_tiles", "pert_winner_bytes", "pert_blob_bytes",
     "pert_shade_fwd", "pert_shade_bwd", "pert_soft_shade_fwd", "pert_soft_shade_bwd", "pert_rast_fwd", "pert_rast_bwd", "pert_argmax_fwd",
-    "pert_argmax_bwd", "pert_noise_fill", "pert_phong_fwd", "pert_phong_bwd", "pert_rasterize_fwd", "pert_rasterize_bwd", "pert_rasterize_num_bins", "pert_rasterize_bin",
+    "pert_argmax_bwd", "pert_noise_fill", "pert_seed_advance", "pert_phong_fwd", "pert_phong_bwd", "pert_rasterize_fwd", "pert_rasterize_bwd", "pert_rasterize_num_bins", "pert_rasterize_bin",
 ]
 
 RAST_CULL_BACKFACES = 1  # PERT_RAST_CULL_BACKFACES
@@ -60,6 +60,7 @@ class PertProblem(C.Structure):
         ("znear", C.c_void_p), ("zfar", C.c_void_p),
         ("noise_rast", C.c_void_p), ("noise_agg", C.c_void_p),
         ("face_colors", C.c_void_p), ("num_faces", C.c_int64),
+        ("seed_device", C.c_void_p),
     ]
 
 
@@ -143,6 +144,8 @@ def load():
         lib.pert_argmax_fwd.argtypes = [vp, i64, i32, i32, i32, i32, f32, u64, i64, vp, u32, vp, vp, vp]
         lib.pert_argmax_bwd.restype = C.c_int
         lib.pert_argmax_bwd.argtypes = [vp, vp, vp, i64, i32, i32, i32, i32, f32, u64, i64, vp, u32, vp, vp, vp, vp]
+        lib.pert_seed_advance.restype = C.c_int
+        lib.pert_seed_advance.argtypes = [vp, vp]
         lib.pert_noise_fill.restype = C.c_int
         lib.pert_noise_fill.argtypes = [u64, i32, i64, i32, i32, i32, i64, vp, vp]
         lib.pert_phong_fwd.restype = C.c_int

@@ -68,6 +68,7 @@ int launch_rasterize_bin(const pert_raster& rs, int32_t* bin_count, const int64_
 int launch_rasterize_fwd(const pert_raster& rs, int64_t* pix_to_face, float* zbuf, float* bary, float* dists, cudaStream_t st);
 int launch_rasterize_bwd(const pert_raster& rs, const int64_t* pix_to_face, const float* grad_zbuf, const float* grad_bary,
                          const float* grad_dists, float* grad_face_verts, cudaStream_t st);
+int launch_seed_advance(uint64_t* seed_device, cudaStream_t st);
 int launch_noise_fill(uint64_t seed, int stage, int64_t P, int slots, int s_begin, int s_end, int64_t pixel_offset,
                       float* out, cudaStream_t st);
 

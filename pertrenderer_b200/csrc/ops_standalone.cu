@@ -397,6 +397,20 @@ int launch_argmax_bwd(const float* grad_l, const float* z, const void* winners, 
     return (int)cudaGetLastError();
 }
 
+// splitmix64 step (Steele, Lea, Flood 2014) of the two device-side seeds
+__global__ void seed_advance_kernel(uint64_t* s) {
+    for (int i = 0; i < 2; ++i) {
+        uint64_t z = (s[i] += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        s[i] = z ^ (z >> 31);
+    }
+}
+int launch_seed_advance(uint64_t* seed_device, cudaStream_t st) {
+    seed_advance_kernel<<<1, 1, 0, st>>>(seed_device);
+    return (int)cudaGetLastError();
+}
+
 int launch_noise_fill(uint64_t seed, int stage, int64_t P, int slots, int s_begin, int s_end, int64_t pixel_offset,
                       float* out, cudaStream_t st) {
     const int qn = ((s_end + 3) >> 2) - (s_begin >> 2);

@@ -101,6 +101,11 @@ struct PhiloxNoiseT {
         const uint64_t gp = (uint64_t)(pixel_local + pixel_offset);
         philox4x32<ROUNDS>(q, slot, (uint32_t)gp, ((uint32_t)(gp >> 32) & 0x7fffffffu) | stage_bit, k0, k1, r);
     }
+    // device-side seed (pert_problem.seed_device): the effective seed is seed ^ v
+    __device__ __forceinline__ void mix(uint64_t v) {
+        k0 ^= (uint32_t)v;
+        k1 ^= (uint32_t)(v >> 32);
+    }
     static constexpr bool kBounded = true;
 };
 using PhiloxNoise = PhiloxNoiseT<10>;
@@ -166,6 +171,7 @@ struct ExplicitNoise {
     int64_t P;
     int32_t slots;
     int32_t S;
+    __device__ __forceinline__ void mix(uint64_t) {}
 
     __device__ __forceinline__ void get4(uint32_t q, uint32_t slot, int64_t pixel_local, float (&n)[4]) const {
 #pragma unroll

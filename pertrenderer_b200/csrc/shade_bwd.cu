@@ -587,7 +587,9 @@ __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& n
 template <class NoiseA, int GT, bool PHASED, bool FACE, bool COMPACT, bool BLOB>
 __global__ void __launch_bounds__(FNT, 25) shade_bwd_kernel(const BwdArgs a, const NoiseA noise_a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    shade_bwd_tile<NoiseA, GT, PHASED, FACE, COMPACT, BLOB>(a, noise_a, blockIdx.x, blockIdx.x, smem_raw, threadIdx.x);
+    NoiseA na = noise_a;
+    if (a.pb.seed_device) na.mix(__ldg(a.pb.seed_device + 1));  // device-side seed, see shade_fwd.cu
+    shade_bwd_tile<NoiseA, GT, PHASED, FACE, COMPACT, BLOB>(a, na, blockIdx.x, blockIdx.x, smem_raw, threadIdx.x);
 }
 
 // Fallback pass of the sparse-first mode (see shade_fwd.cu): work-list tiles as half-size tiles with dense
@@ -597,6 +599,8 @@ __global__ void __launch_bounds__(FBT, 12) shade_bwd_fallback_kernel(const BwdAr
     extern __shared__ __align__(16) unsigned char smem_all[];
     unsigned char* smem_raw = smem_all + (threadIdx.x >> 5) * a.L.warp_smem;  // FBT/32 independent warps per CTA
     const int n = 2 * a.worklist[0];
+    NoiseA na = noise_a;
+    if (a.pb.seed_device) na.mix(__ldg(a.pb.seed_device + 1));
 #pragma unroll 1
     for (;;) {  // persistent warps fetch half-tiles dynamically
         int i = 0;
@@ -605,7 +609,7 @@ __global__ void __launch_bounds__(FBT, 12) shade_bwd_fallback_kernel(const BwdAr
         if (i >= n) break;
         const int64_t tile = (int64_t)a.worklist[4 + (i >> 1)] * 2 + (i & 1);
         if (tile < a.L.ntiles) {
-            shade_bwd_tile<NoiseA, GT, false, FACE, false, false>(a, noise_a, tile, prow0 + i, smem_raw, threadIdx.x & 31);
+            shade_bwd_tile<NoiseA, GT, false, FACE, false, false>(a, na, tile, prow0 + i, smem_raw, threadIdx.x & 31);
         } else if ((threadIdx.x & 31) == 0) {
             reinterpret_cast<float4*>(a.partials)[prow0 + i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }

@@ -419,7 +419,13 @@ __device__ __forceinline__ void shade_fwd_tile(const FwdArgs& a, const NoiseR& n
 template <class NoiseR, class NoiseA, int GT, bool PHASED, bool DEFER = false>
 __global__ void __launch_bounds__(FNT, 32) shade_fwd_kernel(const FwdArgs a, const NoiseR noise_r, const NoiseA noise_a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    shade_fwd_tile<NoiseR, NoiseA, GT, PHASED, DEFER>(a, noise_r, noise_a, blockIdx.x, smem_raw, threadIdx.x);
+    NoiseR nr = noise_r;
+    NoiseA na = noise_a;
+    if (a.pb.seed_device) {  // seeds that live on the device: a captured CUDA graph draws fresh noise at every replay
+        nr.mix(__ldg(a.pb.seed_device));
+        na.mix(__ldg(a.pb.seed_device + 1));
+    }
+    shade_fwd_tile<NoiseR, NoiseA, GT, PHASED, DEFER>(a, nr, na, blockIdx.x, smem_raw, threadIdx.x);
 }
 
 // Fallback pass of the sparse-first mode: the tiles whose valid entries did not fit the compact arrays,
@@ -430,6 +436,12 @@ __global__ void __launch_bounds__(FBT, 12) shade_fwd_fallback_kernel(const FwdAr
     extern __shared__ __align__(16) unsigned char smem_all[];
     unsigned char* smem_raw = smem_all + (threadIdx.x >> 5) * a.L.warp_smem;  // FBT/32 independent warps per CTA
     const int n = 2 * a.worklist[0];
+    NoiseR nr = noise_r;
+    NoiseA na = noise_a;
+    if (a.pb.seed_device) {
+        nr.mix(__ldg(a.pb.seed_device));
+        na.mix(__ldg(a.pb.seed_device + 1));
+    }
 #pragma unroll 1
     for (;;) {  // persistent warps fetch half-tiles dynamically
         int i = 0;
@@ -437,7 +449,7 @@ __global__ void __launch_bounds__(FBT, 12) shade_fwd_fallback_kernel(const FwdAr
         i = __shfl_sync(FULL, i, 0);
         if (i >= n) break;
         const int64_t tile = (int64_t)a.worklist[4 + (i >> 1)] * 2 + (i & 1);
-        if (tile < a.L.ntiles) shade_fwd_tile<NoiseR, NoiseA, GT, false>(a, noise_r, noise_a, tile, smem_raw, threadIdx.x & 31);
+        if (tile < a.L.ntiles) shade_fwd_tile<NoiseR, NoiseA, GT, false>(a, nr, na, tile, smem_raw, threadIdx.x & 31);
         __syncwarp();
     }
 }

@@ -103,6 +103,7 @@ class ShadeProblem:
     noise_rast: Optional[torch.Tensor] = None
     noise_agg: Optional[torch.Tensor] = None
     face_colors: Optional[torch.Tensor] = None  # (F,3): colours gathered through pix_to_face inside the kernels
+    seed_device: Optional[torch.Tensor] = None  # int64 (2,) on the device: effective seeds = seed_* ^ seed_device (graphs)
     _keep: list = field(default_factory=list)
 
     def __post_init__(self):
@@ -173,14 +174,35 @@ class ShadeProblem:
         pb.noise_agg = self.noise_agg.data_ptr() if self.noise_agg is not None else None
         if self.face_colors is not None:
             pb.face_colors, pb.num_faces = self.face_colors.data_ptr(), self.face_colors.shape[0]
+        if self.seed_device is not None:
+            if self.seed_device.dtype != torch.int64 or self.seed_device.numel() != 2 or not self.seed_device.is_cuda:
+                raise ValueError("seed_device must be an int64 CUDA tensor with two elements")
+            pb.seed_device = self.seed_device.data_ptr()
         return pb
 
     def winner_dtype(self):
         return torch.uint8 if self.shape[3] + 1 <= 256 else torch.int16  # int16 storage, read as uint16
 
     def num_tiles(self) -> int:
-        pb = self.c_struct()
-        return int(_cabi.load().pert_num_tiles(pb))
+        return _geometry(self)[0]
+
+    def blob_bytes(self) -> int:
+        return _geometry(self)[1]
+
+
+_GEOMETRY = {}
+
+
+def _geometry(pr: "ShadeProblem"):
+    """(pert_num_tiles, pert_blob_bytes) of a problem: functions of the shape only, cached per shape (the host side of a
+    small problem is a few hundred microseconds: every ctypes call counts)."""
+    key = pr.shape
+    g = _GEOMETRY.get(key)
+    if g is None:
+        lib = _cabi.load()
+        pb = pr.c_struct()
+        g = _GEOMETRY[key] = (int(lib.pert_num_tiles(pb)), int(lib.pert_blob_bytes(pb)))
+    return g
 
 
 @dataclass
@@ -227,7 +249,7 @@ def shade_forward(pr: ShadeProblem, want_hist: bool = False, phases: int = 0, sa
                 winners=torch.empty((N, H, W, sa_loc), dtype=pr.winner_dtype(), device=dev),
                 pixstate=torch.empty((N, H, W), dtype=torch.int16, device=dev),
                 worklist=None if phases else torch.empty((4 + pr.num_tiles(),), dtype=torch.int32, device=dev),
-                blob=torch.empty((int(lib.pert_blob_bytes(pr.c_struct())),), dtype=torch.uint8, device=dev) if prod else None,
+                blob=torch.empty((pr.blob_bytes(),), dtype=torch.uint8, device=dev) if prod else None,
                 hist=torch.empty((N, H, W, K + 1), dtype=torch.int32, device=dev) if want_hist else None)
         do_blend = (phases == 0) or bool(phases & PH_BLEND)
         image = torch.empty((N, H, W, 4), dtype=torch.float32, device=dev) if do_blend else None
@@ -398,3 +420,63 @@ def noise_fill(seed, stage, shape4, S, device, pixel_offset=0, s_range=None):
         rc = lib.pert_noise_fill(seed, stage, N * H * W, slots, s0, s1, pixel_offset, ptr(out), stream_ptr(dev))
     check(rc, "pert_noise_fill")
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# small problems: forward + backward captured in one CUDA graph
+# ---------------------------------------------------------------------------------------------
+def seed_advance(seed_device: torch.Tensor):
+    """pert_seed_advance: one splitmix64 step of the two device-side seeds (capturable)."""
+    lib = _cabi.load()
+    require_cuda(seed_device)
+    with torch.cuda.device(seed_device.device):
+        rc = lib.pert_seed_advance(ptr(seed_device), stream_ptr(seed_device.device))
+    check(rc, "pert_seed_advance")
+
+
+class GraphedShadeStep:
+    """One fused forward + backward of the perturbed shader captured in a CUDA graph, for loops over a FIXED shape where
+    launch overhead dominates (BASELINE config 1; the pose optimisation of experiments/eval.py:341-394 at 64x64..128x128).
+
+    The caller keeps writing its inputs into the tensors it passed (``pix_to_face, zbuf, dists, colors, grad_image``:
+    they are the graph's static inputs) and calls :meth:`replay`; the results appear in ``image, grad_dists, grad_zbuf,
+    grad_colors, grad_scalars`` (static outputs, overwritten by the next replay).  The noise seeds live on the device
+    (``pert_problem.seed_device``) and a ``pert_seed_advance`` node steps them inside the graph, so every replay draws
+    fresh noise although all launch parameters are frozen.  sigma / gamma / alpha / the sample counts are frozen too:
+    re-capture after ``update_smoothing`` / ``update_nb_samples``."""
+
+    def __init__(self, pix_to_face, zbuf, dists, colors, grad_image, *, sigma, gamma, alpha=1.0, eps=1e-10, S_rast, S_agg,
+                 background=(1.0, 1.0, 1.0), znear=1.0, zfar=100.0, seed=None, flags=0, face_colors=None, need_colors=True):
+        dev = pix_to_face.device
+        require_cuda(pix_to_face, zbuf, dists, colors, grad_image, face_colors)
+        s0, s1 = (draw_seed(), draw_seed()) if seed is None else (int(seed), int(seed) ^ 0x9E3779B97F4A7C15 & (2 ** 63 - 1))
+        self.seed_device = torch.tensor([s0, s1], dtype=torch.int64, device=dev)
+        self.problem = ShadeProblem(pix_to_face=pix_to_face, zbuf=zbuf, dists=dists, colors=colors, face_colors=face_colors,
+                                    znear=znear, zfar=zfar, background=tuple(background), sigma=float(sigma), gamma=float(gamma),
+                                    alpha=float(alpha), eps=float(eps), S_rast=int(S_rast), S_agg=int(S_agg), seed_rast=0,
+                                    seed_agg=0, flags=int(flags), seed_device=self.seed_device)
+        if self.problem.zbuf.data_ptr() != zbuf.data_ptr() or self.problem.dists.data_ptr() != dists.data_ptr() or \
+                (colors is not None and self.problem.colors.data_ptr() != colors.data_ptr()):
+            raise ValueError("GraphedShadeStep needs contiguous float32 inputs (they are the graph's static buffers)")
+        self.grad_image = grad_image
+        self.need_colors = need_colors
+
+        def run():
+            seed_advance(self.seed_device)
+            image, saved = shade_forward(self.problem)
+            return (image,) + shade_backward(self.problem, saved, self.grad_image, need_colors=self.need_colors)
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):  # warm-up outside the capture (function attributes, cached device properties)
+            for _ in range(2):
+                run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.image, self.grad_dists, self.grad_zbuf, self.grad_colors, self.grad_scalars = run()
+
+    def replay(self):
+        self.graph.replay()
+        return self.image, self.grad_dists, self.grad_zbuf, self.grad_colors, self.grad_scalars

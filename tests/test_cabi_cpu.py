@@ -34,9 +34,10 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header():
     """ctypes mirror of pert_problem: field order / sizes as in the header (LP64)."""
-    assert ctypes.sizeof(_cabi.PertProblem) == 192
+    assert ctypes.sizeof(_cabi.PertProblem) == 200
     assert _cabi.PertProblem.pix_to_face.offset == 112
     assert _cabi.PertProblem.seed_rast.offset == 80
+    assert _cabi.PertProblem.seed_device.offset == 192
 
 
 def test_argument_validation_without_gpu():

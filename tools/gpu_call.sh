@@ -1,9 +1,9 @@
 #!/bin/bash
-# usage: tools/gpu_call.sh <log-name> <timeout-seconds> '<command>'   -- retries while the pod answers busy (exit 3 / transient)
+# usage: [GPUS=n] tools/gpu_call.sh <log-name> <timeout-seconds> '<command>'   -- retries while the pod answers busy (exit 3 / transient)
 log=gpurun_out/$1.log; shift
 to=$1; shift
 for i in $(seq 1 40); do
-  gpurun --timeout $to -- "$@" > $log 2>&1
+  if [ -n "$GPUS" ]; then gpurun --gpus $GPUS --timeout $to -- "$@" > $log 2>&1; else gpurun --timeout $to -- "$@" > $log 2>&1; fi
   rc=$?
   if grep -q "status=transient\|nothing was charged" $log || [ $rc -eq 3 ]; then sleep 45; continue; fi
   break
