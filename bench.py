@@ -565,7 +565,33 @@ def sample_sharded_leg(dev, world, rank, steps):
         return ms.item()
     ms_sharded, ms_single = timed(True), timed(False)
     units = N * HW * HW * K * S
-    return {"config": cfg["name"], "fragments": "rasterised", "world": world,
+    # the same job with every rank's phases and the three all-reduces captured in one CUDA graph per rank
+    graph = {}
+    try:
+        d, z, c = fr.dists.contiguous(), fr.zbuf.contiguous(), col
+        step = pdist.GraphedSampleShardedStep(fr.pix_to_face, z, d, c, G, sigma=SIGMA, gamma=GAMMA, alpha=ALPHA, eps=EPS,
+                                              S_rast=S, S_agg=S, background=BACKGROUND)
+        for _ in range(3):
+            step.replay()
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(4 * steps):
+            step.replay()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        ms = torch.tensor([e0.elapsed_time(e1) / (4 * steps)], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        img = step.image.clone()
+        dist.broadcast(img, src=0)
+        graph = {"ms_per_step_graph": ms.item(), "speedup_graph": ms_single / ms.item(),
+                 "ranks_agree": bool(torch.equal(img, step.image)), "value_graph": units / (ms.item() * 1e-3)}
+        step.close()  # the graph holds NCCL kernels: release it before the process group goes away
+    except Exception as e:
+        graph = {"graph_error": repr(e)[:300]}
+    return {"config": cfg["name"], "fragments": "rasterised", "world": world, **graph,
             "note": "public API + autograd (smooth_rgb_blend_sample_sharded vs smooth_rgb_blend), default noise flags for "
                     "the timing, PERT_F_PER_SAMPLE_NOISE + synchronised seeds for the comparison",
             "ms_per_step_sharded": ms_sharded, "ms_per_step_one_gpu": ms_single, "speedup": ms_single / ms_sharded,

@@ -142,6 +142,7 @@ static Launch make_launch(const pert_problem* pb, int tp) {
     L.inv_sr = 1.0f / ((float)pb->S_rast * pb->sigma);
     L.invS = 1.0f / (float)pb->S_agg;
     L.inv_gamma = 1.0f / pb->gamma;
+    L.stage_bytes = 0;
     L.t_compound = compound_threshold(pb->s_rast_end - pb->s_rast_begin);
     compound_buckets(pb->s_rast_end - pb->s_rast_begin, L.t_compound, L.t_bucket);
     L.cmp_min = 12;
@@ -173,6 +174,13 @@ static int sparse_tp(int K, int64_t P) {
     while (tp > 4 && (P + tp - 1) / tp < (int64_t)sm_count() * 16) tp >>= 1;
     return tp;
 }
+// tile of the launches that do not run sparse-first (phase-split / explicit-noise / per-sample jobs): the same rule for
+// jobs of few pixels (a sample shard of BASELINE config 4 is 128^2 pixels x 512 samples)
+static int dense_tp(int K, int64_t P) {
+    int tp = pick_tp(K);
+    while (tp > 4 && (P + tp - 1) / tp < (int64_t)sm_count() * 16) tp >>= 1;
+    return tp;
+}
 static int sparse_cap(int K, int tp) {
     int cap = tp * K / 5;
 #ifdef PERT_EXPERIMENTS
@@ -190,10 +198,26 @@ static bool sparse_first_ok(const pert_problem* pb, const void* worklist, bool a
     return true;
 }
 
+// Bulk-copy scan of the forward (tile.cuh scan_valid_staged; TMA 1-D copy + mbarrier, UBLKCP in SASS): bytes of the staging
+// buffer, 0 = register scan.  Measured and REJECTED as a default (round 2, config 2): in the main pass the 6.4 KB stage takes
+// the resident warps from 32 to 23 per SM and the sparse-set forward from 0.281 to 0.297 ms; in the fallback pass (3.2 KB
+// stage, no occupancy cost) the rasterised set gains 0.6 % and the dense set loses 0.8 %: the scan is 1.5 % of that pass's
+// instructions.  Kept behind the tuning build's PERT_BULK_SCAN / PERT_BULK_SCAN_FB for re-measurement on other shapes.
+static int stage_bytes_for(int tp, int K, bool fallback) {
+    int on = 0;
+    (void)fallback;
+#ifdef PERT_EXPERIMENTS
+    if (const char* e = getenv(fallback ? "PERT_BULK_SCAN_FB" : "PERT_BULK_SCAN")) on = atoi(e);
+#endif
+    if (!on) return 0;
+    const int bytes = tp * K * 8;
+    return (bytes % 16 == 0 && bytes <= 16 * 1024) ? bytes : 0;
+}
+
 extern "C" int64_t pert_num_tiles(const pert_problem* pb) {
     if (!pb || pb->K <= 0) return 0;
     const int64_t P = pb->N * pb->H * pb->W;
-    const int a = pick_tp(pb->K), b = sparse_tp(pb->K, P);
+    const int a = dense_tp(pb->K, P), b = sparse_tp(pb->K, P);
     const int tp = a < b ? a : b;  // the finest tile geometry any launch of this problem uses
     return (P + tp - 1) / tp;
 }
@@ -232,13 +256,14 @@ extern "C" int pert_shade_fwd(const pert_problem* pb_in, float* image, uint16_t*
     if (sparse) {  // the fallback pass runs FBT/32 warps per CTA: its tiles must fit that many times
         SmemLayout t;
         const int tp2 = sparse_tp(a.pb.K, a.pb.N * a.pb.H * a.pb.W) / 2;
-        fwd_smem_layout(tp2, tp2 * a.pb.K, t);
+        fwd_smem_layout(tp2, tp2 * a.pb.K, 0, t);
         if ((size_t)t.bytes * (FBT / 32) > 200 * 1024) sparse = false;
     }
-    a.L = make_launch(&a.pb, sparse ? sparse_tp(a.pb.K, a.pb.N * a.pb.H * a.pb.W) : pick_tp(a.pb.K));
+    a.L = make_launch(&a.pb, sparse ? sparse_tp(a.pb.K, a.pb.N * a.pb.H * a.pb.W) : dense_tp(a.pb.K, a.pb.N * a.pb.H * a.pb.W));
     a.L.vec_ok = a.L.vec_ok && aligned16(a.pb.pix_to_face);
     if (sparse) a.L.cap = sparse_cap(a.pb.K, a.L.tp);
-    fwd_smem_layout(a.L.tp, a.L.cap, a.L.sm);
+    a.L.stage_bytes = stage_bytes_for(a.L.tp, a.pb.K, false);
+    fwd_smem_layout(a.L.tp, a.L.cap, a.L.stage_bytes, a.L.sm);
     a.L.warp_smem = a.L.sm.bytes;
     if ((size_t)a.L.warp_smem > 200 * 1024) return PERT_E_UNSUPPORTED;
     if (a.L.ntiles > 0x7fffffff) return PERT_E_UNSUPPORTED;
@@ -257,7 +282,8 @@ extern "C" int pert_shade_fwd(const pert_problem* pb_in, float* image, uint16_t*
     fb.blob = nullptr;
     fb.L = make_launch(&a.pb, a.L.tp / 2);
     fb.L.vec_ok = fb.L.vec_ok && aligned16(a.pb.pix_to_face);
-    fwd_smem_layout(fb.L.tp, fb.L.cap, fb.L.sm);
+    fb.L.stage_bytes = stage_bytes_for(fb.L.tp, a.pb.K, true);
+    fwd_smem_layout(fb.L.tp, fb.L.cap, fb.L.stage_bytes, fb.L.sm);
     fb.L.warp_smem = fb.L.sm.bytes;
     cudaError_t e = cudaMemsetAsync(worklist, 0, 16, st);
     if (e != cudaSuccess) return cuda_fail((int)e);
@@ -297,7 +323,7 @@ extern "C" int pert_shade_bwd(const pert_problem* pb_in, const float* grad_image
     }
     const bool ptr_ok = aligned16(a.pb.pix_to_face) && aligned16(grad_dists) && aligned16(grad_zbuf) &&
                         (a.pb.face_colors || aligned16(grad_colors));
-    a.L = make_launch(&a.pb, sparse ? sparse_tp(a.pb.K, a.pb.N * a.pb.H * a.pb.W) : pick_tp(a.pb.K));
+    a.L = make_launch(&a.pb, sparse ? sparse_tp(a.pb.K, a.pb.N * a.pb.H * a.pb.W) : dense_tp(a.pb.K, a.pb.N * a.pb.H * a.pb.W));
     a.L.vec_ok = a.L.vec_ok && ptr_ok;
     if (sparse) a.L.cap = sparse_cap(a.pb.K, a.L.tp);
     if (a.L.win_bytes == 2 && ((uintptr_t)winners & 1)) return PERT_E_ALIGN;

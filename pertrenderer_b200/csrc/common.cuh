@@ -190,6 +190,7 @@ struct Launch {
     float inv_sigma, invSg, inv_sr, invS;  // 1/sigma, 1/(S_agg gamma), 1/(S_rast sigma), 1/S_agg
     float inv_gamma;  // 1/gamma (SoftAgg, smoothagg.py:181)
     float t_compound; // coverage entries with |x|/sigma >= this are drawn by the compound sampler (tile.cuh)
+    int stage_bytes;   // forward: bytes of the pix_to_face staging buffer of the bulk-copy scan (0: register scan)
     int cmp_min;       // fewer compound entries than this in a tile are drawn by the per-sample loop instead
     int defer_min;     // main pass of the sparse-first mode: tiles with at least this many go to the fallback pass
     float t_bucket[2]; // ... and bucketed by expected flips: [t_compound, t_bucket[0]) many, [.., t_bucket[1]) some, rest rare

@@ -15,7 +15,7 @@
 
 namespace pert {
 
-void fwd_smem_layout(int tp, int cap, SmemLayout& L) {
+void fwd_smem_layout(int tp, int cap, int stage_bytes, SmemLayout& L) {
     Carver cv(L);
     cv.take(cap, 2);       // vlist
     cv.take(cap + tp, 4);  // xs | lz
@@ -27,12 +27,24 @@ void fwd_smem_layout(int tp, int cap, SmemLayout& L) {
     cv.take(tp, 4);        // pinfo
     cv.take(tp, 2);        // plist
     cv.take(64, 2);        // ring (compound sampler)
+    cv.take(stage_bytes ? 16 : 0, 1);  // mbarrier + phase parity of the bulk-copy scan
+    cv.take(stage_bytes, 1);           // stage: the tile's pix_to_face rows
 }
 
 // GT = lanes per pixel as a compile-time constant (1, 2, 4, 8), or 0 to read it from the launch record.
 // PHASED = false is the production instantiation: all three phases in one launch, no global histogram
 // (the phase-split code of the sample-sharded job is compiled out, which keeps the hot code small: the
 // kernel is instruction-fetch sensitive, every warp walks the whole body once per tile).
+// this warp's mbarrier (one arrival: the elected lane's expect_tx) and its phase parity; layout: fwd_smem_layout
+__device__ __forceinline__ void fwd_init_barrier(const FwdArgs& a, unsigned char* smem_raw) {
+    uint64_t* const bar = reinterpret_cast<uint64_t*>(smem_raw + a.L.sm.off[10]);
+    if ((threadIdx.x & 31) == 0) {
+        mbar_init(bar, 1);
+        *reinterpret_cast<unsigned*>(bar + 1) = 0u;
+    }
+    __syncwarp();
+}
+
 // DEFER = true (main pass of the sparse-first mode): a tile with enough entries for the compound coverage sampler is
 // handed to the fallback pass like a tile that overflows the compact arrays, so that this instantiation carries no
 // compound-sampler code at all (the kernel is instruction-fetch bound on sparse fragments: every instruction of a
@@ -73,13 +85,17 @@ __device__ __forceinline__ void shade_fwd_tile(const FwdArgs& a, const NoiseR& n
     int* pinfo = cv.take<int>();  // nlive | a0l << 16 of every pixel
     uint16_t* plist = cv.take<uint16_t>();
     uint16_t* ring = cv.take<uint16_t>();
+    uint64_t* bar = cv.take<uint64_t>();
+    long long* stage = cv.take<long long>();
     const int cap = a.L.cap;
     float* lz = xs;
     int* hl = reinterpret_cast<int*>(rs);
     uint16_t* lj = rlist;
 
     // ---- phase 0 -----------------------------------------------------------------------------------
-    const int nv = scan_valid(pb.pix_to_face + g0, E, a.L.vec_ok, vlist, cap);
+    const int nv = (a.L.stage_bytes && a.L.vec_ok && ((E & 1) == 0))
+                       ? scan_valid_staged(pb.pix_to_face + g0, E, stage, bar, vlist, cap)
+                       : scan_valid(pb.pix_to_face + g0, E, a.L.vec_ok, vlist, cap);
     const int sa_loc = a.L.sa_loc;
     if (nv > cap) {
         // sparse-first mode: this tile has more valid entries than the compact arrays hold: hand it to the
@@ -425,6 +441,7 @@ __global__ void __launch_bounds__(FNT, 32) shade_fwd_kernel(const FwdArgs a, con
         nr.mix(__ldg(a.pb.seed_device));
         na.mix(__ldg(a.pb.seed_device + 1));
     }
+    if (a.L.stage_bytes) fwd_init_barrier(a, smem_raw);
     shade_fwd_tile<NoiseR, NoiseA, GT, PHASED, DEFER>(a, nr, na, blockIdx.x, smem_raw, threadIdx.x);
 }
 
@@ -442,6 +459,7 @@ __global__ void __launch_bounds__(FBT, 12) shade_fwd_fallback_kernel(const FwdAr
         nr.mix(__ldg(a.pb.seed_device));
         na.mix(__ldg(a.pb.seed_device + 1));
     }
+    if (a.L.stage_bytes) fwd_init_barrier(a, smem_raw);
 #pragma unroll 1
     for (;;) {  // persistent warps fetch half-tiles dynamically
         int i = 0;

@@ -77,21 +77,43 @@ def all_reduce_scalar_grads(tensors, group=None, device=None):
 # sample-sharded orchestration
 # ------------------------------------------------------------------------------------------------
 class CudaStages:
-    """The phases of the fused kernels (include/pertshade.h PERT_PH_*) on one rank's sample shard."""
+    """The phases of the fused kernels (include/pertshade.h PERT_PH_*) on one rank's sample shard.
+
+    Everything that is exchanged lives in persistent buffers laid out for the collectives, so that no phase packs or
+    copies: the hit counts are reduced as int32 (AR1; NCCL has no 16-bit integer type), the winner histogram in place
+    (AR2), and ONE flat float buffer holds, back to back, the argmax score sums (P,K1), the two per-pixel sums (P,2) and
+    the coverage score sums rsum (P,K) -- the kernels write / read its three regions through separate pointers and AR3
+    reduces it in one call (rsum is only needed by the last backward phase, SURVEY.md §8e, so it rides along there
+    instead of doubling AR1)."""
 
     def __init__(self, pr):
         from . import _cabi, ops
         self.ops, self.cabi, self.pr = ops, _cabi, pr
-        self.saved = None
+        N, H, W, K = pr.shape
+        dev = pr.device
+        P, K1 = N * H * W, K + 1
+        self.flat = torch.zeros((P * K1 + 2 * P + P * K,), dtype=torch.float32, device=dev)
+        self.acc = self.flat[:P * K1].view(N, H, W, K1)
+        self.pixstat = self.flat[P * K1:P * K1 + 2 * P].view(N, H, W, 2)
+        rsum = self.flat[P * K1 + 2 * P:].view(N, H, W, K)
+        sa_loc = pr.s_agg[1] - pr.s_agg[0]
+        self.saved = ops.ShadeSaved(
+            counts=torch.zeros((N, H, W, K), dtype=torch.int16, device=dev), rsum=rsum,
+            winners=torch.empty((N, H, W, sa_loc), dtype=pr.winner_dtype(), device=dev),
+            pixstate=torch.empty((N, H, W), dtype=torch.int16, device=dev),
+            hist=torch.empty((N, H, W, K1), dtype=torch.int32, device=dev))
+        self.counts32 = torch.empty((N, H, W, K), dtype=torch.int32, device=dev)
 
     def rast(self):
-        _, self.saved = self.ops.shade_forward(self.pr, want_hist=True, phases=self.cabi.PH_RAST)
-        counts = (self.saved.counts.to(torch.int32) & 0xFFFF).float()
-        return counts, self.saved.rsum
+        # entries the kernel does not touch (padding) must be defined: they are summed over ranks
+        self.saved.counts.zero_()
+        self.saved.rsum.zero_()
+        self.ops.shade_forward(self.pr, phases=self.cabi.PH_RAST, saved=self.saved)
+        torch.bitwise_and(self.saved.counts.to(torch.int32), 0xFFFF, out=self.counts32)
+        return self.counts32
 
-    def agg(self, counts, rsum):
-        self.saved.counts.copy_(counts.to(torch.int32).to(torch.int16))  # uint16 bit pattern
-        self.saved.rsum.copy_(rsum)
+    def agg(self, counts32):
+        self.saved.counts.copy_(counts32)  # int32 -> the uint16 bit pattern (S_rast <= 65535)
         self.ops.shade_forward(self.pr, phases=self.cabi.PH_AGG, saved=self.saved)
         return self.saved.hist
 
@@ -102,32 +124,22 @@ class CudaStages:
         return image
 
     def bwd_sample(self, grad_image):
-        N, H, W, K = self.pr.shape
-        dev = self.pr.device
-        acc = torch.empty((N, H, W, K + 3), dtype=torch.float32, device=dev)
-        # the kernel writes acc (P,K1) and pixstat (P,2) separately; pack them for ONE all-reduce
-        a = torch.empty((N, H, W, K + 1), dtype=torch.float32, device=dev)
-        t = torch.empty((N, H, W, 2), dtype=torch.float32, device=dev)
-        self.ops.shade_backward(self.pr, self.saved, grad_image, phases=self.cabi.PH_BWD_SAMPLE, acc=a, pixstat=t,
-                                use_hist=True)
-        acc[..., :K + 1] = a
-        acc[..., K + 1:] = t
-        return acc
+        self.ops.shade_backward(self.pr, self.saved, grad_image, phases=self.cabi.PH_BWD_SAMPLE, acc=self.acc,
+                                pixstat=self.pixstat, use_hist=True)
+        return self.flat  # [acc | pixstat | rsum]: reduced in one call
 
-    def bwd_finish(self, grad_image, packed, need_colors=True):
-        K = self.pr.shape[3]
-        a = packed[..., :K + 1].contiguous()
-        t = packed[..., K + 1:].contiguous()
+    def bwd_finish(self, grad_image, flat, need_colors=True):
+        if flat is not self.flat:
+            self.flat.copy_(flat)
         return self.ops.shade_backward(self.pr, self.saved, grad_image, need_colors=need_colors,
-                                       phases=self.cabi.PH_BWD_FINISH, acc=a, pixstat=t, use_hist=True)
+                                       phases=self.cabi.PH_BWD_FINISH, acc=self.acc, pixstat=self.pixstat, use_hist=True)
 
 
 def sharded_forward(stages, group=None):
     """AR1 and AR2 around the three forward phases.  Returns the image (identical on every rank)."""
-    counts, rsum = stages.rast()
-    packed = torch.stack((counts, rsum))  # counts <= 65535 are exact in fp32
-    dist.all_reduce(packed, group=group)
-    hist = stages.agg(packed[0], packed[1])
+    counts = stages.rast()
+    dist.all_reduce(counts, group=group)  # exact: integers
+    hist = stages.agg(counts)
     dist.all_reduce(hist, group=group)
     return stages.blend(hist)
 
@@ -213,3 +225,72 @@ def smooth_rgb_blend_sample_sharded(colors, fragments, smoothrast, smoothagg, bl
                S_agg=smoothagg.nb_samples, fixed_noise=bool(smoothagg.fixed_noise), group=group, sync_seeds=sync_seeds)
     return _SampleShardedShade.apply(colors, fragments.dists, fragments.zbuf, smoothrast.sigma, smoothagg.gamma,
                                      smoothagg.alpha, fragments.pix_to_face, znear, zfar, cfg)
+
+
+class GraphedSampleShardedStep:
+    """Noise-sample sharded forward + backward captured in ONE CUDA graph per rank (BASELINE config 4: few pixels,
+    thousands of samples): seed advance, the three forward phases, the two backward phases and the three NCCL all-reduces
+    between them are graph nodes, so a step costs the kernels and the collectives, not ~1 ms of host orchestration.
+
+    Inputs are replicated: every rank passes the same ``pix_to_face, zbuf, dists, colors, grad_image`` (the graph's static
+    buffers; write new values into them between replays).  Rank r draws the samples ``sample_range(S, world, r)``.  The
+    noise seeds live on the device, start equal on every rank (broadcast from rank 0 at construction) and are stepped by
+    the same ``pert_seed_advance`` node everywhere, so all ranks draw from one stream without exchanging seeds.
+    Every rank ends a replay with the same ``image, grad_dists, grad_zbuf, grad_colors, grad_scalars``."""
+
+    def __init__(self, pix_to_face, zbuf, dists, colors, grad_image, *, sigma, gamma, alpha=1.0, eps=1e-10, S_rast, S_agg,
+                 background=(1.0, 1.0, 1.0), znear=1.0, zfar=100.0, group=None, seed=None, flags=0, need_colors=True):
+        from . import ops
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        dev = pix_to_face.device
+        check_sample_sharding(int(S_rast), int(S_agg), world)
+        seeds = torch.zeros(2, dtype=torch.int64, device=dev)
+        if rank == 0:
+            s0 = ops.draw_seed() if seed is None else int(seed)
+            seeds.copy_(torch.tensor([s0, (s0 * 0x9E3779B1 + 12345) & (2 ** 62 - 1)], dtype=torch.int64))
+        dist.broadcast(seeds, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        self.seed_device = seeds
+        self.group, self.grad_image, self.need_colors = group, grad_image, need_colors
+        self.problem = ops.ShadeProblem(
+            pix_to_face=pix_to_face, zbuf=zbuf, dists=dists, colors=colors, znear=znear, zfar=zfar, background=tuple(background),
+            sigma=float(sigma), gamma=float(gamma), alpha=float(alpha), eps=float(eps), S_rast=int(S_rast), S_agg=int(S_agg),
+            seed_rast=0, seed_agg=0, flags=int(flags), s_rast=sample_range(int(S_rast), world, rank),
+            s_agg=sample_range(int(S_agg), world, rank), seed_device=self.seed_device)
+        self.stages = CudaStages(self.problem)
+
+        def run():
+            ops.seed_advance(self.seed_device)
+            image = sharded_forward(self.stages, group)
+            return (image,) + tuple(sharded_backward(self.stages, self.grad_image, group, need_colors=need_colors))
+
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):  # warm-up outside the capture: NCCL communicator, function attributes
+            for _ in range(2):
+                run()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        dist.barrier(group=group)
+        self.graph = torch.cuda.CUDAGraph()
+        # thread_local: the NCCL watchdog thread queries events while this thread captures
+        with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            self.image, self.grad_dists, self.grad_zbuf, self.grad_colors, self.grad_scalars = run()
+
+    def replay(self):
+        self.graph.replay()
+        return self.image, self.grad_dists, self.grad_zbuf, self.grad_colors, self.grad_scalars
+
+    def close(self):
+        """Release the captured graph.  Call before ``destroy_process_group``: tearing the NCCL communicator down while a
+        graph that holds its kernels is alive blocks (measured on the GPU box: both ranks stop in
+        destroy_process_group)."""
+        if getattr(self, "graph", None) is not None:
+            torch.cuda.synchronize(self.seed_device.device)
+            self.graph.reset()
+            self.graph = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

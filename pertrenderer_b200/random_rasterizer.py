@@ -59,11 +59,15 @@ class _PerturbedShade(Function):
         image, saved = ops.shade_forward(pr)
         ctx.pr, ctx.saved = pr, saved
         ctx.scalars = (sigma, gamma, alpha)
+        # the kernels of backward re-read the inputs through the pointers in ctx.pr: registering the tensors with autograd
+        # makes an in-place edit between forward and backward raise instead of silently changing the gradients
+        ctx.save_for_backward(colors, dists, zbuf, pix_to_face)
         return image
 
     @staticmethod
     def backward(ctx, grad_image):
         need = ctx.needs_input_grad
+        ctx.saved_tensors  # noqa: B018  (version check of the inputs)
         gd, gz, gc, scal = ops.shade_backward(ctx.pr, ctx.saved, grad_image, need_colors=need[0])
         out_scal = [None, None, None]
         if any(need[3:6]):
@@ -88,11 +92,13 @@ class _SoftShade(Function):
             eps=float(cfg["eps"]), S_rast=4, S_agg=4)
         ctx.pr = pr
         ctx.scalars = (sigma, gamma, alpha)
+        ctx.save_for_backward(colors, dists, zbuf, pix_to_face)  # in-place edits before backward raise (see _PerturbedShade)
         return ops.soft_shade_forward(pr)
 
     @staticmethod
     def backward(ctx, grad_image):
         need = ctx.needs_input_grad
+        ctx.saved_tensors  # noqa: B018
         gd, gz, gc, scal = ops.soft_shade_backward(ctx.pr, grad_image, need_colors=need[0])
         out_scal = [None, None, None]
         if any(need[3:6]):

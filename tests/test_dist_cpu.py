@@ -45,12 +45,11 @@ class OracleStages:
         self.U, self.V = g["U"][sr[0]:sr[1]], g["V"][sa[0]:sa[1]]
 
     def rast(self):
-        counts, rsum = O.rast_shard_sums(self.g["dists"], self.U, self.g["sigma"])
-        return counts, rsum
+        counts, self.rsum_local = O.rast_shard_sums(self.g["dists"], self.U, self.g["sigma"])
+        return counts
 
-    def agg(self, counts, rsum):
+    def agg(self, counts):
         g = self.g
-        self.rsum = rsum
         self.zeta, self.prob, self.aux = O.logits_from_counts(
             g["pix_to_face"], g["zbuf"], counts, int(g["S_r"]), g["znear_t"], g["zfar_t"], g["gamma"], g["alpha"], g["eps"])
         hist, self.a_s, self.a_0 = O.argmax_shard(self.zeta, self.V, g["gamma"])
@@ -62,15 +61,22 @@ class OracleStages:
         return image
 
     def bwd_sample(self, grad_image):
+        # one flat buffer for the one gradient all-reduce: [argmax score sums | per-pixel sums | coverage score sums]
         g = self.g
         grad_w = O._grad_weights(g["colors"], grad_image, g["background"])
-        return O.argmax_score_sums(grad_w, self.a_s, self.a_0, self.V)
+        self.packed_shape = tuple(grad_w.shape[:-1]) + (grad_w.shape[-1] + 2,)
+        packed = O.argmax_score_sums(grad_w, self.a_s, self.a_0, self.V)
+        return torch.cat((packed.flatten(), self.rsum_local.flatten()))
 
-    def bwd_finish(self, grad_image, packed, need_colors=True):
+    def bwd_finish(self, grad_image, flat, need_colors=True):
         g = self.g
+        n = 1
+        for d in self.packed_shape:
+            n *= d
+        packed, rsum = flat[:n].view(self.packed_shape), flat[n:].view(self.rsum_local.shape)
         aux = dict(self.aux, bg=g["background"])
         gr = O.shade_backward_from_sums(self.prob, self.weights, aux, grad_image, g["zbuf"], g["colors"], g["sigma"],
-                                        g["gamma"], g["alpha"], g["eps"], int(g["S_r"]), int(g["S_a"]), self.rsum, packed)
+                                        g["gamma"], g["alpha"], g["eps"], int(g["S_r"]), int(g["S_a"]), rsum, packed)
         return gr["dists"], gr["zbuf"], gr["colors"], torch.stack((gr["sigma"], gr["gamma"], gr["alpha"]))
 
 

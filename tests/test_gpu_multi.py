@@ -105,3 +105,54 @@ def test_nccl_sample_and_batch_sharding_world2(tmp_path):
         assert torch.equal(cat, whole[k]), k  # batch shards: bit-identical union
     assert torch.allclose(outs[0]["batch"]["scal"], whole["scal"], rtol=1e-5, atol=1e-7)
     assert torch.equal(outs[0]["batch"]["scal"], outs[1]["batch"]["scal"])
+
+
+def _graph_worker(rank, world, port, out_dir):
+    import torch.distributed as dist
+    import pertrenderer_b200 as pb
+    from pertrenderer_b200 import dist as pdist
+    from pertrenderer_b200 import ops
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dev = torch.device("cuda", rank)
+    torch.cuda.set_device(dev)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    try:
+        N, S, fr, col, G = _case(dev)
+        p2f, z, d, c, Gd = (t.to(dev).contiguous() for t in (fr.pix_to_face, fr.zbuf, fr.dists, col, G))
+        step = pdist.GraphedSampleShardedStep(p2f, z, d, c, Gd, sigma=1e-3, gamma=1e-2, alpha=1.1, S_rast=S, S_agg=S,
+                                              background=(0.2, 0.5, 0.8), seed=4242, flags=ops.F_PER_SAMPLE_NOISE)
+        out1 = [t.clone().cpu() for t in step.replay()]
+        seeds1 = step.seed_device.clone().cpu()
+        out2 = [t.clone().cpu() for t in step.replay()]
+        step.close()  # before destroy_process_group
+        torch.save(dict(out1=out1, out2=out2, seeds1=seeds1), os.path.join(out_dir, f"g{rank}.pt"))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_nccl_graph_captured_sample_sharded_step_world2(tmp_path):
+    """The sample-sharded step with its three NCCL all-reduces captured in one CUDA graph per rank: ranks agree exactly,
+    the result is the single-GPU job with the same effective seeds (per-sample flag: same sample path), and the next
+    replay draws fresh noise."""
+    import torch.multiprocessing as mp
+    from conftest import rel_err
+    from pertrenderer_b200 import ops
+    world = 2
+    mp.spawn(_graph_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    outs = [torch.load(tmp_path / f"g{r}.pt") for r in range(world)]
+    for a, b in zip(outs[0]["out1"], outs[1]["out1"]):
+        assert torch.equal(a, b)
+    assert torch.equal(outs[0]["seeds1"], outs[1]["seeds1"])
+    assert not torch.equal(outs[0]["out1"][0], outs[0]["out2"][0])
+    N, S, fr, col, G = _case("cuda:0")
+    dev = torch.device("cuda", 0)
+    seeds = outs[0]["seeds1"]
+    pr = ops.ShadeProblem(pix_to_face=fr.pix_to_face.to(dev), zbuf=fr.zbuf.to(dev), dists=fr.dists.to(dev), colors=col.to(dev),
+                          znear=1.0, zfar=100.0, background=(0.2, 0.5, 0.8), sigma=1e-3, gamma=1e-2, alpha=1.1, eps=1e-10,
+                          S_rast=S, S_agg=S, seed_rast=int(seeds[0]), seed_agg=int(seeds[1]), flags=ops.F_PER_SAMPLE_NOISE)
+    image, saved = ops.shade_forward(pr)
+    gd, gz, gc, scal = ops.shade_backward(pr, saved, G.to(dev))
+    o = outs[0]["out1"]
+    assert (o[0] - image.cpu()).abs().max() <= 1e-6
+    assert rel_err(o[1], gd.cpu()) <= 1e-5 and rel_err(o[2], gz.cpu()) <= 1e-5 and rel_err(o[3], gc.cpu()) <= 1e-6
+    assert torch.allclose(o[4], scal.cpu(), rtol=1e-4, atol=1e-6)

@@ -230,3 +230,17 @@ def test_graph_captured_step_matches_eager_and_redraws_noise():
     out3 = [t.clone() for t in step.replay()]
     for a, b in zip(out3, eager(step.seed_device)):
         assert torch.equal(a, b)
+
+
+def test_in_place_edit_of_an_input_before_backward_is_detected():
+    """The backward kernels re-read dists / zbuf / colours: the autograd Function registers them, so an in-place edit
+    between forward and backward raises instead of changing the gradients silently."""
+    import pertrenderer_b200 as pb
+    fr, col = pb.synthetic_fragments(1, 8, 8, 6, kind="dense", device="cuda")
+    d = fr.dists.clone().requires_grad_(True)
+    dd = d * 1.0  # non-leaf, so that an in-place op is legal
+    img = pb.smooth_rgb_blend(col, pb.Fragments(fr.pix_to_face, fr.zbuf, None, dd), pb.GaussianRast(nb_samples=8, sigma=1e-3),
+                              pb.GaussianAgg(nb_samples=8, gamma=1e-2), pb.BlendParams())
+    dd.mul_(2.0)
+    with pytest.raises(RuntimeError, match="modified by an inplace operation"):
+        img.sum().backward()
