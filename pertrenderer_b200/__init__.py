@@ -12,7 +12,7 @@ from .shading import phong_shading, sample_lazy_textures
 from .smoothagg import CauchyAgg, GaussianAgg, GaussianAgg_wovr, HardAgg, SoftAgg, UniformAgg, randomArgmax, randomArgmax_wovr
 from .smoothrast import (AffineRast, ArctanRast, GaussianRast, GaussianRast_wovr, HardRast, SoftRast, randomHeaviside,
                          randomHeaviside_wovr)
-from .structures import (BlendParams, DepthCameras, DirectionalLights, FaceColorMeshes, FaceTexels, Fragments, Materials,
+from .structures import (AtlasTexels, BlendParams, DepthCameras, DirectionalLights, FaceColorMeshes, FaceTexels, Fragments, Materials,
                          PointLights, TexelMeshes, TriMeshes, UVTexels, VertexTexels, ViewCameras, synthetic_bary, synthetic_fragments,
                          synthetic_mesh)
 from .ops import explicit_noise, kernel_flags
@@ -23,6 +23,6 @@ __all__ = [
     "look_at_view_transform", "rasterize_meshes", "Materials", "ViewCameras", "TriMeshes", "VertexTexels", "UVTexels", "sample_lazy_textures", "synthetic_mesh", "synthetic_bary", "smooth_rgb_blend", "GaussianAgg", "SoftAgg", "CauchyAgg", "HardAgg",
     "randomArgmax", "GaussianRast", "GaussianRast_wovr", "GaussianAgg_wovr", "randomHeaviside_wovr", "randomArgmax_wovr", "ArctanRast", "AffineRast", "HardRast",
     "SoftRast", "randomHeaviside", "BlendParams", "DepthCameras", "Fragments", "TexelMeshes",
-    "synthetic_fragments", "explicit_noise", "kernel_flags", "FaceColorMeshes", "FaceTexels",
+    "synthetic_fragments", "explicit_noise", "kernel_flags", "FaceColorMeshes", "FaceTexels", "AtlasTexels",
 ]
 __version__ = "0.1.0"

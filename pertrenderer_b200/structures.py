@@ -125,6 +125,32 @@ class UVTexels:
         return tex * mask[..., None]
 
 
+class AtlasTexels:
+    """Texels of a per-face texture atlas (pytorch3d ``TexturesAtlas``, the ShapeNet models of experiments/eval.py:216-238):
+    ``atlas`` (F,R,R,3) holds an R x R grid of texels per PACKED face; the colour of fragment (n,h,w,k) is the nearest
+    atlas texel at its first two barycentric coordinates, with the cell reflected when the point lies above the grid's
+    diagonal.  Restates ``TexturesAtlas.sample_textures`` of pytorch3d 0.4.0 (renderer/mesh/textures.py; the package is
+    not installable here: parity unpinned, anchored on the known answers of tests/test_cabi_cpu.py).  A nearest lookup:
+    gradients reach the atlas (index scatter, by autograd), not the barycentric coordinates.  One deliberate difference:
+    a barycentric coordinate of exactly 1 indexes cell R in pytorch3d (out of range); here it is clamped to R - 1."""
+
+    def __init__(self, atlas: torch.Tensor):
+        if atlas.dim() != 4 or atlas.shape[1] != atlas.shape[2] or atlas.shape[3] != 3:
+            raise ValueError("atlas must be (F,R,R,3)")
+        self.atlas = atlas
+
+    def materialize(self, pix_to_face: torch.Tensor, bary: torch.Tensor) -> torch.Tensor:
+        R = self.atlas.shape[1]
+        mask = pix_to_face >= 0
+        w01 = torch.where(mask[..., None], bary[..., :2], torch.zeros_like(bary[..., :2]))
+        w_xy = (w01 * R).to(torch.int64).clamp(max=R - 1)
+        below = (w01.sum(dim=-1) * R - w_xy.to(w01.dtype).sum(dim=-1)) <= 1.0
+        w_x, w_y = w_xy.unbind(-1)
+        w_x = torch.where(below, w_x, R - 1 - w_x)
+        w_y = torch.where(below, w_y, R - 1 - w_y)
+        return self.atlas[pix_to_face.clamp(min=0), w_y, w_x] * mask[..., None].to(self.atlas.dtype)
+
+
 class FaceColorMeshes:
     """Stand-in for ``Meshes`` with one colour per (packed) face: ``sample_textures`` returns lazy
     :class:`FaceTexels` instead of a texel tensor."""
@@ -216,10 +242,11 @@ class TriMeshes:
     ``verts_normals_packed`` follows pytorch3d's area-weighted vertex normals (cross products of the face edges
     summed onto the corners, then normalised with eps 1e-6)."""
 
-    def __init__(self, verts, faces, face_colors=None, texels=None, verts_colors=None, uv=None):
+    def __init__(self, verts, faces, face_colors=None, texels=None, verts_colors=None, uv=None, atlas=None):
         self._verts, self._faces = verts, faces.to(torch.int64)
         self.face_colors, self.texels, self.verts_colors = face_colors, texels, verts_colors
         self.uv = uv  # (maps (M,Hm,Wm,3), verts_uvs (Vt,2), faces_uvs (F,3)): a UV-mapped mesh
+        self.atlas = atlas  # (F,R,R,3): a per-face texture atlas (pytorch3d TexturesAtlas)
 
     def __len__(self):
         return self._verts.shape[0] if self._verts.dim() == 3 else 1
@@ -254,6 +281,12 @@ class TriMeshes:
         if self.texels is not None:
             return self.texels
         n = len(self)
+        if self.atlas is not None:
+            # a nearest-texel lookup: materialised with torch indexing (its autograd scatters the gradient into the atlas)
+            if fragments.bary_coords is None:
+                raise ValueError("atlas textures need fragments.bary_coords (N,H,W,K,3)")
+            atlas = self.atlas if n == 1 else self.atlas.repeat(n, 1, 1, 1)
+            return AtlasTexels(atlas).materialize(fragments.pix_to_face, fragments.bary_coords)
         if self.uv is not None:
             maps, verts_uvs, faces_uvs = self.uv
             return UVTexels(maps, verts_uvs, faces_uvs if n == 1 else faces_uvs.repeat(n, 1))
@@ -267,11 +300,11 @@ class TriMeshes:
         if len(self) != 1:
             raise ValueError("extend() needs a single mesh")
         return TriMeshes(self.verts_padded().expand(n, -1, -1).contiguous(), self._faces, self.face_colors, self.texels,
-                         self.verts_colors, self.uv)
+                         self.verts_colors, self.uv, self.atlas)
 
     def update_padded(self, verts):
         """Same topology and textures, new vertex positions (V,3) or (N,V,3) (pytorch3d ``Meshes.update_padded``)."""
-        return TriMeshes(verts, self._faces, self.face_colors, self.texels, self.verts_colors, self.uv)
+        return TriMeshes(verts, self._faces, self.face_colors, self.texels, self.verts_colors, self.uv, self.atlas)
 
     update_verts = update_padded
 

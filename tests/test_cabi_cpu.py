@@ -179,3 +179,41 @@ def test_reference_package_exports_are_present():
     tex = torch.tensor([[[[[0.1, 0.2, 0.3], [0.0, 0.0, 0.0]], [[0.0, 0.0, 0.0], [0.0, 0.0, 0.0]]]]])
     img = pb.SimpleShader(blend_params=pb.BlendParams(background_color=(1.0, 0.5, 0.0)))(frag, pb.TexelMeshes(tex))
     assert torch.allclose(img, torch.tensor([[[[0.1, 0.2, 0.3, 1.0], [1.0, 0.5, 0.0, 0.0]]]]))
+
+
+def test_atlas_texels_known_answers():
+    """AtlasTexels (pytorch3d TexturesAtlas.sample_textures restated; eval.py:216-238): R = 1 is a per-face colour; the cell
+    of a point is floor(bary * R) below the grid's diagonal and reflected above it; padded entries are zero; the gradient
+    is the scatter of the texel gradients into the cells that were hit."""
+    import torch
+    from pertrenderer_b200.structures import AtlasTexels, Fragments, TriMeshes
+    F, R = 3, 4
+    atlas = torch.arange(F * R * R * 3, dtype=torch.float32).reshape(F, R, R, 3).requires_grad_(True)
+    p2f = torch.tensor([[[[0, 1, -1], [2, 2, -1]]]])  # (1,1,2,3)
+    bary = torch.tensor([[[[[0.1, 0.1, 0.8], [0.60, 0.30, 0.10], [0.3, 0.3, 0.4]],
+                           [[0.49, 0.49, 0.02], [0.0, 0.0, 1.0], [0.5, 0.5, 0.0]]]]])
+    tex = AtlasTexels(atlas).materialize(p2f, bary)
+    assert tex.shape == (1, 1, 2, 3, 3)
+    a = atlas.detach()
+    assert torch.equal(tex[0, 0, 0, 0], a[0, 0, 0])           # (0.1, 0.1) * 4 -> cell (0, 0), below the diagonal
+    # (0.6, 0.3) * 4 = (2.4, 1.2): cell (2, 1), 3.6 - 3 = 0.6 <= 1 -> below: atlas[face, w_y = 1, w_x = 2]
+    assert torch.equal(tex[0, 0, 0, 1], a[1, 1, 2])
+    assert (tex[0, 0, 0, 2] == 0).all() and (tex[0, 0, 1, 2] == 0).all()  # padding
+    # (0.49, 0.49) * 4 = (1.96, 1.96): cell (1, 1), 3.92 - 2 = 1.92 > 1 -> above: reflected to (R-1-1, R-1-1) = (2, 2)
+    assert torch.equal(tex[0, 0, 1, 0], a[2, 2, 2])
+    assert torch.equal(tex[0, 0, 1, 1], a[2, 0, 0])
+    g = torch.ones_like(tex)
+    tex.backward(g)
+    hit = atlas.grad.sum(-1) > 0
+    assert hit.sum().item() == 4 and atlas.grad[2, 2, 2, 0].item() == 1.0 and atlas.grad.sum().item() == 12.0
+    # R = 1: the atlas is a per-face colour table
+    one = torch.rand(F, 1, 1, 3)
+    t1 = AtlasTexels(one).materialize(p2f, bary)
+    assert torch.equal(t1[0, 0, 0, 1], one[1, 0, 0]) and torch.equal(t1[0, 0, 1, 0], one[2, 0, 0])
+    # through the mesh container, extended to a batch of poses (atlas repeated per mesh like the packed faces)
+    verts, faces = torch.zeros(4, 3), torch.tensor([[0, 1, 2], [0, 2, 3], [0, 1, 3]])
+    m = TriMeshes(verts, faces, atlas=atlas.detach()).extend(2)
+    p2 = torch.tensor([[[[0, -1]]], [[[4, -1]]]])  # second image: packed face 3 + 1
+    b2 = torch.tensor([[[[[0.1, 0.1, 0.8], [0, 0, 0]]]], [[[[0.1, 0.1, 0.8], [0, 0, 0]]]]], dtype=torch.float32)
+    t2 = m.sample_textures(Fragments(p2, None, b2, None))
+    assert torch.equal(t2[0, 0, 0, 0], a[0, 0, 0]) and torch.equal(t2[1, 0, 0, 0], a[1, 0, 0])

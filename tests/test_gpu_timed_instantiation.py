@@ -244,3 +244,29 @@ def test_in_place_edit_of_an_input_before_backward_is_detected():
     dd.mul_(2.0)
     with pytest.raises(RuntimeError, match="modified by an inplace operation"):
         img.sum().backward()
+
+
+def test_atlas_textured_mesh_through_the_fused_shader():
+    """TexturesAtlas meshes (eval.py:216-238): TriMeshes(atlas=...) -> sample_textures -> the fused pair; the gradient reaches
+    the atlas cells that were hit, and the image equals the one rendered from the materialised texel tensor."""
+    import pertrenderer_b200 as pb
+    dev = "cuda"
+    N, HW, K, F, R = 2, 16, 8, 20, 4
+    fr, _ = pb.synthetic_fragments(N, HW, HW, K, kind="realistic", sigma=SIGMA, n_faces=F, seed=2, device=dev)
+    p2f = fr.pix_to_face.clamp(max=F - 1)
+    bary = pb.synthetic_bary(p2f, seed=1)
+    frag = pb.Fragments(p2f, fr.zbuf, bary, fr.dists)
+    verts, faces = pb.synthetic_mesh(F, device=dev)
+    atlas = torch.rand((F, R, R, 3), device=dev).requires_grad_(True)
+    mesh = pb.TriMeshes(verts, faces, atlas=atlas)
+    shader = pb.RandomSimpleShader(device=dev, cameras=pb.DepthCameras(n=N, device=dev),
+                                   smoothrast=pb.GaussianRast(nb_samples=16, sigma=SIGMA),
+                                   smoothagg=pb.GaussianAgg(nb_samples=16, gamma=GAMMA), blend_params=pb.BlendParams())
+    torch.manual_seed(5)
+    img = shader(frag, mesh)
+    img[..., :3].sum().backward()
+    assert atlas.grad is not None and torch.isfinite(atlas.grad).all() and atlas.grad.abs().sum() > 0
+    tex = pb.AtlasTexels(atlas.detach()).materialize(p2f, bary)
+    torch.manual_seed(5)
+    img2 = shader(frag, pb.TexelMeshes(tex))
+    assert torch.equal(img.detach(), img2.detach())
