@@ -93,9 +93,15 @@ __device__ __forceinline__ void shade_fwd_tile(const FwdArgs& a, const NoiseR& n
     uint16_t* lj = rlist;
 
     // ---- phase 0 -----------------------------------------------------------------------------------
+#ifdef PERT_EXPERIMENTS  // bulk-copy (TMA 1-D) scan: measured and rejected as a default (cabi.cu stage_bytes_for); tuning builds only
     const int nv = (a.L.stage_bytes && a.L.vec_ok && ((E & 1) == 0))
                        ? scan_valid_staged(pb.pix_to_face + g0, E, stage, bar, vlist, cap)
                        : scan_valid(pb.pix_to_face + g0, E, a.L.vec_ok, vlist, cap);
+#else
+    (void)bar;
+    (void)stage;
+    const int nv = scan_valid(pb.pix_to_face + g0, E, a.L.vec_ok, vlist, cap);
+#endif
     const int sa_loc = a.L.sa_loc;
     if (nv > cap) {
         // sparse-first mode: this tile has more valid entries than the compact arrays hold: hand it to the
@@ -441,7 +447,9 @@ __global__ void __launch_bounds__(FNT, 32) shade_fwd_kernel(const FwdArgs a, con
         nr.mix(__ldg(a.pb.seed_device));
         na.mix(__ldg(a.pb.seed_device + 1));
     }
+#ifdef PERT_EXPERIMENTS
     if (a.L.stage_bytes) fwd_init_barrier(a, smem_raw);
+#endif
     shade_fwd_tile<NoiseR, NoiseA, GT, PHASED, DEFER>(a, nr, na, blockIdx.x, smem_raw, threadIdx.x);
 }
 
@@ -459,7 +467,9 @@ __global__ void __launch_bounds__(FBT, 12) shade_fwd_fallback_kernel(const FwdAr
         nr.mix(__ldg(a.pb.seed_device));
         na.mix(__ldg(a.pb.seed_device + 1));
     }
+#ifdef PERT_EXPERIMENTS
     if (a.L.stage_bytes) fwd_init_barrier(a, smem_raw);
+#endif
 #pragma unroll 1
     for (;;) {  // persistent warps fetch half-tiles dynamically
         int i = 0;
