@@ -39,13 +39,21 @@ def cube_mesh(device):
     return v, f, side.repeat_interleave(2, dim=0)
 
 
+_HAT = {}
+
+
 def so3_exp(w):
-    """Rodrigues' formula (pytorch3d.transforms.so3_exponential_map, eval.py:341) for one rotation vector."""
+    """Rodrigues' formula (pytorch3d.transforms.so3_exponential_map, eval.py:341) for one rotation vector.  The hat
+    matrix is one product with a constant (9,3) tensor: a dozen small launches instead of sixty."""
+    hat = _HAT.get(w.device)
+    if hat is None:
+        e = torch.zeros(3, 3, 3)
+        e[0, 1, 2] = e[1, 2, 0] = e[2, 0, 1] = -1.0  # K[i][j] = -eps_ijk k_k
+        e[0, 2, 1] = e[1, 0, 2] = e[2, 1, 0] = 1.0
+        hat = _HAT[w.device] = (e.reshape(9, 3).to(w.device), torch.eye(3, device=w.device))
     th = w.norm().clamp_min(1e-8)
-    k = w / th
-    z = torch.zeros((), device=w.device)
-    K = torch.stack((torch.stack((z, -k[2], k[1])), torch.stack((k[2], z, -k[0])), torch.stack((-k[1], k[0], z))))
-    return torch.eye(3, device=w.device) + torch.sin(th) * K + (1 - torch.cos(th)) * (K @ K)
+    K = (hat[0] @ (w / th)).reshape(3, 3)
+    return hat[1] + torch.sin(th) * K + (1 - torch.cos(th)) * (K @ K)
 
 
 def so3_log(R):
@@ -92,7 +100,7 @@ def optimize_pose(mesh, verts, renderer, target_rgb, w_init, niter, lr, adapt, a
     smoothing is divided by (1.1, 1.5) and the sample count doubled every 50 iterations while the running gamma
     gradient is positive."""
     w = w_init.clone().requires_grad_(True)
-    opt = torch.optim.Adam([w], lr=lr)
+    opt = torch.optim.Adam([w], lr=lr, fused=True)  # one kernel per step
     best, best_w = float("inf"), w.detach().clone()
     v_gamma = 0.0
     for i in range(niter):

@@ -44,10 +44,34 @@ def _rows(v, n_max, device, width=3):
     return t
 
 
+_LIGHTING_CACHE = {}
+
+
 def pack_lighting(lights, materials, cameras, N, device):
     """(rows, PERT_PHONG_STRIDE) float32 table of include/pertshade.h: one row per batch element, or one
-    row when nothing varies over the batch."""
+    row when nothing varies over the batch.  When no source tensor requires grad the table of the same objects is reused
+    (keyed by the tensors' identity and version counters): a pose-optimisation loop re-packs nothing per iteration."""
     directional = not hasattr(lights, "location")
+    srcs = [lights.direction if directional else lights.location, materials.ambient_color, lights.ambient_color,
+            materials.diffuse_color, lights.diffuse_color, materials.specular_color, lights.specular_color,
+            materials.shininess]
+    key = None
+    if all(torch.is_tensor(t) and not t.requires_grad for t in srcs) and hasattr(cameras, "R") and hasattr(cameras, "T") and \
+            torch.is_tensor(cameras.R) and torch.is_tensor(cameras.T) and not cameras.R.requires_grad and not cameras.T.requires_grad:
+        held = srcs + [cameras.R, cameras.T]
+        key = tuple((id(t), t._version) for t in held) + (N, str(device), directional)
+        hit = _LIGHTING_CACHE.get(key)
+        if hit is not None:
+            return hit[0]
+    out = _pack_lighting(lights, materials, cameras, N, device, directional)
+    if key is not None:
+        if len(_LIGHTING_CACHE) > 16:
+            _LIGHTING_CACHE.clear()
+        _LIGHTING_CACHE[key] = (out, held)  # the sources are kept alive: their ids cannot be reused while the entry exists
+    return out
+
+
+def _pack_lighting(lights, materials, cameras, N, device, directional):
     loc = _rows(lights.direction if directional else lights.location, N, device)
     amb = _rows(materials.ambient_color, N, device) * _rows(lights.ambient_color, N, device)
     dif = _rows(materials.diffuse_color, N, device) * _rows(lights.diffuse_color, N, device)

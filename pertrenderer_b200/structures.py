@@ -271,10 +271,10 @@ class TriMeshes:
     def verts_normals_packed(self):
         v, f = self.verts_packed(), self.faces_packed()
         vf = v[f]
-        n = torch.zeros_like(v)
-        n = n.index_add(0, f[:, 1], torch.cross(vf[:, 2] - vf[:, 1], vf[:, 0] - vf[:, 1], dim=1))
-        n = n.index_add(0, f[:, 2], torch.cross(vf[:, 0] - vf[:, 2], vf[:, 1] - vf[:, 2], dim=1))
-        n = n.index_add(0, f[:, 0], torch.cross(vf[:, 1] - vf[:, 0], vf[:, 2] - vf[:, 0], dim=1))
+        # pytorch3d adds, at every corner of a face, the cross product of the two edges leaving that corner: the three
+        # products are the same vector (twice the area normal), so one cross and one scatter do it
+        fn = torch.cross(vf[:, 1] - vf[:, 0], vf[:, 2] - vf[:, 0], dim=1)
+        n = torch.zeros_like(v).index_add(0, f.reshape(-1), fn.repeat_interleave(3, dim=0))
         return torch.nn.functional.normalize(n, eps=1e-6, dim=1)
 
     def sample_textures(self, fragments):
