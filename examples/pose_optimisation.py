@@ -141,7 +141,12 @@ def main():
     ap.add_argument("--nb-samples", type=int, default=16)
     ap.add_argument("--adapt", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--kernel-flags", type=int, default=0, help="PERT_F_* flags for every perturbed op (4 = per-sample noise, 8192 = Philox-7)")
     args = ap.parse_args()
+    if args.kernel_flags:
+        from pertrenderer_b200 import ops
+        ctx = ops.kernel_flags(args.kernel_flags)
+        ctx.__enter__()
     if not torch.cuda.is_available():
         raise SystemExit("needs a CUDA device: the renderer has no CPU fallback")
     dev = "cuda:0"
@@ -157,8 +162,11 @@ def main():
     for noise in args.noise:  # warm-up: lazy module loading (forward AND backward) is not part of the timed iterations
         w = torch.zeros(3, device=dev).add_(0.1).requires_grad_(True)
         r = make_renderer(noise, cameras, lights, args.sigma, args.gamma, args.nb_samples, args.imsize, dev)
+        opt = torch.optim.Adam([w], lr=1e-3, fused=True)
         for _ in range(3):
+            opt.zero_grad()
             r(mesh.update_padded(verts @ so3_exp(w)))[..., :3].mean().backward()
+            opt.step()
     for noise in args.noise:
         errs, inits, t_iter = [], [], []
         for _ in range(args.trials):
