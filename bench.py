@@ -452,9 +452,9 @@ def device_timed(cfg, kind, dev, steps, warmup, world, rank, sampler=None, flags
                           "valid_entries": V, "valid_fraction": V / (P * K)}}
     return {"value": units * world * steps / (total_ms * 1e-3), "ms_per_step": total_ms / steps, "roofline": roof,
             "repeat_ms_per_step": [t / steps for t in totals], "peak_memory_bytes": peak_mem,
-            # kernels of libpertshade.so per step: forward main + fallback pass, backward main + fallback pass,
-            # scalar-gradient finalize
-            "launches": 5 * steps}
+            # kernels of libpertshade.so per step: forward main + fallback pass (two launches: coverage samples,
+            # aggregation + blend), backward main + fallback pass, scalar-gradient finalize
+            "launches": 6 * steps}
 
 
 def leg(res, **extra):
@@ -504,8 +504,8 @@ def graph_leg(dev, kind="rasterised", steps=50):
     eager = device_timed(cfg, kind, dev, steps, 5, 1, 0, fragments=(fr, col))
     units = N * HW * HW * K * S
     return {"config": cfg["name"], "fragments": kind, "ms_per_step_graph": ms, "ms_per_step_eager": eager["ms_per_step"],
-            "value": units / (ms * 1e-3), "unit": UNIT, "launches_per_step": 8,
-            "note": "one graph replay = seed advance + memsets + forward (main + fallback pass) + backward (main + fallback "
+            "value": units / (ms * 1e-3), "unit": UNIT, "launches_per_step": 9,
+            "note": "one graph replay = seed advance + memsets + forward (main + two-launch fallback pass) + backward (main + fallback "
                     "pass) + scalar finalize"}
 
 
@@ -667,7 +667,7 @@ def phong_timed(args, kind, dev, steps, warmup, rank):
             "shade_fwd_ms": seg[1], "shade_bwd_ms": seg[2],
             "phong_bwd": {"ms": seg[3], "min_bytes": pb_b, "gbs": pb_b / seg[3] / 1e6, "frac": pb_b / seg[3] / 1e6 / peak,
                           "api_faithful_bytes": 44 * PF + 156 * F},
-            "peak": peak, "peak_source": peak_src, "launches_per_step": 7}
+            "peak": peak, "peak_source": peak_src, "launches_per_step": 8}
 
 
 def renderer_timed(args, dev, steps, warmup, rank):

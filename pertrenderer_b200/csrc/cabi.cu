@@ -133,6 +133,7 @@ static Launch make_launch(const pert_problem* pb, int tp) {
     L.lpp_shift = lg2(L.lpp);
     L.cap = L.tp * pb->K;
     L.warp_smem = 0;
+    L.warp_smem_rast = 0;
     // 128-bit accesses on the tile rows need every tile to start on a 16-byte boundary in the fp32 tensors
     L.vec_ok = ((L.tp * pb->K) & 3) == 0;
     L.invK = 1.0f / (float)pb->K;
@@ -153,6 +154,10 @@ static Launch make_launch(const pert_problem* pb, int tp) {
     L.defer_min = 48;
 #ifdef PERT_EXPERIMENTS
     if (const char* e = getenv("PERT_DEFER_MIN")) L.defer_min = atoi(e);
+#endif
+    L.fb_split = 1;
+#ifdef PERT_EXPERIMENTS
+    if (const char* e = getenv("PERT_FB_SPLIT")) L.fb_split = atoi(e);
 #endif
     return L;
 }
@@ -283,7 +288,7 @@ extern "C" int pert_shade_fwd(const pert_problem* pb_in, float* image, uint16_t*
     fb.L = make_launch(&a.pb, a.L.tp / 2);
     fb.L.vec_ok = fb.L.vec_ok && aligned16(a.pb.pix_to_face);
     fb.L.stage_bytes = stage_bytes_for(fb.L.tp, a.pb.K, true);
-    fwd_smem_layout(fb.L.tp, fb.L.cap, fb.L.stage_bytes, fb.L.sm);
+    fb.L.warp_smem_rast = fwd_smem_layout(fb.L.tp, fb.L.cap, fb.L.stage_bytes, fb.L.sm);
     fb.L.warp_smem = fb.L.sm.bytes;
     cudaError_t e = cudaMemsetAsync(worklist, 0, 16, st);
     if (e != cudaSuccess) return cuda_fail((int)e);

@@ -182,6 +182,7 @@ struct Launch {
     int lpp, lpp_shift;      // backward: lanes per (pixel, logit) pair = min(8, pow2_floor(local quads))
     int cap;        // capacity (valid entries) of the tile's compact arrays: tp*K, or tp*K/2 in sparse-first mode
     int warp_smem;  // bytes of shared memory per warp
+    int warp_smem_rast;  // ... of the coverage-sample launch of a split fallback pass (forward)
     SmemLayout sm;  // where each array lives
     int vec_ok;     // tile rows are 16-byte aligned in every (P,K) tensor
     float invK;     // 1/K for the entry -> pixel division
@@ -192,6 +193,7 @@ struct Launch {
     float t_compound; // coverage entries with |x|/sigma >= this are drawn by the compound sampler (tile.cuh)
     int stage_bytes;   // forward: bytes of the pix_to_face staging buffer of the bulk-copy scan (0: register scan)
     int cmp_min;       // fewer compound entries than this in a tile are drawn by the per-sample loop instead
+    int fb_split;      // fallback pass of the forward as two launches (coverage samples | aggregation + blend)
     int defer_min;     // main pass of the sparse-first mode: tiles with at least this many go to the fallback pass
     float t_bucket[2]; // ... and bucketed by expected flips: [t_compound, t_bucket[0]) many, [.., t_bucket[1]) some, rest rare
 };

@@ -15,20 +15,22 @@
 
 namespace pert {
 
-void fwd_smem_layout(int tp, int cap, int stage_bytes, SmemLayout& L) {
+int fwd_smem_layout(int tp, int cap, int stage_bytes, SmemLayout& L) {
     Carver cv(L);
     cv.take(cap, 2);       // vlist
     cv.take(cap + tp, 4);  // xs | lz
-    cv.take(cap, 4);       // zs
     cv.take(cap, 2);       // cnt
     cv.take(cap + tp, 4);  // rs | hl
     cv.take(cap + tp, 2);  // rlist | lj
-    cv.take(tp + 1, 4);    // vstart
-    cv.take(tp, 4);        // pinfo
-    cv.take(tp, 2);        // plist
     cv.take(64, 2);        // ring (compound sampler)
     cv.take(stage_bytes ? 16 : 0, 1);  // mbarrier + phase parity of the bulk-copy scan
     cv.take(stage_bytes, 1);           // stage: the tile's pix_to_face rows
+    const int rast_bytes = L.bytes;
+    cv.take(cap, 4);       // zs: from here on, arrays the coverage-sample launch of a split pass never touches
+    cv.take(tp + 1, 4);    // vstart
+    cv.take(tp, 4);        // pinfo
+    cv.take(tp, 2);        // plist
+    return rast_bytes;
 }
 
 // GT = lanes per pixel as a compile-time constant (1, 2, 4, 8), or 0 to read it from the launch record.
@@ -37,7 +39,7 @@ void fwd_smem_layout(int tp, int cap, int stage_bytes, SmemLayout& L) {
 // kernel is instruction-fetch sensitive, every warp walks the whole body once per tile).
 // this warp's mbarrier (one arrival: the elected lane's expect_tx) and its phase parity; layout: fwd_smem_layout
 __device__ __forceinline__ void fwd_init_barrier(const FwdArgs& a, unsigned char* smem_raw) {
-    uint64_t* const bar = reinterpret_cast<uint64_t*>(smem_raw + a.L.sm.off[10]);
+    uint64_t* const bar = reinterpret_cast<uint64_t*>(smem_raw + a.L.sm.off[6]);
     if ((threadIdx.x & 31) == 0) {
         mbar_init(bar, 1);
         *reinterpret_cast<unsigned*>(bar + 1) = 0u;
@@ -49,7 +51,11 @@ __device__ __forceinline__ void fwd_init_barrier(const FwdArgs& a, unsigned char
 // handed to the fallback pass like a tile that overflows the compact arrays, so that this instantiation carries no
 // compound-sampler code at all (the kernel is instruction-fetch bound on sparse fragments: every instruction of a
 // path it rarely takes costs the common path)
-template <class NoiseR, class NoiseA, int GT, bool PHASED, bool DEFER = false>
+// CPH = the phases this instantiation carries when PHASED is false (PERT_PH_* bits; all of them by default).  The
+// fallback pass runs as two launches, coverage samples (CPH = RAST: counts / rsum go to global memory, where backward
+// wants them anyway) and then aggregation + blend (CPH = AGG | BLEND: reads the counts back), because one kernel with
+// both exceeds the 32 KB instruction cache of an SM and every warp walks the whole body once per tile.
+template <class NoiseR, class NoiseA, int GT, bool PHASED, bool DEFER = false, int CPH = 0x70>
 __device__ __forceinline__ void shade_fwd_tile(const FwdArgs& a, const NoiseR& noise_r, const NoiseA& noise_a,
                                                const int64_t tile, unsigned char* smem_raw, const int lane) {
     const pert_problem& pb = a.pb;
@@ -61,8 +67,9 @@ __device__ __forceinline__ void shade_fwd_tile(const FwdArgs& a, const NoiseR& n
     const int E = npx * K;
     const int64_t g0 = pix0 * K;
     const uint32_t flags = pb.flags;
-    const bool do_rast = !PHASED || (flags & PERT_PH_RAST), do_agg = !PHASED || (flags & PERT_PH_AGG),
-               do_blend = !PHASED || (flags & PERT_PH_BLEND);
+    const bool do_rast = PHASED ? (flags & PERT_PH_RAST) != 0 : (CPH & PERT_PH_RAST) != 0,
+               do_agg = PHASED ? (flags & PERT_PH_AGG) != 0 : (CPH & PERT_PH_AGG) != 0,
+               do_blend = PHASED ? (flags & PERT_PH_BLEND) != 0 : (CPH & PERT_PH_BLEND) != 0;
     int32_t* const ghist = PHASED ? a.hist : nullptr;
     const float* const zbuf_t = pb.zbuf + g0;
     const float* const dists_t = pb.dists + g0;
@@ -77,16 +84,16 @@ __device__ __forceinline__ void shade_fwd_tile(const FwdArgs& a, const NoiseR& n
     Taker cv(smem_raw, a.L.sm);  // layout: fwd_smem_layout (every array is compact: `cap` valid entries)
     uint16_t* vlist = cv.take<uint16_t>();
     float* xs = cv.take<float>();          // x = -dists (compact); later lz: logits of the live list
-    float* zs = cv.take<float>();          // zbuf -> zi -> zeta (compact)
     uint16_t* cnt = cv.take<uint16_t>();
     float* rs = cv.take<float>();          // sum_s (h-h0) U (compact); later hl: histogram of the live list
     uint16_t* rlist = cv.take<uint16_t>();  // entries that need coverage samples; later lj: live logit ids
-    int* vstart = cv.take<int>();
-    int* pinfo = cv.take<int>();  // nlive | a0l << 16 of every pixel
-    uint16_t* plist = cv.take<uint16_t>();
     uint16_t* ring = cv.take<uint16_t>();
     uint64_t* bar = cv.take<uint64_t>();
     long long* stage = cv.take<long long>();
+    float* zs = cv.take<float>();          // zbuf -> zi -> zeta (compact)
+    int* vstart = cv.take<int>();
+    int* pinfo = cv.take<int>();  // nlive | a0l << 16 of every pixel
+    uint16_t* plist = cv.take<uint16_t>();
     const int cap = a.L.cap;
     float* lz = xs;
     int* hl = reinterpret_cast<int*>(rs);
@@ -126,7 +133,7 @@ __device__ __forceinline__ void shade_fwd_tile(const FwdArgs& a, const NoiseR& n
         return;
     }
     __syncwarp();
-    pixel_ranges(vlist, nv, K, tp, vstart);
+    if (do_agg || do_blend) pixel_ranges(vlist, nv, K, tp, vstart);
 
     // ---- phase 1: stage valid entries, coverage samples ---------------------------------------------
     const int sr_loc = pb.s_rast_end - pb.s_rast_begin;
@@ -142,8 +149,10 @@ __device__ __forceinline__ void shade_fwd_tile(const FwdArgs& a, const NoiseR& n
         bool need = false, cmp = false;
         if (n < nv) {
             const int e = vlist[n];
-            zs[n] = __ldg(zbuf_t + e);
-            if (!pb.face_colors) prefetch_l1(pb.colors + (g0 + e) * 3);  // blended at the very end of the tile
+            if (do_agg || do_blend) {
+                zs[n] = __ldg(zbuf_t + e);
+                if (!pb.face_colors) prefetch_l1(pb.colors + (g0 + e) * 3);  // blended at the very end of the tile
+            }
             if (do_rast) {
                 const float x = -__ldg(dists_t + e);
                 xs[n] = x;
@@ -456,10 +465,15 @@ __global__ void __launch_bounds__(FNT, 32) shade_fwd_kernel(const FwdArgs a, con
 // Fallback pass of the sparse-first mode: the tiles whose valid entries did not fit the compact arrays,
 // as half-size tiles (GT lanes per pixel = twice the main pass's) with full capacity.  Few persistent CTAs
 // walk the work list; it is empty for sparse (real) fragments.
-template <class NoiseR, class NoiseA, int GT>
-__global__ void __launch_bounds__(FBT, 12) shade_fwd_fallback_kernel(const FwdArgs a, const NoiseR noise_r, const NoiseA noise_a) {
+// CTAs per SM of the fallback launches: 80 registers.  (14 and 16 CTAs per SM -- 72 / 64 registers, the shorter layout of
+// the coverage-sample launch makes room for them -- were measured at -1 % / 0 %: the passes are bound by the FMA and ALU
+// pipes, not by latency; profiles/r2_notes.md)
+constexpr int FB_MIN_CTAS = 12;
+template <class NoiseR, class NoiseA, int GT, int CPH>
+__global__ void __launch_bounds__(FBT, FB_MIN_CTAS) shade_fwd_fallback_kernel(const FwdArgs a, const NoiseR noise_r, const NoiseA noise_a) {
     extern __shared__ __align__(16) unsigned char smem_all[];
-    unsigned char* smem_raw = smem_all + (threadIdx.x >> 5) * a.L.warp_smem;  // FBT/32 independent warps per CTA
+    // FBT/32 independent warps per CTA; the coverage-sample launch of a split pass carries the front of the layout only
+    unsigned char* smem_raw = smem_all + (threadIdx.x >> 5) * (CPH == (int)PERT_PH_RAST ? a.L.warp_smem_rast : a.L.warp_smem);
     const int n = 2 * a.worklist[0];
     NoiseR nr = noise_r;
     NoiseA na = noise_a;
@@ -473,11 +487,13 @@ __global__ void __launch_bounds__(FBT, 12) shade_fwd_fallback_kernel(const FwdAr
 #pragma unroll 1
     for (;;) {  // persistent warps fetch half-tiles dynamically
         int i = 0;
-        if ((threadIdx.x & 31) == 0) i = n > 0 ? atomicAdd(a.worklist + 1, 1) : 0;
+        // the second launch of a split pass walks the list with its own counter
+        if ((threadIdx.x & 31) == 0) i = n > 0 ? atomicAdd(a.worklist + ((CPH & PERT_PH_RAST) ? 1 : 2), 1) : 0;
         i = __shfl_sync(FULL, i, 0);
         if (i >= n) break;
         const int64_t tile = (int64_t)a.worklist[4 + (i >> 1)] * 2 + (i & 1);
-        if (tile < a.L.ntiles) shade_fwd_tile<NoiseR, NoiseA, GT, false>(a, nr, na, tile, smem_raw, threadIdx.x & 31);
+        if (tile < a.L.ntiles)
+            shade_fwd_tile<NoiseR, NoiseA, GT, false, false, CPH>(a, nr, na, tile, smem_raw, threadIdx.x & 31);
         __syncwarp();
     }
 }
@@ -494,16 +510,23 @@ static int launch_fwd_t(const FwdArgs& a, const NR& nr, const NA& na, cudaStream
     return (int)cudaGetLastError();
 }
 
-template <class PN, int GT>
-static int launch_fwd_fallback(const FwdArgs& a, const PN& nr, const PN& na, cudaStream_t st) {
-    const size_t smem = (size_t)a.L.warp_smem * (FBT / 32);
+template <class PN, int GT, int CPH>
+static int launch_fwd_fallback_ph(const FwdArgs& a, const PN& nr, const PN& na, cudaStream_t st) {
+    const size_t smem = (size_t)(CPH == (int)PERT_PH_RAST ? a.L.warp_smem_rast : a.L.warp_smem) * (FBT / 32);
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(shade_fwd_fallback_kernel<PN, PN, GT>,
+        cudaError_t e = cudaFuncSetAttribute(shade_fwd_fallback_kernel<PN, PN, GT, CPH>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    shade_fwd_fallback_kernel<PN, PN, GT><<<sm_count() * 12, FBT, smem, st>>>(a, nr, na);
+    shade_fwd_fallback_kernel<PN, PN, GT, CPH><<<sm_count() * FB_MIN_CTAS, FBT, smem, st>>>(a, nr, na);
     return (int)cudaGetLastError();
+}
+
+template <class PN, int GT>
+static int launch_fwd_fallback(const FwdArgs& a, const PN& nr, const PN& na, cudaStream_t st) {
+    if (!a.L.fb_split) return launch_fwd_fallback_ph<PN, GT, 0x70>(a, nr, na, st);
+    const int rc = launch_fwd_fallback_ph<PN, GT, PERT_PH_RAST>(a, nr, na, st);
+    return rc ? rc : launch_fwd_fallback_ph<PN, GT, PERT_PH_AGG | PERT_PH_BLEND>(a, nr, na, st);
 }
 
 // production path (in-kernel noise in both stages, all phases in one launch); PN = the Philox variant

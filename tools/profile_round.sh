@@ -12,7 +12,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"shade_|final
 cp profiles/traffic.json gpurun_out/traffic_${tag}.json
 for kind in rasterised realistic dense; do
   python tools/prof_driver.py $kind 3 > gpurun_out/plain_${kind}_${tag}.log 2>&1 &&
-  ncu --set full --clock-control none --import-source on -k regex:shade_ -s 4 -c 4 -f -o /tmp/prof_${tag}_${kind} \
+  ncu --set full --clock-control none --import-source on -k regex:shade_ -s 5 -c 5 -f -o /tmp/prof_${tag}_${kind} \
       python tools/prof_driver.py $kind 3 > gpurun_out/ncu_${kind}_${tag}.log 2>&1
   python profiles/ncu_summary.py /tmp/prof_${tag}_${kind}.ncu-rep ${kind}:8x256x50x64 > gpurun_out/${tag}_ncu_full_${kind}.txt 2>&1
   python profiles/ncu_lines.py /tmp/prof_${tag}_${kind}.ncu-rep shade_ 45 > gpurun_out/${tag}_hot_lines_${kind}.txt 2>&1
