@@ -155,6 +155,8 @@ static Launch make_launch(const pert_problem* pb, int tp) {
 #ifdef PERT_EXPERIMENTS
     if (const char* e = getenv("PERT_DEFER_MIN")) L.defer_min = atoi(e);
 #endif
+    L.nab = 8;
+    L.lean = 0;
     L.fb_split = 1;
 #ifdef PERT_EXPERIMENTS
     if (const char* e = getenv("PERT_FB_SPLIT")) L.fb_split = atoi(e);
@@ -196,6 +198,10 @@ static int sparse_cap(int K, int tp) {
     if (cap > tp * K) cap = (tp * K + 1) & ~1;
     return cap;
 }
+
+// Active pixels staged at a time by the fallback pass of backward = the pixels of its tiles: one batch (4 rows of c_s
+// would buy a thirteenth CTA per SM and lose more to the second batch: profiles/r2_notes.md)
+constexpr int kNabFallback = 8;
 
 static bool sparse_first_ok(const pert_problem* pb, const void* worklist, bool all_phases) {
     if (!worklist || !all_phases || pb->noise_rast || pb->noise_agg) return false;
@@ -323,7 +329,7 @@ extern "C" int pert_shade_bwd(const pert_problem* pb_in, const float* grad_image
         const int tp2 = sparse_tp(a.pb.K, a.pb.N * a.pb.H * a.pb.W) / 2;
         const Launch t = make_launch(&a.pb, tp2);
         SmemLayout sl;
-        bwd_smem_layout(tp2, a.pb.K, t.cap, t.sc, t.nchunks, t.win_bytes, false, sl);
+        bwd_smem_layout(tp2, a.pb.K, t.cap, t.sc, t.nchunks, t.win_bytes, false, kNabFallback, 3, sl);
         if ((size_t)sl.bytes * (FBT / 32) > 200 * 1024) sparse = false;
     }
     const bool ptr_ok = aligned16(a.pb.pix_to_face) && aligned16(grad_dists) && aligned16(grad_zbuf) &&
@@ -332,7 +338,10 @@ extern "C" int pert_shade_bwd(const pert_problem* pb_in, const float* grad_image
     a.L.vec_ok = a.L.vec_ok && ptr_ok;
     if (sparse) a.L.cap = sparse_cap(a.pb.K, a.L.tp);
     if (a.L.win_bytes == 2 && ((uintptr_t)winners & 1)) return PERT_E_ALIGN;
-    bwd_smem_layout(a.L.tp, a.pb.K, a.L.cap, a.L.sc, a.L.nchunks, a.L.win_bytes, sparse, a.L.sm);
+#ifdef PERT_EXPERIMENTS
+    if (const char* e = getenv("PERT_LEAN_MAIN")) a.L.lean = atoi(e);
+#endif
+    bwd_smem_layout(a.L.tp, a.pb.K, a.L.cap, a.L.sc, a.L.nchunks, a.L.win_bytes, sparse, a.L.nab, a.L.lean, a.L.sm);
     a.L.warp_smem = a.L.sm.bytes;
     if ((size_t)a.L.warp_smem > 200 * 1024) return PERT_E_UNSUPPORTED;
     if (a.L.ntiles > 0x7fffffff) return PERT_E_UNSUPPORTED;
@@ -357,7 +366,15 @@ extern "C" int pert_shade_bwd(const pert_problem* pb_in, const float* grad_image
     fb.blob = nullptr;
     fb.L = make_launch(&a.pb, a.L.tp / 2);
     fb.L.vec_ok = fb.L.vec_ok && ptr_ok;
-    bwd_smem_layout(fb.L.tp, a.pb.K, fb.L.cap, fb.L.sc, fb.L.nchunks, fb.L.win_bytes, false, fb.L.sm);
+    fb.L.nab = kNabFallback;
+#ifdef PERT_EXPERIMENTS
+    if (const char* e = getenv("PERT_NAB_FB")) fb.L.nab = atoi(e);
+#endif
+    fb.L.lean = 3;
+#ifdef PERT_EXPERIMENTS
+    if (const char* e = getenv("PERT_LEAN_FB")) fb.L.lean = atoi(e);
+#endif
+    bwd_smem_layout(fb.L.tp, a.pb.K, fb.L.cap, fb.L.sc, fb.L.nchunks, fb.L.win_bytes, false, fb.L.nab, fb.L.lean, fb.L.sm);
     fb.L.warp_smem = fb.L.sm.bytes;
     cudaError_t e = cudaMemsetAsync(worklist, 0, 16, st);
     if (e != cudaSuccess) return cuda_fail((int)e);

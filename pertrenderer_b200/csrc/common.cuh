@@ -15,7 +15,6 @@ constexpr int NW = NT / 32;
 // CTA scheduler balances the load per tile.
 constexpr int FNT = 32;
 constexpr int FBT = 64;  // threads per CTA of the fallback pass: two independent warps
-constexpr int NAB = 8;  // backward: active pixels whose per-sample c_s are staged at a time
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -125,6 +124,14 @@ static inline int sm_count() {
     return cached[dev];
 }
 
+// Grid of a persistent kernel: as many CTAs as the device holds at once (registers and shared memory decide)
+template <class Kern>
+static inline unsigned resident_grid(Kern kern, int threads, size_t smem) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, threads, smem) != cudaSuccess || nb < 1) nb = 1;
+    return (unsigned)(sm_count() * nb);
+}
+
 // Shared-memory layout of a kernel: computed ONCE on the host (byte offsets in the launch record), so the
 // kernels spend one add per array instead of re-deriving the layout (the fused kernels are instruction-fetch
 // sensitive: every instruction of glue counts).
@@ -193,6 +200,8 @@ struct Launch {
     float t_compound; // coverage entries with |x|/sigma >= this are drawn by the compound sampler (tile.cuh)
     int stage_bytes;   // forward: bytes of the pix_to_face staging buffer of the bulk-copy scan (0: register scan)
     int cmp_min;       // fewer compound entries than this in a tile are drawn by the per-sample loop instead
+    int nab;           // backward: active pixels whose per-sample c_s are staged at a time (<= 8; shared memory = occupancy)
+    int lean;          // backward: lean shared-memory layout (shade_bwd.cu bwd_smem_layout)
     int fb_split;      // fallback pass of the forward as two launches (coverage samples | aggregation + blend)
     int defer_min;     // main pass of the sparse-first mode: tiles with at least this many go to the fallback pass
     float t_bucket[2]; // ... and bucketed by expected flips: [t_compound, t_bucket[0]) many, [.., t_bucket[1]) some, rest rare

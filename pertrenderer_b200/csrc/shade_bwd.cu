@@ -15,32 +15,33 @@
 //   3  score sums acc_j = sum_s c_s V_sj, t2_j = sum_s c_s V_sj^2 over (pixel, logit) pairs, noise
 //      regenerated from the Philox counters
 //   4  chain rule per valid entry -> scattered stores over the zero-filled rows; scalar partials
+#include <climits>
+#include <cstdlib>
 #include "kernels.h"
 #include "tile.cuh"
 
 namespace pert {
 
-void bwd_smem_layout(int tp, int K, int cap, int sc, int nchunks, int win_bytes, bool compact, SmemLayout& L) {
+// lean (the passes' time follows the warps an SM holds, i.e. the bytes of this layout): bit 0 = the pair list takes over
+// the counts array (phase 4 reads the counts from global memory instead), bit 1 = the saved winners are not staged
+void bwd_smem_layout(int tp, int K, int cap, int sc, int nchunks, int win_bytes, bool compact, int nab, int lean, SmemLayout& L) {
     const size_t ns = compact ? (size_t)cap + 2 * tp : (size_t)tp * (K + 1);
     Carver cv(L);
     cv.take(cap, 2);  // vlist
-    cv.take(cap, 4);  // zs
-    cv.take(cap, 2);  // cnt
+    cv.take(ns > (size_t)cap ? ns : (size_t)cap, 4);  // zs, then accs (the logits are dead once the live ones are marked)
+    cv.take((lean & 1) && ns > (size_t)cap ? ns : (size_t)cap, 2);  // cnt (lean & 1: then the pair list)
     cv.take(ns, 4);   // hj
     cv.take(ns, 4);   // gsel (| t2s when there is one sample chunk)
-    cv.take(ns, 4);   // accs
     cv.take(nchunks > 1 ? ns : 0, 4);  // t2s
-    cv.take(ns, 2);   // pair_j
-    cv.take(ns, 2);   // pair_s
-    cv.take(ns, 1);   // pair_p
-    cv.take((size_t)(tp < NAB ? tp : NAB) * sc, 4);  // cs
+    cv.take((lean & 1) ? 0 : ns, 2);   // pairs
+    cv.take((size_t)(tp < nab ? tp : nab) * sc, 4);  // cs
     cv.take(tp + 1, 4);           // vstart
     cv.take(tp, 4);               // pa0
     cv.take(tp, 4);               // pg0
     cv.take(tp, 4);               // psb
     cv.take(tp, 4);               // pnv
     cv.take(tp, 1);               // apx
-    cv.take(nchunks == 1 ? (size_t)tp * sc * win_bytes : 0, 1);  // wst
+    cv.take(nchunks == 1 && !(lean & 2) ? (size_t)tp * sc * win_bytes : 0, 1);  // wst
 }
 
 // GT = lanes per pixel as a compile-time constant (1, 2, 4, 8), or 0 to read it from the launch record.
@@ -87,15 +88,19 @@ __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& n
     uint16_t* cnt = cv.take<uint16_t>();
     // per-logit arrays.  Slot of logit j of pixel p: dense p*K1 + j, or (COMPACT) vstart[p] + 2p + idx with
     // idx = position among the pixel's valid entries, nvp = background, nvp + 1 = all masked logits together
-    int* hj = cv.take<int>();        // winner histogram (active pixels)
+    // winner histogram (active pixels); INT_MIN marks the logits that can never win a sample (their zeta is not
+    // needed again after phase 2, which lets the score sums take over the zeta array: shared memory = occupancy)
+    int* hj = cv.take<int>();
     float* gsel = cv.take<float>();  // g_j = <G_rgb, colour_j> of the logits that can win
-    float* accs = cv.take<float>();  // sum_s c_s V_sj
+    float* accs = zs;                // sum_s c_s V_sj (from the end of phase 2 on)
     // sum_s c_s V_sj^2: g_j is dead once the c_s of the (only) chunk are staged, so it reuses that array
     float* t2s_own = cv.take<float>();
     float* t2s = a.L.nchunks > 1 ? t2s_own : gsel;
-    uint16_t* pair_j = cv.take<uint16_t>();
-    uint16_t* pair_s = cv.take<uint16_t>();
-    uint8_t* pair_p = cv.take<uint8_t>();
+    // (pixel, logit) pairs that need per-sample noise: logit j (or, COMPACT, its position among the pixel's valid
+    // entries) in bits 0-9 (K <= 1023), the pixel's rank among the staged active pixels in bits 10-12 (nab <= 8)
+    uint16_t* pairs_own = cv.take<uint16_t>();
+    const bool lean = a.L.lean & 1;
+    uint16_t* pairs = lean ? cnt : pairs_own;
     float* cs = cv.take<float>();  // c_s of the current sample chunk, per active pixel
     int* vstart = cv.take<int>();
     int* pa0 = cv.take<int>();
@@ -105,7 +110,7 @@ __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& n
     uint8_t* apx = cv.take<uint8_t>();
     // single-chunk jobs: the tile's saved winners (tp rows of sa_loc entries, contiguous) are copied to
     // shared memory asynchronously at the very start, off the critical path
-    const bool early_w = a.L.nchunks == 1 && ((sa_loc * wb) & 15) == 0 && do_sample && (((uintptr_t)a.winners) & 15) == 0;
+    const bool early_w = !(a.L.lean & 2) && a.L.nchunks == 1 && ((sa_loc * wb) & 15) == 0 && do_sample && (((uintptr_t)a.winners) & 15) == 0;
     unsigned char* wst = cv.take<unsigned char>();
     if (early_w) {
         const unsigned char* src = reinterpret_cast<const unsigned char*>(a.winners) + pix0 * sa_loc * wb;
@@ -254,17 +259,18 @@ __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& n
                 psb[p] = sb;
                 pnv[p] = nvp | (prefix ? 0 : 0x10000);
             }
+            const int nsl = COMPACT ? nvp + 2 : K1;
             if (act) {
-                const int ns = COMPACT ? nvp + 2 : K1;
 #pragma unroll 1
-                for (int j = lig; j < ns; j += G) {
-                    hj[sb + j] = 0;
-                    accs[sb + j] = 0.f;
-                }
+                for (int j = lig; j < nsl; j += G) hj[sb + j] = 0;
+            }
+            __syncwarp();
+            if (act) {
 #pragma unroll 1
                 for (int idx = lig; idx <= nvp; idx += G) {
                     const int j = idx < nvp ? (int)vlist[vs + idx] - p * K : K;
                     const float z = idx < nvp ? zs[vs + idx] : pi.zbg;
+                    const int sl = COMPACT ? sb + idx : sb + j;
                     if (z > -CUDART_INF_F && z >= floor_v) {
                         float gj;
                         if (j < K) {
@@ -273,10 +279,17 @@ __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& n
                         } else {
                             gj = Gi.x * pb.background[0] + Gi.y * pb.background[1] + Gi.z * pb.background[2];
                         }
-                        gsel[COMPACT ? sb + idx : sb + j] = gj;
+                        gsel[sl] = gj;
                         if (j == a0) pg0[p] = gj;
+                    } else {
+                        hj[sl] = INT_MIN;  // can never win
                     }
                 }
+            }
+            __syncwarp();  // every lane has read its logits: the array becomes the score sums
+            if (act) {
+#pragma unroll 1
+                for (int j = lig; j < nsl; j += G) accs[sb + j] = 0.f;
             }
             __syncwarp();
 
@@ -288,11 +301,12 @@ __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& n
                 __syncwarp();
             }
             float C2 = 0.f;
-            // active pixels are processed NAB at a time: the c_s staging buffer holds NAB rows
+            // active pixels are processed nab at a time: the c_s staging buffer holds nab rows
+            const int nab = a.L.nab;
 #pragma unroll 1
-            for (int b0 = 0; b0 < na; b0 += NAB) {
-            const int nb = min(NAB, na - b0);
-            const bool mine = act && my_ai >= b0 && my_ai < b0 + NAB;
+            for (int b0 = 0; b0 < na; b0 += nab) {
+            const int nb = min(nab, na - b0);
+            const bool mine = act && my_ai >= b0 && my_ai < b0 + nab;
             // the (pixel, logit) pairs of this batch that need per-sample noise
             int np2 = 0;
             {
@@ -308,16 +322,13 @@ __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& n
                             want = true;  // every logit, dense in j
                         } else {
                             j = idx < nvp ? (int)vlist[vs + idx] - p * K : K;
-                            const float z = idx < nvp ? zs[vs + idx] : pi.zbg;
-                            want = z > -CUDART_INF_F && z >= floor_v;
+                            want = hj[COMPACT ? sb + idx : sb + j] >= 0;  // can win (phase 2)
                         }
                     }
                     const unsigned wbal = __ballot_sync(FULL, want);
                     if (want) {
                         const int pos = np2 + __popc(wbal & lt);
-                        pair_j[pos] = (uint16_t)j;
-                        pair_s[pos] = (uint16_t)(COMPACT ? sb + idx : sb + j);
-                        pair_p[pos] = (uint8_t)(my_ai - b0);
+                        pairs[pos] = (uint16_t)((COMPACT ? idx : j) | ((my_ai - b0) << 10));
                     }
                     np2 += __popc(wbal);
                 }
@@ -389,10 +400,17 @@ __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& n
                     const int it = it0 + lane;
                     const int pr = it >> lpp_shift;
                     const bool on = pr < np2;
-                    const int j = on ? pair_j[pr] : 0;
-                    const int ps = on ? pair_s[pr] : 0;
-                    const int ai = on ? pair_p[pr] : 0;
+                    const int code = on ? pairs[pr] : 0;
+                    const int ai = code >> 10, cx = code & 1023;
                     const int pp = apx[b0 + ai];
+                    int j = cx, ps;
+                    if (COMPACT) {
+                        const int nvq = pnv[pp] & 0xffff;
+                        ps = psb[pp] + cx;
+                        j = cx < nvq ? (int)vlist[vstart[pp] + cx] - pp * K : K;
+                    } else {
+                        ps = pp * K1 + cx;
+                    }
                     float acc = 0.f, t2 = 0.f;
                     if (on) {
                         const float4* c4p = reinterpret_cast<const float4*>(cs + ai * sc);
@@ -444,9 +462,8 @@ __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& n
 #pragma unroll 1
                         for (int idx = lig; idx <= nvp; idx += G) {
                             const int j = idx < nvp ? (int)vlist[vs + idx] - p * K : K;
-                            const float z = idx < nvp ? zs[vs + idx] : pi.zbg;
                             const int sl = COMPACT ? sb + idx : sb + j;
-                            if (z > -CUDART_INF_F && z >= floor_v) {
+                            if (hj[sl] >= 0) {
                                 nlive++;
                                 t += t2s[sl];
                             } else if (!drop_dead) {
@@ -533,7 +550,7 @@ __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& n
                 if (has_acc) gz = (from_global ? gacc[k] : accs[sl]) * invSg;
                 const float gzi = gz + ((k == pi.argzi && pass) ? gzmax : 0.f);
                 gz_t[e] = -gzi * rdenom;
-                const int c = cnt[n];
+                const int c = lean ? (int)a.counts[g0 + e] : (int)cnt[n];
                 const float pk = (float)c * rS;
                 float gP = 0.f;
                 if (c != 0) {
@@ -584,8 +601,13 @@ __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& n
     }
 }
 
+// CTAs (= warps) per SM the main pass is compiled for: 64 registers, no spills; the shared-memory layout allows 30
+// (25 / 28 / 32 measured on the sparse set: 0.326 / 0.311 / 0.323 ms)
+#ifndef BWD_MAIN_CTAS
+#define BWD_MAIN_CTAS 28
+#endif
 template <class NoiseA, int GT, bool PHASED, bool FACE, bool COMPACT, bool BLOB>
-__global__ void __launch_bounds__(FNT, 25) shade_bwd_kernel(const BwdArgs a, const NoiseA noise_a) {
+__global__ void __launch_bounds__(FNT, BWD_MAIN_CTAS) shade_bwd_kernel(const BwdArgs a, const NoiseA noise_a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     NoiseA na = noise_a;
     if (a.pb.seed_device) na.mix(__ldg(a.pb.seed_device + 1));  // device-side seed, see shade_fwd.cu
@@ -704,9 +726,12 @@ static int launch_bwd_c(const BwdArgs& a, const PN& na, cudaStream_t st) {
 }
 template <class PN, int GT, bool FACE>
 static int launch_bwd_fb(const BwdArgs& a, const PN& na, int64_t prow0, cudaStream_t st) {
-    const size_t smem = (size_t)a.L.warp_smem * (FBT / 32);
+    size_t smem = (size_t)a.L.warp_smem * (FBT / 32);
+#ifdef PERT_EXPERIMENTS  // occupancy sensitivity: pad the CTA's shared memory
+    if (const char* e = getenv("PERT_BWD_PAD")) smem += (size_t)atoi(e);
+#endif
     if (int rc = set_smem(shade_bwd_fallback_kernel<PN, GT, FACE>, smem)) return rc;
-    shade_bwd_fallback_kernel<PN, GT, FACE><<<sm_count() * 12, FBT, smem, st>>>(a, na, prow0);
+    shade_bwd_fallback_kernel<PN, GT, FACE><<<resident_grid(shade_bwd_fallback_kernel<PN, GT, FACE>, FBT, smem), FBT, smem, st>>>(a, na, prow0);
     return (int)cudaGetLastError();
 }
 

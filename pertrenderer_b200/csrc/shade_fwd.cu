@@ -518,7 +518,7 @@ static int launch_fwd_fallback_ph(const FwdArgs& a, const PN& nr, const PN& na, 
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    shade_fwd_fallback_kernel<PN, PN, GT, CPH><<<sm_count() * FB_MIN_CTAS, FBT, smem, st>>>(a, nr, na);
+    shade_fwd_fallback_kernel<PN, PN, GT, CPH><<<resident_grid(shade_fwd_fallback_kernel<PN, PN, GT, CPH>, FBT, smem), FBT, smem, st>>>(a, nr, na);
     return (int)cudaGetLastError();
 }
 
