@@ -3,7 +3,7 @@
 init_renderers :124-194, optimize_pose :320-409, benchmark :576-661) on pertrenderer_b200 alone (no pytorch3d).
 
     python examples/pose_optimisation.py [--noise gaussian softras] [--trials 10] [--imsize 128] [--init 30]
-                                          [--niter 100] [--nb-samples 16] [--adapt]
+                                          [--niter 100] [--nb-samples 16] [--adapt | --graph]
 
 A Rubik-style cube (8 vertices, 12 faces, one colour per side: data/objs/rubiks/cube2.obj + its six-strip UV map) is
 rendered at a random rotation with the hard operators (blur_radius 0, one face per pixel); the rotation is then
@@ -128,6 +128,52 @@ def optimize_pose(mesh, verts, renderer, target_rgb, w_init, niter, lr, adapt, a
     return best_w
 
 
+def optimize_pose_graphed(mesh, verts, renderer, target_rgb, w_init, niter, lr, warmup=3):
+    """The same loop with ONE CUDA graph per iteration (render + loss + backward + best-pose bookkeeping + gradient guard
+    + Adam): the eager loop issues ~250 launches per iteration for < 0.5 ms of kernels, a replay issues one.  What makes
+    the capture possible: the noise seeds live on the device (ops.device_seeds + a seed_advance node per replay), the
+    smoothing scalars do not ask for gradients (no 12-byte read-back in backward), Adam is `capturable`, and the
+    best-loss / exploding-gradient logic of eval.py:371-378 runs on the device (torch.where) instead of through .item().
+    The first `warmup` iterations run eagerly (they are ordinary iterations of the optimisation)."""
+    from pertrenderer_b200 import ops
+    dev = w_init.device
+    for t in renderer.shader.get_smoothing():
+        t.requires_grad_(False)
+    w = w_init.clone().requires_grad_(True)
+    opt = torch.optim.Adam([w], lr=lr, capturable=True)
+    seeds = torch.tensor([ops.draw_seed(), ops.draw_seed()], dtype=torch.int64, device=dev)
+    best = torch.full((), float("inf"), device=dev)
+    best_w = w.detach().clone()
+
+    def iteration():
+        ops.seed_advance(seeds)
+        opt.zero_grad(set_to_none=True)
+        img = renderer(mesh.update_padded(verts @ so3_exp(w)))
+        loss = ((img[..., :3] - target_rgb) ** 2).mean()
+        loss.backward()
+        better = loss.detach() < best
+        best_w.copy_(torch.where(better, w.detach(), best_w))
+        best.copy_(torch.where(better, loss.detach(), best))
+        g = w.grad
+        g.copy_(torch.where(g.norm() > 1000.0, 1e-5 * torch.randn_like(g), g))  # eval.py:375-378
+        opt.step()
+
+    with ops.device_seeds(seeds):
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(min(warmup, niter)):
+                iteration()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        if niter > warmup:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                iteration()
+            for _ in range(niter - warmup):  # the capture itself executes nothing
+                graph.replay()
+    return best_w.clone()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--noise", nargs="+", default=["softras", "gaussian"], choices=["gaussian", "gaussian_wovr", "cauchy", "softras"])
@@ -140,6 +186,7 @@ def main():
     ap.add_argument("--gamma", type=float, default=1e-2)
     ap.add_argument("--nb-samples", type=int, default=16)
     ap.add_argument("--adapt", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="one CUDA graph per iteration (not with --adapt: the smoothing is frozen in it)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--kernel-flags", type=int, default=0, help="PERT_F_* flags for every perturbed op (4 = per-sample noise, 8192 = Philox-7)")
     args = ap.parse_args()
@@ -179,7 +226,10 @@ def main():
             renderer = make_renderer(noise, cameras, lights, args.sigma, args.gamma, args.nb_samples, args.imsize, dev)
             torch.cuda.synchronize()
             t0 = time.perf_counter()
-            w = optimize_pose(mesh, verts, renderer, target, w0, args.niter, args.lr, args.adapt)
+            if args.graph and not args.adapt:
+                w = optimize_pose_graphed(mesh, verts, renderer, target, w0, args.niter, args.lr)
+            else:
+                w = optimize_pose(mesh, verts, renderer, target, w0, args.niter, args.lr, args.adapt)
             torch.cuda.synchronize()
             t_iter.append((time.perf_counter() - t0) / args.niter)
             inits.append(angle_deg(so3_exp(w0), R_true))

@@ -61,6 +61,25 @@ def current_flags() -> int:
     return getattr(_tls, "flags", 0)
 
 
+@contextlib.contextmanager
+def device_seeds(seed_device: Optional[torch.Tensor]):
+    """Within the block every fused perturbed op reads its seeds as ``host seed ^ seed_device[i]`` (``pert_problem.
+    seed_device``; int64 (2,) on the device: coverage stage, aggregation stage).  Inside a captured CUDA graph the
+    host seeds are frozen, so the loop steps the device pair with :func:`seed_advance` (a graph node) and every
+    replay draws fresh noise: this is what lets a whole render + backward + optimiser iteration be captured
+    (examples/pose_optimisation.py)."""
+    prev = getattr(_tls, "seed_device", None)
+    _tls.seed_device = seed_device
+    try:
+        yield
+    finally:
+        _tls.seed_device = prev
+
+
+def current_seed_device() -> Optional[torch.Tensor]:
+    return getattr(_tls, "seed_device", None)
+
+
 def _f32c(t):
     return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.to(torch.float32).contiguous()
 

@@ -55,7 +55,8 @@ class _PerturbedShade(Function):
             background=cfg["background"], sigma=float(sigma), gamma=float(gamma), alpha=float(alpha),
             eps=float(cfg["eps"]), S_rast=int(cfg["S_rast"]), S_agg=int(cfg["S_agg"]),
             seed_rast=seed_r, seed_agg=seed_a, pixel_offset=int(cfg.get("pixel_offset", 0)),
-            flags=ops.current_flags() | int(cfg.get("flags", 0)), noise_rast=noise_r, noise_agg=noise_a)
+            flags=ops.current_flags() | int(cfg.get("flags", 0)), noise_rast=noise_r, noise_agg=noise_a,
+            seed_device=None if (noise_r is not None or noise_a is not None) else ops.current_seed_device())
         image, saved = ops.shade_forward(pr)
         ctx.pr, ctx.saved = pr, saved
         ctx.scalars = (sigma, gamma, alpha)

@@ -246,6 +246,50 @@ def test_renderer_end_to_end_pose_optimisation(pair):
     assert closest < 0.4 * a0 and a_best < 0.6 * a0, (pair, a0, closest, a_best)
 
 
+@pytest.mark.parametrize("pair", ["softras", "gaussian"])
+def test_pose_iteration_captured_in_one_cuda_graph(pair):
+    """examples/pose_optimisation.py --graph: render + loss + backward + best-pose bookkeeping + Adam of eval.py:341-394 as
+    ONE CUDA graph per iteration (device-side seeds: ops.device_seeds + a seed_advance node).  The angle error must drop
+    as in the eager loop, and two runs of the captured loop from the same start must differ for the perturbed pair (every
+    replay draws fresh noise) and agree for the deterministic one."""
+    import os
+    import runpy
+    from conftest import ROOT
+    import pertrenderer_b200 as pb
+    ex = runpy.run_path(os.path.join(ROOT, "examples", "pose_optimisation.py"), run_name="pose_example")
+    torch.manual_seed(0)
+    verts, faces, colors = ex["cube_mesh"](DEV)
+    mesh = pb.TriMeshes(verts, faces, face_colors=colors)
+    R, T = pb.look_at_view_transform(dist=6.7, elev=30.0, azim=120.0, device=DEV)
+    cameras = pb.OpenGLPerspectiveCameras(R=R, T=T, fov=60, device=DEV)
+    lights = pb.PointLights(location=[[0.0, 2.0, -2.0]], device=DEV)
+    hard = ex["make_renderer"]("hard", cameras, lights, 1e-4, 1e-4, 1, 64, DEV)
+    w_true = torch.tensor([0.3, -0.5, 0.2], device=DEV)
+    R_true = ex["so3_exp"](w_true)
+    with torch.no_grad():
+        target = hard(mesh.update_padded(verts @ R_true))[..., :3]
+    axis = torch.tensor([0.6, 0.0, 0.8], device=DEV)
+    w0 = ex["so3_log"](R_true @ ex["so3_exp"](math.radians(15.0) * axis))
+    a0 = ex["angle_deg"](ex["so3_exp"](w0), R_true)
+
+    def run():
+        renderer = ex["make_renderer"](pair, cameras, lights, 1e-3, 1e-2, 16, 64, DEV)
+        return ex["optimize_pose_graphed"](mesh, verts, renderer, target, w0, 60, 5e-2)
+
+    w1, w2 = run(), run()
+    torch.cuda.synchronize()
+    assert torch.isfinite(w1).all() and torch.isfinite(w2).all()
+    if pair == "gaussian":
+        a1, a2 = ex["angle_deg"](ex["so3_exp"](w1), R_true), ex["angle_deg"](ex["so3_exp"](w2), R_true)
+        assert min(a1, a2) < 0.9 * a0, (pair, a0, a1, a2)  # 15 -> ~12 degrees in 60 noisy iterations at 64x64
+        assert not torch.equal(w1, w2)  # fresh seeds per run and per replay
+    else:
+        # the deterministic pair: the captured loop is the eager loop (up to the order of the rasteriser's atomic adds)
+        renderer = ex["make_renderer"](pair, cameras, lights, 1e-3, 1e-2, 16, 64, DEV)
+        w_eager = ex["optimize_pose"](mesh, verts, renderer, target, w0, 60, 5e-2, False)
+        assert (w1 - w2).abs().max().item() < 5e-2 and (w1 - w_eager).abs().max().item() < 5e-2, (w1, w2, w_eager)
+
+
 def test_pose_optimisation_example_and_readme_snippet_run(monkeypatch, capsys):
     """examples/pose_optimisation.py (eval.py's benchmark loop, incl. the adaptive smoothing schedule) and the renderer
     snippet of README.md execute as written."""
