@@ -509,6 +509,42 @@ def graph_leg(dev, kind="rasterised", steps=50):
                     "pass) + scalar finalize"}
 
 
+def pose_iteration_leg(dev, niter=100):
+    """One pose-optimisation trial of examples/pose_optimisation.py (eval.py:320-409: cube, 128x128, K=50, S=16, 100 Adam
+    iterations through MeshRenderer(MeshRasterizer, RandomPhongShader(GaussianRast, GaussianAgg))): wall-clock ms per
+    iteration of the eager loop and of the loop with one CUDA graph per iteration (capture included)."""
+    import math
+    import runpy
+    import time
+    import pertrenderer_b200 as pb
+    ex = runpy.run_path(os.path.join(ROOT, "examples", "pose_optimisation.py"), run_name="pose_example")
+    d = str(dev)
+    verts, faces, colors = ex["cube_mesh"](d)
+    mesh = pb.TriMeshes(verts, faces, face_colors=colors)
+    R, T = pb.look_at_view_transform(dist=6.7, elev=30.0, azim=120.0, device=d)
+    cameras = pb.OpenGLPerspectiveCameras(R=R, T=T, fov=60, device=d)
+    lights = pb.PointLights(location=[[0.0, 2.0, -2.0]], device=d)
+    hard = ex["make_renderer"]("hard", cameras, lights, 1e-4, 1e-4, 1, 128, d)
+    R_true = ex["so3_exp"](torch.tensor([0.3, -0.5, 0.2], device=d))
+    with torch.no_grad():
+        target = hard(mesh.update_padded(verts @ R_true))[..., :3]
+    axis = torch.tensor([0.6, 0.0, 0.8], device=d)
+    w0 = ex["so3_log"](R_true @ ex["so3_exp"](math.radians(30.0) * axis))
+    out = {"workload": "cube (12 faces), 128x128, K=50, S=16, 30 degrees off, %d Adam iterations, lr 5e-2" % niter}
+    for name, fn in (("eager", lambda r: ex["optimize_pose"](mesh, verts, r, target, w0, niter, 5e-2, False)),
+                     ("graph", lambda r: ex["optimize_pose_graphed"](mesh, verts, r, target, w0, niter, 5e-2))):
+        fn(ex["make_renderer"]("gaussian", cameras, lights, SIGMA, GAMMA, 16, 128, d))  # warm-up trial
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        w = fn(ex["make_renderer"]("gaussian", cameras, lights, SIGMA, GAMMA, 16, 128, d))
+        torch.cuda.synchronize(dev)
+        out["ms_per_iteration_" + name] = 1e3 * (time.perf_counter() - t0) / niter
+        out["final_angle_deg_" + name] = ex["angle_deg"](ex["so3_exp"](w), R_true)
+    out["note"] = ("wall clock around a whole trial; graph = 3 eager iterations + capture + replays, every iteration (render + "
+                   "loss + backward + best-pose bookkeeping + gradient guard + Adam) one CUDA graph with device-side seeds")
+    return out
+
+
 def sample_sharded_leg(dev, world, rank, steps):
     """BASELINE config 4 (1 x 128^2, K=50, S=4096) with the noise samples split over the ranks
     (dist.smooth_rgb_blend_sample_sharded: three all-reduces over NCCL), against the unsharded job on every rank:
@@ -870,6 +906,10 @@ def run_b200_arm(args):
             if not args.no_renderer_legs:
                 also["random_phong_shader"] = phong_timed(args, "realistic", dev, n2, 3, rank)
                 also["renderer"] = renderer_timed(args, dev, n4, 3, rank)
+                try:
+                    also["pose_optimisation"] = pose_iteration_leg(dev)
+                except Exception as e:
+                    also["pose_optimisation"] = {"error": repr(e)[:300]}
             try:
                 also["reference_torch_cuda"] = reference_cuda_run(args, dev)
             except Exception as e:
