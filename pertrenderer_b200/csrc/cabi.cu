@@ -329,7 +329,7 @@ extern "C" int pert_shade_bwd(const pert_problem* pb_in, const float* grad_image
         const int tp2 = sparse_tp(a.pb.K, a.pb.N * a.pb.H * a.pb.W) / 2;
         const Launch t = make_launch(&a.pb, tp2);
         SmemLayout sl;
-        bwd_smem_layout(tp2, a.pb.K, t.cap, t.sc, t.nchunks, t.win_bytes, false, kNabFallback, 3, sl);
+        bwd_smem_layout(tp2, a.pb.K, t.cap, t.sc, t.nchunks, t.win_bytes, false, kNabFallback, 1, sl);
         if ((size_t)sl.bytes * (FBT / 32) > 200 * 1024) sparse = false;
     }
     const bool ptr_ok = aligned16(a.pb.pix_to_face) && aligned16(grad_dists) && aligned16(grad_zbuf) &&
@@ -370,7 +370,7 @@ extern "C" int pert_shade_bwd(const pert_problem* pb_in, const float* grad_image
 #ifdef PERT_EXPERIMENTS
     if (const char* e = getenv("PERT_NAB_FB")) fb.L.nab = atoi(e);
 #endif
-    fb.L.lean = 3;
+    fb.L.lean = 1;  // pair list in the counts array; the winners ARE staged (+3 %), the layout still fits 12 CTAs per SM
 #ifdef PERT_EXPERIMENTS
     if (const char* e = getenv("PERT_LEAN_FB")) fb.L.lean = atoi(e);
 #endif

@@ -38,8 +38,8 @@ void bwd_smem_layout(int tp, int K, int cap, int sc, int nchunks, int win_bytes,
     cv.take(tp + 1, 4);           // vstart
     cv.take(tp, 4);               // pa0
     cv.take(tp, 4);               // pg0
-    cv.take(tp, 4);               // psb
-    cv.take(tp, 4);               // pnv
+    cv.take(compact ? tp : 0, 4);  // psb (dense per-logit arrays: the slot base is p * (K + 1))
+    cv.take(compact ? tp : 0, 4);  // pnv
     cv.take(tp, 1);               // apx
     cv.take(nchunks == 1 && !(lean & 2) ? (size_t)tp * sc * win_bytes : 0, 1);  // wst
 }
@@ -256,8 +256,10 @@ __device__ __forceinline__ void shade_bwd_tile(const BwdArgs& a, const NoiseA& n
             if (act && lig == 0) {
                 apx[my_ai] = (uint8_t)p;
                 pa0[p] = a0;
-                psb[p] = sb;
-                pnv[p] = nvp | (prefix ? 0 : 0x10000);
+                if (COMPACT) {
+                    psb[p] = sb;
+                    pnv[p] = nvp | (prefix ? 0 : 0x10000);
+                }
             }
             const int nsl = COMPACT ? nvp + 2 : K1;
             if (act) {
