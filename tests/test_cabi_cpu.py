@@ -152,6 +152,30 @@ def test_seed_follows_torch_generator():
     assert ops.draw_seed() == a and ops.draw_seed() == b and a != b
 
 
+def test_device_seed_context_nests_and_restores():
+    """ops.device_seeds: the seed pair a caller hands to every fused op inside a CUDA-graph capture (pert_problem.seed_device)
+    is thread-local state that nests and is restored on exit, also when the block raises."""
+    import threading
+    from pertrenderer_b200 import ops
+    assert ops.current_seed_device() is None
+    a, b = torch.zeros(2, dtype=torch.int64), torch.ones(2, dtype=torch.int64)
+    with ops.device_seeds(a):
+        assert ops.current_seed_device() is a
+        with ops.device_seeds(b):
+            assert ops.current_seed_device() is b
+        assert ops.current_seed_device() is a
+        seen = []
+        t = threading.Thread(target=lambda: seen.append(ops.current_seed_device()))
+        t.start()
+        t.join()
+        assert seen == [None]  # another thread's ops are not affected
+        with pytest.raises(RuntimeError):
+            with ops.device_seeds(b):
+                raise RuntimeError("boom")
+        assert ops.current_seed_device() is a
+    assert ops.current_seed_device() is None
+
+
 def test_synthetic_fragments_contract():
     for kind in ("dense", "realistic"):
         fr, col = pb.synthetic_fragments(2, 16, 16, 10, kind=kind, device="cpu", seed=3)
