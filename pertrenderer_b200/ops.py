@@ -80,6 +80,14 @@ def current_seed_device() -> Optional[torch.Tensor]:
     return getattr(_tls, "seed_device", None)
 
 
+def refuse_device_seeds(op: str):
+    """The stand-alone operators take host seeds only: inside ``device_seeds`` (i.e. a CUDA-graph capture) they would
+    replay the same noise for ever.  Fail loudly instead."""
+    if current_seed_device() is not None:
+        raise RuntimeError(f"{op}: device-side seeds (ops.device_seeds) are implemented for the fused operator pairs "
+                           "(GaussianRast + GaussianAgg, SoftRast + SoftAgg) only; run this pair outside the block")
+
+
 def _f32c(t):
     return t if (t.dtype == torch.float32 and t.is_contiguous()) else t.to(torch.float32).contiguous()
 

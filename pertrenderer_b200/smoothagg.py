@@ -49,6 +49,7 @@ class randomArgmax(Function):
             torch.manual_seed(1)  # smoothagg.py:18-19: the reference reseeds the GLOBAL generator
         gamma = _scalar(noise_intensity)
         _, noise = ops.current_explicit_noise()
+        ops.refuse_device_seeds("randomArgmax")
         seed = 0 if noise is not None else ops.draw_seed()
         flags = ops.current_flags() | (ops.F_CAUCHY if noise_type == "cauchy" else
                                        _FORWARD_ONLY.get(noise_type, extra_flags))

@@ -47,6 +47,7 @@ class randomHeaviside(Function):
             raise ValueError("distances must be (N,H,W,K)")
         sigma = _scalar(noise_intensity)
         noise, _ = ops.current_explicit_noise()
+        ops.refuse_device_seeds("randomHeaviside")
         seed = 0 if noise is not None else ops.draw_seed()
         # the Cauchy branch of randomHeaviside_wovr drops the control variate too (smoothrast.py:99-101), unlike
         # randomArgmax_wovr's (smoothagg.py:125-128)

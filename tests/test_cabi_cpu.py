@@ -173,7 +173,10 @@ def test_device_seed_context_nests_and_restores():
             with ops.device_seeds(b):
                 raise RuntimeError("boom")
         assert ops.current_seed_device() is a
+        with pytest.raises(RuntimeError):  # stand-alone operators would replay frozen noise inside a graph: refused
+            ops.refuse_device_seeds("randomArgmax")
     assert ops.current_seed_device() is None
+    ops.refuse_device_seeds("randomArgmax")
 
 
 def test_synthetic_fragments_contract():
