@@ -108,6 +108,16 @@ def measured_traffic(kernel, kind, N, HW, K, S):
         return None
 
 
+def measured_issue(kind, N, HW, K, S):
+    """Issue-slot utilisation (smsp__issue_active, % of peak) and ncu duration of every kernel of the step from the same
+    committed capture: the number that says how close the kernels are to the resource that actually binds them."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))[f"{kind}:{N}x{HW}x{K}x{S}"]["kernels"]
+    except Exception:
+        return None
+
+
 def alg_bytes(P, K):
     """SURVEY.md §8d, API-faithful: fwd reads pix_to_face 8 + zbuf 4 + dists 4 + colors 12 per pixel·face and writes RGBA
     16 per pixel; bwd re-reads the same 28, writes grad_dists 4 + grad_zbuf 4 + grad_colors 12 and reads grad_image 16 per
@@ -443,6 +453,7 @@ def device_timed(cfg, kind, dev, steps, warmup, world, rank, sampler=None, flags
     traffic = None if (face or soft or flags) else measured_traffic(dom, kind, N, HW, K, S)
     roof = {"bound": "hbm", "kernel": dom, "achieved": dom_bytes / dom_ms / 1e6, "peak": peak, "unit": "GB/s",
             "frac": dom_bytes / dom_ms / 1e6 / peak, "traffic": traffic, "peak_source": peak_src,
+            "issue_slots": None if (face or soft or flags) else measured_issue(kind, N, HW, K, S),
             "algorithmic_bytes_per_launch": dom_bytes, "kernel_ms": dom_ms,
             "fwd": {"ms": fwd_ms, "alg_bytes": fb, "gbs": fb / fwd_ms / 1e6, "frac": fb / fwd_ms / 1e6 / peak},
             "bwd": {"ms": bwd_ms, "alg_bytes": bb, "gbs": bb / bwd_ms / 1e6, "frac": bb / bwd_ms / 1e6 / peak},
@@ -507,6 +518,50 @@ def graph_leg(dev, kind="rasterised", steps=50):
             "value": units / (ms * 1e-3), "unit": UNIT, "launches_per_step": 9,
             "note": "one graph replay = seed advance + memsets + forward (main + two-launch fallback pass) + backward (main + fallback "
                     "pass) + scalar finalize"}
+
+
+def explicit_noise_leg(dev, kind, steps=5):
+    """"explicit-noise mode where HBM really binds".  BASELINE config 2 with both noise tensors
+    materialised in HBM, U (S,N,H,W,K) and V (S,N,H,W,K+1) -- the reference's own data flow, the parity path of the kernels
+    (bit-comparable with the oracle) -- against the survey's byte count for this mode: the Philox-mode bytes plus
+    4 S (PF + P K1) per pass."""
+    from pertrenderer_b200 import ops
+    cfg = CONFIGS[2]
+    N, HW, K, S = cfg["N"], cfg["HW"], cfg["K"], cfg["S"]
+    fr, col = make_fragments(kind, N, HW, K, S, dev, 0)
+    G = torch.randn((N, HW, HW, 4), device=dev, generator=torch.Generator(device=dev).manual_seed(1))
+    gen = torch.Generator(device=dev).manual_seed(5)
+    U = torch.randn((S, N, HW, HW, K), device=dev, generator=gen)
+    V = torch.randn((S, N, HW, HW, K + 1), device=dev, generator=gen)
+    pr = ops.ShadeProblem(pix_to_face=fr.pix_to_face, zbuf=fr.zbuf, dists=fr.dists, colors=col, znear=1.0, zfar=100.0,
+                          background=BACKGROUND, sigma=SIGMA, gamma=GAMMA, alpha=ALPHA, eps=EPS, S_rast=S, S_agg=S,
+                          noise_rast=U, noise_agg=V)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    for i in range(-2, steps):
+        if i >= 0:
+            ev[i][0].record()
+        image, saved = ops.shade_forward(pr)
+        if i >= 0:
+            ev[i][1].record()
+        ops.shade_backward(pr, saved, G)
+        if i >= 0:
+            ev[i][2].record()
+    torch.cuda.synchronize(dev)
+    fwd = sorted(e[0].elapsed_time(e[1]) for e in ev)[steps // 2]
+    bwd = sorted(e[1].elapsed_time(e[2]) for e in ev)[steps // 2]
+    P = N * HW * HW
+    PF = P * K
+    noise = 4 * S * (PF + P * (K + 1))
+    fb, bb = 28 * PF + 16 * P + noise, 48 * PF + 16 * P + noise
+    peak, peak_src = peaks()
+    del U, V
+    torch.cuda.empty_cache()
+    return {"config": cfg["name"], "fragments": kind, "ms_per_step": fwd + bwd, "value": PF * S / ((fwd + bwd) * 1e-3), "unit": UNIT,
+            "fwd": {"ms": fwd, "alg_bytes": fb, "frac": fb / fwd / 1e6 / peak}, "bwd": {"ms": bwd, "alg_bytes": bb, "frac": bb / bwd / 1e6 / peak},
+            "fwd_bwd_frac": (fb + bb) / (fwd + bwd) / 1e6 / peak, "noise_bytes_per_pass": noise, "peak": peak, "peak_source": peak_src,
+            "note": "explicit noise tensors in HBM (13.5 GB): the exact-noise parity mode of the kernels (phase-split generic "
+                    "instantiation), not the production path; backward reads V only (the coverage sums are saved by forward), "
+                    "the byte count follows SURVEY 8d and charges U to it as well"}
 
 
 def pose_iteration_leg(dev, niter=100):
@@ -906,6 +961,10 @@ def run_b200_arm(args):
             if not args.no_renderer_legs:
                 also["random_phong_shader"] = phong_timed(args, "realistic", dev, n2, 3, rank)
                 also["renderer"] = renderer_timed(args, dev, n4, 3, rank)
+                try:
+                    also["explicit_noise"] = explicit_noise_leg(dev, args.fragments)
+                except Exception as e:
+                    also["explicit_noise"] = {"error": repr(e)[:300]}
                 try:
                     also["pose_optimisation"] = pose_iteration_leg(dev)
                 except Exception as e:

@@ -36,5 +36,14 @@ if len(sys.argv)>2:
         if "fallback" not in kn: n[name]+=1
     for k in tot:
         if n[k]: ent[k]=tot[k]/n[k]
+    # issue-slot utilisation and duration of every kernel of the step (the path is issue-bound, not HBM-bound)
+    kern={}
+    for d in data:
+        kn=d[hdr.index("Kernel Name")]
+        short=("fwd" if "shade_fwd" in kn else "bwd")+("_fallback" if "fallback" in kn else "_main")
+        if "shade_fwd_fallback" in kn: short+="_coverage" if ", 16>" in kn else "_aggregate"
+        i=hdr.index("gpu__time_duration.sum"); us=float(d[i].replace(",",""))*{"ns":1e-3,"us":1,"ms":1e3,"s":1e6}.get(units[i].lower(),1)
+        kern[short]={"issue_active_pct":round(float(d[hdr.index("smsp__issue_active.avg.pct_of_peak_sustained_active")].replace(",","")),1),"ncu_us":round(us,1)}
+    ent["kernels"]=kern
     ent["source"]=os.path.basename(rep)
     json.dump(t,open(path,"w"),indent=1)
