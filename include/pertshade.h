@@ -154,9 +154,11 @@ const char* pert_last_cuda_error(void);
  *   scalar_partials  float  4 * 3T   (one row per tile; rows T..3T belong to the fallback pass)
  *   worklist         int32  4 + T    optional (NULL: off).  Sparse-first mode: the main pass holds half a
  *                    tile's entries in shared memory (real fragments fill a few percent); tiles with more
- *                    valid entries are listed here and redone by a fallback pass as half-size tiles.  The
- *                    library zeroes the counter itself (cudaMemsetAsync on the caller's stream).  Results do
- *                    not depend on which pass handled a tile, up to the association order of float sums. */
+ *                    valid entries are listed here and redone by a fallback pass as half-size tiles (forward:
+ *                    two launches, coverage samples then aggregation + blend).  Words 0..3 are the list length
+ *                    and the work cursors of the fallback launches, words 4.. the tile ids; the library zeroes
+ *                    the header itself (cudaMemsetAsync on the caller's stream).  Results do not depend on
+ *                    which pass handled a tile, up to the association order of float sums. */
 int64_t pert_num_tiles(const pert_problem* pb);
 /* element size in bytes of the winners buffer for this K (1 or 2) */
 int pert_winner_bytes(int32_t K);
