@@ -11,7 +11,6 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
-from oracle import pert_oracle as O  # noqa: E402  (tool, not product)
 from pertrenderer_b200 import ops, synthetic_fragments  # noqa: E402
 
 kind = sys.argv[1] if len(sys.argv) > 1 else "rasterised"
@@ -34,8 +33,12 @@ sel = cov[torch.randperm(cov.numel(), generator=torch.Generator().manual_seed(0)
 p2f = fr.pix_to_face.reshape(P, K)[sel].cpu()[None, None]
 zb = fr.zbuf.reshape(P, K)[sel].cpu()[None, None]
 cnt = ((saved.counts.to(torch.int32) & 0xFFFF).reshape(P, K)[sel].cpu() * valid[sel].cpu())[None, None]
-zeta, prob, aux = O.logits_from_counts(p2f, zb, cnt.float(), S, 1.0, 100.0, gamma, 1.0, 1e-10)
-zeta = zeta[0, 0]  # (n, K+1)
+# logits of smoothagg.py:198-202 from the kernel's own hit counts (alpha = 1, znear = 1, zfar = 100, eps = 1e-10)
+m = (p2f >= 0)[0, 0]
+prob = (cnt[0, 0].float() / S) * m
+zi = (100.0 - zb[0, 0]) / 99.0 * m
+zmx = zi.max(-1, keepdim=True).values.clamp(min=1e-10)
+zeta = torch.cat((gamma * torch.log(prob) + zi - zmx, 1e-10 - zmx), dim=-1)  # (n, K+1); log 0 = -inf: can never win
 zmax = zeta.max(-1, keepdim=True).values
 live = torch.isfinite(zeta) & (zeta >= zmax - 2 * gamma * UMAX)
 nlive = live.sum(-1)
